@@ -1,0 +1,281 @@
+// Evaluation contexts for the circuit templates (templates_*.cuh).
+//
+// The templates are written once, as C++ generic over a mode M:
+//   MCompute : computes every signal over Fr and stores it at its witness index
+//              (device threads in the CUDA kernels; the same code compiled for the host is the
+//              CPU port under oracle/cpu_port used for checking and the CPU baseline);
+//   MLayout  : host-only walk with no arithmetic at all -- assigns witness indexes, records
+//              section offsets for the kernels (Plan) and resolves signal names (the `.sym`
+//              equivalent the reference gets from circom).
+//
+// Witness numbering follows the model in oracle/circuit.py (circom 0.5.45 behaviour, restated):
+// signals are numbered depth-first in declaration order, a sub-component occupies the range
+// where it is instantiated, and `a <== b` with a single signal on the right makes `a` an alias
+// of `b` (no witness entry of its own).  Index 0 is the constant 1.
+#pragma once
+#include "fr.cuh"
+
+#ifndef __CUDA_ARCH__
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstdlib>
+#endif
+
+struct MCompute {};
+struct MLayout {};
+
+#define HZ_NOIDX 0xFFFFFFFFu
+
+// ---- names: only the layout walk ever looks at them ---------------------------------------
+struct Nm {
+    const char* s; int i, j;
+    HZ_HD Nm(const char* s_) : s(s_), i(-1), j(-1) {}
+    HZ_HD Nm(const char* s_, int i_) : s(s_), i(i_), j(-1) {}
+    HZ_HD Nm(const char* s_, int i_, int j_) : s(s_), i(i_), j(j_) {}
+};
+
+// ---- values ------------------------------------------------------------------------------
+template <class M> struct V;
+template <> struct V<MCompute> {
+    Fr v; bool sig;
+};
+template <> struct V<MLayout> {
+    uint32_t idx;   // witness index when the value is a signal, HZ_NOIDX for an expression
+};
+typedef V<MCompute> VC;
+typedef V<MLayout> VL;
+
+HZ_HD VC vc(const Fr& f) { VC r; r.v = f; r.sig = false; return r; }
+HZ_HD VL vl() { VL r; r.idx = HZ_NOIDX; return r; }
+
+template <class M> struct Ops;
+template <> struct Ops<MCompute> {
+    static HZ_HD VC K(uint64_t k) { return vc(fr_from_u64(k)); }
+    static HZ_HD VC KF(const Fr& f) { return vc(f); }
+    static HZ_HD VC pow2(int k) { return vc(fr_pow2(k)); }
+};
+template <> struct Ops<MLayout> {
+    static HZ_HD VL K(uint64_t) { return vl(); }
+    static HZ_HD VL KF(const Fr&) { return vl(); }
+    static HZ_HD VL pow2(int) { return vl(); }
+};
+
+HZ_HD VC operator+(const VC& a, const VC& b) { return vc(fr_add(a.v, b.v)); }
+HZ_HD VC operator-(const VC& a, const VC& b) { return vc(fr_sub(a.v, b.v)); }
+HZ_HD VC operator*(const VC& a, const VC& b) { return vc(fr_mul(a.v, b.v)); }
+HZ_HD VC operator-(const VC& a) { return vc(fr_neg(a.v)); }
+HZ_HD VC operator+(const VC& a, uint64_t k) { return vc(fr_add(a.v, fr_from_u64(k))); }
+HZ_HD VC operator-(const VC& a, uint64_t k) { return vc(fr_sub(a.v, fr_from_u64(k))); }
+HZ_HD VC operator*(const VC& a, uint64_t k) { return vc(fr_mul(a.v, fr_from_u64(k))); }
+HZ_HD VC operator-(uint64_t k, const VC& a) { return vc(fr_sub(fr_from_u64(k), a.v)); }
+HZ_HD VC operator+(uint64_t k, const VC& a) { return vc(fr_add(fr_from_u64(k), a.v)); }
+HZ_HD VC operator*(uint64_t k, const VC& a) { return vc(fr_mul(a.v, fr_from_u64(k))); }
+HZ_HD VC vinv(const VC& a) { return vc(fr_inv(a.v)); }
+HZ_HD VC vdiv(const VC& a, const VC& b) { return vc(fr_mul(a.v, fr_inv(b.v))); }
+HZ_HD uint32_t vbit(const VC& a, int i) { return fr_bit(a.v, i); }
+HZ_HD bool vis0(const VC& a) { return fr_is_zero(a.v); }
+// value of a boolean signal as a machine bit
+HZ_HD uint32_t vlsb(const VC& a) { return a.v.l[0] & 1u; }
+
+HZ_HD VL operator+(const VL&, const VL&) { return vl(); }
+HZ_HD VL operator-(const VL&, const VL&) { return vl(); }
+HZ_HD VL operator*(const VL&, const VL&) { return vl(); }
+HZ_HD VL operator-(const VL&) { return vl(); }
+HZ_HD VL operator+(const VL&, uint64_t) { return vl(); }
+HZ_HD VL operator-(const VL&, uint64_t) { return vl(); }
+HZ_HD VL operator*(const VL&, uint64_t) { return vl(); }
+HZ_HD VL operator-(uint64_t, const VL&) { return vl(); }
+HZ_HD VL operator+(uint64_t, const VL&) { return vl(); }
+HZ_HD VL operator*(uint64_t, const VL&) { return vl(); }
+HZ_HD VL vinv(const VL&) { return vl(); }
+HZ_HD VL vdiv(const VL&, const VL&) { return vl(); }
+HZ_HD uint32_t vbit(const VL&, int) { return 0; }
+HZ_HD bool vis0(const VL&) { return true; }
+HZ_HD uint32_t vlsb(const VL&) { return 0; }
+
+// ---- bit vectors (arrays of 0/1-valued values), capacity 32*W bits -----------------------
+template <class M, int W> struct BVT;
+template <int W> struct BVT<MCompute, W> {
+    uint32_t val[W];   // bit values
+    uint32_t sg[W];    // 1 = the element is a signal (alias-able), 0 = expression / constant
+    int n;
+    HZ_HD VC get(int i) const {
+        VC r; r.v = fr_from_u64((val[i >> 5] >> (i & 31)) & 1u); r.sig = (sg[i >> 5] >> (i & 31)) & 1u; return r;
+    }
+    HZ_HD uint32_t bit(int i) const { return (val[i >> 5] >> (i & 31)) & 1u; }
+    HZ_HD void put(int i, const VC& x) {
+        uint32_t m = 1u << (i & 31);
+        val[i >> 5] = (val[i >> 5] & ~m) | ((x.v.l[0] & 1u) ? m : 0);
+        sg[i >> 5] = (sg[i >> 5] & ~m) | (x.sig ? m : 0);
+    }
+    HZ_HD void clear(int n_) { n = n_; for (int i = 0; i < W; i++) { val[i] = 0; sg[i] = 0; } }
+};
+template <int W> struct BVT<MLayout, W> {
+    uint32_t idx[32 * W];
+    int n;
+    HZ_HD VL get(int i) const { VL r; r.idx = idx[i]; return r; }
+    HZ_HD uint32_t bit(int) const { return 0; }
+    HZ_HD void put(int i, const VL& x) { idx[i] = x.idx; }
+    HZ_HD void clear(int n_) { n = n_; for (int i = 0; i < 32 * W; i++) idx[i] = HZ_NOIDX; }
+};
+
+template <class M, int W, int W2>
+HZ_HD void bv_copy(BVT<M, W>& d, int dpos, const BVT<M, W2>& s, int spos, int n) {
+    for (int i = 0; i < n; i++) d.put(dpos + i, s.get(spos + i));
+}
+
+// ---- constraint failures -----------------------------------------------------------------
+struct HzErrRec { uint32_t cur; uint32_t line; Fr lhs, rhs; };
+#define HZ_MAX_ERR 32
+struct HzErrBuf { uint32_t count; uint32_t pad; HzErrRec rec[HZ_MAX_ERR]; };
+
+// ---- layout sink (host) -------------------------------------------------------------------
+#ifndef __CUDA_ARCH__
+struct LayoutSink {
+    // name recording: every signal whose full name starts with `filter` is reported
+    bool want_names = false;
+    std::string filter;
+    std::vector<std::pair<std::string, uint32_t> >* out = nullptr;
+    // reverse lookup: name of the first signal declared at witness index `find_idx`
+    bool find_mode = false;
+    uint32_t find_idx = 0;
+    std::string found;
+    bool active(const std::string& prefix) const {
+        if (!want_names) return false;
+        if (find_mode) return true;
+        size_t n = prefix.size() < filter.size() ? prefix.size() : filter.size();
+        return prefix.compare(0, n, filter, 0, n) == 0;
+    }
+};
+static inline std::string hz_nm(const Nm& n) {
+    std::string s(n.s);
+    char b[32];
+    if (n.i >= 0) { snprintf(b, sizeof b, "[%d]", n.i); s += b; }
+    if (n.j >= 0) { snprintf(b, sizeof b, "[%d]", n.j); s += b; }
+    return s;
+}
+#endif
+
+// ---- component contexts -------------------------------------------------------------------
+template <class M> struct Comp;
+
+template <> struct Comp<MCompute> {
+    Fr* w;              // witness base
+    uint32_t cur;       // next free witness index
+    uint32_t end;       // reserved range end (HZ_NOIDX when sharing the parent's cursor)
+    Comp* parent;
+    HzErrBuf* err;      // null = sanity check off
+    typedef VC Val;
+
+    HZ_HD Comp(Fr* w_, uint32_t cur_, HzErrBuf* err_) : w(w_), cur(cur_), end(HZ_NOIDX), parent(nullptr), err(err_) {}
+    HZ_HD Comp(Comp* p, bool reserved, uint32_t size) : w(p->w), cur(p->cur), parent(reserved ? nullptr : p), err(p->err) {
+        if (reserved) { end = p->cur + size; p->cur += size; } else end = HZ_NOIDX;
+    }
+    HZ_HD ~Comp() {
+        if (parent) parent->cur = cur;
+#if !defined(__CUDA_ARCH__) && defined(HZ_DEBUG_LAYOUT)
+        if (end != HZ_NOIDX && cur != end) { fprintf(stderr, "reserved size mismatch: %u != %u\n", cur, end); abort(); }
+#endif
+    }
+    Comp(const Comp&) = delete;
+    HZ_HD Comp(Comp&& o) : w(o.w), cur(o.cur), end(o.end), parent(o.parent), err(o.err) { o.parent = nullptr; o.end = HZ_NOIDX; }
+
+    HZ_HD Comp sub(const Nm&) { return Comp(this, false, 0); }
+    HZ_HD Comp sub_reserve(const Nm&, uint32_t size) { return Comp(this, true, size); }
+    HZ_HD void skip(const Nm&, uint32_t size) { cur += size; }
+
+    HZ_HD uint32_t sig(const Nm&) { return cur++; }
+    HZ_HD uint32_t sigs(const Nm&, int n) { uint32_t s = cur; cur += n; return s; }
+    HZ_HD VC set(uint32_t slot, const VC& x) { w[slot] = x.v; VC r = x; r.sig = true; return r; }
+    HZ_HD VC seti(const Nm&, uint32_t slot, const VC& x) { return set(slot, x); }
+    HZ_HD VC alias(const Nm&, const VC& x) { return x; }
+    // `signal s <== x` / wiring of a sub-component input: alias when x is a signal
+    HZ_HD VC def(const Nm&, const VC& x) {
+        if (x.sig) return x;
+        w[cur++] = x.v; VC r = x; r.sig = true; return r;
+    }
+    // main-component signals always own their entry
+    HZ_HD VC own(const Nm&, const VC& x) { w[cur++] = x.v; VC r = x; r.sig = true; return r; }
+    HZ_HD VC load(uint32_t idx) const { VC r; r.v = w[idx]; r.sig = true; return r; }
+    HZ_HD bool sanity() const { return err != nullptr; }
+    HZ_HD void check(const VC& lhs, const VC& rhs, uint32_t line) {
+        if (!err) return;
+        if (fr_eq(lhs.v, rhs.v)) return;
+#ifdef __CUDA_ARCH__
+        uint32_t k = atomicAdd(&err->count, 1u);
+#else
+        uint32_t k = __atomic_fetch_add(&err->count, 1u, __ATOMIC_RELAXED);
+#endif
+        if (k < HZ_MAX_ERR) { err->rec[k].cur = cur; err->rec[k].line = line; err->rec[k].lhs = lhs.v; err->rec[k].rhs = rhs.v; }
+    }
+    HZ_HD void check0(const VC& lhs, uint32_t line) { check(lhs, vc(fr_zero()), line); }
+};
+
+#ifndef __CUDA_ARCH__
+template <> struct Comp<MLayout> {
+    uint32_t cur, end;
+    Comp* parent;
+    LayoutSink* sink;
+    std::string prefix;
+    bool named;
+    typedef VL Val;
+
+    Comp(uint32_t cur_, LayoutSink* s, const std::string& pre) : cur(cur_), end(HZ_NOIDX), parent(nullptr), sink(s), prefix(pre) {
+        named = sink && sink->active(prefix);
+    }
+    Comp(Comp* p, const Nm& nm, bool reserved, uint32_t size) : cur(p->cur), parent(reserved ? nullptr : p), sink(p->sink) {
+        if (reserved) { end = p->cur + size; p->cur += size; } else end = HZ_NOIDX;
+        named = false;
+        if (sink && sink->want_names) {
+            prefix = p->prefix + "." + hz_nm(nm);
+            named = sink->active(prefix);
+        }
+    }
+    ~Comp() {
+        if (parent) parent->cur = cur;
+        if (end != HZ_NOIDX && cur != end) {
+            fprintf(stderr, "hzw layout: reserved size mismatch in %s: used %u, reserved up to %u\n", prefix.c_str(), cur, end);
+            abort();
+        }
+    }
+    Comp(const Comp&) = delete;
+    Comp(Comp&& o) : cur(o.cur), end(o.end), parent(o.parent), sink(o.sink), prefix(o.prefix), named(o.named) { o.parent = nullptr; o.end = HZ_NOIDX; }
+
+    Comp sub(const Nm& nm) { return Comp(this, nm, false, 0); }
+    Comp sub_reserve(const Nm& nm, uint32_t size) { return Comp(this, nm, true, size); }
+    void skip(const Nm&, uint32_t size) { cur += size; }
+
+    void name(const Nm& nm, uint32_t idx) {
+        if (named && sink->find_mode) {
+            if (idx == sink->find_idx && sink->found.empty()) sink->found = prefix + "." + hz_nm(nm);
+            return;
+        }
+        if (named) {
+            std::string full = prefix + "." + hz_nm(nm);
+            if (full.compare(0, sink->filter.size(), sink->filter) == 0) sink->out->push_back(std::make_pair(full, idx));
+        }
+    }
+    uint32_t sig(const Nm& nm) { name(nm, cur); return cur++; }
+    uint32_t sigs(const Nm& nm, int n) {
+        uint32_t s = cur;
+        if (named) for (int i = 0; i < n; i++) name(Nm(nm.s, i), s + i);
+        cur += n; return s;
+    }
+    VL set(uint32_t slot, const VL&) { VL r; r.idx = slot; return r; }
+    VL seti(const Nm& nm, uint32_t slot, const VL&) { name(nm, slot); VL r; r.idx = slot; return r; }
+    VL alias(const Nm& nm, const VL& x) { name(nm, x.idx); return x; }
+    VL def(const Nm& nm, const VL& x) {
+        if (x.idx != HZ_NOIDX) { name(nm, x.idx); return x; }
+        name(nm, cur); VL r; r.idx = cur++; return r;
+    }
+    VL own(const Nm& nm, const VL&) { name(nm, cur); VL r; r.idx = cur++; return r; }
+    VL load(uint32_t idx) const { VL r; r.idx = idx; return r; }
+    bool sanity() const { return false; }
+    void check(const VL&, const VL&, uint32_t) {}
+    void check0(const VL&, uint32_t) {}
+};
+#endif
+
+#define HZ_CHECK(c, lhs, rhs) do { if ((c).sanity()) (c).check((lhs), (rhs), __LINE__); } while (0)
+#define HZ_CHECK0(c, lhs) do { if ((c).sanity()) (c).check0((lhs), __LINE__); } while (0)

@@ -1,0 +1,145 @@
+// Backend-independent half of the C ABI (include/hzwitness.h): context, input table, layout
+// queries, `.wtns`.  The backend (CUDA in hzw.cu; host threads in oracle/cpu_port, the
+// checker) supplies hz_backend_create().
+#pragma once
+#include "host_common.hpp"
+#include "../../include/hzwitness.h"
+#include <memory>
+
+struct HzBackend {
+    virtual ~HzBackend() {}
+    // inputs: n_inputs x 32 B; witness_out may be null when resident
+    virtual int calculate(const uint8_t* inputs, int sanity, uint8_t* witness_out, bool resident, float* kernel_ms,
+                          HzErrBuf* errs) = 0;
+    uint64_t launches = 0, h2d = 0, d2h = 0;
+};
+HzBackend* hz_backend_create(const hzw_params& prm, const HzLayout& L, int* status);
+
+struct hzw_ctx {
+    hzw_params prm;
+    HzParams P;
+    HzLayout L;
+    std::unique_ptr<HzBackend> be;
+};
+
+static inline void hz_fr_to_le32(const Fr& f, uint8_t* o) {
+    for (int i = 0; i < 8; i++) for (int b = 0; b < 4; b++) o[4 * i + b] = (uint8_t)(f.l[i] >> (8 * b));
+}
+
+static inline std::string hz_dec(const Fr& f) {
+    // decimal string of a 256-bit value
+    uint32_t t[8]; for (int i = 0; i < 8; i++) t[i] = f.l[i];
+    std::string s;
+    bool nz = true;
+    while (nz) {
+        uint64_t rem = 0; nz = false;
+        for (int i = 7; i >= 0; i--) { uint64_t cur = (rem << 32) | t[i]; t[i] = (uint32_t)(cur / 10); rem = cur % 10; if (t[i]) nz = true; }
+        s.insert(s.begin(), (char)('0' + rem));
+    }
+    return s;
+}
+
+extern "C" {
+
+int hzw_create(const hzw_params* prm, const char* /*layout_map_path*/, hzw_ctx** out) {
+    if (!prm || !out) return HZW_E_PARAM;
+    if (prm->circuit_kind != HZW_CIRCUIT_ROLLUP_MAIN) return HZW_E_PARAM;
+    HzParams P; P.nTx = prm->nTx; P.nLevels = prm->nLevels; P.maxL1Tx = prm->maxL1Tx; P.maxFeeTx = prm->maxFeeTx;
+    if (!hz_params_ok(P)) return HZW_E_PARAM;
+    hzw_ctx* c = new hzw_ctx();
+    c->prm = *prm; c->P = P;
+    hz_layout_walk(P, nullptr, c->L);
+    int st = 0;
+    c->be.reset(hz_backend_create(*prm, c->L, &st));
+    if (!c->be) { delete c; return st ? st : HZW_E_DEVICE; }
+    *out = c;
+    return HZW_OK;
+}
+void hzw_destroy(hzw_ctx* ctx) { delete ctx; }
+uint64_t hzw_nvars(const hzw_ctx* ctx) { return ctx ? ctx->L.plan.nvars : 0; }
+uint64_t hzw_ninputs(const hzw_ctx* ctx) { return ctx ? ctx->L.plan.n_inputs : 0; }
+
+int hzw_input_index(const hzw_ctx* ctx, const char* name, uint64_t* offset, uint64_t* len) {
+    if (!ctx || !name) return HZW_E_PARAM;
+    for (int f = 0; f < IN_COUNT; f++)
+        if (!strcmp(name, HZ_INPUT_NAMES[f])) {
+            if (offset) *offset = ctx->L.plan.in_off[f] - 2;
+            if (len) *len = (uint64_t)ctx->L.plan.in_d0[f] * ctx->L.plan.in_d1[f];
+            return HZW_OK;
+        }
+    return HZW_E_NOSIGNAL;
+}
+
+static int hz_report(hzw_ctx* ctx, HzErrBuf& eb, hzw_error* err) {
+    if (eb.count == 0) { if (err) memset(err, 0, sizeof *err); return HZW_OK; }
+    uint32_t n = eb.count < HZ_MAX_ERR ? eb.count : HZ_MAX_ERR, best = 0;
+    for (uint32_t k = 1; k < n; k++) if (eb.rec[k].cur < eb.rec[best].cur) best = k;
+    if (err) {
+        memset(err, 0, sizeof *err);
+        err->code = HZW_E_CONSTRAINT; err->line = eb.rec[best].line; err->witness_index = eb.rec[best].cur;
+        hz_fr_to_le32(eb.rec[best].lhs, err->lhs); hz_fr_to_le32(eb.rec[best].rhs, err->rhs);
+        // component path: name of the last signal declared before the failing check
+        if (ctx->L.plan.nvars < 40000000u && eb.rec[best].cur > 1) {
+            LayoutSink sk; sk.want_names = true; sk.find_mode = true; sk.find_idx = eb.rec[best].cur - 1;
+            HzLayout tmp; hz_layout_walk(ctx->P, &sk, tmp);
+            size_t dot = sk.found.rfind('.');
+            std::string path = dot == std::string::npos ? sk.found : sk.found.substr(0, dot);
+            snprintf(err->where, sizeof err->where, "%s", path.c_str());
+        }
+    }
+    return HZW_E_CONSTRAINT;
+}
+
+int hzw_calculate(hzw_ctx* ctx, const uint8_t* inputs, int sanity, uint8_t* witness_out, hzw_error* err) {
+    if (!ctx || !inputs || !witness_out) return HZW_E_PARAM;
+    HzErrBuf eb; memset(&eb, 0, sizeof eb);
+    int st = ctx->be->calculate(inputs, sanity, witness_out, false, nullptr, &eb);
+    if (st) { if (err) { memset(err, 0, sizeof *err); err->code = st; } return st; }
+    return hz_report(ctx, eb, err);
+}
+int hzw_calculate_resident(hzw_ctx* ctx, const uint8_t* inputs, int sanity, float* kernel_ms, hzw_error* err) {
+    if (!ctx || !inputs) return HZW_E_PARAM;
+    HzErrBuf eb; memset(&eb, 0, sizeof eb);
+    int st = ctx->be->calculate(inputs, sanity, nullptr, true, kernel_ms, &eb);
+    if (st) { if (err) { memset(err, 0, sizeof *err); err->code = st; } return st; }
+    return hz_report(ctx, eb, err);
+}
+int hzw_calculate_batch(hzw_ctx* ctx, uint64_t n, const uint8_t* inputs, int sanity, uint8_t* witness_out, hzw_error* err) {
+    if (!ctx || !inputs || !witness_out) return HZW_E_PARAM;
+    for (uint64_t k = 0; k < n; k++) {
+        int st = hzw_calculate(ctx, inputs + k * 32 * hzw_ninputs(ctx), sanity, witness_out + k * 32 * hzw_nvars(ctx), err);
+        if (st) return st;
+    }
+    return HZW_OK;
+}
+int hzw_write_wtns(const hzw_ctx* ctx, const uint8_t* witness, const char* path) {
+    if (!ctx || !witness || !path) return HZW_E_PARAM;
+    return hz_write_wtns(path, witness, ctx->L.plan.nvars) ? HZW_E_IO : HZW_OK;
+}
+int hzw_get_signal(const hzw_ctx* ctx, const uint8_t* witness, const char* name, uint8_t out[32]) {
+    if (!ctx || !witness || !name || !out) return HZW_E_PARAM;
+    std::vector<std::pair<std::string, uint32_t> > v;
+    LayoutSink sk; sk.want_names = true; sk.filter = name; sk.out = &v;
+    HzLayout tmp; hz_layout_walk(ctx->P, &sk, tmp);
+    for (auto& e : v) if (e.first == name && e.second != HZ_NOIDX) { memcpy(out, witness + 32ull * e.second, 32); return HZW_OK; }
+    return HZW_E_NOSIGNAL;
+}
+int hzw_dump_sym(const hzw_ctx* ctx, const char* prefix, const char* path) {
+    if (!ctx || !path) return HZW_E_PARAM;
+    std::vector<std::pair<std::string, uint32_t> > v;
+    LayoutSink sk; sk.want_names = true; sk.filter = prefix ? prefix : ""; sk.out = &v;
+    HzLayout tmp; hz_layout_walk(ctx->P, &sk, tmp);
+    FILE* f = fopen(path, "w");
+    if (!f) return HZW_E_IO;
+    for (auto& e : v) fprintf(f, "%u,%s\n", e.second, e.first.c_str());
+    fclose(f);
+    return HZW_OK;
+}
+int hzw_last_stats(const hzw_ctx* ctx, uint64_t* launches, uint64_t* h2d, uint64_t* d2h) {
+    if (!ctx) return HZW_E_PARAM;
+    if (launches) *launches = ctx->be->launches;
+    if (h2d) *h2d = ctx->be->h2d;
+    if (d2h) *d2h = ctx->be->d2h;
+    return HZW_OK;
+}
+}  // extern "C"

@@ -40,7 +40,7 @@ def build_tx_compressed_data(tx, chain_id):
 
 def build_tx_compressed_data_v2(tx):
     """src/decode-tx.circom:179-212 (L2 only; L1 keeps just the toBjjSign bit)."""
-    sign = tx.get("toBjjSign", 0) << 192
+    sign = tx.get("toBjjSign", 0) << 216
     if tx.get("onChain"):
         return sign
     return (tx.get("fromIdx", 0) | (tx.get("toIdx", 0) << 48) | (tx.get("amountF", 0) << 96)

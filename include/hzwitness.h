@@ -1,0 +1,87 @@
+/* hzwitness.h -- C ABI of the B200 witness generator for the Hermez circuits.
+ *
+ * This is the drop-in boundary: the entry points a Node N-API shim,
+ * a Python ctypes binding or a C++ host would bind in place of the reference's witness
+ * calculators.  Reference interfaces replaced, by entry point:
+ *
+ *   hzw_create / hzw_destroy      circom_runtime `builder(code, options)` that the reference's
+ *                                 tests obtain through `tester(path, {reduceConstraints:false})`
+ *                                 (/root/reference/test/rollup-main.test.js:52) and the compiled
+ *                                 binary started at /root/reference/tools/helpers/actions.js:139;
+ *                                 circuit parameters are the template parameters of
+ *                                 /root/reference/src/rollup-main.circom:82 and withdraw.circom:21
+ *   hzw_calculate                 `circuit.calculateWitness(input, opts)` /
+ *                                 `calculateBinWitness`  (/root/reference/test/helpers/helpers.js:149,
+ *                                 test/rollup-main.test.js:873) and `./circuit input.json witness.wtns`
+ *                                 (/root/reference/tools/helpers/actions.js:139-143)
+ *   hzw_input_index               the runtime's input-name lookup (`getSignalOffset32`), i.e. the keys
+ *                                 of `bb.getInput()` (/root/reference/src/rollup-main.circom:105-196)
+ *   hzw_get_signal / hzw_dump_sym circom tester `getSignal(w, name)` / `.sym` lookup behind
+ *                                 `assertOut` (/root/reference/test/helpers/helpers.js:151-154,170)
+ *   hzw_write_wtns                snarkjs `wtns calculate` output (`.wtns`, the witness file
+ *                                 /root/reference/tools/helpers/actions.js:139 produces)
+ *   hzw_calculate_batch           many independent witnesses of one circuit in a single call
+ *                                 (withdraw, /root/reference/test/withdraw.test.js:105-160)
+ *
+ * All buffers are caller-owned.  Field elements cross the boundary as 32-byte little-endian
+ * canonical residues of the BN254 scalar field.  A context is not re-entrant; distinct
+ * contexts may be used from distinct threads.  Return value 0 = success, negative = error.
+ */
+#ifndef HZWITNESS_H
+#define HZWITNESS_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HZW_CIRCUIT_ROLLUP_MAIN 0
+#define HZW_CIRCUIT_WITHDRAW 1
+
+#define HZW_OK 0
+#define HZW_E_PARAM (-1)        /* bad parameters / null pointers */
+#define HZW_E_IO (-2)           /* file could not be written */
+#define HZW_E_NOSIGNAL (-3)     /* "Signal <name> is not an input of the circuit." / unknown signal */
+#define HZW_E_CONSTRAINT (-4)   /* "Constraint doesn't match <lhs> != <rhs>" (sanity_check only) */
+#define HZW_E_DEVICE (-5)       /* CUDA error; no CPU fallback exists */
+
+typedef struct hzw_ctx hzw_ctx;
+
+typedef struct {
+    int32_t circuit_kind;       /* HZW_CIRCUIT_* */
+    int32_t nTx, nLevels, maxL1Tx, maxFeeTx;   /* withdraw uses nLevels only */
+    int32_t device;             /* CUDA device ordinal */
+    uint32_t flags;             /* reserved, 0 */
+} hzw_params;
+
+typedef struct {
+    int32_t code;
+    uint32_t line;              /* template source line of the failed `===` */
+    uint64_t witness_index;     /* witness cursor where it failed: resolves to a component path */
+    uint8_t lhs[32], rhs[32];
+    char where[256];            /* component path when it could be resolved */
+} hzw_error;
+
+int hzw_create(const hzw_params* params, const char* layout_map_path /* nullable */, hzw_ctx** out);
+void hzw_destroy(hzw_ctx* ctx);
+uint64_t hzw_nvars(const hzw_ctx* ctx);
+uint64_t hzw_ninputs(const hzw_ctx* ctx);
+/* offset (in field elements, inside the packed input vector) and element count of a main input */
+int hzw_input_index(const hzw_ctx* ctx, const char* name, uint64_t* offset, uint64_t* len);
+/* inputs_le32: hzw_ninputs() x 32 B in declaration order; witness_out: hzw_nvars() x 32 B */
+int hzw_calculate(hzw_ctx* ctx, const uint8_t* inputs_le32, int sanity_check, uint8_t* witness_out, hzw_error* err);
+/* n independent instances: inputs n x ninputs x 32 B, witnesses n x nvars x 32 B (withdraw) */
+int hzw_calculate_batch(hzw_ctx* ctx, uint64_t n, const uint8_t* inputs_le32, int sanity_check, uint8_t* witness_out,
+                        hzw_error* err);
+/* same computation, witness left in device memory (no device->host copy); kernel_ms = device time */
+int hzw_calculate_resident(hzw_ctx* ctx, const uint8_t* inputs_le32, int sanity_check, float* kernel_ms, hzw_error* err);
+int hzw_write_wtns(const hzw_ctx* ctx, const uint8_t* witness, const char* path);
+int hzw_get_signal(const hzw_ctx* ctx, const uint8_t* witness, const char* name, uint8_t out[32]);
+/* writes "index,name" lines (the `.sym` equivalent) for every signal whose name starts with prefix */
+int hzw_dump_sym(const hzw_ctx* ctx, const char* prefix, const char* path);
+/* static description of what the last calculate launched: kernels and bytes, for the bench */
+int hzw_last_stats(const hzw_ctx* ctx, uint64_t* gpu_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
