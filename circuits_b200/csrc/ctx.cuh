@@ -15,7 +15,7 @@
 #pragma once
 #include "fr.cuh"
 
-#ifndef __CUDA_ARCH__
+#ifndef HZ_DEVICE_ONLY
 #include <string>
 #include <vector>
 #include <cstdio>
@@ -131,7 +131,7 @@ struct HzErrRec { uint32_t cur; uint32_t line; Fr lhs, rhs; };
 struct HzErrBuf { uint32_t count; uint32_t pad; HzErrRec rec[HZ_MAX_ERR]; };
 
 // ---- layout sink (host) -------------------------------------------------------------------
-#ifndef __CUDA_ARCH__
+#ifndef HZ_DEVICE_ONLY
 struct LayoutSink {
     // name recording: every signal whose full name starts with `filter` is reported
     bool want_names = false;
@@ -212,7 +212,7 @@ template <> struct Comp<MCompute> {
     HZ_HD void check0(const VC& lhs, uint32_t line) { check(lhs, vc(fr_zero()), line); }
 };
 
-#ifndef __CUDA_ARCH__
+#ifndef HZ_DEVICE_ONLY
 template <> struct Comp<MLayout> {
     uint32_t cur, end;
     Comp* parent;

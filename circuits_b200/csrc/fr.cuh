@@ -13,12 +13,19 @@
 #pragma once
 #include <stdint.h>
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && defined(HZ_DEVICE_ONLY)
+// CUDA translation unit: device code only (the host half of the library is compiled by g++)
+#define HZ_HD __device__ __forceinline__
+#define HZ_HDN __device__ __noinline__
+#define HZ_FN __device__ __noinline__
+#elif defined(__CUDACC__)
 #define HZ_HD __host__ __device__ __forceinline__
 #define HZ_HDN __host__ __device__ __noinline__
+#define HZ_FN __host__ __device__ __noinline__
 #else
 #define HZ_HD inline
-#define HZ_HDN
+#define HZ_HDN inline
+#define HZ_FN inline
 #endif
 
 struct Fr { uint32_t l[8]; };
@@ -183,7 +190,7 @@ HZ_HD Fr fr_barrett(const uint32_t* t) {
     return out;
 }
 
-HZ_HD Fr fr_mul(const Fr& a, const Fr& b) {
+HZ_HDN Fr fr_mul(const Fr& a, const Fr& b) {
     uint32_t t[16];
     fr_mul_wide(t, a, b);
     return fr_barrett(t);
@@ -193,7 +200,7 @@ HZ_HD Fr fr_mul_u64(const Fr& a, uint64_t k) { return fr_mul(a, fr_from_u64(k));
 
 // ---- Montgomery row: sum_{j<n} s[j] * cR[j]  (cR = c * 2^256 mod p)  -> canonical -----------
 // n <= 7: the unreduced sum stays below 7 p^2 < 2^511.
-HZ_HD Fr fr_dot_mont(const Fr* s, const Fr* cR, int n) {
+HZ_HDN Fr fr_dot_mont(const Fr* s, const Fr* cR, int n) {
     uint32_t t[17];
     for (int i = 0; i < 17; i++) t[i] = 0;
     for (int k = 0; k < n; k++) {

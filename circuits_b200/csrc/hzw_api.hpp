@@ -11,6 +11,7 @@ struct HzBackend {
     // inputs: n_inputs x 32 B; witness_out may be null when resident
     virtual int calculate(const uint8_t* inputs, int sanity, uint8_t* witness_out, bool resident, float* kernel_ms,
                           HzErrBuf* errs) = 0;
+    virtual int kernel_ms(float*, const char**, int) { return 0; }
     uint64_t launches = 0, h2d = 0, d2h = 0;
 };
 HzBackend* hz_backend_create(const hzw_params& prm, const HzLayout& L, int* status);
@@ -98,7 +99,7 @@ int hzw_calculate(hzw_ctx* ctx, const uint8_t* inputs, int sanity, uint8_t* witn
     return hz_report(ctx, eb, err);
 }
 int hzw_calculate_resident(hzw_ctx* ctx, const uint8_t* inputs, int sanity, float* kernel_ms, hzw_error* err) {
-    if (!ctx || !inputs) return HZW_E_PARAM;
+    if (!ctx) return HZW_E_PARAM;
     HzErrBuf eb; memset(&eb, 0, sizeof eb);
     int st = ctx->be->calculate(inputs, sanity, nullptr, true, kernel_ms, &eb);
     if (st) { if (err) { memset(err, 0, sizeof *err); err->code = st; } return st; }
@@ -134,6 +135,10 @@ int hzw_dump_sym(const hzw_ctx* ctx, const char* prefix, const char* path) {
     for (auto& e : v) fprintf(f, "%u,%s\n", e.second, e.first.c_str());
     fclose(f);
     return HZW_OK;
+}
+int hzw_last_kernel_ms(const hzw_ctx* ctx, float* ms, const char** names, int cap) {
+    if (!ctx || !ms || cap <= 0) return HZW_E_PARAM;
+    return ctx->be->kernel_ms(ms, names, cap);
 }
 int hzw_last_stats(const hzw_ctx* ctx, uint64_t* launches, uint64_t* h2d, uint64_t* d2h) {
     if (!ctx) return HZW_E_PARAM;

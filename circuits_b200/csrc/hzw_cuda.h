@@ -1,0 +1,15 @@
+// Interface between the host half of the library (hzw_host.cpp: C ABI, layout walk) and the
+// CUDA half (hzw_kernels.cu: device memory, kernels, streams).
+#pragma once
+#include "rollup_main.cuh"
+
+struct HzCuda;   // device state of one context
+// returns null and sets *status (HZW_E_DEVICE) when no usable CUDA device / allocation failure
+HzCuda* hz_cuda_create(int device, const HzPlan& plan_host, const uint32_t* off_decode, const uint32_t* off_rollup,
+                       const uint32_t* off_fee, int* status);
+void hz_cuda_destroy(HzCuda*);
+// inputs: n_inputs x 32 B host; witness_out: nvars x 32 B host or null (resident)
+int hz_cuda_calculate(HzCuda*, const uint8_t* inputs, int sanity, uint8_t* witness_out, float* kernel_ms,
+                      HzErrBuf* errs, uint64_t* launches, uint64_t* h2d, uint64_t* d2h);
+// per-kernel device times of the last calculate
+int hz_cuda_kernel_ms(HzCuda*, float* ms, const char** names, int cap);

@@ -67,7 +67,7 @@ TM HZ_HD V<M> hz_in(const Comp<M>& c, const HzPlan& pl, int f, int a = 0, int b 
 }
 
 // ---- section B/C: decodeTx[i]  (:223-265) ---------------------------------------------------
-TM HZ_HDN void sec_decode(Comp<M>& c, const HzPlan& pl, int i, DecodeOut<M>& o, PreBits<M>& pre) {
+TM HZ_FN void sec_decode(Comp<M>& c, const HzPlan& pl, int i, DecodeOut<M>& o, PreBits<M>& pre) {
     const HzParams& P = pl.P;
     DecodeIn<M> in;
     in.previousOnChain = i == 0 ? Ops<M>::K(1) : hz_in(c, pl, IN_imOnChain, i - 1);
@@ -120,7 +120,7 @@ TM HZ_HDN void sec_decode(Comp<M>& c, const HzPlan& pl, int i, DecodeOut<M>& o, 
 }
 
 // ---- section D/E: rollupTx[i]  (:269-389, :427-431) ------------------------------------------
-TM HZ_HDN void sec_rollup(Comp<M>& c, const HzPlan& pl, int i, const DecodeOut<M>& d, RollupTxOut<M>& o,
+TM HZ_FN void sec_rollup(Comp<M>& c, const HzPlan& pl, int i, const DecodeOut<M>& d, RollupTxOut<M>& o,
                           PreBits<M>& pre, const EddsaHook<M>& hook) {
     const HzParams& P = pl.P;
     const int nTx = P.nTx, L = P.nLevels + 1;
@@ -192,7 +192,7 @@ TM HZ_HDN void sec_rollup(Comp<M>& c, const HzPlan& pl, int i, const DecodeOut<M
 }
 
 // ---- section F/G: feeTx[i]  (:393-426) --------------------------------------------------------
-TM HZ_HDN V<M> sec_fee(Comp<M>& c, const HzPlan& pl, int i) {
+TM HZ_FN V<M> sec_fee(Comp<M>& c, const HzPlan& pl, int i) {
     const HzParams& P = pl.P;
     V<M> sib[HZ_MAX_LEVELS];
     for (int k = 0; k < P.nLevels + 1; k++) sib[k] = hz_in(c, pl, IN_siblings3, i, k);
@@ -207,7 +207,7 @@ TM HZ_HDN V<M> sec_fee(Comp<M>& c, const HzPlan& pl, int i) {
 
 // ---- section H: hasherInputs (src/hash-inputs.circom:23-185) ----------------------------------
 // head: everything before the first sha256compression; the pre-image gets its remaining bits
-TM HZ_HDN void sec_hasher_head(Comp<M>& c, const HzPlan& pl, PreBits<M>& pre, uint32_t* off_blocks, W32<M>* ha) {
+TM HZ_FN void sec_hasher_head(Comp<M>& c, const HzPlan& pl, PreBits<M>& pre, uint32_t* off_blocks, W32<M>* ha) {
     const HzParams& P = pl.P;
     const int nL = P.nLevels, nL2 = 2 * nL + 48;
     V<M> oldLastIdx = c.def("oldLastIdx", hz_in(c, pl, IN_oldLastIdx));
@@ -284,18 +284,18 @@ TM HZ_HDN void sec_hasher_head(Comp<M>& c, const HzPlan& pl, PreBits<M>& pre, ui
 }
 
 // one sha256compression; `sh` is the Sha256 component positioned at the block's base
-TM HZ_HDN void sec_sha_block(Comp<M>& sh, int b, const W32<M>* hin, const W32<M>* msg, W32<M>* outw) {
+TM HZ_FN void sec_sha_block(Comp<M>& sh, int b, const W32<M>* hin, const W32<M>* msg, W32<M>* outw) {
     Sha256compression(sh.sub(Nm("sha256compression", b)), hin, msg, outw);
 }
 
 HZ_HD VC w32_get(const W32<MCompute>& x, int k) { VC r; r.v = fr_from_u64((x.v >> k) & 1u); r.sig = true; return r; }
-#ifndef __CUDA_ARCH__
+#ifndef HZ_DEVICE_ONLY
 inline VL w32_get(const W32<MLayout>& x, int k) { VL r; r.idx = x.idx[k]; return r; }
 #endif
 
 // tail: digest bits -> field element (src/hash-inputs.circom:179-184); `c` = hasherInputs after
 // the blocks, `sh` = the Sha256 component (its out[] are wires to the last block)
-TM HZ_HDN V<M> sec_hasher_tail(Comp<M>& c, Comp<M>& sh, const W32<M>* digest) {
+TM HZ_FN V<M> sec_hasher_tail(Comp<M>& c, Comp<M>& sh, const W32<M>* digest) {
     BV<M> bits; bits.clear(256);
     for (int q = 0; q < 256; q++) {
         V<M> h = w32_get(digest[q >> 5], 31 - (q & 31));      // h[q], MSB first

@@ -24,7 +24,7 @@ template <class M> using BV = BVT<M, 8>;
 // ---------------------------------------------------------------------------
 // bitify.circom (src/decode-tx.circom:96 and throughout)
 // ---------------------------------------------------------------------------
-TM HZ_HD BV<M> Num2Bits(Comp<M>&& c, int n, const V<M>& x) {
+TM HZ_FN BV<M> Num2Bits(Comp<M>&& c, int n, const V<M>& x) {
     V<M> in_ = c.def("in", x);
     BV<M> out; out.clear(n);
     for (int i = 0; i < n; i++) out.put(i, c.def(Nm("out", i), Ops<M>::K(vbit(in_, i))));
@@ -42,7 +42,7 @@ TM HZ_HD BV<M> Num2Bits(Comp<M>&& c, int n, const V<M>& x) {
 }
 
 // value of sum(bits[i] 2^i) mod p
-TM HZ_HD V<M> bits_lc(const BV<M>& b, int from, int n);
+TM HZ_FN V<M> bits_lc(const BV<M>& b, int from, int n);
 template <> HZ_HD VC bits_lc<MCompute>(const BVC& b, int from, int n) {
     Fr r = fr_zero();
     for (int i = 0; i < n && i < 254; i++) if (b.bit(from + i)) r.l[i >> 5] |= 1u << (i & 31);
@@ -55,11 +55,11 @@ template <> HZ_HD VC bits_lc<MCompute>(const BVC& b, int from, int n) {
     }
     return v;
 }
-#ifndef __CUDA_ARCH__
+#ifndef HZ_DEVICE_ONLY
 template <> inline VL bits_lc<MLayout>(const BVT<MLayout, 8>&, int, int) { return vl(); }
 #endif
 
-TM HZ_HD V<M> Bits2Num(Comp<M>&& c, const BV<M>& bits, int from, int n) {
+TM HZ_FN V<M> Bits2Num(Comp<M>&& c, const BV<M>& bits, int from, int n) {
     BV<M> ins; ins.clear(n);
     for (int i = 0; i < n; i++) ins.put(i, c.def(Nm("in", i), bits.get(from + i)));
     return c.def("out", bits_lc<M>(ins, 0, n));
@@ -69,7 +69,7 @@ TM HZ_HD V<M> Bits2Num(Comp<M>&& c, const BV<M>& bits, int from, int n) {
 // compconstant.circom / aliascheck.circom
 // ---------------------------------------------------------------------------
 #define HZ_SZ_COMPCONSTANT 263   /* 127 parts + sout + Num2Bits(135) outs, inputs wired */
-TM HZ_HD V<M> CompConstant(Comp<M>&& c, const Fr& ct, const BV<M>& bits) {
+TM HZ_FN V<M> CompConstant(Comp<M>&& c, const Fr& ct, const BV<M>& bits) {
     BV<M> ins; ins.clear(254);
     for (int i = 0; i < 254; i++) ins.put(i, c.def(Nm("in", i), bits.get(i)));
     uint32_t parts = c.sigs("parts", 127);
@@ -107,14 +107,14 @@ HZ_HD Fr fr_const_suborder_m1() {
     return r;
 }
 
-TM HZ_HD void AliasCheck(Comp<M>&& c, const BV<M>& bits) {
+TM HZ_FN void AliasCheck(Comp<M>&& c, const BV<M>& bits) {
     BV<M> ins; ins.clear(254);
     for (int i = 0; i < 254; i++) ins.put(i, c.def(Nm("in", i), bits.get(i)));
     V<M> o = CompConstant(c.sub("compConstant"), fr_const_pm1(), ins);
     HZ_CHECK0(c, o);
 }
 
-TM HZ_HD BV<M> Num2Bits_strict(Comp<M>&& c, const V<M>& x) {
+TM HZ_FN BV<M> Num2Bits_strict(Comp<M>&& c, const V<M>& x) {
     V<M> in_ = c.def("in", x);
     Comp<M> ac = c.sub_reserve("aliasCheck", HZ_SZ_COMPCONSTANT);
     BV<M> bits = Num2Bits(c.sub("n2b"), 254, in_);
@@ -126,7 +126,7 @@ TM HZ_HD BV<M> Num2Bits_strict(Comp<M>&& c, const V<M>& x) {
 // ---------------------------------------------------------------------------
 // comparators.circom
 // ---------------------------------------------------------------------------
-TM HZ_HD V<M> IsZero(Comp<M>&& c, const V<M>& x) {
+TM HZ_FN V<M> IsZero(Comp<M>&& c, const V<M>& x) {
     V<M> in_ = c.def("in", x);
     uint32_t out = c.sig("out");
     V<M> inv_ = c.def("inv", vinv(in_));
@@ -135,7 +135,7 @@ TM HZ_HD V<M> IsZero(Comp<M>&& c, const V<M>& x) {
     return o;
 }
 // IsZero with the inverse supplied (batched inversions)
-TM HZ_HD V<M> IsZeroWithInv(Comp<M>&& c, const V<M>& x, const V<M>& xinv) {
+TM HZ_FN V<M> IsZeroWithInv(Comp<M>&& c, const V<M>& x, const V<M>& xinv) {
     V<M> in_ = c.def("in", x);
     uint32_t out = c.sig("out");
     V<M> inv_ = c.def("inv", xinv);
@@ -144,14 +144,14 @@ TM HZ_HD V<M> IsZeroWithInv(Comp<M>&& c, const V<M>& x, const V<M>& xinv) {
     return o;
 }
 
-TM HZ_HD V<M> IsEqual(Comp<M>&& c, const V<M>& a, const V<M>& b) {
+TM HZ_FN V<M> IsEqual(Comp<M>&& c, const V<M>& a, const V<M>& b) {
     V<M> i0 = c.def(Nm("in", 0), a);
     V<M> i1 = c.def(Nm("in", 1), b);
     V<M> o = IsZero(c.sub("isz"), i1 - i0);
     return c.alias("out", o);
 }
 
-TM HZ_HD void ForceEqualIfEnabled(Comp<M>&& c, const V<M>& enabled, const V<M>& a, const V<M>& b) {
+TM HZ_FN void ForceEqualIfEnabled(Comp<M>&& c, const V<M>& enabled, const V<M>& a, const V<M>& b) {
     V<M> en = c.def("enabled", enabled);
     V<M> i0 = c.def(Nm("in", 0), a);
     V<M> i1 = c.def(Nm("in", 1), b);
@@ -159,7 +159,7 @@ TM HZ_HD void ForceEqualIfEnabled(Comp<M>&& c, const V<M>& enabled, const V<M>& 
     HZ_CHECK0(c, (1 - o) * en);
 }
 
-TM HZ_HD V<M> LessThan(Comp<M>&& c, int n, const V<M>& a, const V<M>& b) {
+TM HZ_FN V<M> LessThan(Comp<M>&& c, int n, const V<M>& a, const V<M>& b) {
     V<M> i0 = c.def(Nm("in", 0), a);
     V<M> i1 = c.def(Nm("in", 1), b);
     uint32_t out = c.sig("out");
@@ -167,7 +167,7 @@ TM HZ_HD V<M> LessThan(Comp<M>&& c, int n, const V<M>& a, const V<M>& b) {
     return c.set(out, 1 - bits.get(n));
 }
 
-TM HZ_HD V<M> GreaterEqThan(Comp<M>&& c, int n, const V<M>& a, const V<M>& b) {
+TM HZ_FN V<M> GreaterEqThan(Comp<M>&& c, int n, const V<M>& a, const V<M>& b) {
     V<M> i0 = c.def(Nm("in", 0), a);
     V<M> i1 = c.def(Nm("in", 1), b);
     V<M> o = LessThan(c.sub("lt"), n, i1, i0 + 1);
@@ -177,18 +177,18 @@ TM HZ_HD V<M> GreaterEqThan(Comp<M>&& c, int n, const V<M>& a, const V<M>& b) {
 // ---------------------------------------------------------------------------
 // gates.circom
 // ---------------------------------------------------------------------------
-TM HZ_HD V<M> XOR(Comp<M>&& c, const V<M>& a, const V<M>& b) {
+TM HZ_FN V<M> XOR(Comp<M>&& c, const V<M>& a, const V<M>& b) {
     V<M> a_ = c.def("a", a);
     V<M> b_ = c.def("b", b);
     return c.def("out", a_ + b_ - 2 * (a_ * b_));
 }
-TM HZ_HD V<M> AND(Comp<M>&& c, const V<M>& a, const V<M>& b) {
+TM HZ_FN V<M> AND(Comp<M>&& c, const V<M>& a, const V<M>& b) {
     V<M> a_ = c.def("a", a);
     V<M> b_ = c.def("b", b);
     return c.def("out", a_ * b_);
 }
 // MultiAND(n) for n in {3, 4} (smtprocessor / smtverifier keysOk)
-TM HZ_HD V<M> MultiAND(Comp<M>&& c, const V<M>* xs, int n) {
+TM HZ_FN V<M> MultiAND(Comp<M>&& c, const V<M>* xs, int n) {
     V<M> ins[4];
     for (int i = 0; i < n; i++) ins[i] = c.def(Nm("in", i), xs[i]);
     if (n == 1) return c.alias("out", ins[0]);
@@ -203,7 +203,7 @@ TM HZ_HD V<M> MultiAND(Comp<M>&& c, const V<M>* xs, int n) {
 // ---------------------------------------------------------------------------
 // mux1..mux4.circom
 // ---------------------------------------------------------------------------
-TM HZ_HD V<M> Mux1(Comp<M>&& c, const V<M>& c0, const V<M>& c1, const V<M>& s) {
+TM HZ_FN V<M> Mux1(Comp<M>&& c, const V<M>& c0, const V<M>& c1, const V<M>& s) {
     V<M> k0 = c.def(Nm("c", 0), c0);
     V<M> k1 = c.def(Nm("c", 1), c1);
     V<M> s_ = c.def("s", s);
@@ -213,7 +213,7 @@ TM HZ_HD V<M> Mux1(Comp<M>&& c, const V<M>& c0, const V<M>& c1, const V<M>& s) {
     return c.alias("out", o);
 }
 
-TM HZ_HD V<M> Mux2(Comp<M>&& c, const V<M>* cs, const V<M>* s) {
+TM HZ_FN V<M> Mux2(Comp<M>&& c, const V<M>* cs, const V<M>* s) {
     V<M> k[4], ss[2];
     for (int i = 0; i < 4; i++) k[i] = c.def(Nm("c", i), cs[i]);
     for (int i = 0; i < 2; i++) ss[i] = c.def(Nm("s", i), s[i]);
@@ -233,7 +233,7 @@ TM HZ_HD V<M> Mux2(Comp<M>&& c, const V<M>* cs, const V<M>* s) {
 
 // MultiMux3 with n outputs (n = 1 via Mux3, n = 2 in WindowMulFix); cs[i][8]
 #define HZ_SZ_MULTIMUX3(n) (8 * (n) + 1)
-TM HZ_HD void MultiMux3(Comp<M>&& m, int n, const V<M> (*k)[8], const V<M>* ss, V<M>* outs) {
+TM HZ_FN void MultiMux3(Comp<M>&& m, int n, const V<M> (*k)[8], const V<M>* ss, V<M>* outs) {
     for (int i = 0; i < n; i++) for (int j = 0; j < 8; j++) m.alias(Nm("c", i, j), k[i][j]);
     for (int i = 0; i < 3; i++) m.alias(Nm("s", i), ss[i]);
     uint32_t out = m.sigs("out", n);
@@ -253,7 +253,7 @@ TM HZ_HD void MultiMux3(Comp<M>&& m, int n, const V<M> (*k)[8], const V<M>* ss, 
         outs[i] = m.set(out + i, (v210 + v21 + v20 + v2) * ss[2] + (v10 + v1 + v0 + q[0]));
     }
 }
-TM HZ_HD V<M> Mux3(Comp<M>&& c, const V<M>* cs, const V<M>* s) {
+TM HZ_FN V<M> Mux3(Comp<M>&& c, const V<M>* cs, const V<M>* s) {
     V<M> k[1][8], ss[3], o[1];
     for (int i = 0; i < 8; i++) k[0][i] = c.def(Nm("c", i), cs[i]);
     for (int i = 0; i < 3; i++) ss[i] = c.def(Nm("s", i), s[i]);
@@ -262,7 +262,7 @@ TM HZ_HD V<M> Mux3(Comp<M>&& c, const V<M>* cs, const V<M>* s) {
 }
 
 #define HZ_SZ_MUX4_WIRED 20
-TM HZ_HD V<M> Mux4(Comp<M>&& c, const V<M>* cs, const V<M>* s) {
+TM HZ_FN V<M> Mux4(Comp<M>&& c, const V<M>* cs, const V<M>* s) {
     V<M> k[16], ss[4];
     for (int i = 0; i < 16; i++) k[i] = c.def(Nm("c", i), cs[i]);
     for (int i = 0; i < 4; i++) ss[i] = c.def(Nm("s", i), s[i]);
@@ -304,7 +304,7 @@ TM HZ_HD V<M> Mux4(Comp<M>&& c, const V<M>* cs, const V<M>* s) {
 // ---------------------------------------------------------------------------
 // switcher.circom
 // ---------------------------------------------------------------------------
-TM HZ_HD void Switcher(Comp<M>&& c, const V<M>& sel, const V<M>& L, const V<M>& R, V<M>& outL, V<M>& outR) {
+TM HZ_FN void Switcher(Comp<M>&& c, const V<M>& sel, const V<M>& L, const V<M>& R, V<M>& outL, V<M>& outR) {
     V<M> sel_ = c.def("sel", sel);
     V<M> L_ = c.def("L", L);
     V<M> R_ = c.def("R", R);
@@ -341,7 +341,7 @@ template <> struct PoseidonMath<MLayout> {
     static HZ_HD VL mix(const VL*, int, int) { return vl(); }
 };
 
-TM HZ_HDN V<M> Poseidon(Comp<M>&& c, const V<M>* inputs, int n) {
+TM HZ_FN V<M> Poseidon(Comp<M>&& c, const V<M>* inputs, int n) {
     const int t = n + 1, rp = poseidon_rp(t), R = 8 + rp;
     V<M> st[7];
     st[0] = Ops<M>::K(0);
@@ -375,14 +375,14 @@ TM HZ_HDN V<M> Poseidon(Comp<M>&& c, const V<M>* inputs, int n) {
 // ---------------------------------------------------------------------------
 // smt/*.circom  (src/rollup-tx.circom:537,559; src/fee-tx.circom:97; src/withdraw.circom:47)
 // ---------------------------------------------------------------------------
-TM HZ_HD V<M> SMTHash1(Comp<M>&& c, const V<M>& key, const V<M>& value) {
+TM HZ_FN V<M> SMTHash1(Comp<M>&& c, const V<M>& key, const V<M>& value) {
     V<M> in[3];
     in[0] = c.def("key", key);
     in[1] = c.def("value", value);
     in[2] = Ops<M>::K(1);
     return c.alias("out", Poseidon<M>(c.sub("h"), in, 3));
 }
-TM HZ_HD V<M> SMTHash2(Comp<M>&& c, const V<M>& L, const V<M>& R) {
+TM HZ_FN V<M> SMTHash2(Comp<M>&& c, const V<M>& L, const V<M>& R) {
     V<M> in[2];
     in[0] = c.def("L", L);
     in[1] = c.def("R", R);
@@ -390,7 +390,7 @@ TM HZ_HD V<M> SMTHash2(Comp<M>&& c, const V<M>& L, const V<M>& R) {
 }
 
 #define HZ_MAX_LEVELS 49
-TM HZ_HD void SMTLevIns(Comp<M>&& c, int n, const V<M>& enabled, const V<M>* siblings, V<M>* levIns) {
+TM HZ_FN void SMTLevIns(Comp<M>&& c, int n, const V<M>& enabled, const V<M>* siblings, V<M>* levIns) {
     V<M> en = c.def("enabled", enabled);
     V<M> sib[HZ_MAX_LEVELS], isz[HZ_MAX_LEVELS];
     for (int i = 0; i < n; i++) sib[i] = c.def(Nm("siblings", i), siblings[i]);
@@ -409,7 +409,7 @@ TM HZ_HD void SMTLevIns(Comp<M>&& c, int n, const V<M>& enabled, const V<M>* sib
 
 struct SMState { /* marker */ };
 // prev / st tuples: (top, old0, bot, new1, na, upd)
-TM HZ_HD void SMTProcessorSM(Comp<M>&& c, const V<M>& xor_, const V<M>& is0, const V<M>& levIns,
+TM HZ_FN void SMTProcessorSM(Comp<M>&& c, const V<M>& xor_, const V<M>& is0, const V<M>& levIns,
                              const V<M>* fnc, const V<M>* prev, V<M>* st) {
     V<M> x = c.def("xor", xor_);
     V<M> z = c.def("is0", is0);
@@ -435,7 +435,7 @@ TM HZ_HD void SMTProcessorSM(Comp<M>&& c, const V<M>& xor_, const V<M>& is0, con
 }
 
 #define HZ_SZ_SMTHASH2_WIRED (poseidon_size(3))
-TM HZ_HD void SMTProcessorLevel(Comp<M>&& c, const V<M>* st, const V<M>& sibling, const V<M>& old1leaf,
+TM HZ_FN void SMTProcessorLevel(Comp<M>&& c, const V<M>* st, const V<M>& sibling, const V<M>& old1leaf,
                                 const V<M>& new1leaf, const V<M>& newlrbit, const V<M>& oldChild,
                                 const V<M>& newChild, V<M>& oldRootOut, V<M>& newRootOut) {
     V<M> st_top = c.def("st_top", st[0]);
@@ -469,7 +469,7 @@ TM HZ_HD void SMTProcessorLevel(Comp<M>&& c, const V<M>* st, const V<M>& sibling
     newRootOut = c.set(newRoot, a3 + n1 * (st_old0 + st_upd));
 }
 
-TM HZ_HDN V<M> SMTProcessor(Comp<M>&& c, int nLevels, const V<M>& oldRoot, const V<M>* siblings,
+TM HZ_FN V<M> SMTProcessor(Comp<M>&& c, int nLevels, const V<M>& oldRoot, const V<M>* siblings,
                             const V<M>& oldKey, const V<M>& oldValue, const V<M>& isOld0,
                             const V<M>& newKey, const V<M>& newValue, const V<M>* fnc) {
     V<M> oldRoot_ = c.def("oldRoot", oldRoot);
@@ -525,7 +525,7 @@ TM HZ_HDN V<M> SMTProcessor(Comp<M>&& c, int nLevels, const V<M>& oldRoot, const
 }
 
 // prev / st tuples: (top, i0, iold, inew, na)
-TM HZ_HD void SMTVerifierSM(Comp<M>&& c, const V<M>& is0, const V<M>& levIns, const V<M>& fnc,
+TM HZ_FN void SMTVerifierSM(Comp<M>&& c, const V<M>& is0, const V<M>& levIns, const V<M>& fnc,
                             const V<M>* prev, V<M>* st) {
     V<M> z = c.def("is0", is0);
     V<M> li = c.def("levIns", levIns);
@@ -546,7 +546,7 @@ TM HZ_HD void SMTVerifierSM(Comp<M>&& c, const V<M>& is0, const V<M>& levIns, co
     st[4] = c.set(s_na, p_na + p_inew + p_iold + p_i0);
 }
 
-TM HZ_HD V<M> SMTVerifierLevel(Comp<M>&& c, const V<M>* st, const V<M>& sibling, const V<M>& old1leaf,
+TM HZ_FN V<M> SMTVerifierLevel(Comp<M>&& c, const V<M>* st, const V<M>& sibling, const V<M>& old1leaf,
                                const V<M>& new1leaf, const V<M>& lrbit, const V<M>& child) {
     V<M> st_top = c.def("st_top", st[0]);
     c.def("st_i0", st[1]);
@@ -569,7 +569,7 @@ TM HZ_HD V<M> SMTVerifierLevel(Comp<M>&& c, const V<M>* st, const V<M>& sibling,
     return c.set(root, a0 + a1 + n1 * st_inew);
 }
 
-TM HZ_HDN void SMTVerifier(Comp<M>&& c, int nLevels, const V<M>& enabled, const V<M>& root,
+TM HZ_FN void SMTVerifier(Comp<M>&& c, int nLevels, const V<M>& enabled, const V<M>& root,
                            const V<M>* siblings, const V<M>& oldKey, const V<M>& oldValue,
                            const V<M>& isOld0, const V<M>& key, const V<M>& value, const V<M>& fnc) {
     V<M> en = c.def("enabled", enabled);
@@ -628,7 +628,7 @@ HZ_HD Fr fr_base8_y() {
 }
 
 #define HZ_SZ_BABYADD_WIRED 6
-TM HZ_HD PtV<M> BabyAdd(Comp<M>&& c, const V<M>& x1_, const V<M>& y1_, const V<M>& x2_, const V<M>& y2_) {
+TM HZ_FN PtV<M> BabyAdd(Comp<M>&& c, const V<M>& x1_, const V<M>& y1_, const V<M>& x2_, const V<M>& y2_) {
     V<M> x1 = c.def("x1", x1_), y1 = c.def("y1", y1_), x2 = c.def("x2", x2_), y2 = c.def("y2", y2_);
     uint32_t xout = c.sig("xout"), yout = c.sig("yout");
     V<M> beta = c.def("beta", x1 * y2);
@@ -643,19 +643,19 @@ TM HZ_HD PtV<M> BabyAdd(Comp<M>&& c, const V<M>& x1_, const V<M>& y1_, const V<M
     HZ_CHECK(c, (1 - dt) * r.y, delta + HZ_BJ_A * beta - gamma);
     return r;
 }
-TM HZ_HD PtV<M> BabyDbl(Comp<M>&& c, const V<M>& x, const V<M>& y) {
+TM HZ_FN PtV<M> BabyDbl(Comp<M>&& c, const V<M>& x, const V<M>& y) {
     V<M> x_ = c.def("x", x), y_ = c.def("y", y);
     PtV<M> r = BabyAdd(c.sub("adder"), x_, y_, x_, y_);
     c.alias("xout", r.x); c.alias("yout", r.y);
     return r;
 }
-TM HZ_HD void BabyCheck(Comp<M>&& c, const V<M>& x, const V<M>& y) {
+TM HZ_FN void BabyCheck(Comp<M>&& c, const V<M>& x, const V<M>& y) {
     V<M> x_ = c.def("x", x), y_ = c.def("y", y);
     V<M> x2 = c.def("x2", x_ * x_);
     V<M> y2 = c.def("y2", y_ * y_);
     HZ_CHECK(c, HZ_BJ_A * x2 + y2, 1 + HZ_BJ_D * (x2 * y2));
 }
-TM HZ_HD PtV<M> Edwards2Montgomery(Comp<M>&& c, const V<M>& x, const V<M>& y) {
+TM HZ_FN PtV<M> Edwards2Montgomery(Comp<M>&& c, const V<M>& x, const V<M>& y) {
     V<M> i0 = c.def(Nm("in", 0), x), i1 = c.def(Nm("in", 1), y);
     PtV<M> r;
     r.x = c.def(Nm("out", 0), vdiv(1 + i1, 1 - i1));
@@ -664,7 +664,7 @@ TM HZ_HD PtV<M> Edwards2Montgomery(Comp<M>&& c, const V<M>& x, const V<M>& y) {
     HZ_CHECK(c, r.y * i0, r.x);
     return r;
 }
-TM HZ_HD PtV<M> Montgomery2Edwards(Comp<M>&& c, const V<M>& u, const V<M>& v) {
+TM HZ_FN PtV<M> Montgomery2Edwards(Comp<M>&& c, const V<M>& u, const V<M>& v) {
     V<M> i0 = c.def(Nm("in", 0), u), i1 = c.def(Nm("in", 1), v);
     PtV<M> r;
     r.x = c.def(Nm("out", 0), vdiv(i0, i1));
@@ -673,7 +673,7 @@ TM HZ_HD PtV<M> Montgomery2Edwards(Comp<M>&& c, const V<M>& u, const V<M>& v) {
     HZ_CHECK(c, r.y * (i0 + 1), i0 - 1);
     return r;
 }
-TM HZ_HD PtV<M> MontgomeryAdd(Comp<M>&& c, const PtV<M>& p1, const PtV<M>& p2) {
+TM HZ_FN PtV<M> MontgomeryAdd(Comp<M>&& c, const PtV<M>& p1, const PtV<M>& p2) {
     V<M> a0 = c.def(Nm("in1", 0), p1.x), a1 = c.def(Nm("in1", 1), p1.y);
     V<M> b0 = c.def(Nm("in2", 0), p2.x), b1 = c.def(Nm("in2", 1), p2.y);
     uint32_t out = c.sigs("out", 2);
@@ -684,7 +684,7 @@ TM HZ_HD PtV<M> MontgomeryAdd(Comp<M>&& c, const PtV<M>& p1, const PtV<M>& p2) {
     r.y = c.set(out + 1, lam * (a0 - r.x) - a1);
     return r;
 }
-TM HZ_HD PtV<M> MontgomeryDouble(Comp<M>&& c, const PtV<M>& p) {
+TM HZ_FN PtV<M> MontgomeryDouble(Comp<M>&& c, const PtV<M>& p) {
     V<M> i0 = c.def(Nm("in", 0), p.x), i1 = c.def(Nm("in", 1), p.y);
     uint32_t out = c.sigs("out", 2);
     uint32_t lamda = c.sig("lamda");
@@ -701,7 +701,7 @@ TM HZ_HD PtV<M> MontgomeryDouble(Comp<M>&& c, const PtV<M>& p) {
 // ---------------------------------------------------------------------------
 // escalarmulany.circom
 // ---------------------------------------------------------------------------
-TM HZ_HD PtV<M> Multiplexor2(Comp<M>&& c, const V<M>& sel, const PtV<M>& in0, const PtV<M>& in1) {
+TM HZ_FN PtV<M> Multiplexor2(Comp<M>&& c, const V<M>& sel, const PtV<M>& in0, const PtV<M>& in1) {
     V<M> s = c.def("sel", sel);
     V<M> a0 = c.def(Nm("in", 0, 0), in0.x), a1 = c.def(Nm("in", 0, 1), in0.y);
     V<M> b0 = c.def(Nm("in", 1, 0), in1.x), b1 = c.def(Nm("in", 1, 1), in1.y);
@@ -710,7 +710,7 @@ TM HZ_HD PtV<M> Multiplexor2(Comp<M>&& c, const V<M>& sel, const PtV<M>& in0, co
     r.y = c.def(Nm("out", 1), (b1 - a1) * s + a1);
     return r;
 }
-TM HZ_HD void BitElementMulAny(Comp<M>&& c, const V<M>& sel, PtV<M>& dbl, PtV<M>& add) {
+TM HZ_FN void BitElementMulAny(Comp<M>&& c, const V<M>& sel, PtV<M>& dbl, PtV<M>& add) {
     V<M> s = c.def("sel", sel);
     PtV<M> d, a;
     d.x = c.def(Nm("dblIn", 0), dbl.x); d.y = c.def(Nm("dblIn", 1), dbl.y);
@@ -724,7 +724,7 @@ TM HZ_HD void BitElementMulAny(Comp<M>&& c, const V<M>& sel, PtV<M>& dbl, PtV<M>
 }
 // wired size of SegmentMulAny(n) (e and p wired signals)
 #define HZ_SZ_SEGMENTMULANY(n) (13 + 9 * ((n) - 1))
-TM HZ_HDN void SegmentMulAny(Comp<M>&& c, const BV<M>& e, int from, int n, const PtV<M>& p, PtV<M>& out, PtV<M>& dblOut) {
+TM HZ_FN void SegmentMulAny(Comp<M>&& c, const BV<M>& e, int from, int n, const PtV<M>& p, PtV<M>& out, PtV<M>& dblOut) {
     BV<M> e_; e_.clear(n);
     for (int i = 0; i < n; i++) e_.put(i, c.def(Nm("e", i), e.get(from + i)));
     PtV<M> p_;
@@ -740,7 +740,7 @@ TM HZ_HDN void SegmentMulAny(Comp<M>&& c, const BV<M>& e, int from, int n, const
     out = ls; dblOut = d;
 }
 // EscalarMulAny(254) as used by EdDSAPoseidonVerifier: two segments (148 + 106 bits)
-TM HZ_HDN PtV<M> EscalarMulAny254(Comp<M>&& c, const BV<M>& e, const PtV<M>& p) {
+TM HZ_FN PtV<M> EscalarMulAny254(Comp<M>&& c, const BV<M>& e, const PtV<M>& p) {
     const int n = 254, nsegments = 2, nlast = n - 148;
     BV<M> e_; e_.clear(n);
     for (int i = 0; i < n; i++) e_.put(i, c.def(Nm("e", i), e.get(i)));
@@ -769,7 +769,7 @@ TM HZ_HDN PtV<M> EscalarMulAny254(Comp<M>&& c, const BV<M>& e, const PtV<M>& p) 
 // ---------------------------------------------------------------------------
 // escalarmulfix.circom
 // ---------------------------------------------------------------------------
-TM HZ_HD void WindowMulFix(Comp<M>&& c, const V<M>* in3, const PtV<M>& base, PtV<M>& out, PtV<M>& out8) {
+TM HZ_FN void WindowMulFix(Comp<M>&& c, const V<M>* in3, const PtV<M>& base, PtV<M>& out, PtV<M>& out8) {
     V<M> ins[3];
     for (int i = 0; i < 3; i++) ins[i] = c.def(Nm("in", i), in3[i]);
     PtV<M> b;
@@ -790,7 +790,7 @@ TM HZ_HD void WindowMulFix(Comp<M>&& c, const V<M>* in3, const PtV<M>& base, PtV
 
 #define HZ_SZ_MONTDOUBLE_WIRED 4
 // e: nW*3 bit values (signals, or constant 0 padding)
-TM HZ_HDN void SegmentMulFix(Comp<M>&& c, const BV<M>& e, int nW, const PtV<M>& base, PtV<M>& out, PtV<M>& dblOut) {
+TM HZ_FN void SegmentMulFix(Comp<M>&& c, const BV<M>& e, int nW, const PtV<M>& base, PtV<M>& out, PtV<M>& dblOut) {
     BV<M> e_; e_.clear(nW * 3);
     for (int i = 0; i < nW * 3; i++) e_.put(i, c.def(Nm("e", i), e.get(i)));
     PtV<M> b;
@@ -824,7 +824,7 @@ TM HZ_HDN void SegmentMulFix(Comp<M>&& c, const BV<M>& e, int nW, const PtV<M>& 
 }
 
 // EscalarMulFix(253, BASE8): segment 0 = 249 bits (83 windows), segment 1 = 4 bits (2 windows)
-TM HZ_HDN PtV<M> EscalarMulFix253(Comp<M>&& c, const BV<M>& e) {
+TM HZ_FN PtV<M> EscalarMulFix253(Comp<M>&& c, const BV<M>& e) {
     BV<M> e_; e_.clear(253);
     for (int i = 0; i < 253; i++) e_.put(i, c.def(Nm("e", i), e.get(i)));
     PtV<M> B;
@@ -853,7 +853,7 @@ TM HZ_HDN PtV<M> EscalarMulFix253(Comp<M>&& c, const BV<M>& e) {
 // ---------------------------------------------------------------------------
 // eddsaposeidon.circom  (src/rollup-tx.circom:472)
 // ---------------------------------------------------------------------------
-TM HZ_HDN void EdDSAPoseidonVerifier(Comp<M>&& c, const V<M>& enabled, const V<M>& Ax, const V<M>& Ay,
+TM HZ_FN void EdDSAPoseidonVerifier(Comp<M>&& c, const V<M>& enabled, const V<M>& Ax, const V<M>& Ay,
                                      const V<M>& S, const V<M>& R8x, const V<M>& R8y, const V<M>& Msg) {
     V<M> en = c.def("enabled", enabled);
     V<M> Ax_ = c.def("Ax", Ax), Ay_ = c.def("Ay", Ay), S_ = c.def("S", S);
@@ -931,7 +931,7 @@ template <> struct SqrtMath<MLayout> {
 };
 
 // bits: 256 elements
-TM HZ_HDN PtV<M> Bits2Point_Strict(Comp<M>&& c, const BV<M>& bits) {
+TM HZ_FN PtV<M> Bits2Point_Strict(Comp<M>&& c, const BV<M>& bits) {
     BV<M> ins; ins.clear(256);
     for (int i = 0; i < 256; i++) ins.put(i, c.def(Nm("in", i), bits.get(i)));
     uint32_t out0 = c.sig(Nm("out", 0));
@@ -966,7 +966,7 @@ HZ_HD W32<MCompute> w32_def(Comp<MCompute>& c, const char*, uint64_t value, int 
 HZ_HD void w32_alias(Comp<MCompute>&, const char*, const W32<MCompute>&) {}
 HZ_HD W32<MCompute> w32_rotr(const W32<MCompute>& x, int r) { W32<MCompute> o; o.v = (x.v >> r) | (x.v << (32 - r)); return o; }
 HZ_HD uint32_t w32_val(const W32<MCompute>& x) { return x.v; }
-#ifndef __CUDA_ARCH__
+#ifndef HZ_DEVICE_ONLY
 inline W32<MLayout> w32_def(Comp<MLayout>& c, const char* nm, uint64_t, int nout) {
     W32<MLayout> r;
     for (int k = 0; k < 32; k++) r.idx[k] = HZ_NOIDX;
@@ -989,7 +989,7 @@ HZ_HD W32<MCompute> hz_sha_out_word(Comp<MCompute>& c, int, uint32_t v) {
     for (int k = 0; k < 32; k++) { f.l[0] = (v >> (31 - k)) & 1u; c.w[c.cur++] = f; }
     W32<MCompute> r; r.v = v; return r;
 }
-#ifndef __CUDA_ARCH__
+#ifndef HZ_DEVICE_ONLY
 inline void hz_binsum_names(Comp<MLayout>& c, int j, const W32<MLayout>& x) {
     if (c.named) for (int k = 0; k < 32; k++) c.name(Nm("in", j, k), x.idx[k]);
 }
@@ -1005,7 +1005,7 @@ inline W32<MLayout> hz_sha_out_word(Comp<MLayout>& c, int j, uint32_t) {
 }
 #endif
 
-TM HZ_HD W32<M> RotR(Comp<M>&& c, const W32<M>& x, int r) {
+TM HZ_FN W32<M> RotR(Comp<M>&& c, const W32<M>& x, int r) {
     w32_alias(c, "in", x);
     W32<M> o = w32_rotr(x, r);
     w32_alias(c, "out", o);
@@ -1017,7 +1017,7 @@ HZ_HD W32<MCompute> ShR(Comp<MCompute>&& c, const W32<MCompute>& x, int r) {
     for (int i = 0; i < r; i++) c.w[c.cur++] = z;
     W32<MCompute> o; o.v = x.v >> r; return o;
 }
-#ifndef __CUDA_ARCH__
+#ifndef HZ_DEVICE_ONLY
 inline W32<MLayout> ShR(Comp<MLayout>&& c, const W32<MLayout>& x, int r) {
     w32_alias(c, "in", x);
     W32<MLayout> o;
@@ -1028,13 +1028,13 @@ inline W32<MLayout> ShR(Comp<MLayout>&& c, const W32<MLayout>& x, int r) {
     return o;
 }
 #endif
-TM HZ_HD W32<M> Xor3(Comp<M>&& c, const W32<M>& a, const W32<M>& b, const W32<M>& cc) {
+TM HZ_FN W32<M> Xor3(Comp<M>&& c, const W32<M>& a, const W32<M>& b, const W32<M>& cc) {
     w32_alias(c, "a", a); w32_alias(c, "b", b); w32_alias(c, "c", cc);
     W32<M> o = w32_def(c, "out", w32_val(a) ^ w32_val(b) ^ w32_val(cc), 32);
     w32_def(c, "mid", w32_val(b) & w32_val(cc), 32);
     return o;
 }
-TM HZ_HD W32<M> SmallSigma(Comp<M>&& c, const W32<M>& x, int ra, int rb, int rc) {
+TM HZ_FN W32<M> SmallSigma(Comp<M>&& c, const W32<M>& x, int ra, int rb, int rc) {
     w32_alias(c, "in", x);
     W32<M> rota = RotR(c.sub("rota"), x, ra);
     W32<M> rotb = RotR(c.sub("rotb"), x, rb);
@@ -1043,7 +1043,7 @@ TM HZ_HD W32<M> SmallSigma(Comp<M>&& c, const W32<M>& x, int ra, int rb, int rc)
     w32_alias(c, "out", o);
     return o;
 }
-TM HZ_HD W32<M> BigSigma(Comp<M>&& c, const W32<M>& x, int ra, int rb, int rc) {
+TM HZ_FN W32<M> BigSigma(Comp<M>&& c, const W32<M>& x, int ra, int rb, int rc) {
     w32_alias(c, "in", x);
     W32<M> rota = RotR(c.sub("rota"), x, ra);
     W32<M> rotb = RotR(c.sub("rotb"), x, rb);
@@ -1052,12 +1052,12 @@ TM HZ_HD W32<M> BigSigma(Comp<M>&& c, const W32<M>& x, int ra, int rb, int rc) {
     w32_alias(c, "out", o);
     return o;
 }
-TM HZ_HD W32<M> Ch_t(Comp<M>&& c, const W32<M>& a, const W32<M>& b, const W32<M>& cc) {
+TM HZ_FN W32<M> Ch_t(Comp<M>&& c, const W32<M>& a, const W32<M>& b, const W32<M>& cc) {
     w32_alias(c, "a", a); w32_alias(c, "b", b); w32_alias(c, "c", cc);
     uint32_t av = w32_val(a);
     return w32_def(c, "out", (av & w32_val(b)) | (~av & w32_val(cc)), 32);
 }
-TM HZ_HD W32<M> Maj_t(Comp<M>&& c, const W32<M>& a, const W32<M>& b, const W32<M>& cc) {
+TM HZ_FN W32<M> Maj_t(Comp<M>&& c, const W32<M>& a, const W32<M>& b, const W32<M>& cc) {
     w32_alias(c, "a", a); w32_alias(c, "b", b); w32_alias(c, "c", cc);
     uint32_t av = w32_val(a), bv = w32_val(b), cv = w32_val(cc);
     W32<M> o = w32_def(c, "out", (av & bv) ^ (av & cv) ^ (bv & cv), 32);
@@ -1065,7 +1065,7 @@ TM HZ_HD W32<M> Maj_t(Comp<M>&& c, const W32<M>& a, const W32<M>& b, const W32<M
     return o;
 }
 HZ_HD int hz_binsum_nout(int nops) { return nops == 2 ? 33 : (nops == 4 ? 34 : 35); }
-TM HZ_HD W32<M> BinSum(Comp<M>&& c, const W32<M>* ops, int nops) {
+TM HZ_FN W32<M> BinSum(Comp<M>&& c, const W32<M>* ops, int nops) {
     uint64_t sum = 0;
     for (int j = 0; j < nops; j++) { sum += w32_val(ops[j]); }
     for (int j = 0; j < nops; j++) hz_binsum_names(c, j, ops[j]);
@@ -1075,7 +1075,7 @@ TM HZ_HD W32<M> BinSum(Comp<M>&& c, const W32<M>* ops, int nops) {
 #define HZ_SZ_T1 131
 #define HZ_SZ_T2 161
 #define HZ_SZ_SHA_BLOCK (256 + 48 * HZ_SZ_SIGMAPLUS + 64 * 32 + 64 * HZ_SZ_T1 + 64 * HZ_SZ_T2 + 64 * 33 + 64 * 33 + 8 * 33)
-TM HZ_HD W32<M> SigmaPlus(Comp<M>&& c, const W32<M>& in2, const W32<M>& in7, const W32<M>& in15, const W32<M>& in16) {
+TM HZ_FN W32<M> SigmaPlus(Comp<M>&& c, const W32<M>& in2, const W32<M>& in7, const W32<M>& in15, const W32<M>& in16) {
     w32_alias(c, "in2", in2); w32_alias(c, "in7", in7); w32_alias(c, "in15", in15); w32_alias(c, "in16", in16);
     W32<M> ops[4];
     ops[0] = SmallSigma(c.sub("sigma1"), in2, 17, 19, 10);
@@ -1086,7 +1086,7 @@ TM HZ_HD W32<M> SigmaPlus(Comp<M>&& c, const W32<M>& in2, const W32<M>& in7, con
     w32_alias(c, "out", o);
     return o;
 }
-TM HZ_HD W32<M> T1(Comp<M>&& c, const W32<M>& h, const W32<M>& e, const W32<M>& f, const W32<M>& g,
+TM HZ_FN W32<M> T1(Comp<M>&& c, const W32<M>& h, const W32<M>& e, const W32<M>& f, const W32<M>& g,
                    const W32<M>& k, const W32<M>& w) {
     w32_alias(c, "h", h); w32_alias(c, "e", e); w32_alias(c, "f", f); w32_alias(c, "g", g);
     w32_alias(c, "k", k); w32_alias(c, "w", w);
@@ -1101,7 +1101,7 @@ TM HZ_HD W32<M> T1(Comp<M>&& c, const W32<M>& h, const W32<M>& e, const W32<M>& 
     w32_alias(c, "out", o);
     return o;
 }
-TM HZ_HD W32<M> T2(Comp<M>&& c, const W32<M>& a, const W32<M>& b, const W32<M>& cc) {
+TM HZ_FN W32<M> T2(Comp<M>&& c, const W32<M>& a, const W32<M>& b, const W32<M>& cc) {
     w32_alias(c, "a", a); w32_alias(c, "b", b); w32_alias(c, "c", cc);
     W32<M> ops[2];
     ops[0] = BigSigma(c.sub("bigsigma0"), a, 2, 13, 22);
@@ -1152,7 +1152,7 @@ HZ_HD void hz_sha256_compress(uint32_t* st /*8, in/out*/, const uint32_t* blk /*
 
 // hin[j]: chaining word j, LSB-first signals; msg[t]: message word t (bit k = inp[32 t + 31 - k]);
 // outw[j]: digest word j as LSB-first view of out[32 j + 31 - k]
-TM HZ_HDN void Sha256compression(Comp<M>&& c, const W32<M>* hin, const W32<M>* msg, W32<M>* outw) {
+TM HZ_FN void Sha256compression(Comp<M>&& c, const W32<M>* hin, const W32<M>* msg, W32<M>* outw) {
     hz_sha_in_names(c, hin, msg);
     uint32_t st[8], blk[16];
     for (int j = 0; j < 8; j++) st[j] = w32_val(hin[j]);

@@ -15,7 +15,7 @@ HZ_HD uint64_t hz_fee_shift(int i) {
 // ---------------------------------------------------------------------------
 // src/lib/decode-float.circom:12-44
 // ---------------------------------------------------------------------------
-TM HZ_HD V<M> DecodeFloatBin(Comp<M>&& c, const BV<M>& bits) {
+TM HZ_FN V<M> DecodeFloatBin(Comp<M>&& c, const BV<M>& bits) {
     BV<M> ins; ins.clear(40);
     for (int i = 0; i < 40; i++) ins.put(i, c.def(Nm("in", i), bits.get(i)));
     uint32_t out = c.sig("out");
@@ -30,7 +30,7 @@ TM HZ_HD V<M> DecodeFloatBin(Comp<M>&& c, const BV<M>& bits) {
 }
 
 // src/lib/decode-float.circom:51-65 (used only stand-alone; kept for the unit vectors)
-TM HZ_HD V<M> DecodeFloat(Comp<M>&& c, const V<M>& x) {
+TM HZ_FN V<M> DecodeFloat(Comp<M>&& c, const V<M>& x) {
     V<M> in_ = c.def("in", x);
     BV<M> bits = Num2Bits(c.sub("n2b"), 40, in_);
     return c.alias("out", DecodeFloatBin(c.sub("decoder"), bits));
@@ -40,7 +40,7 @@ TM HZ_HD V<M> DecodeFloat(Comp<M>&& c, const V<M>& x) {
 // src/lib/mux256.circom:10-51 -- table inputs are the constants of feeShiftTable
 // ---------------------------------------------------------------------------
 #define HZ_SZ_MUX256_FEE (8 + 256 + 17 * HZ_SZ_MUX4_WIRED)
-TM HZ_HDN V<M> Mux256Fee(Comp<M>&& c, const V<M>* s) {
+TM HZ_FN V<M> Mux256Fee(Comp<M>&& c, const V<M>* s) {
     V<M> s_[8];
     for (int i = 0; i < 8; i++) s_[i] = c.def(Nm("s", i), s[i]);
     uint32_t in0 = c.cur;
@@ -57,7 +57,7 @@ TM HZ_HDN V<M> Mux256Fee(Comp<M>&& c, const V<M>* s) {
 // ---------------------------------------------------------------------------
 // src/compute-fee.circom:12-94
 // ---------------------------------------------------------------------------
-TM HZ_HDN V<M> ComputeFee(Comp<M>&& c, const V<M>& feeSel, const V<M>& amount, const V<M>& applyFee) {
+TM HZ_FN V<M> ComputeFee(Comp<M>&& c, const V<M>& feeSel, const V<M>& amount, const V<M>& applyFee) {
     V<M> feeSel_ = c.def("feeSel", feeSel);
     V<M> amount_ = c.def("amount", amount);
     V<M> applyFee_ = c.def("applyFee", applyFee);
@@ -88,7 +88,7 @@ TM HZ_HDN V<M> ComputeFee(Comp<M>&& c, const V<M>& feeSel, const V<M>& amount, c
 // src/balance-updater.circom:24-112
 // ---------------------------------------------------------------------------
 TM struct BalanceOut { V<M> newS, newR, isP2Nop, fee2Charge, isAmountNullified; };
-TM HZ_HDN BalanceOut<M> BalanceUpdater(Comp<M>&& c, const V<M>& oldS, const V<M>& oldR, const V<M>& amount,
+TM HZ_FN BalanceOut<M> BalanceUpdater(Comp<M>&& c, const V<M>& oldS, const V<M>& oldR, const V<M>& amount,
                                        const V<M>& loadAmount, const V<M>& feeSelector, const V<M>& onChain,
                                        const V<M>& nop, const V<M>& nullifyLoadAmount, const V<M>& nullifyAmount) {
     V<M> bs = c.def("oldStBalanceSender", oldS);
@@ -126,7 +126,7 @@ TM HZ_HDN BalanceOut<M> BalanceUpdater(Comp<M>&& c, const V<M>& oldS, const V<M>
 // ---------------------------------------------------------------------------
 // src/fee-accumulator.circom:17-45, 56-91
 // ---------------------------------------------------------------------------
-TM HZ_HD void FeeAccumulatorStep(Comp<M>&& c, const V<M>& tokenID, const V<M>& plan, const V<M>& selIn,
+TM HZ_FN void FeeAccumulatorStep(Comp<M>&& c, const V<M>& tokenID, const V<M>& plan, const V<M>& selIn,
                                  const V<M>& fee, const V<M>& accIn, V<M>& selOut, V<M>& accOut) {
     V<M> tokenID_ = c.def("tokenID", tokenID);
     V<M> plan_ = c.def("feePlanTokenID", plan);
@@ -139,7 +139,7 @@ TM HZ_HD void FeeAccumulatorStep(Comp<M>&& c, const V<M>& tokenID, const V<M>& p
     accOut = c.alias("accFeeOut", Mux1(c.sub("mux"), accIn_, accIn_ + fee_, eq * (1 - selIn_)));
 }
 #define HZ_MAX_FEE 64
-TM HZ_HDN void FeeAccumulator(Comp<M>&& c, int n, const V<M>& tokenID, const V<M>& fee2Charge,
+TM HZ_FN void FeeAccumulator(Comp<M>&& c, int n, const V<M>& tokenID, const V<M>& fee2Charge,
                               const V<M>* feePlanTokenID, const V<M>* accFeeIn, V<M>* accFeeOut) {
     V<M> tokenID_ = c.def("tokenID", tokenID);
     V<M> fee = c.def("fee2Charge", fee2Charge);
@@ -159,7 +159,7 @@ TM HZ_HDN void FeeAccumulator(Comp<M>&& c, int n, const V<M>& tokenID, const V<M
 // ---------------------------------------------------------------------------
 // src/lib/hash-state.circom:18-40
 // ---------------------------------------------------------------------------
-TM HZ_HD V<M> HashState(Comp<M>&& c, const V<M>& tokenID, const V<M>& nonce, const V<M>& sign,
+TM HZ_FN V<M> HashState(Comp<M>&& c, const V<M>& tokenID, const V<M>& nonce, const V<M>& sign,
                         const V<M>& balance, const V<M>& ay, const V<M>& ethAddr) {
     V<M> in[4];
     V<M> tokenID_ = c.def("tokenID", tokenID);
@@ -175,13 +175,13 @@ TM HZ_HD V<M> HashState(Comp<M>&& c, const V<M>& tokenID, const V<M>& nonce, con
 // ---------------------------------------------------------------------------
 // src/lib/utils-bjj.circom:12-28, 37-57
 // ---------------------------------------------------------------------------
-TM HZ_HD void BitsCompressed2AySign(Comp<M>&& c, const BV<M>& bits, V<M>& ay, V<M>& sign) {
+TM HZ_FN void BitsCompressed2AySign(Comp<M>&& c, const BV<M>& bits, V<M>& ay, V<M>& sign) {
     BV<M> ins; ins.clear(256);
     for (int i = 0; i < 256; i++) ins.put(i, c.def(Nm("bjjCompressed", i), bits.get(i)));
     ay = c.alias("ay", Bits2Num(c.sub("b2nAy"), ins, 0, 254));
     sign = c.alias("sign", ins.get(255));
 }
-TM HZ_HDN V<M> AySign2Ax(Comp<M>&& c, const V<M>& ay, const V<M>& sign) {
+TM HZ_FN V<M> AySign2Ax(Comp<M>&& c, const V<M>& ay, const V<M>& sign) {
     V<M> ay_ = c.def("ay", ay);
     V<M> sign_ = c.def("sign", sign);
     BV<M> bits = Num2Bits(c.sub("n2bAy"), 254, ay_);
@@ -196,7 +196,7 @@ TM HZ_HDN V<M> AySign2Ax(Comp<M>&& c, const V<M>& ay, const V<M>& sign) {
 // src/rq-tx-verifier.circom:19-94
 // ---------------------------------------------------------------------------
 TM struct RqWin { V<M> futV2[3], pastV2[4], futEth[3], pastEth[4], futAy[3], pastAy[4]; };
-TM HZ_HDN void RqTxVerifier(Comp<M>&& c, const RqWin<M>& w, const V<M>& rqV2, const V<M>& rqEth,
+TM HZ_FN void RqTxVerifier(Comp<M>&& c, const RqWin<M>& w, const V<M>& rqV2, const V<M>& rqEth,
                             const V<M>& rqAy, const V<M>& rqTxOffset) {
     V<M> fV2[3], pV2[4], fEth[3], pEth[4], fAy[3], pAy[4];
     for (int i = 0; i < 3; i++) fV2[i] = c.def(Nm("futureTxCompressedDataV2", i), w.futV2[i]);
@@ -235,7 +235,7 @@ TM struct StatesOut {
     V<M> isP1Insert, isP2Insert, key1, key2, P1_fnc0, P1_fnc1, P2_fnc0, P2_fnc1, isExit, verifySignEnabled,
         nop, checkToEthAddr, checkToBjj, nullifyLoadAmount, nullifyAmount;
 };
-TM HZ_HDN StatesOut<M> RollupTxStates(Comp<M>&& c, const V<M>& fromIdx_, const V<M>& toIdx_, const V<M>& toEthAddr_,
+TM HZ_FN StatesOut<M> RollupTxStates(Comp<M>&& c, const V<M>& fromIdx_, const V<M>& toIdx_, const V<M>& toEthAddr_,
                                       const V<M>& auxFromIdx_, const V<M>& auxToIdx_, const V<M>& amount_,
                                       const V<M>& newExit_, const V<M>& loadAmount_, const V<M>& newAccount_,
                                       const V<M>& onChain_, const V<M>& fromEthAddr_, const V<M>& ethAddr1_,
@@ -346,7 +346,7 @@ TM struct DecodeIn {
     BV<M> fromBjjCompressed;
 };
 
-TM HZ_HDN void DecodeTx(Comp<M>&& c, int nLevels, const DecodeIn<M>& in, DecodeOut<M>& o) {
+TM HZ_FN void DecodeTx(Comp<M>&& c, int nLevels, const DecodeIn<M>& in, DecodeOut<M>& o) {
     V<M> previousOnChain = c.def("previousOnChain", in.previousOnChain);
     V<M> txCompressedData = c.def("txCompressedData", in.txCompressedData);
     V<M> maxNumBatch = c.def("maxNumBatch", in.maxNumBatch);
@@ -481,7 +481,7 @@ template <> struct EddsaHook<MLayout> {
     HzSizes* sz_out;                // sizes recorded by the layout walk (may be null)
 };
 
-TM HZ_HD void hz_phaseF(Comp<M>& c, const V<M>& vse, const V<M>& signSignature, const V<M>& aySignature,
+TM HZ_FN void hz_phaseF(Comp<M>& c, const V<M>& vse, const V<M>& signSignature, const V<M>& aySignature,
                         const V<M>& s1Ay, const V<M>& S, const V<M>& R8x, const V<M>& R8y, const V<M>& Msg) {
     V<M> ax = AySign2Ax(c.sub("getAx"), aySignature, signSignature);
     EdDSAPoseidonVerifier(c.sub("sigVerifier"), vse, ax, s1Ay, S, R8x, R8y, Msg);
@@ -494,7 +494,7 @@ HZ_HD void hz_phaseF_hook(Comp<MCompute>& c, const EddsaHook<MCompute>& hk, cons
     j->S = S.v; j->R8x = R8x.v; j->R8y = R8y.v; j->M = Msg.v; j->cur = c.cur;
     c.cur += hk.sz->getAx + hk.sz->sigVerifier;
 }
-#ifndef __CUDA_ARCH__
+#ifndef HZ_DEVICE_ONLY
 inline void hz_phaseF_hook(Comp<MLayout>& c, const EddsaHook<MLayout>& hk, const VL& vse, const VL& signSignature,
                            const VL& aySignature, const VL& s1Ay, const VL& S, const VL& R8x, const VL& R8y, const VL& Msg) {
     uint32_t c0 = c.cur;
@@ -505,7 +505,7 @@ inline void hz_phaseF_hook(Comp<MLayout>& c, const EddsaHook<MLayout>& hk, const
 }
 #endif
 
-TM HZ_HDN void RollupTx(Comp<M>&& c, int nLevels, int maxFeeTx, const RollupTxIn<M>& i, RollupTxOut<M>& o,
+TM HZ_FN void RollupTx(Comp<M>&& c, int nLevels, int maxFeeTx, const RollupTxIn<M>& i, RollupTxOut<M>& o,
                         const EddsaHook<M>& hook) {
     V<M> feePlanTokens[HZ_MAX_FEE], accFeeIn[HZ_MAX_FEE];
     for (int k = 0; k < maxFeeTx; k++) feePlanTokens[k] = c.def(Nm("feePlanTokens", k), i.feePlanTokens[k]);
@@ -617,7 +617,7 @@ TM HZ_HDN void RollupTx(Comp<M>&& c, int nLevels, int maxFeeTx, const RollupTxIn
 // ---------------------------------------------------------------------------
 // src/fee-tx.circom:26-111
 // ---------------------------------------------------------------------------
-TM HZ_HDN V<M> FeeTx(Comp<M>&& c, int nLevels, const V<M>& oldStateRoot_, const V<M>& feePlanToken_,
+TM HZ_FN V<M> FeeTx(Comp<M>&& c, int nLevels, const V<M>& oldStateRoot_, const V<M>& feePlanToken_,
                      const V<M>& feeIdx_, const V<M>& accFee_, const V<M>& tokenID_, const V<M>& nonce_,
                      const V<M>& sign_, const V<M>& balance_, const V<M>& ay_, const V<M>& ethAddr_, const V<M>* siblings) {
     V<M> oldStateRoot = c.def("oldStateRoot", oldStateRoot_);

@@ -1,0 +1,138 @@
+"""Seeded synthetic batches for tests and the benchmark.
+
+Stands in for /root/reference/tools/generate-input.js (+ helpers/gen-inputs-utils.js), which
+drives @hermeznetwork/commonjs with an unseeded `Math.random` and cannot run offline: the state
+tree is pre-populated with accounts, then one batch is built with `maxL1Tx` L1
+`createAccountDeposit` txs (generate-input.js:88-90) followed by L2 transfers of 20 % of the
+sender's balance with `userFee` 176 (gen-inputs-utils.js:27-70), one fee token and one fee
+collector (generate-input.js:102-103).
+"""
+import hashlib
+import random
+
+from . import babyjub, float40
+from .rollupdb import RollupDB, Account
+
+SEED = 20261017
+_B8_DOUBLES = None
+
+
+def _mul_base8(k):
+    """Fixed-base scalar multiplication on the precomputed doubles of Base8 (host speed only)."""
+    global _B8_DOUBLES
+    if _B8_DOUBLES is None:
+        t, pt = [], babyjub.BASE8
+        for _ in range(254):
+            t.append(pt)
+            pt = babyjub.add(pt, pt)
+        _B8_DOUBLES = t
+    acc = (0, 1)
+    i = 0
+    while k:
+        if k & 1:
+            acc = babyjub.add(acc, _B8_DOUBLES[i])
+        k >>= 1
+        i += 1
+    return acc
+
+
+class FastAccount(Account):
+    """Account whose key generation / signing use the fixed-base table."""
+
+    def __init__(self, seed):
+        h = hashlib.sha256(b"hermez-account-%d" % seed).digest()
+        kp = babyjub.KeyPair.__new__(babyjub.KeyPair)
+        kp.a = int.from_bytes(h, "big") % babyjub.SUBORDER or 1
+        kp.s = kp.a * 8
+        kp.pub = _mul_base8(kp.a)
+
+        def sign(msg, nonce_seed, kp=kp):
+            r = (nonce_seed % (babyjub.SUBORDER - 1)) + 1
+            R8 = _mul_base8(r)
+            hm = babyjub.poseidon([R8[0], R8[1], kp.pub[0], kp.pub[1], msg])
+            return R8, (r + hm * kp.s) % babyjub.SUBORDER
+        kp.sign = sign
+        self.key = kp
+        self.ax, self.ay = kp.pub
+        self.sign = babyjub.sign_of(self.ax)
+        self.ethAddr = int.from_bytes(hashlib.sha256(b"eth-%d" % seed).digest()[:20], "big")
+        self.bjjCompressed = babyjub.pack_bits(kp.pub)
+        self._n = 0
+
+
+def _deposit(acc, amount, token=1):
+    return dict(fromIdx=0, loadAmountF=float40.floor_fix2float(amount), tokenID=token,
+                fromBjjCompressed=acc.bjjCompressed, fromEthAddr=acc.ethAddr, toIdx=0, onChain=1)
+
+
+def small_batch(nTx=3, nLevels=16, maxL1Tx=2, maxFeeTx=2):
+    """Two deposits consolidated, then one signed transfer with a fee and a fee collector."""
+    db = RollupDB(chain_id=0)
+    a1, a2 = Account(1), Account(2)
+    bb = db.buildBatch(nTx, nLevels, maxL1Tx, maxFeeTx)
+    bb.addTx(_deposit(a1, 1000))
+    bb.addTx(_deposit(a2, 1000))
+    bb.build()
+    db.consolidate(bb)
+    bb = db.buildBatch(nTx, nLevels, maxL1Tx, maxFeeTx)
+    tx = dict(fromIdx=256, toIdx=257, tokenID=1, amountF=float40.fix2float(50), nonce=0, userFee=126, onChain=0)
+    a1.sign_tx(tx, 0)
+    bb.addTx(tx)
+    bb.addToken(1)
+    bb.addFeeIdx(257)
+    bb.build()
+    return bb
+
+
+def bench_batch(nTx, nLevels, maxL1Tx, maxFeeTx, n_accounts=None, n_keys=64, seed=SEED, n_l2=None):
+    """The benchmark batch: `maxL1Tx` deposits + (nTx - maxL1Tx) signed transfers.
+
+    `n_keys` distinct key pairs are shared round-robin by the accounts (key generation is the slow
+    part of the host-side setup and is not part of what is measured)."""
+    rng = random.Random(seed)
+    if n_accounts is None:
+        n_accounts = max(2 * nTx, 16)
+    keys = [FastAccount(k) for k in range(n_keys)]
+    db = RollupDB(chain_id=0)
+    owners = {}
+    # populate: batches of createAccountDeposit (generate-input.js:61-82)
+    todo = n_accounts
+    while todo > 0:
+        n = min(todo, maxL1Tx) if maxL1Tx > 0 else 0
+        if n == 0:
+            break
+        pb = db.buildBatch(max(n, 1), nLevels, max(n, 1), 1)
+        for _ in range(n):
+            acc = keys[len(owners) % n_keys]
+            owners[256 + len(owners)] = acc
+            pb.addTx(_deposit(acc, rng.randrange(1 << 40, 1 << 96)))
+        pb.build()
+        db.consolidate(pb)
+        todo -= n
+    bb = db.buildBatch(nTx, nLevels, maxL1Tx, maxFeeTx)
+    n_l1 = maxL1Tx
+    for _ in range(n_l1):
+        acc = keys[rng.randrange(n_keys)]
+        bb.addTx(_deposit(acc, rng.randrange(1 << 40, 1 << 96)))
+    idxs = sorted(owners)
+    nonces = {}
+    bal = {i: db.states[i]["balance"] for i in idxs}
+    n_l2 = nTx - n_l1 if n_l2 is None else n_l2
+    for _ in range(n_l2):
+        a, b = rng.sample(idxs, 2)
+        amountF = float40.floor_fix2float(bal[a] // 5)
+        amount = float40.float2fix(amountF)
+        from .feetable import compute_fee
+        fee = compute_fee(amount, 176)
+        if bal[a] < amount + fee:
+            amountF, amount, fee = 0, 0, 0
+        tx = dict(fromIdx=a, toIdx=b, tokenID=1, amountF=amountF, nonce=nonces.get(a, 0), userFee=176, onChain=0)
+        owners[a].sign_tx(tx, 0)
+        bb.addTx(tx)
+        nonces[a] = nonces.get(a, 0) + 1
+        bal[a] -= amount + fee
+        bal[b] += amount
+    bb.addToken(1)
+    bb.addFeeIdx(idxs[rng.randrange(len(idxs))])
+    bb.build()
+    return bb

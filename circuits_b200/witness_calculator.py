@@ -1,0 +1,238 @@
+"""Host-side mirror of the witness-calculator surface the reference drives its circuits with.
+
+`WitnessCalculator` reproduces the interface of circom_runtime 0.1.12 `WitnessCalculator`
+(the object `tester(path)` / `builder(wasm)` hand to the reference's tests,
+/root/reference/test/rollup-main.test.js:52, test/helpers/helpers.js:142-155):
+`calculateWitness(input, sanityCheck) -> list[int]`, `calculateBinWitness(input, sanityCheck)
+-> bytes` (NVars x 32 B little-endian), plus the tester helpers `assertOut`, `getSignal` and a
+`.wtns` writer (snarkjs `wtns calculate`).  Errors follow the runtime's wording: a violated
+`===` raises `WitnessError("Constraint doesn't match <lhs> != <rhs> ...")`, an unknown key
+`"Signal <k> is not an input of the circuit."`.
+
+All arithmetic happens in `libhzwitness.so` (hand-written CUDA, sm_100a) through the C ABI of
+`include/hzwitness.h`; there is no CPU path -- construction fails when the library or a CUDA
+device is missing.
+"""
+import ctypes
+import os
+
+from .field import P
+
+HZW_CIRCUIT_ROLLUP_MAIN = 0
+HZW_CIRCUIT_WITHDRAW = 1
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "libhzwitness.so")
+
+
+class WitnessError(Exception):
+    """Mirrors the `Error` circom_runtime throws."""
+
+
+class _Params(ctypes.Structure):
+    _fields_ = [("circuit_kind", ctypes.c_int32), ("nTx", ctypes.c_int32), ("nLevels", ctypes.c_int32),
+                ("maxL1Tx", ctypes.c_int32), ("maxFeeTx", ctypes.c_int32), ("device", ctypes.c_int32),
+                ("flags", ctypes.c_uint32)]
+
+
+class _Error(ctypes.Structure):
+    _fields_ = [("code", ctypes.c_int32), ("line", ctypes.c_uint32), ("witness_index", ctypes.c_uint64),
+                ("lhs", ctypes.c_uint8 * 32), ("rhs", ctypes.c_uint8 * 32), ("where", ctypes.c_char * 256)]
+
+
+EXPORTS = ["hzw_create", "hzw_destroy", "hzw_nvars", "hzw_ninputs", "hzw_input_index", "hzw_calculate",
+           "hzw_calculate_batch", "hzw_calculate_resident", "hzw_write_wtns", "hzw_get_signal", "hzw_dump_sym",
+           "hzw_last_stats", "hzw_last_kernel_ms"]
+
+
+def load_library(path=None):
+    path = path or DEFAULT_LIB
+    if not os.path.exists(path):
+        raise WitnessError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)" % path)
+    lib = ctypes.CDLL(path)
+    lib.hzw_nvars.restype = ctypes.c_uint64
+    lib.hzw_ninputs.restype = ctypes.c_uint64
+    lib.hzw_create.argtypes = [ctypes.POINTER(_Params), ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+    lib.hzw_destroy.argtypes = [ctypes.c_void_p]
+    lib.hzw_nvars.argtypes = [ctypes.c_void_p]
+    lib.hzw_ninputs.argtypes = [ctypes.c_void_p]
+    lib.hzw_input_index.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64),
+                                    ctypes.POINTER(ctypes.c_uint64)]
+    lib.hzw_calculate.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                  ctypes.POINTER(_Error)]
+    lib.hzw_calculate_batch.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.POINTER(_Error)]
+    lib.hzw_calculate_resident.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                           ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_Error)]
+    lib.hzw_write_wtns.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p]
+    lib.hzw_get_signal.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
+    lib.hzw_dump_sym.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
+    lib.hzw_last_kernel_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float),
+                                       ctypes.POINTER(ctypes.c_char_p), ctypes.c_int]
+    lib.hzw_last_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64),
+                                   ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    return lib
+
+
+def _flatten(v, out):
+    if isinstance(v, (list, tuple)):
+        for x in v:
+            _flatten(x, out)
+    else:
+        out.append(int(v) % P)
+
+
+def _addr(buf):
+    """Address of a writable/readable buffer (bytearray, ctypes array, numpy / torch storage)."""
+    if isinstance(buf, int):
+        return buf
+    if hasattr(buf, "data_ptr"):
+        return buf.data_ptr()
+    if hasattr(buf, "ctypes"):
+        return buf.ctypes.data
+    return ctypes.addressof((ctypes.c_uint8 * len(buf)).from_buffer(buf))
+
+
+class WitnessCalculator:
+    prime = P
+    n64 = 4
+
+    def __init__(self, nTx, nLevels, maxL1Tx, maxFeeTx, circuit="rollup-main", device=0, lib_path=None):
+        self._lib = load_library(lib_path)
+        kind = {"rollup-main": HZW_CIRCUIT_ROLLUP_MAIN, "withdraw": HZW_CIRCUIT_WITHDRAW}[circuit]
+        self.params = (nTx, nLevels, maxL1Tx, maxFeeTx)
+        prm = _Params(kind, nTx, nLevels, maxL1Tx, maxFeeTx, device, 0)
+        self._ctx = ctypes.c_void_p()
+        st = self._lib.hzw_create(ctypes.byref(prm), None, ctypes.byref(self._ctx))
+        if st != 0:
+            self._ctx = None
+            raise WitnessError("hzw_create failed with code %d (no CUDA device? bad parameters?)" % st)
+        self.NVars = int(self._lib.hzw_nvars(self._ctx))
+        self.NInputs = int(self._lib.hzw_ninputs(self._ctx))
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.hzw_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- input packing: what circom_runtime's `setSignal` loop does ------------------------
+    def inputIndex(self, name):
+        off, ln = ctypes.c_uint64(), ctypes.c_uint64()
+        if self._lib.hzw_input_index(self._ctx, name.encode(), ctypes.byref(off), ctypes.byref(ln)) != 0:
+            raise WitnessError("Signal %s is not an input of the circuit." % name)
+        return off.value, ln.value
+
+    def packInput(self, inp, out=None):
+        """Flatten an input object (keys = main input names) into NInputs x 32 B."""
+        buf = out if out is not None else bytearray(32 * self.NInputs)
+        mv = memoryview(buf)
+        seen = 0
+        for name, v in inp.items():
+            off, ln = self.inputIndex(name)
+            vals = []
+            _flatten(v, vals)
+            if len(vals) != ln:
+                raise WitnessError("Invalid number of values for input signal %s: %d != %d" % (name, len(vals), ln))
+            mv[32 * off:32 * (off + ln)] = b"".join(x.to_bytes(32, "little") for x in vals)
+            seen += ln
+        if seen != self.NInputs:
+            raise WitnessError("Not all inputs have been set. Only %d out of %d" % (seen, self.NInputs))
+        return buf
+
+    def _raise(self, st, err):
+        if st == -4:
+            lhs = int.from_bytes(bytes(err.lhs), "little")
+            rhs = int.from_bytes(bytes(err.rhs), "little")
+            raise WitnessError("Constraint doesn't match %d != %d %s (template line %d)"
+                               % (lhs, rhs, err.where.decode(), err.line))
+        raise WitnessError("hzw_calculate failed with code %d" % st)
+
+    # -- circom_runtime surface ----------------------------------------------------------------
+    def calculateBinWitness(self, inp, sanityCheck=False, out=None):
+        packed = inp if isinstance(inp, (bytes, bytearray)) or hasattr(inp, "data_ptr") else self.packInput(inp)
+        if isinstance(packed, bytes):
+            packed = bytearray(packed)
+        wit = out if out is not None else bytearray(32 * self.NVars)
+        err = _Error()
+        st = self._lib.hzw_calculate(self._ctx, _addr(packed), 1 if sanityCheck else 0, _addr(wit), ctypes.byref(err))
+        if st != 0:
+            self._raise(st, err)
+        return wit
+
+    def calculateWitness(self, inp, sanityCheck=False):
+        b = bytes(self.calculateBinWitness(inp, sanityCheck))
+        return [int.from_bytes(b[32 * i:32 * i + 32], "little") for i in range(self.NVars)]
+
+    def calculateResident(self, packed, sanityCheck=False):
+        """Witness left in device memory; returns the device time of the kernels in ms."""
+        ms = ctypes.c_float()
+        err = _Error()
+        st = self._lib.hzw_calculate_resident(self._ctx, None if packed is None else _addr(packed),
+                                              1 if sanityCheck else 0, ctypes.byref(ms),
+                                              ctypes.byref(err))
+        if st != 0:
+            self._raise(st, err)
+        return ms.value
+
+    def lastKernelMs(self):
+        """[(kernel name, device ms)] of the last calculate, in launch order."""
+        ms = (ctypes.c_float * 16)()
+        names = (ctypes.c_char_p * 16)()
+        n = self._lib.hzw_last_kernel_ms(self._ctx, ms, names, 16)
+        return [(names[i].decode(), ms[i]) for i in range(max(n, 0))]
+
+    def lastStats(self):
+        a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        self._lib.hzw_last_stats(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return dict(gpu_launches=a.value, h2d_bytes=b.value, d2h_bytes=c.value)
+
+    # -- circom tester helpers (test/helpers/helpers.js:151-154,170) ------------------------------
+    def getSignal(self, witness, name):
+        wb = witness if isinstance(witness, (bytes, bytearray)) else b"".join(int(x).to_bytes(32, "little") for x in witness)
+        wb = bytearray(wb)
+        out = (ctypes.c_uint8 * 32)()
+        if self._lib.hzw_get_signal(self._ctx, _addr(wb), name.encode(), out) != 0:
+            raise WitnessError("Signal %s not found" % name)
+        return int.from_bytes(bytes(out), "little")
+
+    def assertOut(self, witness, expected):
+        for k, v in expected.items():
+            vals = []
+            _flatten(v, vals)
+            if isinstance(v, (list, tuple)):
+                for i, e in enumerate(vals):
+                    got = self.getSignal(witness, "main.%s[%d]" % (k, i))
+                    if got != e:
+                        raise AssertionError("main.%s[%d]: %d != %d" % (k, i, got, e))
+            else:
+                got = self.getSignal(witness, "main." + k)
+                if got != vals[0]:
+                    raise AssertionError("main.%s: %d != %d" % (k, got, vals[0]))
+
+    def symbols(self, prefix="main"):
+        """name -> witness index for every signal under `prefix` (the `.sym` equivalent)."""
+        import tempfile
+        with tempfile.NamedTemporaryFile(suffix=".sym", delete=False) as f:
+            path = f.name
+        try:
+            if self._lib.hzw_dump_sym(self._ctx, prefix.encode(), path.encode()) != 0:
+                raise WitnessError("hzw_dump_sym failed")
+            table = {}
+            with open(path) as fh:
+                for line in fh:
+                    i, n = line.rstrip("\n").split(",", 1)
+                    table[n] = int(i)
+            return table
+        finally:
+            os.unlink(path)
+
+    def writeWtns(self, witness, path):
+        wb = bytearray(witness)
+        if self._lib.hzw_write_wtns(self._ctx, _addr(wb), path.encode()) != 0:
+            raise WitnessError("cannot write %s" % path)

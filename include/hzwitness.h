@@ -72,12 +72,16 @@ int hzw_calculate(hzw_ctx* ctx, const uint8_t* inputs_le32, int sanity_check, ui
 /* n independent instances: inputs n x ninputs x 32 B, witnesses n x nvars x 32 B (withdraw) */
 int hzw_calculate_batch(hzw_ctx* ctx, uint64_t n, const uint8_t* inputs_le32, int sanity_check, uint8_t* witness_out,
                         hzw_error* err);
-/* same computation, witness left in device memory (no device->host copy); kernel_ms = device time */
+/* same computation, witness left in device memory (no device->host copy); kernel_ms = device time.
+ * inputs_le32 == NULL re-uses the inputs already resident in device memory from the previous call. */
 int hzw_calculate_resident(hzw_ctx* ctx, const uint8_t* inputs_le32, int sanity_check, float* kernel_ms, hzw_error* err);
 int hzw_write_wtns(const hzw_ctx* ctx, const uint8_t* witness, const char* path);
 int hzw_get_signal(const hzw_ctx* ctx, const uint8_t* witness, const char* name, uint8_t out[32]);
 /* writes "index,name" lines (the `.sym` equivalent) for every signal whose name starts with prefix */
 int hzw_dump_sym(const hzw_ctx* ctx, const char* prefix, const char* path);
+/* device time of each kernel of the last calculate, in launch order; names are static strings.
+ * Returns the number of kernels (<= cap). */
+int hzw_last_kernel_ms(const hzw_ctx* ctx, float* ms, const char** names, int cap);
 /* static description of what the last calculate launched: kernels and bytes, for the bench */
 int hzw_last_stats(const hzw_ctx* ctx, uint64_t* gpu_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 

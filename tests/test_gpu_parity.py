@@ -1,0 +1,69 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle."""
+import hashlib
+
+import pytest
+
+from conftest import cpu_port_calculator
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda(*params):
+    from circuits_b200.witness_calculator import WitnessCalculator
+    return WitnessCalculator(*params)
+
+
+def test_small_batch_equals_oracle_signal_by_signal(built, small_bb, small_oracle):
+    w_ref, sym_ref = small_oracle
+    wc = _cuda(3, 16, 2, 2)
+    assert wc.NVars == len(w_ref)
+    w = wc.calculateWitness(small_bb.getInput(), True)
+    bad = [i for i in range(len(w)) if w[i] != w_ref[i]]
+    assert not bad, (len(bad), bad[:8])
+    assert wc.symbols("main.rollupTx[1].processor1.levels[3]") == {
+        k: v for k, v in sym_ref.items() if k.startswith("main.rollupTx[1].processor1.levels[3]")}
+    assert wc.lastStats()["gpu_launches"] > 0
+
+
+def test_nlevels32_batch_equals_cpu_port_and_hashlib(built):
+    """24 slots at nLevels=32 (8 L1 deposits + 16 signed transfers): byte-exact against the CPU
+    port (itself pinned to the oracle), and hashGlobalInputs against hashlib's SHA-256."""
+    from circuits_b200.synth import bench_batch
+    prm = (24, 32, 8, 4)
+    bb = bench_batch(*prm, n_accounts=16)
+    wc = _cuda(*prm)
+    ref = cpu_port_calculator(*prm)
+    packed = wc.packInput(bb.getInput())
+    wg = bytes(wc.calculateBinWitness(packed, True))
+    wr = bytes(ref.calculateBinWitness(packed, True))
+    assert len(wg) == len(wr) == 32 * wc.NVars
+    if wg != wr:
+        first = next(i for i in range(wc.NVars) if wg[32 * i:32 * i + 32] != wr[32 * i:32 * i + 32])
+        raise AssertionError("first differing witness index %d" % first)
+    assert int.from_bytes(wg[32:64], "little") == bb.getHashInputs()
+
+
+def test_all_nop_batch(built):
+    """Empty `bb.build()` (tools/helpers/actions.js:84-91): every slot is NOP padding."""
+    from circuits_b200.rollupdb import RollupDB
+    prm = (4, 8, 2, 2)
+    bb = RollupDB(chain_id=0).buildBatch(*prm)
+    bb.build()
+    wc = _cuda(*prm)
+    ref = cpu_port_calculator(*prm)
+    packed = wc.packInput(bb.getInput())
+    wg = bytes(wc.calculateBinWitness(packed, True))
+    assert wg == bytes(ref.calculateBinWitness(packed, True))
+    assert int.from_bytes(wg[32:64], "little") == bb.getHashInputs()
+
+
+def test_constraint_violation_on_gpu(built, small_bb):
+    from circuits_b200.witness_calculator import WitnessError
+    wc = _cuda(3, 16, 2, 2)
+    inp = dict(small_bb.getInput())
+    inp["balance1"] = list(inp["balance1"])
+    inp["balance1"][0] += 1
+    with pytest.raises(WitnessError, match="Constraint doesn't match 1 != 0") as e:
+        wc.calculateWitness(inp, True)
+    assert "main.rollupTx[0].processor1.checkOldInput" in str(e.value)
+    assert len(wc.calculateWitness(inp, False)) == wc.NVars
