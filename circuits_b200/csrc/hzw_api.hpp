@@ -136,6 +136,17 @@ int hzw_dump_sym(const hzw_ctx* ctx, const char* prefix, const char* path) {
     fclose(f);
     return HZW_OK;
 }
+int hzw_plan_info(const hzw_ctx* ctx, uint64_t out[9]) {
+    if (!ctx || !out) return HZW_E_PARAM;
+    const HzPlan& pl = ctx->L.plan;
+    const HzParams& P = ctx->P;
+    out[0] = pl.nvars; out[1] = pl.n_inputs; out[2] = pl.sz.getAx; out[3] = pl.sz.sigVerifier;
+    out[4] = HZ_SZ_SHA_BLOCK; out[5] = pl.nblocks;
+    out[6] = (P.maxFeeTx > 1 ? ctx->L.off_fee[1] : pl.off_hasher) - ctx->L.off_fee[0];
+    out[7] = P.nTx > 2 ? ctx->L.off_decode[2] - ctx->L.off_decode[1] : 0;
+    out[8] = P.nTx > 2 ? ctx->L.off_rollup[2] - ctx->L.off_rollup[1] : 0;
+    return HZW_OK;
+}
 int hzw_last_kernel_ms(const hzw_ctx* ctx, float* ms, const char** names, int cap) {
     if (!ctx || !ms || cap <= 0) return HZW_E_PARAM;
     return ctx->be->kernel_ms(ms, names, cap);

@@ -41,7 +41,7 @@ class _Error(ctypes.Structure):
 
 EXPORTS = ["hzw_create", "hzw_destroy", "hzw_nvars", "hzw_ninputs", "hzw_input_index", "hzw_calculate",
            "hzw_calculate_batch", "hzw_calculate_resident", "hzw_write_wtns", "hzw_get_signal", "hzw_dump_sym",
-           "hzw_last_stats", "hzw_last_kernel_ms"]
+           "hzw_last_stats", "hzw_last_kernel_ms", "hzw_plan_info"]
 
 
 def load_library(path=None):
@@ -69,6 +69,7 @@ def load_library(path=None):
     lib.hzw_dump_sym.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
     lib.hzw_last_kernel_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float),
                                        ctypes.POINTER(ctypes.c_char_p), ctypes.c_int]
+    lib.hzw_plan_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
     lib.hzw_last_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64),
                                    ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
     return lib
@@ -179,6 +180,12 @@ class WitnessCalculator:
         if st != 0:
             self._raise(st, err)
         return ms.value
+
+    def planInfo(self):
+        out = (ctypes.c_uint64 * 9)()
+        self._lib.hzw_plan_info(self._ctx, out)
+        keys = ["nvars", "ninputs", "getAx", "sigVerifier", "sha_block", "sha_blocks", "feeTx", "decodeTx", "rollupTx"]
+        return dict(zip(keys, [int(x) for x in out]))
 
     def lastKernelMs(self):
         """[(kernel name, device ms)] of the last calculate, in launch order."""

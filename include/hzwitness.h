@@ -79,6 +79,9 @@ int hzw_write_wtns(const hzw_ctx* ctx, const uint8_t* witness, const char* path)
 int hzw_get_signal(const hzw_ctx* ctx, const uint8_t* witness, const char* name, uint8_t out[32]);
 /* writes "index,name" lines (the `.sym` equivalent) for every signal whose name starts with prefix */
 int hzw_dump_sym(const hzw_ctx* ctx, const char* prefix, const char* path);
+/* sizes the layout walk derived, in witness entries: [0] nvars, [1] ninputs, [2] getAx, [3] sigVerifier,
+ * [4] one sha256compression, [5] sha blocks, [6] feeTx[0], [7] decodeTx[1], [8] rollupTx[1] (0 if nTx < 2) */
+int hzw_plan_info(const hzw_ctx* ctx, uint64_t out[9]);
 /* device time of each kernel of the last calculate, in launch order; names are static strings.
  * Returns the number of kernels (<= cap). */
 int hzw_last_kernel_ms(const hzw_ctx* ctx, float* ms, const char** names, int cap);

@@ -39,10 +39,14 @@ struct CpuBackend : HzBackend {
         w[0].l[0] = 1;
         memcpy(&w[2], inputs, 32ull * pl.n_inputs);
         HzErrBuf* err = sanity ? errs : nullptr;
+        // bounded sample for the CPU-baseline timing: only every `stride`-th slot / fee tx / block
+        int stride = 1;
+        { const char* e = getenv("HZW_CPU_SAMPLE_STRIDE"); if (e && atoi(e) > 1) stride = atoi(e); }
         std::vector<uint8_t> preb((size_t)pl.nblocks * 512, 0);
         PreBits<MCompute> pre; pre.b = preb.data();
         EddsaHook<MCompute> hook; hook.job = nullptr; hook.sz = &pl.sz;
         hz_parallel_for(P.nTx, [&](int i) {
+            if (i % stride) return;
             Comp<MCompute> c(w, pl.off_decode[i], err);
             DecodeOut<MCompute> d;
             PreBits<MCompute> p2 = pre;
@@ -52,6 +56,7 @@ struct CpuBackend : HzBackend {
             sec_rollup(c, pl, i, d, o, p2, hook);
         });
         hz_parallel_for(P.maxFeeTx, [&](int i) {
+            if (i % stride) return;
             Comp<MCompute> c(w, pl.off_fee[i], err);
             sec_fee(c, pl, i);
         });
@@ -74,6 +79,7 @@ struct CpuBackend : HzBackend {
             for (int j = 0; j < 8; j++) chain[(size_t)(b + 1) * 8 + j] = st[j];
         }
         hz_parallel_for((int)pl.nblocks, [&](int b) {
+            if (b % stride) return;
             Comp<MCompute> sh(w, off_blocks + (uint32_t)b * HZ_SZ_SHA_BLOCK, err);
             W32<MCompute> hin[8], msg[16], outw[8];
             for (int j = 0; j < 8; j++) hin[j].v = chain[(size_t)b * 8 + j];
