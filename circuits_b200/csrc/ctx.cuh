@@ -25,6 +25,28 @@
 struct MCompute {};
 struct MLayout {};
 
+// ---- lane groups (device) ------------------------------------------------------------------
+// On the device every circuit section is evaluated by a GROUP of HZ_G = 8 consecutive lanes in
+// lock-step.  Scalar glue is computed redundantly by all lanes (free under SIMT: the warp
+// issues the instruction once either way); what differs per lane is
+//   * stores: witness entry `idx` is written by lane (idx mod 8) only, so the 32-byte stores of
+//     a section spread over the group instead of serialising on one lane;
+//   * Poseidon: lane j holds state element j, the S-boxes of a full round run side by side and
+//     the MDS row of each lane is gathered with warp shuffles (templates_circomlib.cuh);
+//   * constraint failures: reported by lane 0.
+// Host builds (CPU port, layout walk) have no groups: HZ_G = 1.
+#ifdef HZ_DEVICE_ONLY
+#define HZ_G 8
+__device__ __forceinline__ uint32_t hz_glane() { return threadIdx.x & (HZ_G - 1); }
+__device__ __forceinline__ void hz_store_fr(Fr* p, const Fr& v) {
+    uint4 a = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]), b = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    __stcs(reinterpret_cast<uint4*>(p), a);
+    __stcs(reinterpret_cast<uint4*>(p) + 1, b);
+}
+#else
+#define HZ_G 1
+#endif
+
 #define HZ_NOIDX 0xFFFFFFFFu
 
 // ---- names: only the layout walk ever looks at them ---------------------------------------
@@ -157,6 +179,32 @@ static inline std::string hz_nm(const Nm& n) {
 }
 #endif
 
+// ---- inverse hints -------------------------------------------------------------------------
+// `x <-- a / b` costs a field inversion per call when evaluated as written, and the EdDSA verifier
+// has ~1300 of them per transaction, each waiting for the previous one.  A division site can take
+// its 1/b from a stream instead (hint class):
+//   class 1, constant stream: sites whose denominator does not depend on the inputs (the window
+//            tables of EscalarMulFix over BASE8) -- recorded once per context by running the
+//            template in record mode;
+//   class 2, data stream: the Montgomery ladder of EscalarMulAny and the accumulating adders of
+//            EscalarMulFix -- produced per transaction by hints.cuh, which walks the same points
+//            in projective Edwards coordinates and inverts all denominators with one inversion.
+// With no stream installed (CPU port by default, layout walk) a site inverts on the spot.  A wrong
+// hint cannot pass unnoticed: every such site is followed by its `===` check.
+#define HZ_HINT_SCRATCH (4 * 300)
+#define HZ_HINT_MAX 300                    /* data hints of one component (SegmentMulAny(148): 294) */
+#define HZ_EDTAB_SEG1 (83 * 16 + 2)        /* window table: per window 8 points (u, v), then dblLast */
+#define HZ_EDTAB_LEN (HZ_EDTAB_SEG1 + 2 * 16 + 2)
+#define HZ_CST_MAX 720                     /* constant inverses of EscalarMulFix(253) */
+struct HzHints {
+    const Fr* cst; uint32_t ci;            // constant stream, read position
+    Fr* dat; uint32_t di;                  // data stream of the current component (null: none)
+    Fr* rec; uint32_t ri;                  // record mode: constant inverses are appended here
+    const Fr* edtab;                       // window entries of EscalarMulFix (affine Montgomery points)
+    Fr* edrec; uint32_t ei;                // record mode for the table
+    Fr* scratch;                           // HZ_HINT_SCRATCH entries owned by this lane group / thread
+};
+
 // ---- component contexts -------------------------------------------------------------------
 template <class M> struct Comp;
 
@@ -166,10 +214,11 @@ template <> struct Comp<MCompute> {
     uint32_t end;       // reserved range end (HZ_NOIDX when sharing the parent's cursor)
     Comp* parent;
     HzErrBuf* err;      // null = sanity check off
+    HzHints* hints;     // null = every division inverts on the spot
     typedef VC Val;
 
-    HZ_HD Comp(Fr* w_, uint32_t cur_, HzErrBuf* err_) : w(w_), cur(cur_), end(HZ_NOIDX), parent(nullptr), err(err_) {}
-    HZ_HD Comp(Comp* p, bool reserved, uint32_t size) : w(p->w), cur(p->cur), parent(reserved ? nullptr : p), err(p->err) {
+    HZ_HD Comp(Fr* w_, uint32_t cur_, HzErrBuf* err_, HzHints* h_ = nullptr) : w(w_), cur(cur_), end(HZ_NOIDX), parent(nullptr), err(err_), hints(h_) {}
+    HZ_HD Comp(Comp* p, bool reserved, uint32_t size) : w(p->w), cur(p->cur), parent(reserved ? nullptr : p), err(p->err), hints(p->hints) {
         if (reserved) { end = p->cur + size; p->cur += size; } else end = HZ_NOIDX;
     }
     HZ_HD ~Comp() {
@@ -179,29 +228,63 @@ template <> struct Comp<MCompute> {
 #endif
     }
     Comp(const Comp&) = delete;
-    HZ_HD Comp(Comp&& o) : w(o.w), cur(o.cur), end(o.end), parent(o.parent), err(o.err) { o.parent = nullptr; o.end = HZ_NOIDX; }
+    HZ_HD Comp(Comp&& o) : w(o.w), cur(o.cur), end(o.end), parent(o.parent), err(o.err), hints(o.hints) { o.parent = nullptr; o.end = HZ_NOIDX; }
+    // two divisions whose denominators are both known: one inversion
+    HZ_HD void div2(const VC& a1, const VC& b1, const VC& a2, const VC& b2, VC& q1, VC& q2) {
+        // exactly one inversion whatever the data (the device batches inversions across a warp)
+        const bool z1 = fr_is_zero(b1.v), z2 = fr_is_zero(b2.v);
+        const Fr d1 = z1 ? fr_one() : b1.v, d2 = z2 ? fr_one() : b2.v;
+        Fr t = fr_inv(fr_mul(d1, d2));
+        q1 = vc(z1 ? fr_zero() : fr_mul(a1.v, fr_mul(t, d2)));
+        q2 = vc(z2 ? fr_zero() : fr_mul(a2.v, fr_mul(t, d1)));
+    }
+    // a / b at a division site of hint class `cls` (0: none)
+    HZ_HD VC div(const VC& a, const VC& b, int cls) {
+        if (hints && cls == 1) {
+            if (hints->rec) { Fr iv = fr_inv(b.v); hints->rec[hints->ri++] = iv; return vc(fr_mul(a.v, iv)); }
+            if (hints->cst) return vc(fr_mul(a.v, hints->cst[hints->ci++]));
+        } else if (hints && cls == 2 && hints->dat) {
+            return vc(fr_mul(a.v, hints->dat[hints->di++]));
+        }
+        return vdiv(a, b);
+    }
 
     HZ_HD Comp sub(const Nm&) { return Comp(this, false, 0); }
     HZ_HD Comp sub_reserve(const Nm&, uint32_t size) { return Comp(this, true, size); }
     HZ_HD void skip(const Nm&, uint32_t size) { cur += size; }
 
+    // the one place a witness entry is written
+    HZ_HD void put(uint32_t slot, const Fr& v) {
+#ifdef HZ_DEVICE_ONLY
+        if (((slot ^ threadIdx.x) & (HZ_G - 1)) == 0) hz_store_fr(&w[slot], v);
+#else
+        w[slot] = v;
+#endif
+    }
     HZ_HD uint32_t sig(const Nm&) { return cur++; }
     HZ_HD uint32_t sigs(const Nm&, int n) { uint32_t s = cur; cur += n; return s; }
-    HZ_HD VC set(uint32_t slot, const VC& x) { w[slot] = x.v; VC r = x; r.sig = true; return r; }
+    HZ_HD VC set(uint32_t slot, const VC& x) { put(slot, x.v); VC r = x; r.sig = true; return r; }
     HZ_HD VC seti(const Nm&, uint32_t slot, const VC& x) { return set(slot, x); }
     HZ_HD VC alias(const Nm&, const VC& x) { return x; }
     // `signal s <== x` / wiring of a sub-component input: alias when x is a signal
     HZ_HD VC def(const Nm&, const VC& x) {
         if (x.sig) return x;
-        w[cur++] = x.v; VC r = x; r.sig = true; return r;
+        put(cur++, x.v); VC r = x; r.sig = true; return r;
     }
     // main-component signals always own their entry
-    HZ_HD VC own(const Nm&, const VC& x) { w[cur++] = x.v; VC r = x; r.sig = true; return r; }
+    HZ_HD VC own(const Nm&, const VC& x) { put(cur++, x.v); VC r = x; r.sig = true; return r; }
+    // only for entries written by an EARLIER kernel or by the caller (main inputs): within a
+    // kernel the lanes of a group do not see each other's stores
     HZ_HD VC load(uint32_t idx) const { VC r; r.v = w[idx]; r.sig = true; return r; }
+    // a signal whose value the caller already holds (no read-back)
+    HZ_HD VC known(uint32_t, const VC& x) const { VC r = x; r.sig = true; return r; }
     HZ_HD bool sanity() const { return err != nullptr; }
     HZ_HD void check(const VC& lhs, const VC& rhs, uint32_t line) {
         if (!err) return;
         if (fr_eq(lhs.v, rhs.v)) return;
+#ifdef HZ_DEVICE_ONLY
+        if (hz_glane() != 0) return;
+#endif
 #ifdef __CUDA_ARCH__
         uint32_t k = atomicAdd(&err->count, 1u);
 #else
@@ -271,6 +354,9 @@ template <> struct Comp<MLayout> {
     }
     VL own(const Nm& nm, const VL&) { name(nm, cur); VL r; r.idx = cur++; return r; }
     VL load(uint32_t idx) const { VL r; r.idx = idx; return r; }
+    VL known(uint32_t idx, const VL&) const { VL r; r.idx = idx; return r; }
+    VL div(const VL&, const VL&, int) { return vl(); }
+    void div2(const VL&, const VL&, const VL&, const VL&, VL& q1, VL& q2) { q1 = vl(); q2 = vl(); }
     bool sanity() const { return false; }
     void check(const VL&, const VL&, uint32_t) {}
     void check0(const VL&, uint32_t) {}

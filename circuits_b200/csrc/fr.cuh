@@ -190,11 +190,75 @@ HZ_HD Fr fr_barrett(const uint32_t* t) {
     return out;
 }
 
+// ---- generated carry-chain products (tools/gen_frmul.py): the device multiplier ----------------
+#include "fr_mulgen.inc"
+
+// d = r - k (8 limbs); returns the borrow (0 / 1)
+HZ_HD uint32_t fr_sub8(uint32_t* d, const uint32_t* r, const uint32_t* k) {
+#if defined(__CUDA_ARCH__)
+    uint32_t brw;
+    asm("sub.cc.u32 %0, %9, %17; subc.cc.u32 %1, %10, %18; subc.cc.u32 %2, %11, %19; subc.cc.u32 %3, %12, %20; "
+        "subc.cc.u32 %4, %13, %21; subc.cc.u32 %5, %14, %22; subc.cc.u32 %6, %15, %23; subc.cc.u32 %7, %16, %24; "
+        "subc.u32 %8, 0, 0;"
+        : "=&r"(d[0]), "=&r"(d[1]), "=&r"(d[2]), "=&r"(d[3]), "=&r"(d[4]), "=&r"(d[5]), "=&r"(d[6]), "=&r"(d[7]), "=&r"(brw)
+        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(k[0]), "r"(k[1]), "r"(k[2]), "r"(k[3]), "r"(k[4]), "r"(k[5]), "r"(k[6]), "r"(k[7]));
+    return brw & 1u;
+#else
+    int64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (int64_t)r[i] - (int64_t)k[i]; d[i] = (uint32_t)c; c >>= 32; }
+    return (uint32_t)(c & 1);
+#endif
+}
+// r < 4p (8 limbs)  ->  r mod p, branch-free: subtract 2p, then p, when they fit
+HZ_HD void fr_fold4p(uint32_t* r) {
+    const uint32_t p2[8] = {0xe0000002u, 0x87c3eb27u, 0xf372e122u, 0x5067d090u, 0x0302b0bau, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u};
+    const uint32_t p1[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+    uint32_t d[8];
+    uint32_t b = fr_sub8(d, r, p2);
+    for (int i = 0; i < 8; i++) r[i] = b ? r[i] : d[i];
+    b = fr_sub8(d, r, p1);
+    for (int i = 0; i < 8; i++) r[i] = b ? r[i] : d[i];
+}
+// canonical x canonical -> canonical: 512-bit product, Barrett quotient from the top 9 limbs
+// (error <= 3, so the remainder is below 4p < 2^256 and 8 limbs carry it)
+HZ_HD Fr fr_mul_chain(const Fr& a, const Fr& b) {
+    uint32_t t[16], q3[9], qp[8];
+    fr_gen_mulwide(t, a, b);
+    fr_gen_qmu(q3, t);
+    fr_gen_qp(qp, q3);
+    Fr r;
+    fr_sub8(r.l, t, qp);
+    fr_fold4p(r.l);
+    return r;
+}
+// sum_{k<N} s[k] * cR[k] with cR in Montgomery form -> canonical (N <= 7: below 3p before folding)
+template <int N> HZ_HD Fr fr_dot_mont_chain(const Fr* s, const Fr* cR) {
+    uint32_t T[17], m[8], r[9];
+    if (N == 1) { fr_gen_mulwide(T, s[0], cR[0]); T[16] = 0; }
+    else if (N == 2) fr_gen_dot2(T, s, cR);
+    else if (N == 3) fr_gen_dot3(T, s, cR);
+    else if (N == 4) fr_gen_dot4(T, s, cR);
+    else if (N == 5) fr_gen_dot5(T, s, cR);
+    else if (N == 6) fr_gen_dot6(T, s, cR);
+    else fr_gen_dot7(T, s, cR);
+    fr_gen_mlow(m, T);
+    fr_gen_mpadd(r, m, T);
+    Fr o;
+    for (int i = 0; i < 8; i++) o.l[i] = r[i];
+    fr_fold4p(o.l);
+    return o;
+}
+
+#ifdef HZ_DEVICE_ONLY
+HZ_HDN Fr fr_mul(const Fr& a, const Fr& b) { return fr_mul_chain(a, b); }
+#else
 HZ_HDN Fr fr_mul(const Fr& a, const Fr& b) {
     uint32_t t[16];
     fr_mul_wide(t, a, b);
     return fr_barrett(t);
 }
+#endif
 HZ_HD Fr fr_sqr(const Fr& a) { return fr_mul(a, a); }
 HZ_HD Fr fr_mul_u64(const Fr& a, uint64_t k) { return fr_mul(a, fr_from_u64(k)); }
 
@@ -253,6 +317,7 @@ HZ_HD void fr_half_mod(Fr& x) {         // x/2 mod p
         fr_shr1(x, 0);
     }
 }
+#ifndef HZ_DEVICE_ONLY
 HZ_HDN Fr fr_inv(const Fr& a) {
     if (fr_is_zero(a)) return a;
     Fr u = a, v = fr_P(), x1 = fr_one(), x2 = fr_zero();
@@ -265,6 +330,108 @@ HZ_HDN Fr fr_inv(const Fr& a) {
     }
     return fr_eq(u, one) ? x1 : x2;
 }
+#else
+// ---- device inversion --------------------------------------------------------------------------
+// (1) the same binary extended Euclid, on registers with carry-chain PTX;
+// (2) warp-cooperative batching: on the device a warp is four 8-lane groups, each group holding one
+//     value in all its lanes.  When the whole warp arrives together the four values are inverted
+//     with ONE Euclid run (Montgomery's trick over the groups, two shuffle rounds), which every
+//     lane executes on the same number -- no divergence.  If the warp is not whole at the call
+//     (a group took a fallback path), every group inverts on its own.
+__device__ __forceinline__ uint32_t hz_add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t cy;
+    asm("add.cc.u32 %0, %9, %17; addc.cc.u32 %1, %10, %18; addc.cc.u32 %2, %11, %19; addc.cc.u32 %3, %12, %20; "
+        "addc.cc.u32 %4, %13, %21; addc.cc.u32 %5, %14, %22; addc.cc.u32 %6, %15, %23; addc.cc.u32 %7, %16, %24; "
+        "addc.u32 %8, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(cy)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return cy;
+}
+__device__ __forceinline__ void hz_shr8(uint32_t* a, uint32_t top) {
+#pragma unroll
+    for (int i = 0; i < 7; i++) a[i] = __funnelshift_r(a[i], a[i + 1], 1);
+    a[7] = __funnelshift_r(a[7], top, 1);
+}
+// x <- x / 2 mod p
+__device__ __forceinline__ void hz_half8(uint32_t* x) {
+    const uint32_t p1[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+    if (x[0] & 1u) {
+        uint32_t t[8];
+        uint32_t cy = hz_add8(t, x, p1);
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = t[i];
+        hz_shr8(x, cy);
+    } else {
+        hz_shr8(x, 0);
+    }
+}
+// x <- x - y mod p
+__device__ __forceinline__ void hz_submod8(uint32_t* x, const uint32_t* y) {
+    const uint32_t p1[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+    uint32_t d[8], e[8];
+    uint32_t b = fr_sub8(d, x, y);
+    hz_add8(e, d, p1);
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = b ? e[i] : d[i];
+}
+__device__ __forceinline__ bool hz_is_one8(const uint32_t* a) {
+    return (a[0] == 1u) && ((a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7]) == 0u);
+}
+// a != 0
+__device__ __noinline__ Fr fr_inv_euclid(const Fr& a) {
+    uint32_t u[8], v[8], x1[8], x2[8];
+    const uint32_t p1[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+#pragma unroll
+    for (int i = 0; i < 8; i++) { u[i] = a.l[i]; v[i] = p1[i]; x1[i] = i == 0 ? 1u : 0u; x2[i] = 0u; }
+    while (!hz_is_one8(u) && !hz_is_one8(v)) {
+        if (!(u[0] & 1u)) { hz_shr8(u, 0); hz_half8(x1); }
+        else if (!(v[0] & 1u)) { hz_shr8(v, 0); hz_half8(x2); }
+        else {
+            uint32_t d[8];
+            uint32_t b = fr_sub8(d, u, v);
+            if (!b) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) u[i] = d[i];
+                hz_submod8(x1, x2);
+            } else {
+                fr_sub8(d, v, u);
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = d[i];
+                hz_submod8(x2, x1);
+            }
+        }
+    }
+    Fr r;
+    bool fu = hz_is_one8(u);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = fu ? x1[i] : x2[i];
+    return r;
+}
+__device__ __forceinline__ Fr hz_shfl_xor_fr(const Fr& v, int m) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_xor_sync(0xffffffffu, v.l[i], m);
+    return r;
+}
+__device__ __noinline__ Fr fr_inv(const Fr& a) {
+    const bool z = fr_is_zero(a);
+    Fr x = a;
+    if (z) x.l[0] = 1u;
+    if (__activemask() != 0xffffffffu) {
+        Fr r = fr_inv_euclid(x);
+        if (z) r.l[0] = 0u;
+        return r;
+    }
+    Fr v1 = hz_shfl_xor_fr(x, 8);            // the neighbouring group's value
+    Fr p2 = fr_mul(x, v1);
+    Fr q2 = hz_shfl_xor_fr(p2, 16);          // the other pair's product
+    Fr t = fr_inv_euclid(fr_mul(p2, q2));    // the same number in all 32 lanes
+    Fr r = fr_mul(fr_mul(t, q2), v1);
+    if (z) r = fr_from_u64(0);
+    return r;
+}
+#endif
 HZ_HD Fr fr_div(const Fr& a, const Fr& b) { return fr_mul(a, fr_inv(b)); }
 
 // a^e, e given as 8 limbs

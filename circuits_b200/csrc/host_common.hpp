@@ -80,7 +80,7 @@ static inline void hz_layout_walk(const HzParams& P, LayoutSink* sink, HzLayout&
     R.off_decode.resize(P.nTx); R.off_rollup.resize(P.nTx); R.off_fee.resize(P.maxFeeTx);
     for (int i = 0; i < P.nTx; i++) { R.off_decode[i] = main.cur; sec_decode(main, pl, i, dec[i], pre); }
     pl.idx_newLastIdx = dec[P.nTx - 1].outIdx.idx;
-    EddsaHook<MLayout> hook; hook.sz_out = &pl.sz;
+    SlotHook<MLayout> hook; hook.sz_out = &pl.sz;
     for (int i = 0; i < P.nTx; i++) {
         R.off_rollup[i] = main.cur;
         RollupTxOut<MLayout> o;
@@ -89,7 +89,8 @@ static inline void hz_layout_walk(const HzParams& P, LayoutSink* sink, HzLayout&
     }
     for (int i = 0; i < P.maxFeeTx; i++) {
         R.off_fee[i] = main.cur;
-        VL r = sec_fee(main, pl, i);
+        FeeHook<MLayout> fh; fh.unused = 0;
+        VL r = sec_fee(main, pl, i, fh);
         if (i == P.maxFeeTx - 1) pl.idx_newStateRoot = r.idx;
     }
     pl.off_hasher = main.cur;

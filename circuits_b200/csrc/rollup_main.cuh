@@ -120,8 +120,24 @@ TM HZ_FN void sec_decode(Comp<M>& c, const HzPlan& pl, int i, DecodeOut<M>& o, P
 }
 
 // ---- section D/E: rollupTx[i]  (:269-389, :427-431) ------------------------------------------
+HZ_HD bool hz_roots_deferred(const SlotHook<MCompute>& hk) { return hk.smt != nullptr; }
+#ifndef HZ_DEVICE_ONLY
+inline bool hz_roots_deferred(const SlotHook<MLayout>&) { return false; }
+#endif
+
+// E (:383-389) / G (:427-431): the roots a slot produced against the intermediary inputs
+TM HZ_FN void sec_rollup_root_checks(Comp<M>& c, const HzPlan& pl, int i, const V<M>& newStateRoot, const V<M>& newExitRoot) {
+    if (!c.sanity()) return;
+    if (i < pl.P.nTx - 1) {
+        c.check(newStateRoot, hz_in(c, pl, IN_imStateRoot, i), __LINE__);
+        c.check(newExitRoot, hz_in(c, pl, IN_imExitRoot, i), __LINE__);
+    } else {
+        c.check(newStateRoot, hz_in(c, pl, IN_imInitStateRootFee), __LINE__);
+    }
+}
+
 TM HZ_FN void sec_rollup(Comp<M>& c, const HzPlan& pl, int i, const DecodeOut<M>& d, RollupTxOut<M>& o,
-                          PreBits<M>& pre, const EddsaHook<M>& hook) {
+                          PreBits<M>& pre, const SlotHook<M>& hook) {
     const HzParams& P = pl.P;
     const int nTx = P.nTx, L = P.nLevels + 1;
     RollupTxIn<M> t;
@@ -169,18 +185,14 @@ TM HZ_FN void sec_rollup(Comp<M>& c, const HzPlan& pl, int i, const DecodeOut<M>
     t.isOld0_2 = hz_in(c, pl, IN_isOld0_2, i); t.oldKey2 = hz_in(c, pl, IN_oldKey2, i); t.oldValue2 = hz_in(c, pl, IN_oldValue2, i);
     t.oldStateRoot = i == 0 ? hz_in(c, pl, IN_oldStateRoot) : hz_in(c, pl, IN_imStateRoot, i - 1);
     t.oldExitRoot = i == 0 ? Ops<M>::K(0) : hz_in(c, pl, IN_imExitRoot, i - 1);
+    t.sib1_idx = pl.in_off[IN_siblings1] + (uint32_t)i * pl.in_d1[IN_siblings1];
+    t.sib2_idx = pl.in_off[IN_siblings2] + (uint32_t)i * pl.in_d1[IN_siblings2];
     RollupTx(c.sub(Nm("rollupTx", i)), P.nLevels, P.maxFeeTx, t, o, hook);
     if (c.sanity()) {
-        if (i < nTx - 1) {
-            // E (:383-389)
-            c.check(o.newStateRoot, hz_in(c, pl, IN_imStateRoot, i), __LINE__);
-            c.check(o.newExitRoot, hz_in(c, pl, IN_imExitRoot, i), __LINE__);
-            for (int k = 0; k < P.maxFeeTx; k++) c.check(o.accFeeOut[k], hz_in(c, pl, IN_imAccFeeOut, i, k), __LINE__);
-        } else {
-            // G (:427-431)
-            c.check(o.newStateRoot, hz_in(c, pl, IN_imInitStateRootFee), __LINE__);
-            for (int k = 0; k < P.maxFeeTx; k++) c.check(o.accFeeOut[k], hz_in(c, pl, IN_imFinalAccFee, k), __LINE__);
-        }
+        // E (:383-389) / G (:427-431); with the processors handed off the roots are checked by the tail
+        if (!hz_roots_deferred(hook)) sec_rollup_root_checks(c, pl, i, o.newStateRoot, o.newExitRoot);
+        for (int k = 0; k < P.maxFeeTx; k++)
+            c.check(o.accFeeOut[k], i < nTx - 1 ? hz_in(c, pl, IN_imAccFeeOut, i, k) : hz_in(c, pl, IN_imFinalAccFee, k), __LINE__);
     }
     // H - L1L2TxData with the amount nullified (:452-461): what hasherInputs.L1L2TxsData[] holds
     const int nL2 = 2 * P.nLevels + 48;
@@ -192,7 +204,7 @@ TM HZ_FN void sec_rollup(Comp<M>& c, const HzPlan& pl, int i, const DecodeOut<M>
 }
 
 // ---- section F/G: feeTx[i]  (:393-426) --------------------------------------------------------
-TM HZ_FN V<M> sec_fee(Comp<M>& c, const HzPlan& pl, int i) {
+TM HZ_FN V<M> sec_fee(Comp<M>& c, const HzPlan& pl, int i, const FeeHook<M>& hook, bool deferred = false) {
     const HzParams& P = pl.P;
     V<M> sib[HZ_MAX_LEVELS];
     for (int k = 0; k < P.nLevels + 1; k++) sib[k] = hz_in(c, pl, IN_siblings3, i, k);
@@ -200,10 +212,61 @@ TM HZ_FN V<M> sec_fee(Comp<M>& c, const HzPlan& pl, int i) {
                    i == 0 ? hz_in(c, pl, IN_imInitStateRootFee) : hz_in(c, pl, IN_imStateRootFee, i - 1),
                    hz_in(c, pl, IN_feePlanTokens, i), hz_in(c, pl, IN_feeIdxs, i), hz_in(c, pl, IN_imFinalAccFee, i),
                    hz_in(c, pl, IN_tokenID3, i), hz_in(c, pl, IN_nonce3, i), hz_in(c, pl, IN_sign3, i),
-                   hz_in(c, pl, IN_balance3, i), hz_in(c, pl, IN_ay3, i), hz_in(c, pl, IN_ethAddr3, i), sib);
-    if (c.sanity() && i < P.maxFeeTx - 1) c.check(r, hz_in(c, pl, IN_imStateRootFee, i), __LINE__);
+                   hz_in(c, pl, IN_balance3, i), hz_in(c, pl, IN_ay3, i), hz_in(c, pl, IN_ethAddr3, i), sib, hook);
+    if (!deferred && c.sanity() && i < P.maxFeeTx - 1) c.check(r, hz_in(c, pl, IN_imStateRootFee, i), __LINE__);
     return r;
 }
+
+#ifdef HZ_DEVICE_ONLY
+// ---- device only: bodies and tops of the SMT processors as their own sections -------------------
+__device__ __forceinline__ VC hz_sigv(const Fr& f, bool sig) { VC r; r.v = f; r.sig = sig; return r; }
+
+// one SMTProcessor body from its job record (k_smt)
+__device__ __noinline__ void sec_smt_body(Fr* w, HzErrBuf* err, int nLevels1, const HzSmtJob& j, HzSmtMid& out) {
+    Comp<MCompute> c(w, j.cur, err);
+    VC sib[HZ_MAX_LEVELS];
+    for (int k = 0; k < nLevels1; k++) sib[k] = c.load(j.sib + k);
+    VC f[2];
+    f[0] = hz_sigv(j.fnc0, j.sigmask & 32u); f[1] = hz_sigv(j.fnc1, j.sigmask & 64u);
+    SMTMid<MCompute> mid;
+    // the old root is not needed by the body (wired signal: no entry); the top gets the real one
+    SMTProcessorBody<MCompute>(c, nLevels1, hz_sigv(fr_zero(), true), sib, hz_sigv(j.oldKey, j.sigmask & 1u),
+                               hz_sigv(j.oldValue, j.sigmask & 2u), hz_sigv(j.isOld0, j.sigmask & 4u),
+                               hz_sigv(j.newKey, j.sigmask & 8u), hz_sigv(j.newValue, j.sigmask & 16u), f, mid);
+    if (hz_glane() == 0) {
+        out.enabled = mid.enabled.v; out.oldKey = mid.oldKey.v; out.newKey = mid.newKey.v; out.fnc0 = mid.fnc0.v;
+        out.fnc1 = mid.fnc1.v; out.tL = mid.tL.v; out.tR = mid.tR.v; out.cur = c.cur; out.newRootIdx = mid.newRootIdx;
+    }
+}
+__device__ __forceinline__ VC hz_smt_top(Comp<MCompute>& c, const HzSmtMid& m, const VC& oldRoot) {
+    SMTMid<MCompute> mid;
+    mid.oldRoot = oldRoot; mid.enabled = hz_sigv(m.enabled, true); mid.oldKey = hz_sigv(m.oldKey, true);
+    mid.newKey = hz_sigv(m.newKey, true); mid.fnc0 = hz_sigv(m.fnc0, true); mid.fnc1 = hz_sigv(m.fnc1, true);
+    mid.tL = hz_sigv(m.tL, true); mid.tR = hz_sigv(m.tR, true); mid.newRootIdx = m.newRootIdx;
+    c.cur = m.cur;
+    return SMTProcessorTop<MCompute>(c, mid);
+}
+// tops of processor 1 and 2, s3, s4, s5 and the root checks of slot i (k_tail)
+__device__ __noinline__ void sec_rollup_tail(Fr* w, HzErrBuf* err, const HzPlan& pl, int i, const HzSmtMid* mids, const Fr& isExit_) {
+    Comp<MCompute> c(w, mids[0].cur, err);
+    VC oldStateRoot = i == 0 ? hz_in(c, pl, IN_oldStateRoot) : hz_in(c, pl, IN_imStateRoot, i - 1);
+    VC oldExitRoot = i == 0 ? hz_sigv(fr_zero(), true) : hz_in(c, pl, IN_imExitRoot, i - 1);
+    VC isExit = hz_sigv(isExit_, true);
+    VC p1 = hz_smt_top(c, mids[0], oldStateRoot);
+    VC s3 = Mux1(c.sub("s3"), p1, oldExitRoot, isExit);
+    VC p2 = hz_smt_top(c, mids[1], s3);
+    VC newStateRoot = Mux1(c.sub("s4"), p2, p1, isExit);
+    VC newExitRoot = Mux1(c.sub("s5"), oldExitRoot, p2, isExit);
+    sec_rollup_root_checks(c, pl, i, newStateRoot, newExitRoot);
+}
+// top of the processor of fee tx i
+__device__ __noinline__ void sec_fee_tail(Fr* w, HzErrBuf* err, const HzPlan& pl, int i, const HzSmtMid& mid) {
+    Comp<MCompute> c(w, mid.cur, err);
+    VC oldStateRoot = i == 0 ? hz_in(c, pl, IN_imInitStateRootFee) : hz_in(c, pl, IN_imStateRootFee, i - 1);
+    VC r = hz_smt_top(c, mid, oldStateRoot);
+    if (c.sanity() && i < pl.P.maxFeeTx - 1) c.check(r, hz_in(c, pl, IN_imStateRootFee, i), __LINE__);
+}
+#endif
 
 // ---- section H: hasherInputs (src/hash-inputs.circom:23-185) ----------------------------------
 // head: everything before the first sha256compression; the pre-image gets its remaining bits

@@ -9,6 +9,7 @@
 // the range is reserved (`sub_reserve`) with its closed-form size.
 #pragma once
 #include "ctx.cuh"
+#include "hints.cuh"
 #include "poseidon_constants.inc"
 
 #define HZ_MV(x) static_cast<decltype(x)&&>(x)
@@ -341,7 +342,8 @@ template <> struct PoseidonMath<MLayout> {
     static HZ_HD VL mix(const VL*, int, int) { return vl(); }
 };
 
-TM HZ_FN V<M> Poseidon(Comp<M>&& c, const V<M>* inputs, int n) {
+TM HZ_FN V<M> Poseidon(Comp<M>&& c, const V<M>* inputs, int n);
+TM HZ_FN V<M> PoseidonGeneric(Comp<M>&& c, const V<M>* inputs, int n) {
     const int t = n + 1, rp = poseidon_rp(t), R = 8 + rp;
     V<M> st[7];
     st[0] = Ops<M>::K(0);
@@ -372,6 +374,122 @@ TM HZ_FN V<M> Poseidon(Comp<M>&& c, const V<M>* inputs, int n) {
     return c.alias("out", st[0]);
 }
 
+#ifdef HZ_DEVICE_ONLY
+// ---- the permutation on a lane group ---------------------------------------------------------
+// Lane `base + j` of the 8-lane group holds state element j (j < T); a group runs one permutation
+// (base = 0) or two side by side (bases 0 and 4, T <= 4: the old-path / new-path hashes of an SMT
+// level).  Per round each lane adds its round constant, the S-box lanes do x -> x^5 (all T lanes
+// in a full round, lane `base` alone in a partial one), then every lane gathers the T S-box
+// outputs of its permutation with shuffles and reduces its own MDS row (constants in Montgomery
+// form: one reduction per row).  Every signal is stored by the lane that computed it, at the
+// witness index the layout walk gives it: per round `ark.out[T]`, `mix.out[T]`, then
+// (out, in2, in4) per S-box.
+__device__ __forceinline__ Fr hz_shfl_fr(const Fr& v, int src) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], src, HZ_G);
+    return r;
+}
+template <int T> __device__ __noinline__ Fr hz_poseidon_lanes(Fr* w, uint32_t cur, Fr s, int base) {
+    const int rp = poseidon_rp(T), R = 8 + rp;
+    const int lane = (int)hz_glane();
+    const int j = lane - base;
+    const bool mine = j >= 0 && j < T;
+    const int jj = mine ? j : 0;
+    const Fr* C = &hz_poseidon_c(T, 0);
+    const Fr* Mrow = hz_poseidon_mr(T, jj);
+    Fr mreg[T <= 4 ? T : 1];
+    if (T <= 4) {
+#pragma unroll
+        for (int k = 0; k < (T <= 4 ? T : 1); k++) mreg[k] = Mrow[k];
+    }
+    for (int i = 0; i < R; i++) {
+        s = fr_add(s, C[T * i + jj]);
+        if (mine) hz_store_fr(&w[cur + jj], s);
+        const bool full = i < 4 || i >= rp + 4;
+        const uint32_t sg = cur + 2 * T;
+        if (mine && (full || j == 0)) {
+            Fr in2 = fr_mul_chain(s, s);
+            Fr in4 = fr_mul_chain(in2, in2);
+            s = fr_mul_chain(in4, s);
+            hz_store_fr(&w[sg + 3 * jj], s);
+            hz_store_fr(&w[sg + 3 * jj + 1], in2);
+            hz_store_fr(&w[sg + 3 * jj + 2], in4);
+        }
+        Fr a[T];
+#pragma unroll
+        for (int k = 0; k < T; k++) a[k] = hz_shfl_fr(s, base + k);
+        s = fr_dot_mont_chain<T>(a, T <= 4 ? mreg : Mrow);
+        if (mine) hz_store_fr(&w[cur + T + jj], s);
+        cur += 2 * T + (full ? 3 * T : 3);
+    }
+    return hz_shfl_fr(s, base);
+}
+__device__ __forceinline__ Fr hz_poseidon_dispatch(Fr* w, int t, uint32_t cur, const Fr& s, int base) {
+    switch (t) {
+        case 3: return hz_poseidon_lanes<3>(w, cur, s, base);
+        case 4: return hz_poseidon_lanes<4>(w, cur, s, base);
+        case 5: return hz_poseidon_lanes<5>(w, cur, s, base);
+        case 6: return hz_poseidon_lanes<6>(w, cur, s, base);
+        default: return hz_poseidon_lanes<7>(w, cur, s, base);
+    }
+}
+// declares the `inputs` / `ark[0].in[0]` entries exactly as PoseidonGeneric does and returns the
+// witness index where round 0's ark.out starts
+__device__ __forceinline__ uint32_t hz_poseidon_head(Comp<MCompute>& c, const VC* inputs, int n) {
+    for (int i = 0; i < n; i++) c.def(Nm("inputs", i), inputs[i]);
+    c.def(Nm("in", 0), vc(fr_zero()));
+    return c.cur;
+}
+template <> __device__ __noinline__ VC Poseidon<MCompute>(Comp<MCompute>&& c, const VC* inputs, int n) {
+    const int t = n + 1;
+    const uint32_t c0 = c.cur;
+    uint32_t n_own = 0;
+    for (int i = 0; i < n; i++) n_own += inputs[i].sig ? 0u : 1u;
+    uint32_t cur = hz_poseidon_head(c, inputs, n);
+    const int lane = (int)hz_glane();
+    Fr s = (lane >= 1 && lane <= n) ? inputs[lane - 1].v : fr_zero();
+    Fr o = hz_poseidon_dispatch(c.w, t, cur, s, 0);
+    c.cur = c0 + n_own + poseidon_size(t);
+    VC r; r.v = o; r.sig = true;
+    return r;
+}
+#else
+template <> inline VC Poseidon<MCompute>(Comp<MCompute>&& c, const VC* inputs, int n) {
+    return PoseidonGeneric<MCompute>(HZ_MV(c), inputs, n);
+}
+template <> inline VL Poseidon<MLayout>(Comp<MLayout>&& c, const VL* inputs, int n) {
+    return PoseidonGeneric<MLayout>(HZ_MV(c), inputs, n);
+}
+#endif
+
+// two permutations of the same width in two components that do not depend on each other
+TM HZ_FN void PoseidonDual(Comp<M>&& cA, const V<M>* inA, Comp<M>&& cB, const V<M>* inB, int n, V<M>& oA, V<M>& oB) {
+    oA = Poseidon<M>(HZ_MV(cA), inA, n);
+    oB = Poseidon<M>(HZ_MV(cB), inB, n);
+}
+#ifdef HZ_DEVICE_ONLY
+template <> __device__ __noinline__ void PoseidonDual<MCompute>(Comp<MCompute>&& cA, const VC* inA, Comp<MCompute>&& cB,
+                                                               const VC* inB, int n, VC& oA, VC& oB) {
+    const int t = n + 1;            // t <= 4: both fit the 8-lane group
+    uint32_t a0 = cA.cur, b0 = cB.cur, ownA = 0, ownB = 0;
+    for (int i = 0; i < n; i++) { ownA += inA[i].sig ? 0u : 1u; ownB += inB[i].sig ? 0u : 1u; }
+    uint32_t curA = hz_poseidon_head(cA, inA, n);
+    uint32_t curB = hz_poseidon_head(cB, inB, n);
+    const int lane = (int)hz_glane();
+    const bool second = lane >= 4;
+    const int j = lane & 3;
+    const VC* in = second ? inB : inA;
+    Fr s = (j >= 1 && j <= n) ? in[j - 1].v : fr_zero();
+    Fr o = hz_poseidon_dispatch(cA.w, t, second ? curB : curA, s, second ? 4 : 0);
+    // every lane needs both digests: lanes 0..3 hold A's, lanes 4..7 hold B's
+    oA.v = hz_shfl_fr(o, 0); oA.sig = true;
+    oB.v = hz_shfl_fr(o, 4); oB.sig = true;
+    cA.cur = a0 + ownA + poseidon_size(t);
+    cB.cur = b0 + ownB + poseidon_size(t);
+}
+#endif
+
 // ---------------------------------------------------------------------------
 // smt/*.circom  (src/rollup-tx.circom:537,559; src/fee-tx.circom:97; src/withdraw.circom:47)
 // ---------------------------------------------------------------------------
@@ -388,6 +506,48 @@ TM HZ_FN V<M> SMTHash2(Comp<M>&& c, const V<M>& L, const V<M>& R) {
     in[1] = c.def("R", R);
     return c.alias("out", Poseidon<M>(c.sub("h"), in, 2));
 }
+// the two leaf hashes / the two proof hashes of a level: independent, evaluated side by side
+// (both components must own their witness range: sub_reserve)
+#define HZ_SZ_SMTHASH1_WIRED (poseidon_size(4) + 1)      /* the constant input 1 owns an entry */
+TM HZ_FN void SMTHash1Pair(Comp<M>&& cA, const V<M>& keyA, const V<M>& valA, Comp<M>&& cB, const V<M>& keyB,
+                           const V<M>& valB, V<M>& oA, V<M>& oB) {
+    V<M> a[3], b[3];
+    a[0] = cA.def("key", keyA); a[1] = cA.def("value", valA); a[2] = Ops<M>::K(1);
+    b[0] = cB.def("key", keyB); b[1] = cB.def("value", valB); b[2] = Ops<M>::K(1);
+    PoseidonDual<M>(cA.sub("h"), a, cB.sub("h"), b, 3, oA, oB);
+    cA.alias("out", oA); cB.alias("out", oB);
+}
+TM HZ_FN void SMTHash2Pair(Comp<M>&& cA, const V<M>& LA, const V<M>& RA, Comp<M>&& cB, const V<M>& LB,
+                           const V<M>& RB, V<M>& oA, V<M>& oB) {
+    V<M> a[2], b[2];
+    a[0] = cA.def("L", LA); a[1] = cA.def("R", RA);
+    b[0] = cB.def("L", LB); b[1] = cB.def("R", RB);
+    PoseidonDual<M>(cA.sub("h"), a, cB.sub("h"), b, 2, oA, oB);
+    cA.alias("out", oA); cB.alias("out", oB);
+}
+
+// 1 / x[i] for all i with one field inversion (Montgomery's trick); 1/0 = 0 as everywhere else
+TM struct BatchInv;
+template <> struct BatchInv<MCompute> {
+    static HZ_HD void run(const VC* x, VC* inv, int n) {
+        Fr acc = fr_one();
+        // prefix products over the non-zero entries, kept in inv[]
+        for (int i = 0; i < n; i++) {
+            inv[i].v = acc; inv[i].sig = false;
+            if (!fr_is_zero(x[i].v)) acc = fr_mul(acc, x[i].v);
+        }
+        Fr t = fr_inv(acc);
+        for (int i = n - 1; i >= 0; i--) {
+            if (fr_is_zero(x[i].v)) { inv[i].v = fr_zero(); continue; }
+            Fr pre = inv[i].v;
+            inv[i].v = fr_mul(t, pre);
+            t = fr_mul(t, x[i].v);
+        }
+    }
+};
+template <> struct BatchInv<MLayout> {
+    static HZ_HD void run(const VL*, VL* inv, int n) { for (int i = 0; i < n; i++) inv[i] = vl(); }
+};
 
 #define HZ_MAX_LEVELS 49
 TM HZ_FN void SMTLevIns(Comp<M>&& c, int n, const V<M>& enabled, const V<M>* siblings, V<M>* levIns) {
@@ -396,7 +556,11 @@ TM HZ_FN void SMTLevIns(Comp<M>&& c, int n, const V<M>& enabled, const V<M>* sib
     for (int i = 0; i < n; i++) sib[i] = c.def(Nm("siblings", i), siblings[i]);
     uint32_t li = c.sigs("levIns", n);
     uint32_t dn = c.sigs("done", n - 2);       // done[n-2] is wired to levIns[n-1]: no entry of its own
-    for (int i = 0; i < n; i++) isz[i] = IsZero(c.sub(Nm("isZero", i)), sib[i]);
+    {
+        V<M> inv[HZ_MAX_LEVELS];
+        BatchInv<M>::run(sib, inv, n);
+        for (int i = 0; i < n; i++) isz[i] = IsZeroWithInv(c.sub(Nm("isZero", i)), sib[i], inv[i]);
+    }
     HZ_CHECK0(c, (isz[n - 1] - 1) * en);
     levIns[n - 1] = c.set(li + n - 1, 1 - isz[n - 2]);
     V<M> done = c.alias(Nm("done", n - 2), levIns[n - 1]);
@@ -456,24 +620,30 @@ TM HZ_FN void SMTProcessorLevel(Comp<M>&& c, const V<M>* st, const V<M>& sibling
     Comp<M> newProofHash = c.sub_reserve("newProofHash", HZ_SZ_SMTHASH2_WIRED);
     Comp<M> oldSwitcher = c.sub_reserve("oldSwitcher", 3);
     Comp<M> newSwitcher = c.sub_reserve("newSwitcher", 5);
-    V<M> oL, oR, nL, nR;
+    V<M> oL, oR, nL, nR, oph, nph;
     Switcher(HZ_MV(oldSwitcher), lr, oc, sib, oL, oR);
-    V<M> oph = SMTHash2(HZ_MV(oldProofHash), oL, oR);
-    V<M> a0 = c.set(aux + 0, o1 * (st_bot + st_new1 + st_upd));
-    oldRootOut = c.set(oldRoot, a0 + oph * st_top);
     V<M> a1 = c.set(aux + 1, nc * (st_top + st_bot));
     V<M> a2 = c.set(aux + 2, sib * st_top);
     Switcher(HZ_MV(newSwitcher), lr, a1 + n1 * st_new1, a2 + o1 * st_new1, nL, nR);
-    V<M> nph = SMTHash2(HZ_MV(newProofHash), nL, nR);
+    SMTHash2Pair<M>(HZ_MV(oldProofHash), oL, oR, HZ_MV(newProofHash), nL, nR, oph, nph);
+    V<M> a0 = c.set(aux + 0, o1 * (st_bot + st_new1 + st_upd));
+    oldRootOut = c.set(oldRoot, a0 + oph * st_top);
     V<M> a3 = c.set(aux + 3, nph * (st_top + st_bot + st_new1));
     newRootOut = c.set(newRoot, a3 + n1 * (st_old0 + st_upd));
 }
 
-TM HZ_FN V<M> SMTProcessor(Comp<M>&& c, int nLevels, const V<M>& oldRoot, const V<M>* siblings,
-                            const V<M>& oldKey, const V<M>& oldValue, const V<M>& isOld0,
-                            const V<M>& newKey, const V<M>& newValue, const V<M>* fnc) {
-    V<M> oldRoot_ = c.def("oldRoot", oldRoot);
-    uint32_t newRoot = c.sig("newRoot");
+// SMTProcessor in two parts.  The level hashes (the body: everything up to topSwitcher) need the
+// siblings and the leaf values but not `oldRoot`; only the top (checkOldInput, newRoot, keysOk)
+// does.  The device evaluates the bodies of all processors of a batch at once and the tops
+// afterwards, when processor 2's old root (= processor 1's new root, src/rollup-tx.circom:553-560)
+// is known; everywhere else the two run back to back.
+TM struct SMTMid { V<M> oldRoot, enabled, oldKey, newKey, fnc0, fnc1, tL, tR; uint32_t newRootIdx; };
+
+TM HZ_FN void SMTProcessorBody(Comp<M>& c, int nLevels, const V<M>& oldRoot, const V<M>* siblings,
+                               const V<M>& oldKey, const V<M>& oldValue, const V<M>& isOld0,
+                               const V<M>& newKey, const V<M>& newValue, const V<M>* fnc, SMTMid<M>& mid) {
+    mid.oldRoot = c.def("oldRoot", oldRoot);
+    mid.newRootIdx = c.sig("newRoot");
     V<M> sib[HZ_MAX_LEVELS];
     for (int i = 0; i < nLevels; i++) sib[i] = c.def(Nm("siblings", i), siblings[i]);
     V<M> oldKey_ = c.def("oldKey", oldKey);
@@ -485,8 +655,12 @@ TM HZ_FN V<M> SMTProcessor(Comp<M>&& c, int nLevels, const V<M>& oldRoot, const 
     f[0] = c.def(Nm("fnc", 0), fnc[0]);
     f[1] = c.def(Nm("fnc", 1), fnc[1]);
     V<M> enabled = c.def("enabled", f[0] + f[1] - f[0] * f[1]);
-    V<M> hash1Old = SMTHash1(c.sub("hash1Old"), oldKey_, oldValue_);
-    V<M> hash1New = SMTHash1(c.sub("hash1New"), newKey_, newValue_);
+    V<M> hash1Old, hash1New;
+    {
+        Comp<M> h1o = c.sub_reserve("hash1Old", HZ_SZ_SMTHASH1_WIRED);
+        Comp<M> h1n = c.sub_reserve("hash1New", HZ_SZ_SMTHASH1_WIRED);
+        SMTHash1Pair<M>(HZ_MV(h1o), oldKey_, oldValue_, HZ_MV(h1n), newKey_, newValue_, hash1Old, hash1New);
+    }
     BV<M> n2bOld = Num2Bits_strict(c.sub("n2bOld"), oldKey_);
     BV<M> n2bNew = Num2Bits_strict(c.sub("n2bNew"), newKey_);
     V<M> levIns[HZ_MAX_LEVELS];
@@ -512,16 +686,27 @@ TM HZ_FN V<M> SMTProcessor(Comp<M>&& c, int nLevels, const V<M>& oldRoot, const 
         SMTProcessorLevel(c.sub(Nm("levels", i)), sm[i], sib[i], hash1Old, hash1New, n2bNew.get(i), oc, nc, o, n);
         oc = o; nc = n;
     }
-    V<M> tL, tR;
-    Switcher(c.sub("topSwitcher"), f[0] * f[1], oc, nc, tL, tR);
-    ForceEqualIfEnabled(c.sub("checkOldInput"), enabled, oldRoot_, tL);
-    V<M> nr = c.set(newRoot, enabled * (tR - oldRoot_) + oldRoot_);
-    V<M> eq = IsEqual(c.sub("areKeyEquals"), oldKey_, newKey_);
+    Switcher(c.sub("topSwitcher"), f[0] * f[1], oc, nc, mid.tL, mid.tR);
+    mid.enabled = enabled; mid.oldKey = oldKey_; mid.newKey = newKey_; mid.fnc0 = f[0]; mid.fnc1 = f[1];
+}
+
+TM HZ_FN V<M> SMTProcessorTop(Comp<M>& c, const SMTMid<M>& mid) {
+    ForceEqualIfEnabled(c.sub("checkOldInput"), mid.enabled, mid.oldRoot, mid.tL);
+    V<M> nr = c.set(mid.newRootIdx, mid.enabled * (mid.tR - mid.oldRoot) + mid.oldRoot);
+    V<M> eq = IsEqual(c.sub("areKeyEquals"), mid.oldKey, mid.newKey);
     V<M> xs[3];
-    xs[0] = 1 - f[0]; xs[1] = f[1]; xs[2] = 1 - eq;
+    xs[0] = 1 - mid.fnc0; xs[1] = mid.fnc1; xs[2] = 1 - eq;
     V<M> ok = MultiAND(c.sub("keysOk"), xs, 3);
     HZ_CHECK0(c, ok);
     return nr;
+}
+
+TM HZ_FN V<M> SMTProcessor(Comp<M>&& c, int nLevels, const V<M>& oldRoot, const V<M>* siblings,
+                            const V<M>& oldKey, const V<M>& oldValue, const V<M>& isOld0,
+                            const V<M>& newKey, const V<M>& newValue, const V<M>* fnc) {
+    SMTMid<M> mid;
+    SMTProcessorBody<M>(c, nLevels, oldRoot, siblings, oldKey, oldValue, isOld0, newKey, newValue, fnc, mid);
+    return SMTProcessorTop<M>(c, mid);
 }
 
 // prev / st tuples: (top, i0, iold, inew, na)
@@ -627,6 +812,22 @@ HZ_HD Fr fr_base8_y() {
     Fr r; const uint32_t h[8] = HZ_BASE8_Y_LIMBS; for (int i = 0; i < 8; i++) r.l[i] = h[i]; return r;
 }
 
+TM struct HintGen;
+template <> struct HintGen<MCompute> {
+    static HZ_HD void seg_any(Comp<MCompute>& c, const VC& px, const VC& py, const BVC& e, int n) { hz_hints_segment_any(c.hints, px.v, py.v, e, n); }
+    static HZ_HD void seg_fix(Comp<MCompute>& c, const BVC& e, int nW, int seg) { hz_hints_segment_fix(c.hints, e, nW, seg); }
+    static HZ_HD void done(Comp<MCompute>& c) { hz_hints_done(c.hints); }
+    static HZ_HD void record(Comp<MCompute>& c, const VC& u, const VC& v) { hz_hints_record_point(c.hints, u.v, v.v); }
+};
+#ifndef HZ_DEVICE_ONLY
+template <> struct HintGen<MLayout> {
+    static void seg_any(Comp<MLayout>&, const VL&, const VL&, const BVT<MLayout, 8>&, int) {}
+    static void seg_fix(Comp<MLayout>&, const BVT<MLayout, 8>&, int, int) {}
+    static void done(Comp<MLayout>&) {}
+    static void record(Comp<MLayout>&, const VL&, const VL&) {}
+};
+#endif
+
 #define HZ_SZ_BABYADD_WIRED 6
 TM HZ_FN PtV<M> BabyAdd(Comp<M>&& c, const V<M>& x1_, const V<M>& y1_, const V<M>& x2_, const V<M>& y2_) {
     V<M> x1 = c.def("x1", x1_), y1 = c.def("y1", y1_), x2 = c.def("x2", x2_), y2 = c.def("y2", y2_);
@@ -637,9 +838,11 @@ TM HZ_FN PtV<M> BabyAdd(Comp<M>&& c, const V<M>& x1_, const V<M>& y1_, const V<M
     V<M> tau = c.def("tau", beta * gamma);
     V<M> dt = HZ_BJ_D * tau;
     PtV<M> r;
-    r.x = c.set(xout, vdiv(beta + gamma, 1 + dt));
+    V<M> qx, qy;
+    c.div2(beta + gamma, 1 + dt, delta + HZ_BJ_A * beta - gamma, 1 - dt, qx, qy);
+    r.x = c.set(xout, qx);
     HZ_CHECK(c, (1 + dt) * r.x, beta + gamma);
-    r.y = c.set(yout, vdiv(delta + HZ_BJ_A * beta - gamma, 1 - dt));
+    r.y = c.set(yout, qy);
     HZ_CHECK(c, (1 - dt) * r.y, delta + HZ_BJ_A * beta - gamma);
     return r;
 }
@@ -655,42 +858,42 @@ TM HZ_FN void BabyCheck(Comp<M>&& c, const V<M>& x, const V<M>& y) {
     V<M> y2 = c.def("y2", y_ * y_);
     HZ_CHECK(c, HZ_BJ_A * x2 + y2, 1 + HZ_BJ_D * (x2 * y2));
 }
-TM HZ_FN PtV<M> Edwards2Montgomery(Comp<M>&& c, const V<M>& x, const V<M>& y) {
+TM HZ_FN PtV<M> Edwards2Montgomery(Comp<M>&& c, const V<M>& x, const V<M>& y, int hc = 0) {
     V<M> i0 = c.def(Nm("in", 0), x), i1 = c.def(Nm("in", 1), y);
     PtV<M> r;
-    r.x = c.def(Nm("out", 0), vdiv(1 + i1, 1 - i1));
-    r.y = c.def(Nm("out", 1), vdiv(r.x, i0));
+    r.x = c.def(Nm("out", 0), c.div(1 + i1, 1 - i1, hc));
+    r.y = c.def(Nm("out", 1), c.div(r.x, i0, hc));
     HZ_CHECK(c, r.x * (1 - i1), 1 + i1);
     HZ_CHECK(c, r.y * i0, r.x);
     return r;
 }
-TM HZ_FN PtV<M> Montgomery2Edwards(Comp<M>&& c, const V<M>& u, const V<M>& v) {
+TM HZ_FN PtV<M> Montgomery2Edwards(Comp<M>&& c, const V<M>& u, const V<M>& v, int hc = 0) {
     V<M> i0 = c.def(Nm("in", 0), u), i1 = c.def(Nm("in", 1), v);
     PtV<M> r;
-    r.x = c.def(Nm("out", 0), vdiv(i0, i1));
-    r.y = c.def(Nm("out", 1), vdiv(i0 - 1, i0 + 1));
+    r.x = c.def(Nm("out", 0), c.div(i0, i1, hc));
+    r.y = c.def(Nm("out", 1), c.div(i0 - 1, i0 + 1, hc));
     HZ_CHECK(c, r.x * i1, i0);
     HZ_CHECK(c, r.y * (i0 + 1), i0 - 1);
     return r;
 }
-TM HZ_FN PtV<M> MontgomeryAdd(Comp<M>&& c, const PtV<M>& p1, const PtV<M>& p2) {
+TM HZ_FN PtV<M> MontgomeryAdd(Comp<M>&& c, const PtV<M>& p1, const PtV<M>& p2, int hc = 0) {
     V<M> a0 = c.def(Nm("in1", 0), p1.x), a1 = c.def(Nm("in1", 1), p1.y);
     V<M> b0 = c.def(Nm("in2", 0), p2.x), b1 = c.def(Nm("in2", 1), p2.y);
     uint32_t out = c.sigs("out", 2);
-    V<M> lam = c.def("lamda", vdiv(b1 - a1, b0 - a0));
+    V<M> lam = c.def("lamda", c.div(b1 - a1, b0 - a0, hc));
     HZ_CHECK(c, lam * (b0 - a0), b1 - a1);
     PtV<M> r;
     r.x = c.set(out, lam * lam - HZ_MONT_A - a0 - b0);
     r.y = c.set(out + 1, lam * (a0 - r.x) - a1);
     return r;
 }
-TM HZ_FN PtV<M> MontgomeryDouble(Comp<M>&& c, const PtV<M>& p) {
+TM HZ_FN PtV<M> MontgomeryDouble(Comp<M>&& c, const PtV<M>& p, int hc = 0) {
     V<M> i0 = c.def(Nm("in", 0), p.x), i1 = c.def(Nm("in", 1), p.y);
     uint32_t out = c.sigs("out", 2);
     uint32_t lamda = c.sig("lamda");
     V<M> x1_2 = c.def("x1_2", i0 * i0);
     V<M> num = 3 * x1_2 + (2 * HZ_MONT_A) * i0 + 1;
-    V<M> lam = c.set(lamda, vdiv(num, 2 * i1));
+    V<M> lam = c.set(lamda, c.div(num, 2 * i1, hc));
     HZ_CHECK(c, lam * (2 * i1), num);
     PtV<M> r;
     r.x = c.set(out, lam * lam - HZ_MONT_A - 2 * i0);
@@ -715,8 +918,8 @@ TM HZ_FN void BitElementMulAny(Comp<M>&& c, const V<M>& sel, PtV<M>& dbl, PtV<M>
     PtV<M> d, a;
     d.x = c.def(Nm("dblIn", 0), dbl.x); d.y = c.def(Nm("dblIn", 1), dbl.y);
     a.x = c.def(Nm("addIn", 0), add.x); a.y = c.def(Nm("addIn", 1), add.y);
-    PtV<M> dd = MontgomeryDouble(c.sub("doubler"), d);
-    PtV<M> ad = MontgomeryAdd(c.sub("adder"), dd, a);
+    PtV<M> dd = MontgomeryDouble(c.sub("doubler"), d, 2);
+    PtV<M> ad = MontgomeryAdd(c.sub("adder"), dd, a, 2);
     PtV<M> so = Multiplexor2(c.sub("selector"), s, a, ad);
     c.alias(Nm("dblOut", 0), dd.x); c.alias(Nm("dblOut", 1), dd.y);
     c.alias(Nm("addOut", 0), so.x); c.alias(Nm("addOut", 1), so.y);
@@ -731,7 +934,9 @@ TM HZ_FN void SegmentMulAny(Comp<M>&& c, const BV<M>& e, int from, int n, const 
     p_.x = c.def(Nm("p", 0), p.x); p_.y = c.def(Nm("p", 1), p.y);
     PtV<M> m = Edwards2Montgomery(c.sub("e2m"), p_.x, p_.y);
     PtV<M> d = m, a = m;
+    HintGen<M>::seg_any(c, p_.x, p_.y, e_, n);
     for (int i = 0; i < n - 1; i++) BitElementMulAny(c.sub(Nm("bits", i)), e_.get(i + 1), d, a);
+    HintGen<M>::done(c);
     c.alias(Nm("dbl", 0), d.x); c.alias(Nm("dbl", 1), d.y);
     PtV<M> ed = Montgomery2Edwards(c.sub("m2e"), a.x, a.y);
     PtV<M> ex = BabyAdd(c.sub("eadder"), ed.x, ed.y, -p_.x, p_.y);
@@ -777,9 +982,11 @@ TM HZ_FN void WindowMulFix(Comp<M>&& c, const V<M>* in3, const PtV<M>& base, PtV
     Comp<M> mux = c.sub_reserve("mux", HZ_SZ_MULTIMUX3(2));
     PtV<M> pts[8];
     pts[0] = b;
-    pts[1] = MontgomeryDouble(c.sub("dbl2"), b);
+    // the base is a constant point: every division in here reads the constant stream
+    pts[1] = MontgomeryDouble(c.sub("dbl2"), b, 1);
     const char* adr[6] = {"adr3", "adr4", "adr5", "adr6", "adr7", "adr8"};
-    for (int k = 2; k < 8; k++) pts[k] = MontgomeryAdd(c.sub(adr[k - 2]), b, pts[k - 1]);
+    for (int k = 2; k < 8; k++) pts[k] = MontgomeryAdd(c.sub(adr[k - 2]), b, pts[k - 1], 1);
+    for (int k = 0; k < 8; k++) HintGen<M>::record(c, pts[k].x, pts[k].y);
     V<M> kk[2][8], mo[2];
     for (int k = 0; k < 8; k++) { kk[0][k] = pts[k].x; kk[1][k] = pts[k].y; }
     MultiMux3<M>(HZ_MV(mux), 2, kk, ins, mo);
@@ -790,12 +997,12 @@ TM HZ_FN void WindowMulFix(Comp<M>&& c, const V<M>* in3, const PtV<M>& base, PtV
 
 #define HZ_SZ_MONTDOUBLE_WIRED 4
 // e: nW*3 bit values (signals, or constant 0 padding)
-TM HZ_FN void SegmentMulFix(Comp<M>&& c, const BV<M>& e, int nW, const PtV<M>& base, PtV<M>& out, PtV<M>& dblOut) {
+TM HZ_FN void SegmentMulFix(Comp<M>&& c, const BV<M>& e, int nW, const PtV<M>& base, PtV<M>& out, PtV<M>& dblOut, int seg) {
     BV<M> e_; e_.clear(nW * 3);
     for (int i = 0; i < nW * 3; i++) e_.put(i, c.def(Nm("e", i), e.get(i)));
     PtV<M> b;
     b.x = c.def(Nm("base", 0), base.x); b.y = c.def(Nm("base", 1), base.y);
-    PtV<M> m = Edwards2Montgomery(c.sub("e2m"), b.x, b.y);
+    PtV<M> m = Edwards2Montgomery(c.sub("e2m"), b.x, b.y, 1);
     Comp<M> dblLast_c = c.sub_reserve("dblLast", HZ_SZ_MONTDOUBLE_WIRED);
     // windows and carry adders are instantiated first; the accumulating adders follow, so the
     // window outputs are kept: read them back from the witness when accumulating
@@ -807,16 +1014,20 @@ TM HZ_FN void SegmentMulFix(Comp<M>&& c, const BV<M>& e, int nW, const PtV<M>& b
         WindowMulFix(c.sub(Nm("windows", i)), in3, wbase, win_out[i], o8);
         wbase = o8;
         if (i < nW - 1) {
-            cad = MontgomeryAdd(c.sub(Nm("cadders", i)), cad, o8);
+            cad = MontgomeryAdd(c.sub(Nm("cadders", i)), cad, o8, 1);
         } else {
-            dblLast = MontgomeryDouble(HZ_MV(dblLast_c), o8);
-            cad = MontgomeryAdd(c.sub(Nm("cadders", i)), cad, dblLast);
+            dblLast = MontgomeryDouble(HZ_MV(dblLast_c), o8, 1);
+            HintGen<M>::record(c, dblLast.x, dblLast.y);
+            cad = MontgomeryAdd(c.sub(Nm("cadders", i)), cad, dblLast, 1);
         }
     }
+    // the accumulating adders depend on the scalar: data stream
+    HintGen<M>::seg_fix(c, e_, nW, seg);
     PtV<M> acc = dblLast;
-    for (int i = 0; i < nW; i++) acc = MontgomeryAdd(c.sub(Nm("adders", i)), acc, win_out[i]);
+    for (int i = 0; i < nW; i++) acc = MontgomeryAdd(c.sub(Nm("adders", i)), acc, win_out[i], 2);
+    HintGen<M>::done(c);
     PtV<M> ed = Montgomery2Edwards(c.sub("m2e"), acc.x, acc.y);
-    PtV<M> ced = Montgomery2Edwards(c.sub("cm2e"), cad.x, cad.y);
+    PtV<M> ced = Montgomery2Edwards(c.sub("cm2e"), cad.x, cad.y, 1);
     PtV<M> cs = BabyAdd(c.sub("cAdd"), ed.x, ed.y, -ced.x, ced.y);
     c.alias(Nm("out", 0), cs.x); c.alias(Nm("out", 1), cs.y);
     c.alias(Nm("dbl", 0), wbase.x); c.alias(Nm("dbl", 1), wbase.y);
@@ -833,21 +1044,35 @@ TM HZ_FN PtV<M> EscalarMulFix253(Comp<M>&& c, const BV<M>& e) {
     {
         BV<M> b0; b0.clear(249);
         bv_copy(b0, 0, e_, 0, 249);
-        SegmentMulFix(c.sub(Nm("segments", 0)), b0, 83, B, o0, d0);
+        SegmentMulFix(c.sub(Nm("segments", 0)), b0, 83, B, o0, d0, 0);
     }
     // wired SegmentMulFix(nW = 2) with two constant padding bits: 17 + 45 * 2 + 2
     Comp<M> seg1 = c.sub_reserve(Nm("segments", 1), 109);
-    PtV<M> ed = Montgomery2Edwards(c.sub(Nm("m2e", 0)), d0.x, d0.y);
+    PtV<M> ed = Montgomery2Edwards(c.sub(Nm("m2e", 0)), d0.x, d0.y, 1);
     Comp<M> add0 = c.sub_reserve(Nm("adders", 0), HZ_SZ_BABYADD_WIRED);
     {
         BV<M> b1; b1.clear(6);
         bv_copy(b1, 0, e_, 249, 4);
         b1.put(4, Ops<M>::K(0)); b1.put(5, Ops<M>::K(0));
-        SegmentMulFix(HZ_MV(seg1), b1, 2, ed, o1, d1);
+        SegmentMulFix(HZ_MV(seg1), b1, 2, ed, o1, d1, 1);
     }
     PtV<M> fin = BabyAdd(HZ_MV(add0), o0.x, o0.y, o1.x, o1.y);
     c.alias(Nm("out", 0), fin.x); c.alias(Nm("out", 1), fin.y);
     return fin;
+}
+
+// one-time pass over EscalarMulFix(253, BASE8) in record mode: the inverses of its constant
+// division sites (in evaluation order) and its window entries as Edwards points (hints.cuh)
+HZ_FN void hz_record_fix_consts(Fr* wtmp, Fr* cst, Fr* edtab, uint32_t* counts) {
+    HzHints h;
+    h.cst = nullptr; h.ci = 0; h.dat = nullptr; h.di = 0; h.rec = cst; h.ri = 0;
+    h.edtab = nullptr; h.edrec = edtab; h.ei = 0; h.scratch = nullptr;
+    Comp<MCompute> c(wtmp, 0, nullptr, &h);
+    BVC e; e.clear(253);
+    VC z = vc(fr_zero()); z.sig = true;
+    for (int i = 0; i < 253; i++) e.put(i, z);
+    EscalarMulFix253<MCompute>(c.sub("mulFix"), e);
+    counts[0] = h.ri; counts[1] = h.ei;
 }
 
 // ---------------------------------------------------------------------------
@@ -1151,56 +1376,67 @@ HZ_HD void hz_sha256_compress(uint32_t* st /*8, in/out*/, const uint32_t* blk /*
 }
 
 // hin[j]: chaining word j, LSB-first signals; msg[t]: message word t (bit k = inp[32 t + 31 - k]);
-// outw[j]: digest word j as LSB-first view of out[32 j + 31 - k]
+// outw[j]: digest word j as LSB-first view of out[32 j + 31 - k].
+// The component is cut into UNITS with fixed offsets from its base so that the device can give
+// each unit to its own thread (k_sha_blocks): the digest words, 48 sigmaPlus, 64 rounds
+// (ct_k, t1, t2, sume, suma) and 8 final sums.
+#define HZ_SHA_OFF_SP 256
+#define HZ_SHA_OFF_CK (HZ_SHA_OFF_SP + 48 * HZ_SZ_SIGMAPLUS)
+#define HZ_SHA_OFF_T1 (HZ_SHA_OFF_CK + 64 * 32)
+#define HZ_SHA_OFF_T2 (HZ_SHA_OFF_T1 + 64 * HZ_SZ_T1)
+#define HZ_SHA_OFF_SA (HZ_SHA_OFF_T2 + 64 * HZ_SZ_T2)
+#define HZ_SHA_OFF_SE (HZ_SHA_OFF_SA + 64 * 33)
+#define HZ_SHA_OFF_FS (HZ_SHA_OFF_SE + 64 * 33)
+// message-schedule word t (16 <= t < 64); c = the sha256compression component, base = its start
+TM HZ_FN W32<M> Sha256UnitSigmaPlus(Comp<M>& c, uint32_t base, int t, const W32<M>& w2, const W32<M>& w7,
+                                     const W32<M>& w15, const W32<M>& w16) {
+    c.cur = base + HZ_SHA_OFF_SP + (uint32_t)(t - 16) * HZ_SZ_SIGMAPLUS;
+    return SigmaPlus(c.sub(Nm("sigmaPlus", t - 16)), w2, w7, w15, w16);
+}
+// round t on the working variables v[0..7] = (a, b, c, d, e, f, g, h): returns the new a and e
+TM HZ_FN void Sha256UnitRound(Comp<M>& c, uint32_t base, int t, const W32<M>* v, const W32<M>& wt, W32<M>& na, W32<M>& ne) {
+    c.cur = base + HZ_SHA_OFF_CK + (uint32_t)t * 32;
+    W32<M> kt;
+    { Comp<M> kc = c.sub(Nm("ct_k", t)); kt = w32_def(kc, "out", hz_sha_k(t), 32); }
+    c.cur = base + HZ_SHA_OFF_T1 + (uint32_t)t * HZ_SZ_T1;
+    W32<M> t1 = T1(c.sub(Nm("t1", t)), v[7], v[4], v[5], v[6], kt, wt);
+    c.cur = base + HZ_SHA_OFF_T2 + (uint32_t)t * HZ_SZ_T2;
+    W32<M> t2 = T2(c.sub(Nm("t2", t)), v[0], v[1], v[2]);
+    W32<M> ops[2];
+    c.cur = base + HZ_SHA_OFF_SE + (uint32_t)t * 33;
+    ops[0] = v[3]; ops[1] = t1;
+    ne = BinSum<M>(c.sub(Nm("sume", t)), ops, 2);
+    c.cur = base + HZ_SHA_OFF_SA + (uint32_t)t * 33;
+    ops[0] = t1; ops[1] = t2;
+    na = BinSum<M>(c.sub(Nm("suma", t)), ops, 2);
+}
+TM HZ_FN W32<M> Sha256UnitFinal(Comp<M>& c, uint32_t base, int j, const W32<M>& hin, const W32<M>& fin) {
+    c.cur = base + HZ_SHA_OFF_FS + (uint32_t)j * 33;
+    W32<M> ops[2];
+    ops[0] = hin; ops[1] = fin;
+    return BinSum<M>(c.sub(Nm("fsum", j)), ops, 2);
+}
 TM HZ_FN void Sha256compression(Comp<M>&& c, const W32<M>* hin, const W32<M>* msg, W32<M>* outw) {
     hz_sha_in_names(c, hin, msg);
     uint32_t st[8], blk[16];
     for (int j = 0; j < 8; j++) st[j] = w32_val(hin[j]);
     for (int t = 0; t < 16; t++) blk[t] = w32_val(msg[t]);
     hz_sha256_compress(st, blk);
+    const uint32_t base = c.cur;
     for (int j = 0; j < 8; j++) outw[j] = hz_sha_out_word(c, j, st[j]);
-    uint32_t b_sp = c.cur;  c.skip("", 48 * HZ_SZ_SIGMAPLUS);
-    uint32_t b_ck = c.cur;  c.skip("", 64 * 32);
-    uint32_t b_t1 = c.cur;  c.skip("", 64 * HZ_SZ_T1);
-    uint32_t b_t2 = c.cur;  c.skip("", 64 * HZ_SZ_T2);
-    uint32_t b_sa = c.cur;  c.skip("", 64 * 33);
-    uint32_t b_se = c.cur;  c.skip("", 64 * 33);
-    uint32_t b_fs = c.cur;  c.skip("", 8 * 33);
-    uint32_t b_end = c.cur;
     W32<M> w[64];
+    for (int t = 0; t < 64; t++) w[t] = t < 16 ? msg[t] : Sha256UnitSigmaPlus(c, base, t, w[t - 2], w[t - 7], w[t - 15], w[t - 16]);
+    W32<M> v[8];
+    for (int j = 0; j < 8; j++) v[j] = hin[j];
     for (int t = 0; t < 64; t++) {
-        if (t < 16) w[t] = msg[t];
-        else {
-            c.cur = b_sp + (t - 16) * HZ_SZ_SIGMAPLUS;
-            w[t] = SigmaPlus(c.sub(Nm("sigmaPlus", t - 16)), w[t - 2], w[t - 7], w[t - 15], w[t - 16]);
-        }
+        W32<M> na, ne;
+        Sha256UnitRound(c, base, t, v, w[t], na, ne);
+        v[7] = v[6]; v[6] = v[5]; v[5] = v[4]; v[4] = ne; v[3] = v[2]; v[2] = v[1]; v[1] = v[0]; v[0] = na;
     }
-    W32<M> a = hin[0], b = hin[1], cc = hin[2], d = hin[3], e = hin[4], f = hin[5], g = hin[6], h = hin[7];
-    for (int t = 0; t < 64; t++) {
-        c.cur = b_ck + t * 32;
-        W32<M> kt;
-        { Comp<M> kc = c.sub(Nm("ct_k", t)); kt = w32_def(kc, "out", hz_sha_k(t), 32); }
-        c.cur = b_t1 + t * HZ_SZ_T1;
-        W32<M> t1 = T1(c.sub(Nm("t1", t)), h, e, f, g, kt, w[t]);
-        c.cur = b_t2 + t * HZ_SZ_T2;
-        W32<M> t2 = T2(c.sub(Nm("t2", t)), a, b, cc);
-        W32<M> ops[2];
-        c.cur = b_se + t * 33;
-        ops[0] = d; ops[1] = t1;
-        W32<M> se = BinSum<M>(c.sub(Nm("sume", t)), ops, 2);
-        c.cur = b_sa + t * 33;
-        ops[0] = t1; ops[1] = t2;
-        W32<M> sa = BinSum<M>(c.sub(Nm("suma", t)), ops, 2);
-        h = g; g = f; f = e; e = se; d = cc; cc = b; b = a; a = sa;
-    }
-    W32<M> fin[8] = {a, b, cc, d, e, f, g, h};
     for (int j = 0; j < 8; j++) {
-        c.cur = b_fs + j * 33;
-        W32<M> ops[2];
-        ops[0] = hin[j]; ops[1] = fin[j];
-        W32<M> fs = BinSum<M>(c.sub(Nm("fsum", j)), ops, 2);
+        W32<M> fs = Sha256UnitFinal(c, base, j, hin[j], v[j]);
         if (c.sanity() && w32_val(fs) != st[j])
             c.check(Ops<M>::K(w32_val(fs)), Ops<M>::K(st[j]), __LINE__);
     }
-    c.cur = b_end;
+    c.cur = base + HZ_SZ_SHA_BLOCK;
 }

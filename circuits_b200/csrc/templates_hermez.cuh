@@ -48,7 +48,7 @@ TM HZ_FN V<M> Mux256Fee(Comp<M>&& c, const V<M>* s) {
     V<M> outs[16];
     for (int i = 0; i < 16; i++) {
         V<M> k[16];
-        for (int j = 0; j < 16; j++) k[j] = c.load(in0 + 16 * i + j);
+        for (int j = 0; j < 16; j++) k[j] = c.known(in0 + 16 * i + j, Ops<M>::K(hz_fee_shift(16 * i + j)));
         outs[i] = Mux4(c.sub(Nm("mux", i)), k, s_);
     }
     return c.alias("out", Mux4(c.sub(Nm("mux", 16)), outs, s_ + 4));
@@ -465,19 +465,34 @@ TM struct RollupTxIn {
     V<M> isOld0_1, oldKey1, oldValue1, tokenID2, nonce2, sign2, balance2, newExit, ay2, ethAddr2;
     V<M> siblings2[HZ_MAX_LEVELS];
     V<M> isOld0_2, oldKey2, oldValue2, oldStateRoot, oldExitRoot;
+    uint32_t sib1_idx, sib2_idx;      // witness index of siblings1[i][0] / siblings2[i][0] (main inputs)
 };
 TM struct RollupTxOut { V<M> accFeeOut[HZ_MAX_FEE]; V<M> newStateRoot, newExitRoot, isAmountNullified; };
 
-// hand-off of the signature sub-graph (phase F) to its own kernel
+// ---- hand-offs between the device kernels ------------------------------------------------------
+// The device does not walk a slot start to end in one thread group.  The front kernel evaluates
+// DecodeTx and RollupTx up to the sub-graphs below and records their inputs as jobs; each
+// sub-graph then runs in the kernel shaped for it:
+//   phase F (AySign2Ax + EdDSAPoseidonVerifier)       -> HzEddsaJob  -> k_eddsa
+//   SMTProcessor bodies (level hashes) of phase J     -> HzSmtJob    -> k_smt     -> HzSmtMid
+//   SMTProcessor tops, s3/s4/s5 and the root checks   -> k_tail (needs processor 1's new root)
+// Host builds (CPU port, layout walk) pass no job pointers and evaluate everything in place.
 struct HzEddsaJob { Fr aySignature, signSignature, enabled, s1Ay, S, R8x, R8y, M; uint32_t cur; uint32_t pad[7]; };
-struct HzSizes { uint32_t getAx, sigVerifier; };
+// inputs of one SMTProcessor body; sigmask bit k set = input k is a wired signal (no entry of its
+// own), k: 0 oldKey, 1 oldValue, 2 isOld0, 3 newKey, 4 newValue, 5 fnc[0], 6 fnc[1]
+struct HzSmtJob { Fr oldKey, oldValue, isOld0, newKey, newValue, fnc0, fnc1; uint32_t cur, sib, sigmask, pad[5]; };
+// what a body leaves for its top; cur = witness cursor where the top continues
+struct HzSmtMid { Fr enabled, oldKey, newKey, fnc0, fnc1, tL, tR; uint32_t cur, newRootIdx, pad[6]; };
+struct HzSizes { uint32_t getAx, sigVerifier, phaseJK, p2_off; };   // p2_off: processor2 start within phases J-K
 
-TM struct EddsaHook;
-template <> struct EddsaHook<MCompute> {
-    HzEddsaJob* job;                // null: evaluate phase F inline
+TM struct SlotHook;
+template <> struct SlotHook<MCompute> {
+    HzEddsaJob* eddsa;              // null: evaluate phase F in place
+    HzSmtJob* smt;                  // null: evaluate phases J, K in place; else 2 jobs (processor 1, 2)
+    Fr* isExit;                     // with smt: the selector the tail needs
     const HzSizes* sz;
 };
-template <> struct EddsaHook<MLayout> {
+template <> struct SlotHook<MLayout> {
     HzSizes* sz_out;                // sizes recorded by the layout walk (may be null)
 };
 
@@ -486,16 +501,16 @@ TM HZ_FN void hz_phaseF(Comp<M>& c, const V<M>& vse, const V<M>& signSignature, 
     V<M> ax = AySign2Ax(c.sub("getAx"), aySignature, signSignature);
     EdDSAPoseidonVerifier(c.sub("sigVerifier"), vse, ax, s1Ay, S, R8x, R8y, Msg);
 }
-HZ_HD void hz_phaseF_hook(Comp<MCompute>& c, const EddsaHook<MCompute>& hk, const VC& vse, const VC& signSignature,
+HZ_HD void hz_phaseF_hook(Comp<MCompute>& c, const SlotHook<MCompute>& hk, const VC& vse, const VC& signSignature,
                           const VC& aySignature, const VC& s1Ay, const VC& S, const VC& R8x, const VC& R8y, const VC& Msg) {
-    if (!hk.job) { hz_phaseF(c, vse, signSignature, aySignature, s1Ay, S, R8x, R8y, Msg); return; }
-    HzEddsaJob* j = hk.job;
+    if (!hk.eddsa) { hz_phaseF(c, vse, signSignature, aySignature, s1Ay, S, R8x, R8y, Msg); return; }
+    HzEddsaJob* j = hk.eddsa;
     j->aySignature = aySignature.v; j->signSignature = signSignature.v; j->enabled = vse.v; j->s1Ay = s1Ay.v;
     j->S = S.v; j->R8x = R8x.v; j->R8y = R8y.v; j->M = Msg.v; j->cur = c.cur;
     c.cur += hk.sz->getAx + hk.sz->sigVerifier;
 }
 #ifndef HZ_DEVICE_ONLY
-inline void hz_phaseF_hook(Comp<MLayout>& c, const EddsaHook<MLayout>& hk, const VL& vse, const VL& signSignature,
+inline void hz_phaseF_hook(Comp<MLayout>& c, const SlotHook<MLayout>& hk, const VL& vse, const VL& signSignature,
                            const VL& aySignature, const VL& s1Ay, const VL& S, const VL& R8x, const VL& R8y, const VL& Msg) {
     uint32_t c0 = c.cur;
     V<MLayout> ax = AySign2Ax(c.sub("getAx"), aySignature, signSignature);
@@ -505,8 +520,56 @@ inline void hz_phaseF_hook(Comp<MLayout>& c, const EddsaHook<MLayout>& hk, const
 }
 #endif
 
+// phases J and K of RollupTx (src/rollup-tx.circom:537-590)
+TM struct PhaseJKIn {
+    V<M> oldStateRoot, oldExitRoot, isExit;
+    const V<M>* siblings1; V<M> oldKey1, oldValue1, isOld0_1, key1, newValue1, f1[2];
+    const V<M>* siblings2; V<M> oldKey2, oldValue2, isOld0_2, key2, newValue2, f2[2];
+    uint32_t sib1_idx, sib2_idx;
+};
+TM HZ_FN void hz_phaseJK(Comp<M>& c, int nLevels, const PhaseJKIn<M>& in, V<M>& newStateRoot, V<M>& newExitRoot,
+                         uint32_t* p2_start = nullptr) {
+    // J - smt processors (:537-570)
+    V<M> p1 = SMTProcessor(c.sub("processor1"), nLevels + 1, in.oldStateRoot, in.siblings1, in.oldKey1, in.oldValue1,
+                           in.isOld0_1, in.key1, in.newValue1, in.f1);
+    V<M> s3 = Mux1(c.sub("s3"), p1, in.oldExitRoot, in.isExit);
+    if (p2_start) *p2_start = c.cur;
+    V<M> p2 = SMTProcessor(c.sub("processor2"), nLevels + 1, s3, in.siblings2, in.oldKey2, in.oldValue2,
+                           in.isOld0_2, in.key2, in.newValue2, in.f2);
+    // K - select output roots (:577-590)
+    newStateRoot = c.alias("newStateRoot", Mux1(c.sub("s4"), p2, p1, in.isExit));
+    newExitRoot = c.alias("newExitRoot", Mux1(c.sub("s5"), in.oldExitRoot, p2, in.isExit));
+}
+HZ_HD void hz_smt_job(HzSmtJob* j, uint32_t cur, uint32_t sib, const VC& oldKey, const VC& oldValue, const VC& isOld0,
+                      const VC& newKey, const VC& newValue, const VC* f) {
+    j->oldKey = oldKey.v; j->oldValue = oldValue.v; j->isOld0 = isOld0.v; j->newKey = newKey.v; j->newValue = newValue.v;
+    j->fnc0 = f[0].v; j->fnc1 = f[1].v; j->cur = cur; j->sib = sib;
+    j->sigmask = (oldKey.sig ? 1u : 0u) | (oldValue.sig ? 2u : 0u) | (isOld0.sig ? 4u : 0u) | (newKey.sig ? 8u : 0u) |
+                 (newValue.sig ? 16u : 0u) | (f[0].sig ? 32u : 0u) | (f[1].sig ? 64u : 0u);
+}
+HZ_HD void hz_phaseJK_hook(Comp<MCompute>& c, const SlotHook<MCompute>& hk, int nLevels, const PhaseJKIn<MCompute>& in,
+                           VC& newStateRoot, VC& newExitRoot) {
+    if (!hk.smt) { hz_phaseJK(c, nLevels, in, newStateRoot, newExitRoot); return; }
+    // the bodies are jobs; processor 2 starts after processor 1 and s3 -- the tail recomputes the
+    // cursors from the body records, here only the two component starts are needed
+    (void)nLevels;
+    hz_smt_job(&hk.smt[0], c.cur, in.sib1_idx, in.oldKey1, in.oldValue1, in.isOld0_1, in.key1, in.newValue1, in.f1);
+    hz_smt_job(&hk.smt[1], c.cur + hk.sz->p2_off, in.sib2_idx, in.oldKey2, in.oldValue2, in.isOld0_2, in.key2, in.newValue2, in.f2);
+    *hk.isExit = in.isExit.v;
+    c.cur += hk.sz->phaseJK;
+    newStateRoot = vc(fr_zero()); newExitRoot = vc(fr_zero());
+}
+#ifndef HZ_DEVICE_ONLY
+inline void hz_phaseJK_hook(Comp<MLayout>& c, const SlotHook<MLayout>& hk, int nLevels, const PhaseJKIn<MLayout>& in,
+                            VL& newStateRoot, VL& newExitRoot) {
+    uint32_t c0 = c.cur, p2 = 0;
+    hz_phaseJK(c, nLevels, in, newStateRoot, newExitRoot, &p2);
+    if (hk.sz_out) { hk.sz_out->phaseJK = c.cur - c0; hk.sz_out->p2_off = p2 - c0; }
+}
+#endif
+
 TM HZ_FN void RollupTx(Comp<M>&& c, int nLevels, int maxFeeTx, const RollupTxIn<M>& i, RollupTxOut<M>& o,
-                        const EddsaHook<M>& hook) {
+                        const SlotHook<M>& hook) {
     V<M> feePlanTokens[HZ_MAX_FEE], accFeeIn[HZ_MAX_FEE];
     for (int k = 0; k < maxFeeTx; k++) feePlanTokens[k] = c.def(Nm("feePlanTokens", k), i.feePlanTokens[k]);
     for (int k = 0; k < maxFeeTx; k++) accFeeIn[k] = c.def(Nm("accFeeIn", k), i.accFeeIn[k]);
@@ -600,26 +663,38 @@ TM HZ_FN void RollupTx(Comp<M>&& c, int nLevels, int maxFeeTx, const RollupTxIn<
     // I - compute hash new states (:517-532)
     V<M> newSt1Hash = HashState(c.sub("newSt1Hash"), s1TokenID, s1Nonce + (1 - oc), s1Sign, bo.newS, s1Ay, s1EthAddr);
     V<M> newSt2Hash = HashState(c.sub("newSt2Hash"), s2TokenID, s2Nonce, s2Sign, bo.newR, s2Ay, s2EthAddr);
-    // J - smt processors (:537-570)
-    V<M> f1[2], f2[2];
-    f1[0] = st.P1_fnc0; f1[1] = st.P1_fnc1;
-    V<M> p1 = SMTProcessor(c.sub("processor1"), nLevels + 1, oldStateRoot, siblings1, s1OldKey, s1OldValue, isOld0_1,
-                           st.key1, newSt1Hash, f1);
-    V<M> s3 = Mux1(c.sub("s3"), p1, oldExitRoot, st.isExit);
-    f2[0] = st.P2_fnc0 * bo.isP2Nop; f2[1] = st.P2_fnc1 * bo.isP2Nop;
-    V<M> p2 = SMTProcessor(c.sub("processor2"), nLevels + 1, s3, siblings2, s2OldKey, s2OldValue, isOld0_2,
-                           st.key2, newSt2Hash, f2);
-    // K - select output roots (:577-590)
-    o.newStateRoot = c.alias("newStateRoot", Mux1(c.sub("s4"), p2, p1, st.isExit));
-    o.newExitRoot = c.alias("newExitRoot", Mux1(c.sub("s5"), oldExitRoot, p2, st.isExit));
+    // J, K - smt processors and output roots (:537-590)
+    PhaseJKIn<M> jk;
+    jk.oldStateRoot = oldStateRoot; jk.oldExitRoot = oldExitRoot; jk.isExit = st.isExit;
+    jk.siblings1 = siblings1; jk.oldKey1 = s1OldKey; jk.oldValue1 = s1OldValue; jk.isOld0_1 = isOld0_1;
+    jk.key1 = st.key1; jk.newValue1 = newSt1Hash; jk.f1[0] = st.P1_fnc0; jk.f1[1] = st.P1_fnc1;
+    jk.siblings2 = siblings2; jk.oldKey2 = s2OldKey; jk.oldValue2 = s2OldValue; jk.isOld0_2 = isOld0_2;
+    jk.key2 = st.key2; jk.newValue2 = newSt2Hash;
+    jk.f2[0] = st.P2_fnc0 * bo.isP2Nop; jk.f2[1] = st.P2_fnc1 * bo.isP2Nop;
+    jk.sib1_idx = i.sib1_idx; jk.sib2_idx = i.sib2_idx;
+    hz_phaseJK_hook(c, hook, nLevels, jk, o.newStateRoot, o.newExitRoot);
 }
 
 // ---------------------------------------------------------------------------
 // src/fee-tx.circom:26-111
 // ---------------------------------------------------------------------------
+TM struct FeeHook;
+template <> struct FeeHook<MCompute> { HzSmtJob* smt; uint32_t sib_idx; };   // smt null: evaluate the processor in place
+template <> struct FeeHook<MLayout> { int unused; };
+HZ_HD bool hz_fee_job(const FeeHook<MCompute>& hk, uint32_t cur, const VC& oldKey, const VC& oldValue, const VC& isOld0,
+                      const VC& newKey, const VC& newValue, const VC* f) {
+    if (!hk.smt) return false;
+    hz_smt_job(hk.smt, cur, hk.sib_idx, oldKey, oldValue, isOld0, newKey, newValue, f);
+    return true;
+}
+#ifndef HZ_DEVICE_ONLY
+inline bool hz_fee_job(const FeeHook<MLayout>&, uint32_t, const VL&, const VL&, const VL&, const VL&, const VL&, const VL*) { return false; }
+#endif
+
 TM HZ_FN V<M> FeeTx(Comp<M>&& c, int nLevels, const V<M>& oldStateRoot_, const V<M>& feePlanToken_,
                      const V<M>& feeIdx_, const V<M>& accFee_, const V<M>& tokenID_, const V<M>& nonce_,
-                     const V<M>& sign_, const V<M>& balance_, const V<M>& ay_, const V<M>& ethAddr_, const V<M>* siblings) {
+                     const V<M>& sign_, const V<M>& balance_, const V<M>& ay_, const V<M>& ethAddr_, const V<M>* siblings,
+                     const FeeHook<M>& hook) {
     V<M> oldStateRoot = c.def("oldStateRoot", oldStateRoot_);
     V<M> feePlanToken = c.def("feePlanToken", feePlanToken_);
     V<M> feeIdx = c.def("feeIdx", feeIdx_);
@@ -640,6 +715,8 @@ TM HZ_FN V<M> FeeTx(Comp<M>&& c, int nLevels, const V<M>& oldStateRoot_, const V
     f[1] = c.def("p_fnc1", 1 - z);
     V<M> oldH = HashState(c.sub("oldStFeePck"), tokenID, nonce, sign, balance, ay, ethAddr);
     V<M> newH = HashState(c.sub("newStFeePck"), tokenID, nonce, sign, accFee + balance, ay, ethAddr);
+    // the processor is the last thing in the component: as a job nothing is left to do here
+    if (hz_fee_job(hook, c.cur, feeIdx, oldH, Ops<M>::K(0), feeIdx, newH, f)) return Ops<M>::K(0);
     V<M> nr = SMTProcessor(c.sub("processor"), nLevels + 1, oldStateRoot, sib, feeIdx, oldH, Ops<M>::K(0), feeIdx, newH, f);
     return c.alias("newStateRoot", nr);
 }

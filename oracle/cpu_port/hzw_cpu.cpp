@@ -28,7 +28,22 @@ template <class F> static void hz_parallel_for(int n, F f) {
 
 struct CpuBackend : HzBackend {
     const HzLayout& L;
-    explicit CpuBackend(const HzLayout& l) : L(l) {}
+    // HZW_CPU_HINTS=1: evaluate the EdDSA ladders with the inverse-hint streams of hints.cuh (the
+    // device's way) instead of one inversion per division (the reference's way, the default and
+    // what the CPU baseline times); the tests run both and expect the same witness
+    bool use_hints = false;
+    std::vector<Fr> cst, edtab;
+    explicit CpuBackend(const HzLayout& l) : L(l) {
+        const char* e = getenv("HZW_CPU_HINTS");
+        use_hints = e && atoi(e) > 0;
+        if (use_hints) {
+            cst.assign(HZ_CST_MAX, fr_zero()); edtab.assign(HZ_EDTAB_LEN, fr_zero());
+            std::vector<Fr> tmp((size_t)L.plan.sz.sigVerifier + 64);
+            uint32_t counts[2];
+            hz_record_fix_consts(tmp.data(), cst.data(), edtab.data(), counts);
+            if (counts[0] > HZ_CST_MAX || counts[1] != HZ_EDTAB_LEN) { fprintf(stderr, "hzw cpu port: hint table sizes %u %u\n", counts[0], counts[1]); abort(); }
+        }
+    }
     int calculate(const uint8_t* inputs, int sanity, uint8_t* out, bool resident, float* ms, HzErrBuf* errs) override {
         if (resident || !out) return HZW_E_PARAM;
         (void)ms;
@@ -44,10 +59,14 @@ struct CpuBackend : HzBackend {
         { const char* e = getenv("HZW_CPU_SAMPLE_STRIDE"); if (e && atoi(e) > 1) stride = atoi(e); }
         std::vector<uint8_t> preb((size_t)pl.nblocks * 512, 0);
         PreBits<MCompute> pre; pre.b = preb.data();
-        EddsaHook<MCompute> hook; hook.job = nullptr; hook.sz = &pl.sz;
+        SlotHook<MCompute> hook; hook.eddsa = nullptr; hook.smt = nullptr; hook.isExit = nullptr; hook.sz = &pl.sz;
         hz_parallel_for(P.nTx, [&](int i) {
             if (i % stride) return;
-            Comp<MCompute> c(w, pl.off_decode[i], err);
+            std::vector<Fr> scratch(use_hints ? HZ_HINT_SCRATCH : 0);
+            HzHints h;
+            h.cst = cst.data(); h.ci = 0; h.dat = nullptr; h.di = 0; h.rec = nullptr; h.ri = 0;
+            h.edtab = edtab.data(); h.edrec = nullptr; h.ei = 0; h.scratch = scratch.data();
+            Comp<MCompute> c(w, pl.off_decode[i], err, use_hints ? &h : nullptr);
             DecodeOut<MCompute> d;
             PreBits<MCompute> p2 = pre;
             sec_decode(c, pl, i, d, p2);
@@ -58,7 +77,8 @@ struct CpuBackend : HzBackend {
         hz_parallel_for(P.maxFeeTx, [&](int i) {
             if (i % stride) return;
             Comp<MCompute> c(w, pl.off_fee[i], err);
-            sec_fee(c, pl, i);
+            FeeHook<MCompute> fh; fh.smt = nullptr; fh.sib_idx = 0;
+            sec_fee(c, pl, i, fh);
         });
         Comp<MCompute> hc(w, pl.off_hasher, err);
         uint32_t off_blocks = 0;

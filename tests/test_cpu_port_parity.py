@@ -96,3 +96,24 @@ def test_constraint_violation_is_reported_like_the_runtime(built, small_bb):
     # without sanityCheck the witness is emitted regardless (production CLI behaviour)
     w = wc.calculateWitness(inp, False)
     assert len(w) == wc.NVars
+
+
+def test_inverse_hint_streams_give_the_same_witness(built, small_bb, small_oracle, monkeypatch):
+    """The device evaluates the EdDSA ladders with inverse hints (csrc/hints.cuh: projective
+    Edwards walk + one batched inversion, constant window tables recorded once).  The same code
+    runs on the host with HZW_CPU_HINTS=1: signal by signal equal to the oracle, and equal to the
+    hint-free evaluation on a signed nLevels=32 batch."""
+    w_ref, _ = small_oracle
+    monkeypatch.setenv("HZW_CPU_HINTS", "1")
+    wc = cpu_port_calculator(3, 16, 2, 2)
+    assert wc.calculateWitness(small_bb.getInput(), True) == w_ref
+    from circuits_b200.synth import bench_batch
+    prm = (12, 32, 4, 2)
+    bb = bench_batch(*prm, n_accounts=8)
+    wh = cpu_port_calculator(*prm)
+    packed = wh.packInput(bb.getInput())
+    with_hints = bytes(wh.calculateBinWitness(packed, True))
+    monkeypatch.delenv("HZW_CPU_HINTS")
+    plain = bytes(cpu_port_calculator(*prm).calculateBinWitness(packed, True))
+    assert with_hints == plain
+    assert int.from_bytes(plain[32:64], "little") == bb.getHashInputs()
