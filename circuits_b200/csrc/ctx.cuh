@@ -205,6 +205,14 @@ struct HzHints {
     Fr* scratch;                           // HZ_HINT_SCRATCH entries owned by this lane group / thread
 };
 
+// ---- deferred inverses -----------------------------------------------------------------------
+// IsZero needs 1/in only for its `inv` entry: `out` is simply (in == 0).  With a pending list
+// installed the entry is reserved, the value queued, and all queued values of a section are
+// inverted together (one inversion) when the list is flushed.  Without one (CPU port, the
+// reference's way) IsZero inverts on the spot.
+#define HZ_PEND_CAP 96
+struct HzPending { uint32_t n; uint32_t idx[HZ_PEND_CAP]; Fr val[HZ_PEND_CAP]; };
+
 // ---- component contexts -------------------------------------------------------------------
 template <class M> struct Comp;
 
@@ -215,10 +223,12 @@ template <> struct Comp<MCompute> {
     Comp* parent;
     HzErrBuf* err;      // null = sanity check off
     HzHints* hints;     // null = every division inverts on the spot
+    HzPending* pend;    // null = IsZero inverts on the spot
     typedef VC Val;
 
-    HZ_HD Comp(Fr* w_, uint32_t cur_, HzErrBuf* err_, HzHints* h_ = nullptr) : w(w_), cur(cur_), end(HZ_NOIDX), parent(nullptr), err(err_), hints(h_) {}
-    HZ_HD Comp(Comp* p, bool reserved, uint32_t size) : w(p->w), cur(p->cur), parent(reserved ? nullptr : p), err(p->err), hints(p->hints) {
+    HZ_HD Comp(Fr* w_, uint32_t cur_, HzErrBuf* err_, HzHints* h_ = nullptr, HzPending* p_ = nullptr)
+        : w(w_), cur(cur_), end(HZ_NOIDX), parent(nullptr), err(err_), hints(h_), pend(p_) {}
+    HZ_HD Comp(Comp* p, bool reserved, uint32_t size) : w(p->w), cur(p->cur), parent(reserved ? nullptr : p), err(p->err), hints(p->hints), pend(p->pend) {
         if (reserved) { end = p->cur + size; p->cur += size; } else end = HZ_NOIDX;
     }
     HZ_HD ~Comp() {
@@ -228,7 +238,34 @@ template <> struct Comp<MCompute> {
 #endif
     }
     Comp(const Comp&) = delete;
-    HZ_HD Comp(Comp&& o) : w(o.w), cur(o.cur), end(o.end), parent(o.parent), err(o.err), hints(o.hints) { o.parent = nullptr; o.end = HZ_NOIDX; }
+    HZ_HD Comp(Comp&& o) : w(o.w), cur(o.cur), end(o.end), parent(o.parent), err(o.err), hints(o.hints), pend(o.pend) { o.parent = nullptr; o.end = HZ_NOIDX; }
+    // the `inv` entry and the `out` value of IsZero(x) (comparators.circom): inv <-- x != 0 ? 1/x : 0
+    HZ_HD VC iszero_inv(const Nm&, const VC& x) {
+        const uint32_t slot = cur++;
+        const bool z = fr_is_zero(x.v);
+        if (pend) {
+            if (pend->n == HZ_PEND_CAP) flush_pending();
+            pend->idx[pend->n] = slot; pend->val[pend->n] = x.v; pend->n++;
+        } else {
+            put(slot, fr_inv(x.v));
+        }
+        return vc(z ? fr_one() : fr_zero());
+    }
+    HZ_HD void flush_pending() {
+        if (!pend || pend->n == 0) return;
+        // Montgomery's trick; zeros keep inverse 0
+        Fr acc = fr_one();
+        Fr pre[HZ_PEND_CAP];
+        const int n = (int)pend->n;
+        for (int i = 0; i < n; i++) { pre[i] = acc; if (!fr_is_zero(pend->val[i])) acc = fr_mul(acc, pend->val[i]); }
+        Fr t = fr_inv(acc);
+        for (int i = n - 1; i >= 0; i--) {
+            if (fr_is_zero(pend->val[i])) { put(pend->idx[i], fr_zero()); continue; }
+            put(pend->idx[i], fr_mul(t, pre[i]));
+            t = fr_mul(t, pend->val[i]);
+        }
+        pend->n = 0;
+    }
     // two divisions whose denominators are both known: one inversion
     HZ_HD void div2(const VC& a1, const VC& b1, const VC& a2, const VC& b2, VC& q1, VC& q2) {
         // exactly one inversion whatever the data (the device batches inversions across a warp)
@@ -355,6 +392,8 @@ template <> struct Comp<MLayout> {
     VL own(const Nm& nm, const VL&) { name(nm, cur); VL r; r.idx = cur++; return r; }
     VL load(uint32_t idx) const { VL r; r.idx = idx; return r; }
     VL known(uint32_t idx, const VL&) const { VL r; r.idx = idx; return r; }
+    VL iszero_inv(const Nm& nm, const VL&) { name(nm, cur); cur++; return vl(); }
+    void flush_pending() {}
     VL div(const VL&, const VL&, int) { return vl(); }
     void div2(const VL&, const VL&, const VL&, const VL&, VL& q1, VL& q2) { q1 = vl(); q2 = vl(); }
     bool sanity() const { return false; }

@@ -12,8 +12,54 @@ struct HzBackend {
     virtual int calculate(const uint8_t* inputs, int sanity, uint8_t* witness_out, bool resident, float* kernel_ms,
                           HzErrBuf* errs) = 0;
     virtual int kernel_ms(float*, const char**, int) { return 0; }
+    // sharded evaluation: records live in the backend's memory space (device memory for CUDA)
+    virtual int set_shard(int rank, int world) = 0;
+    virtual uint64_t exchange_bytes() = 0;
+    virtual int pieces(uint64_t* table, int cap) = 0;
+    virtual int shard_phase1(const uint8_t* inputs, int sanity, void* record_out, HzErrBuf* errs) = 0;
+    virtual int shard_phase2(const void* records, int sanity, uint8_t* shard_out, float* kernel_ms, HzErrBuf* errs) = 0;
     uint64_t launches = 0, h2d = 0, d2h = 0;
 };
+
+// ---- shard geometry shared by the backends ------------------------------------------------------
+struct HzShard { int rank = 0, world = 1, per = 0, s0 = 0, ns = 0, f0 = 0, nf = 0; uint32_t b0 = 0, nb = 0; };
+static inline HzShard hz_shard_ranges(const HzPlan& pl, int rank, int world) {
+    const HzParams& P = pl.P;
+    HzShard d; d.rank = rank; d.world = world;
+    d.per = (P.nTx + world - 1) / world;
+    d.s0 = rank * d.per < P.nTx ? rank * d.per : P.nTx;
+    d.ns = (d.s0 + d.per <= P.nTx ? d.per : P.nTx - d.s0);
+    int perf = (P.maxFeeTx + world - 1) / world;
+    d.f0 = rank * perf < P.maxFeeTx ? rank * perf : P.maxFeeTx;
+    d.nf = (d.f0 + perf <= P.maxFeeTx ? perf : P.maxFeeTx - d.f0);
+    uint32_t perb = (pl.nblocks + (uint32_t)world - 1) / (uint32_t)world;
+    d.b0 = (uint32_t)rank * perb < pl.nblocks ? (uint32_t)rank * perb : pl.nblocks;
+    d.nb = d.b0 + perb <= pl.nblocks ? perb : pl.nblocks - d.b0;
+    return d;
+}
+// witness pieces a shard owns, (first index, count) pairs in witness order: rank 0 carries the header,
+// the main inputs and the head / tail of hasherInputs besides its slots
+static inline int hz_shard_pieces(const HzLayout& L, const HzShard& d, uint64_t* table, int cap) {
+    const HzPlan& pl = L.plan;
+    const HzParams& P = pl.P;
+    int n = 0;
+    auto add = [&](uint64_t a, uint64_t b) { if (b > a && n < cap) { table[2 * n] = a; table[2 * n + 1] = b - a; n++; } };
+    if (d.rank == 0) add(0, 2 + pl.n_inputs);
+    if (d.ns > 0) {
+        add(L.off_decode[d.s0], d.s0 + d.ns < P.nTx ? L.off_decode[d.s0 + d.ns] : L.off_rollup[0]);
+        add(L.off_rollup[d.s0], d.s0 + d.ns < P.nTx ? L.off_rollup[d.s0 + d.ns] : L.off_fee[0]);
+    }
+    if (d.nf > 0) add(L.off_fee[d.f0], d.f0 + d.nf < P.maxFeeTx ? L.off_fee[d.f0 + d.nf] : pl.off_hasher);
+    if (d.rank == 0) add(pl.off_hasher, pl.off_sha_blocks);
+    add((uint64_t)pl.off_sha_blocks + (uint64_t)d.b0 * HZ_SZ_SHA_BLOCK, (uint64_t)pl.off_sha_blocks + (uint64_t)(d.b0 + d.nb) * HZ_SZ_SHA_BLOCK);
+    if (d.rank == 0) add(pl.off_hasher_tail, pl.nvars);
+    return n;
+}
+// exchange record of one rank (see k_pack in hzw_kernels.cu): per own slot 624 + nL2 bytes of pre-image
+// bits, then newLastIdx / newStateRoot / newExitRoot (3 x 32 B) and 3 x 4 B "this rank produced it" flags
+static inline uint32_t hz_xrec_slot_bytes(const HzParams& P) { return 624u + 2u * (uint32_t)P.nLevels + 48u; }
+static inline uint32_t hz_xrec_vals_off(const HzParams& P, int per) { return ((uint32_t)per * hz_xrec_slot_bytes(P) + 3u) & ~3u; }
+static inline uint32_t hz_xrec_bytes(const HzParams& P, int per) { return (hz_xrec_vals_off(P, per) + 3 * 32 + 3 * 4 + 15u) & ~15u; }
 HzBackend* hz_backend_create(const hzw_params& prm, const HzLayout& L, int* status);
 
 struct hzw_ctx {
@@ -136,7 +182,7 @@ int hzw_dump_sym(const hzw_ctx* ctx, const char* prefix, const char* path) {
     fclose(f);
     return HZW_OK;
 }
-int hzw_plan_info(const hzw_ctx* ctx, uint64_t out[9]) {
+int hzw_plan_info(const hzw_ctx* ctx, uint64_t out[12]) {
     if (!ctx || !out) return HZW_E_PARAM;
     const HzPlan& pl = ctx->L.plan;
     const HzParams& P = ctx->P;
@@ -145,11 +191,41 @@ int hzw_plan_info(const hzw_ctx* ctx, uint64_t out[9]) {
     out[6] = (P.maxFeeTx > 1 ? ctx->L.off_fee[1] : pl.off_hasher) - ctx->L.off_fee[0];
     out[7] = P.nTx > 2 ? ctx->L.off_decode[2] - ctx->L.off_decode[1] : 0;
     out[8] = P.nTx > 2 ? ctx->L.off_rollup[2] - ctx->L.off_rollup[1] : 0;
+    out[9] = pl.sz.phaseJK; out[10] = pl.sz.p2_off; out[11] = pl.off_sha_blocks - pl.off_hasher;
     return HZW_OK;
 }
 int hzw_last_kernel_ms(const hzw_ctx* ctx, float* ms, const char** names, int cap) {
     if (!ctx || !ms || cap <= 0) return HZW_E_PARAM;
     return ctx->be->kernel_ms(ms, names, cap);
+}
+int hzw_set_shard(hzw_ctx* ctx, int32_t rank, int32_t world) {
+    if (!ctx || world < 1 || rank < 0 || rank >= world) return HZW_E_PARAM;
+    return ctx->be->set_shard(rank, world);
+}
+uint64_t hzw_exchange_bytes(const hzw_ctx* ctx) { return ctx ? ctx->be->exchange_bytes() : 0; }
+int hzw_shard_pieces(const hzw_ctx* ctx, uint64_t* table, int32_t cap) {
+    if (!ctx || !table || cap <= 0) return HZW_E_PARAM;
+    return ctx->be->pieces(table, cap);
+}
+uint64_t hzw_shard_nvars(const hzw_ctx* ctx) {
+    if (!ctx) return 0;
+    uint64_t t[32]; int n = ctx->be->pieces(t, 16); uint64_t tot = 0;
+    for (int k = 0; k < n; k++) tot += t[2 * k + 1];
+    return tot;
+}
+int hzw_shard_phase1(hzw_ctx* ctx, const uint8_t* inputs, int sanity, void* record_out, hzw_error* err) {
+    if (!ctx || !record_out) return HZW_E_PARAM;
+    HzErrBuf eb; memset(&eb, 0, sizeof eb);
+    int st = ctx->be->shard_phase1(inputs, sanity, record_out, &eb);
+    if (st) { if (err) { memset(err, 0, sizeof *err); err->code = st; } return st; }
+    return hz_report(ctx, eb, err);
+}
+int hzw_shard_phase2(hzw_ctx* ctx, const void* records, int sanity, uint8_t* shard_out, float* kernel_ms, hzw_error* err) {
+    if (!ctx || !records) return HZW_E_PARAM;
+    HzErrBuf eb; memset(&eb, 0, sizeof eb);
+    int st = ctx->be->shard_phase2(records, sanity, shard_out, kernel_ms, &eb);
+    if (st) { if (err) { memset(err, 0, sizeof *err); err->code = st; } return st; }
+    return hz_report(ctx, eb, err);
 }
 int hzw_last_stats(const hzw_ctx* ctx, uint64_t* launches, uint64_t* h2d, uint64_t* d2h) {
     if (!ctx) return HZW_E_PARAM;

@@ -13,3 +13,10 @@ int hz_cuda_calculate(HzCuda*, const uint8_t* inputs, int sanity, uint8_t* witne
                       HzErrBuf* errs, uint64_t* launches, uint64_t* h2d, uint64_t* d2h);
 // per-kernel device times of the last calculate
 int hz_cuda_kernel_ms(HzCuda*, float* ms, const char** names, int cap);
+
+// ---- sharded evaluation (one context per GPU; include/hzwitness.h, hzw_shard_*) -------------------
+int hz_cuda_set_shard(HzCuda*, int rank, int world);
+uint64_t hz_cuda_exchange_bytes(const HzCuda*);
+int hz_cuda_shard_phase1(HzCuda*, const uint8_t* inputs, int sanity, void* record_out_dev, HzErrBuf* errs);
+int hz_cuda_shard_phase2(HzCuda*, const void* records_dev, int sanity, uint8_t* shard_out, const uint64_t* pieces, int npieces,
+                         float* kernel_ms, HzErrBuf* errs, uint64_t* d2h);

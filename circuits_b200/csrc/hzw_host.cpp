@@ -13,10 +13,31 @@ struct CudaBackend : HzBackend {
         return hz_cuda_calculate(d, inputs, sanity, resident ? nullptr : out, ms, errs, &launches, &h2d, &d2h);
     }
     int kernel_ms(float* ms, const char** names, int cap) override { return hz_cuda_kernel_ms(d, ms, names, cap); }
+    const HzLayout* L = nullptr;
+    HzShard sh;
+    int set_shard(int rank, int world) override {
+        int st = hz_cuda_set_shard(d, rank, world);
+        if (!st) sh = hz_shard_ranges(L->plan, rank, world);
+        return st;
+    }
+    uint64_t exchange_bytes() override { return hz_cuda_exchange_bytes(d); }
+    int pieces(uint64_t* table, int cap) override { return hz_shard_pieces(*L, sh, table, cap); }
+    int shard_phase1(const uint8_t* inputs, int sanity, void* record_out, HzErrBuf* errs) override {
+        h2d = inputs ? 32ull * L->plan.n_inputs : 0;
+        return hz_cuda_shard_phase1(d, inputs, sanity, record_out, errs);
+    }
+    int shard_phase2(const void* records, int sanity, uint8_t* shard_out, float* ms, HzErrBuf* errs) override {
+        uint64_t t[32]; int n = hz_shard_pieces(*L, sh, t, 16);
+        launches = 11;
+        return hz_cuda_shard_phase2(d, records, sanity, shard_out, t, n, ms, errs, &d2h);
+    }
 };
 
 HzBackend* hz_backend_create(const hzw_params& prm, const HzLayout& L, int* status) {
     HzCuda* d = hz_cuda_create(prm.device, L.plan, L.off_decode.data(), L.off_rollup.data(), L.off_fee.data(), status);
     if (!d) return nullptr;
-    return new CudaBackend(d);
+    CudaBackend* b = new CudaBackend(d);
+    b->L = &L;
+    b->sh = hz_shard_ranges(L.plan, 0, 1);
+    return b;
 }

@@ -43,10 +43,16 @@ struct HzCuda {
     HzErrBuf* err;
     uint32_t *off_decode, *off_rollup, *off_fee;
     uint32_t* off_blocks;      // 1
+    // shard of this context: rank / world and the ranges it evaluates (everything when world == 1)
+    int rank, world, per, s0, ns, f0, nf;
+    uint32_t b0, nb;
+    uint8_t* recs;             // world x rec_bytes: the gathered exchange records (own one while packing)
     cudaStream_t stream, stream2;
     cudaEvent_t ev0, ev1, ev_front, ev_eddsa;
     cudaEvent_t kev[HZ_NKERN + 2];
 };
+
+static void hz_set_ranges(HzCuda* d, int rank, int world);
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "hzw: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return HZW_E_DEVICE; } } while (0)
 
@@ -59,28 +65,49 @@ __device__ __forceinline__ int hz_item(int n, bool& real) {
 }
 static inline unsigned hz_grid(int items) { return (unsigned)((items * HZ_G + HZ_BLOCK - 1) / HZ_BLOCK); }
 
-__global__ void __launch_bounds__(HZ_BLOCK) k_front(HzPlan pl, Fr* w, uint8_t* preb, HzErrBuf* err, HzEddsaJob* jobs, HzSmtJob* smt, Fr* isExit) {
-    bool real; int i = hz_item(pl.P.nTx, real);
+// ---- Poseidon alone (the second metric of BASELINE.json: permutations per second) ----------------
+// The SMT level hashes as k_smt evaluates them -- a lane group runs the old-path and the new-path
+// Poseidon(2) side by side -- but on free-standing inputs: pair q hashes (in[4q], in[4q+1]) and
+// (in[4q+2], in[4q+3]) and stores all 2 x 633 signals of the two components at sig[q * 2 * size].
+__global__ void __launch_bounds__(HZ_BLOCK, 3) k_poseidon_pairs(const Fr* in, Fr* sig, Fr* digests, int npairs) {
+    bool real; int q = hz_item(npairs, real);
+    const uint32_t size = poseidon_size(3);
+    Comp<MCompute> ca(sig, (uint32_t)q * 2 * size, nullptr), cb(sig, (uint32_t)q * 2 * size + size, nullptr);
+    VC a[2], b[2], oa, ob;
+    for (int k = 0; k < 2; k++) { a[k].v = in[4 * q + k]; a[k].sig = true; b[k].v = in[4 * q + 2 + k]; b[k].sig = true; }
+    PoseidonDual<MCompute>(static_cast<Comp<MCompute>&&>(ca), a, static_cast<Comp<MCompute>&&>(cb), b, 2, oa, ob);
+    if (hz_glane() == 0) { digests[2 * q] = oa.v; digests[2 * q + 1] = ob.v; }
+}
+
+// [s0, s0 + ns): the tx slots of this shard (all of them on one GPU)
+__global__ void __launch_bounds__(HZ_BLOCK, 3) k_front(HzPlan pl, Fr* w, uint8_t* preb, HzErrBuf* err, HzEddsaJob* jobs, HzSmtJob* smt, Fr* isExit, int s0, int ns) {
+    bool real; int i = s0 + hz_item(ns, real);
     PreBits<MCompute> pre; pre.b = preb;
     SlotHook<MCompute> hook; hook.eddsa = &jobs[i]; hook.smt = &smt[2 * i]; hook.isExit = &isExit[i]; hook.sz = &pl.sz;
-    Comp<MCompute> c(w, pl.off_decode[i], real ? err : nullptr);
+    HzPending pend; pend.n = 0;
+    Comp<MCompute> c(w, pl.off_decode[i], real ? err : nullptr, nullptr, &pend);
     DecodeOut<MCompute> d;
     sec_decode(c, pl, i, d, pre);
     c.cur = pl.off_rollup[i];
     RollupTxOut<MCompute> o;
     sec_rollup(c, pl, i, d, o, pre, hook);
+    c.flush_pending();
 }
 
-__global__ void __launch_bounds__(HZ_BLOCK) k_fee_front(HzPlan pl, Fr* w, HzErrBuf* err, HzSmtJob* smt) {
-    bool real; int i = hz_item(pl.P.maxFeeTx, real);
-    Comp<MCompute> c(w, pl.off_fee[i], real ? err : nullptr);
+__global__ void __launch_bounds__(HZ_BLOCK) k_fee_front(HzPlan pl, Fr* w, HzErrBuf* err, HzSmtJob* smt, int f0, int nf) {
+    bool real; int i = f0 + hz_item(nf, real);
+    HzPending pend; pend.n = 0;
+    Comp<MCompute> c(w, pl.off_fee[i], real ? err : nullptr, nullptr, &pend);
     FeeHook<MCompute> hook; hook.smt = &smt[i];
     hook.sib_idx = pl.in_off[IN_siblings3] + (uint32_t)i * pl.in_d1[IN_siblings3];
     sec_fee(c, pl, i, hook, true);
+    c.flush_pending();
 }
 
-__global__ void __launch_bounds__(HZ_BLOCK) k_smt(HzPlan pl, Fr* w, HzErrBuf* err, const HzSmtJob* smt, HzSmtMid* mids, int njobs) {
-    bool real; int q = hz_item(njobs, real);
+// jobs of the shard: 2 per own slot, then 1 per own fee tx
+__global__ void __launch_bounds__(HZ_BLOCK, 3) k_smt(HzPlan pl, Fr* w, HzErrBuf* err, const HzSmtJob* smt, HzSmtMid* mids, int s0, int ns, int f0, int nf) {
+    bool real; int q = hz_item(2 * ns + nf, real);
+    q = q < 2 * ns ? 2 * s0 + q : 2 * pl.P.nTx + f0 + (q - 2 * ns);
     sec_smt_body(w, real ? err : nullptr, pl.P.nLevels + 1, smt[q], mids[q]);
 }
 
@@ -89,25 +116,83 @@ __global__ void k_fix_consts(Fr* wtmp, Fr* cst, Fr* tab, uint32_t* counts) {
     hz_record_fix_consts(wtmp, cst, tab, counts);
 }
 
-__global__ void __launch_bounds__(HZ_BLOCK) k_eddsa(HzPlan pl, Fr* w, HzErrBuf* err, const HzEddsaJob* jobs,
-                                                    const Fr* cst, const Fr* tab, Fr* scratch) {
-    bool real; int i = hz_item(pl.P.nTx, real);
+__global__ void __launch_bounds__(HZ_BLOCK, 3) k_eddsa(HzPlan pl, Fr* w, HzErrBuf* err, const HzEddsaJob* jobs,
+                                                    const Fr* cst, const Fr* tab, Fr* scratch, int s0, int ns) {
+    bool real; int i = s0 + hz_item(ns, real);
     const HzEddsaJob& j = jobs[i];
     HzHints h;
     h.cst = cst; h.ci = 0; h.dat = nullptr; h.di = 0; h.rec = nullptr; h.ri = 0;
     h.edtab = tab; h.edrec = nullptr; h.ei = 0; h.scratch = scratch + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) / HZ_G) * HZ_HINT_SCRATCH;   // per group, not per slot: padding groups redo a slot
-    Comp<MCompute> c(w, j.cur, real ? err : nullptr, &h);
+    HzPending pend; pend.n = 0;
+    Comp<MCompute> c(w, j.cur, real ? err : nullptr, &h, &pend);
     VC vse, sgn, ay, s1Ay, S, R8x, R8y, Msg;
     vse.v = j.enabled; sgn.v = j.signSignature; ay.v = j.aySignature; s1Ay.v = j.s1Ay;
     S.v = j.S; R8x.v = j.R8x; R8y.v = j.R8y; Msg.v = j.M;
     vse.sig = sgn.sig = ay.sig = s1Ay.sig = S.sig = R8x.sig = R8y.sig = Msg.sig = true;
     hz_phaseF(c, vse, sgn, ay, s1Ay, S, R8x, R8y, Msg);
+    c.flush_pending();
 }
 
-__global__ void __launch_bounds__(HZ_BLOCK) k_tail(HzPlan pl, Fr* w, HzErrBuf* err, const HzSmtMid* mids, const Fr* isExit) {
-    bool real; int i = hz_item(pl.P.nTx + pl.P.maxFeeTx, real);
-    if (i < pl.P.nTx) sec_rollup_tail(w, real ? err : nullptr, pl, i, &mids[2 * i], isExit[i]);
-    else sec_fee_tail(w, real ? err : nullptr, pl, i - pl.P.nTx, mids[2 * pl.P.nTx + (i - pl.P.nTx)]);
+__global__ void __launch_bounds__(HZ_BLOCK) k_tail(HzPlan pl, Fr* w, HzErrBuf* err, const HzSmtMid* mids, const Fr* isExit, int s0, int ns, int f0, int nf) {
+    bool real; int q = hz_item(ns + nf, real);
+    if (q < ns) { int i = s0 + q; sec_rollup_tail(w, real ? err : nullptr, pl, i, &mids[2 * i], isExit[i]); }
+    else { int i = f0 + (q - ns); sec_fee_tail(w, real ? err : nullptr, pl, i, mids[2 * pl.P.nTx + i]); }
+}
+
+// ---- the exchange between shards (one all-gather, done by the host binding) ---------------------
+// What hasherInputs needs from slots this GPU did not evaluate: their SHA pre-image bits
+// (L1TxFullData, 624 bits for the first maxL1Tx slots, and L1L2TxData with the amount nullified,
+// 2 nLevels + 48 bits) and the three values that close the chains (newLastIdx, newStateRoot,
+// newExitRoot).  A rank's record: per own slot 624 + nL2 bytes (one bit per byte), then 3 x 32 B
+// values and 3 x 4 B flags saying which of them this rank produced.
+__host__ __device__ static inline uint32_t hz_rec_slot_bytes(const HzParams& P) { return 624u + 2u * (uint32_t)P.nLevels + 48u; }
+__host__ __device__ static inline uint32_t hz_rec_vals_off(const HzParams& P, int per) { return ((uint32_t)per * hz_rec_slot_bytes(P) + 3u) & ~3u; }
+__host__ __device__ static inline uint32_t hz_rec_bytes(const HzParams& P, int per) { return (hz_rec_vals_off(P, per) + 3 * 32 + 3 * 4 + 15u) & ~15u; }
+__global__ void k_pack(HzPlan pl, const Fr* w, const uint8_t* pre, uint8_t* rec, int s0, int ns, int per, int own_last_slot, int own_last_fee) {
+    const HzParams& P = pl.P;
+    const uint32_t sb = hz_rec_slot_bytes(P), nL2 = 2u * (uint32_t)P.nLevels + 48u;
+    const uint32_t p1 = hz_pre_pos_l1(P), p2 = hz_pre_pos_l2(P);
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (uint32_t e = gid; e < (uint32_t)per * sb; e += gsz) {
+        uint32_t q = e / sb, k = e % sb, i = (uint32_t)s0 + q;
+        uint8_t v = 0;
+        if ((int)q < ns) {
+            if (k < 624) v = (int)i < P.maxL1Tx ? pre[p1 + i * 624 + k] : 0;
+            else v = pre[p2 + i * nL2 + (k - 624)];
+        }
+        rec[e] = v;
+    }
+    if (gid == 0) {
+        uint32_t* out = reinterpret_cast<uint32_t*>(rec + hz_rec_vals_off(P, per));
+        Fr z = fr_zero();
+        const Fr& a = own_last_slot ? w[pl.idx_newLastIdx] : z;
+        const Fr& b = own_last_fee ? w[pl.idx_newStateRoot] : z;
+        const Fr& c = own_last_slot ? w[pl.idx_newExitRoot] : z;
+        for (int k = 0; k < 8; k++) { out[k] = a.l[k]; out[8 + k] = b.l[k]; out[16 + k] = c.l[k]; }
+        out[24] = (uint32_t)own_last_slot; out[25] = (uint32_t)own_last_fee; out[26] = (uint32_t)own_last_slot;
+    }
+}
+__global__ void k_unpack(HzPlan pl, Fr* w, uint8_t* pre, const uint8_t* recs, int world, int per, uint32_t rec_bytes) {
+    const HzParams& P = pl.P;
+    const uint32_t sb = hz_rec_slot_bytes(P), nL2 = 2u * (uint32_t)P.nLevels + 48u;
+    const uint32_t p1 = hz_pre_pos_l1(P), p2 = hz_pre_pos_l2(P);
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    const uint32_t tot = (uint32_t)world * (uint32_t)per * sb;
+    for (uint32_t e = gid; e < tot; e += gsz) {
+        uint32_t r = e / ((uint32_t)per * sb), x = e % ((uint32_t)per * sb);
+        uint32_t q = x / sb, k = x % sb, i = r * (uint32_t)per + q;
+        if ((int)i >= P.nTx) continue;
+        uint8_t v = recs[(size_t)r * rec_bytes + x];
+        if (k < 624) { if ((int)i < P.maxL1Tx) pre[p1 + i * 624 + k] = v; }
+        else pre[p2 + i * nL2 + (k - 624)] = v;
+    }
+    if (gid < 3) {
+        const uint32_t idx = gid == 0 ? pl.idx_newLastIdx : (gid == 1 ? pl.idx_newStateRoot : pl.idx_newExitRoot);
+        for (int r = 0; r < world; r++) {
+            const uint32_t* in = reinterpret_cast<const uint32_t*>(recs + (size_t)r * rec_bytes + hz_rec_vals_off(P, per));
+            if (in[24 + gid]) { Fr f; for (int k = 0; k < 8; k++) f.l[k] = in[8 * gid + k]; w[idx] = f; }
+        }
+    }
 }
 
 // ---- hasherInputs (src/hash-inputs.circom:23-185) ------------------------------------------------
@@ -271,8 +356,8 @@ __global__ void __launch_bounds__(256) k_sha_chain(HzPlan pl, const uint8_t* pre
 // thread recomputes the word values it needs from the block's chaining value and message words
 // (a few hundred integer instructions) and then emits the unit's ~450 bit signals.
 #define HZ_SHA_THREADS 128
-__global__ void __launch_bounds__(HZ_SHA_THREADS) k_sha_blocks(HzPlan pl, Fr* w, HzErrBuf* err, const uint32_t* chain, const uint32_t* msgw, const uint32_t* off_blocks) {
-    const uint32_t b = blockIdx.x;
+__global__ void __launch_bounds__(HZ_SHA_THREADS) k_sha_blocks(HzPlan pl, Fr* w, HzErrBuf* err, const uint32_t* chain, const uint32_t* msgw, const uint32_t* off_blocks, uint32_t b0) {
+    const uint32_t b = b0 + blockIdx.x;
     const int u = (int)threadIdx.x;
     const uint32_t base = *off_blocks + b * (uint32_t)HZ_SZ_SHA_BLOCK;
     uint32_t wv[64], hin[8];
@@ -335,6 +420,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     memset(d, 0, sizeof *d);
     d->device = device;
     d->plan = ph;
+    hz_set_ranges(d, 0, 1);
     const HzParams& P = ph.P;
     bool ok = true;
     if (ph.off_hasher + hz_head_off(ph).end != ph.off_sha_blocks) {
@@ -366,7 +452,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaEventCreateWithFlags(&d->ev_eddsa, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; k < HZ_NKERN + 2; k++) ok = ok && cudaEventCreate(&d->kev[k]) == cudaSuccess;
     // the per-thread frames of the circuit templates are large (sibling arrays, state machines)
-    ok = ok && cudaDeviceSetLimit(cudaLimitStackSize, 64 * 1024) == cudaSuccess;
+    ok = ok && cudaDeviceSetLimit(cudaLimitStackSize, 80 * 1024) == cudaSuccess;
     if (ok) {
         // record the input-independent part of the EdDSA fixed-base multiplication once
         Fr* wtmp = nullptr; uint32_t* counts = nullptr; uint32_t hc[2] = {0, 0};
@@ -397,7 +483,7 @@ void hz_cuda_destroy(HzCuda* d) {
     cudaSetDevice(d->device);
     cudaFree(d->w); cudaFree(d->pre); cudaFree(d->chain); cudaFree(d->msgw); cudaFree(d->jobs); cudaFree(d->err);
     cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit);
-    cudaFree(d->hint_cst); cudaFree(d->hint_tab); cudaFree(d->hint_scratch);
+    cudaFree(d->hint_cst); cudaFree(d->hint_tab); cudaFree(d->hint_scratch); cudaFree(d->recs);
     cudaFree(d->off_decode); cudaFree(d->off_rollup); cudaFree(d->off_fee); cudaFree(d->off_blocks);
     if (d->stream) cudaStreamDestroy(d->stream);
     if (d->stream2) cudaStreamDestroy(d->stream2);
@@ -409,46 +495,87 @@ void hz_cuda_destroy(HzCuda* d) {
     delete d;
 }
 
-int hz_cuda_calculate(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* witness_out, float* kernel_ms,
-                      HzErrBuf* errs, uint64_t* launches, uint64_t* h2d, uint64_t* d2h) {
+static void hz_set_ranges(HzCuda* d, int rank, int world) {
+    const HzParams& P = d->plan.P;
+    d->rank = rank; d->world = world;
+    d->per = (P.nTx + world - 1) / world;
+    d->s0 = rank * d->per < P.nTx ? rank * d->per : P.nTx;
+    d->ns = (d->s0 + d->per <= P.nTx ? d->per : P.nTx - d->s0);
+    int perf = (P.maxFeeTx + world - 1) / world;
+    d->f0 = rank * perf < P.maxFeeTx ? rank * perf : P.maxFeeTx;
+    d->nf = (d->f0 + perf <= P.maxFeeTx ? perf : P.maxFeeTx - d->f0);
+    uint32_t perb = (d->plan.nblocks + (uint32_t)world - 1) / (uint32_t)world;
+    d->b0 = (uint32_t)rank * perb < d->plan.nblocks ? (uint32_t)rank * perb : d->plan.nblocks;
+    d->nb = d->b0 + perb <= d->plan.nblocks ? perb : d->plan.nblocks - d->b0;
+}
+int hz_cuda_set_shard(HzCuda* d, int rank, int world) {
+    if (world < 1 || rank < 0 || rank >= world) return HZW_E_PARAM;
     CK(cudaSetDevice(d->device));
+    hz_set_ranges(d, rank, world);
+    if (d->recs) { cudaFree(d->recs); d->recs = nullptr; }
+    if (world > 1) CK(cudaMalloc(&d->recs, (size_t)world * hz_rec_bytes(d->plan.P, d->per)));
+    return 0;
+}
+uint64_t hz_cuda_exchange_bytes(const HzCuda* d) { return hz_rec_bytes(d->plan.P, d->per); }
+
+// phase 1: inputs to the device, then everything per slot / fee tx of the shard
+static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     const HzPlan& pl = d->plan;
-    const HzParams& P = pl.P;
-    cudaStream_t s = d->stream;
+    cudaStream_t s = d->stream, s2 = d->stream2;
     HzErrBuf* err = sanity ? d->err : nullptr;
     CK(cudaMemsetAsync(d->err, 0, sizeof(HzErrBuf), s));
     CK(cudaMemsetAsync(d->pre, 0, (size_t)pl.nblocks * 512, s));
     if (inputs) CK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(d->w) + 64, inputs, 32ull * pl.n_inputs, cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(d->ev0, s));
-    const int nTx = P.nTx, F = P.maxFeeTx, njobs = 2 * nTx + F;
-    cudaStream_t s2 = d->stream2;
+    const int s0 = d->s0, ns = d->ns, f0 = d->f0, nf = d->nf;
     CK(cudaEventRecord(d->kev[0], s));
-    k_front<<<hz_grid(nTx), HZ_BLOCK, 0, s>>>(pl, d->w, d->pre, err, d->jobs, d->smt, d->isExit);
+    if (ns > 0) k_front<<<hz_grid(ns), HZ_BLOCK, 0, s>>>(pl, d->w, d->pre, err, d->jobs, d->smt, d->isExit, s0, ns);
     CK(cudaEventRecord(d->kev[1], s));
     CK(cudaEventRecord(d->ev_front, s));
     // the signatures run beside the merkle levels: neither fills the machine alone
     CK(cudaStreamWaitEvent(s2, d->ev_front, 0));
     CK(cudaEventRecord(d->kev[9], s2));
-    k_eddsa<<<hz_grid(nTx), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_scratch);
+    if (ns > 0) k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_scratch, s0, ns);
     CK(cudaEventRecord(d->kev[10], s2));
     CK(cudaEventRecord(d->ev_eddsa, s2));
-    k_fee_front<<<hz_grid(F), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt + 2 * nTx);
+    if (nf > 0) k_fee_front<<<hz_grid(nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt + 2 * pl.P.nTx, f0, nf);
     CK(cudaEventRecord(d->kev[2], s));
-    k_smt<<<hz_grid(njobs), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt, d->mids, njobs);
+    if (2 * ns + nf > 0) k_smt<<<hz_grid(2 * ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt, d->mids, s0, ns, f0, nf);
     CK(cudaEventRecord(d->kev[3], s));
-    k_tail<<<hz_grid(nTx + F), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->mids, d->isExit);
+    if (ns + nf > 0) k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->mids, d->isExit, s0, ns, f0, nf);
     CK(cudaEventRecord(d->kev[4], s));
-    k_hash_head<<<148, 256, 0, s>>>(pl, d->w, d->pre, err, d->off_blocks);
+    return 0;
+}
+// phase 2: hasherInputs; every shard walks the whole SHA chain (it is serial and short) and expands
+// its own range of blocks
+static int hz_phase2(HzCuda* d, int sanity) {
+    const HzPlan& pl = d->plan;
+    cudaStream_t s = d->stream;
+    HzErrBuf* err = sanity ? d->err : nullptr;
+    k_hash_head<<<148, 256, 0, s>>>(pl, d->w, d->pre, d->rank == 0 ? err : nullptr, d->off_blocks);
     CK(cudaEventRecord(d->kev[5], s));
     k_sha_chain<<<1, 256, 0, s>>>(pl, d->pre, d->chain, d->msgw);
     CK(cudaEventRecord(d->kev[6], s));
-    k_sha_blocks<<<pl.nblocks, HZ_SHA_THREADS, 0, s>>>(pl, d->w, err, d->chain, d->msgw, d->off_blocks);
+    if (d->nb > 0) k_sha_blocks<<<d->nb, HZ_SHA_THREADS, 0, s>>>(pl, d->w, err, d->chain, d->msgw, d->off_blocks, d->b0);
     CK(cudaEventRecord(d->kev[7], s));
-    k_hash_tail<<<1, 32, 0, s>>>(pl, d->w, err, d->chain);
+    k_hash_tail<<<1, 32, 0, s>>>(pl, d->w, d->rank == 0 ? err : nullptr, d->chain);
     CK(cudaEventRecord(d->kev[8], s));
     CK(cudaStreamWaitEvent(s, d->ev_eddsa, 0));
     CK(cudaGetLastError());
     CK(cudaEventRecord(d->ev1, s));
+    return 0;
+}
+
+int hz_cuda_calculate(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* witness_out, float* kernel_ms,
+                      HzErrBuf* errs, uint64_t* launches, uint64_t* h2d, uint64_t* d2h) {
+    CK(cudaSetDevice(d->device));
+    if (d->world != 1) return HZW_E_PARAM;        // sharded contexts go through the two phases
+    const HzPlan& pl = d->plan;
+    cudaStream_t s = d->stream;
+    int st = hz_phase1(d, inputs, sanity);
+    if (st) return st;
+    st = hz_phase2(d, sanity);
+    if (st) return st;
     if (witness_out) CK(cudaMemcpyAsync(witness_out, d->w, 32ull * pl.nvars, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(errs, d->err, sizeof(HzErrBuf), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -456,6 +583,44 @@ int hz_cuda_calculate(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* wit
     if (launches) *launches = HZ_NKERN;
     if (h2d) *h2d = inputs ? 32ull * pl.n_inputs : 0;
     if (d2h) *d2h = (witness_out ? 32ull * pl.nvars : 0) + sizeof(HzErrBuf);
+    return 0;
+}
+
+// sharded phase 1: own slots / fee txs, then this rank's exchange record into `record_out` (device memory)
+int hz_cuda_shard_phase1(HzCuda* d, const uint8_t* inputs, int sanity, void* record_out, HzErrBuf* errs) {
+    CK(cudaSetDevice(d->device));
+    if (!record_out) return HZW_E_PARAM;
+    int st = hz_phase1(d, inputs, sanity);
+    if (st) return st;
+    const HzParams& P = d->plan.P;
+    int last_slot = d->ns > 0 && d->s0 + d->ns == P.nTx, last_fee = d->nf > 0 && d->f0 + d->nf == P.maxFeeTx;
+    k_pack<<<148, 256, 0, d->stream>>>(d->plan, d->w, d->pre, reinterpret_cast<uint8_t*>(record_out), d->s0, d->ns, d->per, last_slot, last_fee);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(errs, d->err, sizeof(HzErrBuf), cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));         // the host binding runs the all-gather on its own stream
+    return 0;
+}
+// sharded phase 2: `records` = the gathered records of all ranks (device memory); the shard's witness
+// pieces are copied to `shard_out` (host) back to back in hz_cuda_pieces order
+int hz_cuda_shard_phase2(HzCuda* d, const void* records, int sanity, uint8_t* shard_out, const uint64_t* pieces, int npieces,
+                         float* kernel_ms, HzErrBuf* errs, uint64_t* d2h) {
+    CK(cudaSetDevice(d->device));
+    if (!records) return HZW_E_PARAM;
+    cudaStream_t s = d->stream;
+    k_unpack<<<148, 256, 0, s>>>(d->plan, d->w, d->pre, reinterpret_cast<const uint8_t*>(records), d->world, d->per, hz_rec_bytes(d->plan.P, d->per));
+    int st = hz_phase2(d, sanity);
+    if (st) return st;
+    uint64_t bytes = 0;
+    if (shard_out)
+        for (int k = 0; k < npieces; k++) {
+            CK(cudaMemcpyAsync(shard_out + bytes, reinterpret_cast<const uint8_t*>(d->w) + 32ull * pieces[2 * k], 32ull * pieces[2 * k + 1], cudaMemcpyDeviceToHost, s));
+            bytes += 32ull * pieces[2 * k + 1];
+        }
+    CK(cudaMemcpyAsync(errs, d->err, sizeof(HzErrBuf), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(d->stream2));
+    if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, d->ev0, d->ev1));
+    if (d2h) *d2h = bytes + sizeof(HzErrBuf);
     return 0;
 }
 
@@ -468,4 +633,32 @@ int hz_cuda_kernel_ms(HzCuda* d, float* ms, const char** names, int cap) {
         if (names) names[k] = HZ_KERN_NAMES[k];
     }
     return n;
+}
+
+extern "C" int hzw_poseidon_bench(int device, uint64_t npairs, int reps, const uint8_t* inputs_le32 /* 4 x npairs */,
+                                  uint8_t* digests_le32 /* 2 x npairs, nullable */, float* ms_per_rep) {
+    if (npairs == 0 || npairs > (1u << 22) || !inputs_le32) return HZW_E_PARAM;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return HZW_E_DEVICE;
+    CK(cudaSetDevice(device));
+    const uint32_t size = 1 + 2 * 3 * 65 + 3 * (8 * 3 + 57);   // poseidon_size(3): entries of a wired Poseidon(2)
+    Fr *in = nullptr, *sig = nullptr, *dg = nullptr;
+    cudaEvent_t e0, e1;
+    CK(cudaMalloc(&in, 128ull * npairs));
+    CK(cudaMalloc(&sig, 64ull * size * npairs));
+    CK(cudaMalloc(&dg, 64ull * npairs));
+    CK(cudaMemcpy(in, inputs_le32, 128ull * npairs, cudaMemcpyHostToDevice));
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    k_poseidon_pairs<<<hz_grid((int)npairs), HZ_BLOCK>>>(in, sig, dg, (int)npairs);      // warm-up
+    CK(cudaEventRecord(e0));
+    for (int r = 0; r < reps; r++) k_poseidon_pairs<<<hz_grid((int)npairs), HZ_BLOCK>>>(in, sig, dg, (int)npairs);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms_per_rep) *ms_per_rep = ms / (reps > 0 ? reps : 1);
+    if (digests_le32) CK(cudaMemcpy(digests_le32, dg, 64ull * npairs, cudaMemcpyDeviceToHost));
+    cudaFree(in); cudaFree(sig); cudaFree(dg); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
 }

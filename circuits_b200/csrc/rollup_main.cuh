@@ -248,7 +248,8 @@ __device__ __forceinline__ VC hz_smt_top(Comp<MCompute>& c, const HzSmtMid& m, c
 }
 // tops of processor 1 and 2, s3, s4, s5 and the root checks of slot i (k_tail)
 __device__ __noinline__ void sec_rollup_tail(Fr* w, HzErrBuf* err, const HzPlan& pl, int i, const HzSmtMid* mids, const Fr& isExit_) {
-    Comp<MCompute> c(w, mids[0].cur, err);
+    HzPending pend; pend.n = 0;
+    Comp<MCompute> c(w, mids[0].cur, err, nullptr, &pend);
     VC oldStateRoot = i == 0 ? hz_in(c, pl, IN_oldStateRoot) : hz_in(c, pl, IN_imStateRoot, i - 1);
     VC oldExitRoot = i == 0 ? hz_sigv(fr_zero(), true) : hz_in(c, pl, IN_imExitRoot, i - 1);
     VC isExit = hz_sigv(isExit_, true);
@@ -258,13 +259,16 @@ __device__ __noinline__ void sec_rollup_tail(Fr* w, HzErrBuf* err, const HzPlan&
     VC newStateRoot = Mux1(c.sub("s4"), p2, p1, isExit);
     VC newExitRoot = Mux1(c.sub("s5"), oldExitRoot, p2, isExit);
     sec_rollup_root_checks(c, pl, i, newStateRoot, newExitRoot);
+    c.flush_pending();
 }
 // top of the processor of fee tx i
 __device__ __noinline__ void sec_fee_tail(Fr* w, HzErrBuf* err, const HzPlan& pl, int i, const HzSmtMid& mid) {
-    Comp<MCompute> c(w, mid.cur, err);
+    HzPending pend; pend.n = 0;
+    Comp<MCompute> c(w, mid.cur, err, nullptr, &pend);
     VC oldStateRoot = i == 0 ? hz_in(c, pl, IN_imInitStateRootFee) : hz_in(c, pl, IN_imStateRootFee, i - 1);
     VC r = hz_smt_top(c, mid, oldStateRoot);
     if (c.sanity() && i < pl.P.maxFeeTx - 1) c.check(r, hz_in(c, pl, IN_imStateRootFee, i), __LINE__);
+    c.flush_pending();
 }
 #endif
 

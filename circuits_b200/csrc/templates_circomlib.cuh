@@ -130,8 +130,8 @@ TM HZ_FN BV<M> Num2Bits_strict(Comp<M>&& c, const V<M>& x) {
 TM HZ_FN V<M> IsZero(Comp<M>&& c, const V<M>& x) {
     V<M> in_ = c.def("in", x);
     uint32_t out = c.sig("out");
-    V<M> inv_ = c.def("inv", vinv(in_));
-    V<M> o = c.set(out, 1 - in_ * inv_);
+    // out = -in * inv + 1 is (in == 0) for the inv the template prescribes; the inverse itself may be deferred
+    V<M> o = c.set(out, c.iszero_inv("inv", in_));
     HZ_CHECK0(c, in_ * o);
     return o;
 }
@@ -861,8 +861,16 @@ TM HZ_FN void BabyCheck(Comp<M>&& c, const V<M>& x, const V<M>& y) {
 TM HZ_FN PtV<M> Edwards2Montgomery(Comp<M>&& c, const V<M>& x, const V<M>& y, int hc = 0) {
     V<M> i0 = c.def(Nm("in", 0), x), i1 = c.def(Nm("in", 1), y);
     PtV<M> r;
-    r.x = c.def(Nm("out", 0), c.div(1 + i1, 1 - i1, hc));
-    r.y = c.def(Nm("out", 1), c.div(r.x, i0, hc));
+    if (hc == 0) {
+        // u = (1+y)/(1-y), v = u/x = (1+y)/((1-y) x): one inversion for both
+        V<M> u, v;
+        c.div2(1 + i1, 1 - i1, 1 + i1, (1 - i1) * i0, u, v);
+        r.x = c.def(Nm("out", 0), u);
+        r.y = c.def(Nm("out", 1), v);
+    } else {
+        r.x = c.def(Nm("out", 0), c.div(1 + i1, 1 - i1, hc));
+        r.y = c.def(Nm("out", 1), c.div(r.x, i0, hc));
+    }
     HZ_CHECK(c, r.x * (1 - i1), 1 + i1);
     HZ_CHECK(c, r.y * i0, r.x);
     return r;
@@ -870,8 +878,15 @@ TM HZ_FN PtV<M> Edwards2Montgomery(Comp<M>&& c, const V<M>& x, const V<M>& y, in
 TM HZ_FN PtV<M> Montgomery2Edwards(Comp<M>&& c, const V<M>& u, const V<M>& v, int hc = 0) {
     V<M> i0 = c.def(Nm("in", 0), u), i1 = c.def(Nm("in", 1), v);
     PtV<M> r;
-    r.x = c.def(Nm("out", 0), c.div(i0, i1, hc));
-    r.y = c.def(Nm("out", 1), c.div(i0 - 1, i0 + 1, hc));
+    if (hc == 0) {
+        V<M> x, y;
+        c.div2(i0, i1, i0 - 1, i0 + 1, x, y);
+        r.x = c.def(Nm("out", 0), x);
+        r.y = c.def(Nm("out", 1), y);
+    } else {
+        r.x = c.def(Nm("out", 0), c.div(i0, i1, hc));
+        r.y = c.def(Nm("out", 1), c.div(i0 - 1, i0 + 1, hc));
+    }
     HZ_CHECK(c, r.x * i1, i0);
     HZ_CHECK(c, r.y * (i0 + 1), i0 - 1);
     return r;

@@ -41,7 +41,8 @@ class _Error(ctypes.Structure):
 
 EXPORTS = ["hzw_create", "hzw_destroy", "hzw_nvars", "hzw_ninputs", "hzw_input_index", "hzw_calculate",
            "hzw_calculate_batch", "hzw_calculate_resident", "hzw_write_wtns", "hzw_get_signal", "hzw_dump_sym",
-           "hzw_last_stats", "hzw_last_kernel_ms", "hzw_plan_info"]
+           "hzw_last_stats", "hzw_last_kernel_ms", "hzw_plan_info", "hzw_set_shard", "hzw_exchange_bytes",
+           "hzw_shard_pieces", "hzw_shard_nvars", "hzw_shard_phase1", "hzw_shard_phase2", "hzw_poseidon_bench"]
 
 
 def load_library(path=None):
@@ -72,6 +73,16 @@ def load_library(path=None):
     lib.hzw_plan_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
     lib.hzw_last_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64),
                                    ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    lib.hzw_set_shard.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32]
+    lib.hzw_exchange_bytes.argtypes = [ctypes.c_void_p]
+    lib.hzw_exchange_bytes.restype = ctypes.c_uint64
+    lib.hzw_shard_pieces.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int32]
+    lib.hzw_shard_nvars.argtypes = [ctypes.c_void_p]
+    lib.hzw_shard_nvars.restype = ctypes.c_uint64
+    lib.hzw_shard_phase1.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.POINTER(_Error)]
+    lib.hzw_shard_phase2.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_Error)]
     return lib
 
 
@@ -182,9 +193,10 @@ class WitnessCalculator:
         return ms.value
 
     def planInfo(self):
-        out = (ctypes.c_uint64 * 9)()
+        out = (ctypes.c_uint64 * 12)()
         self._lib.hzw_plan_info(self._ctx, out)
-        keys = ["nvars", "ninputs", "getAx", "sigVerifier", "sha_block", "sha_blocks", "feeTx", "decodeTx", "rollupTx"]
+        keys = ["nvars", "ninputs", "getAx", "sigVerifier", "sha_block", "sha_blocks", "feeTx", "decodeTx", "rollupTx",
+                "processors", "processor2_off", "hasher_head"]
         return dict(zip(keys, [int(x) for x in out]))
 
     def lastKernelMs(self):
@@ -243,3 +255,109 @@ class WitnessCalculator:
         wb = bytearray(witness)
         if self._lib.hzw_write_wtns(self._ctx, _addr(wb), path.encode()) != 0:
             raise WitnessError("cannot write %s" % path)
+
+
+class ShardedWitnessCalculator(WitnessCalculator):
+    """One batch on `world` GPUs, one process per GPU (`torch.distributed`).
+
+    The circuit cuts every cross-slot dependency with its `im*` inputs
+    (/root/reference/src/rollup-main.circom:93-99; the reference runs a thread per RollupTx /
+    DecodeTx / FeeTx component on that basis, tools/helpers/actions.js:41).  Rank r evaluates a
+    contiguous range of tx slots, fee txs and SHA blocks; what hasherInputs needs from the other
+    ranks (their slots' pre-image bits and the three chain ends) travels in ONE all-gather between
+    the two phases.  Each rank ends up with the witness pieces it owns (`pieces()`), copied back to
+    back into its own host buffer -- the 8 GB witness never crosses NVLink.
+
+    `record_device`: "cuda" for libhzwitness.so (records are device memory, collective = NCCL),
+    "cpu" for the CPU port used by the gloo tests.
+    """
+
+    def __init__(self, nTx, nLevels, maxL1Tx, maxFeeTx, rank, world, device=0, lib_path=None, group=None,
+                 record_device="cuda"):
+        super().__init__(nTx, nLevels, maxL1Tx, maxFeeTx, device=device, lib_path=lib_path)
+        import torch
+        self.rank, self.world, self.group = rank, world, group
+        if self._lib.hzw_set_shard(self._ctx, rank, world) != 0:
+            raise WitnessError("hzw_set_shard(%d, %d) failed" % (rank, world))
+        self.recBytes = int(self._lib.hzw_exchange_bytes(self._ctx))
+        dev = torch.device("cuda", device) if record_device == "cuda" else torch.device("cpu")
+        self._rec = torch.zeros(self.recBytes, dtype=torch.uint8, device=dev)
+        self._recs = torch.zeros(self.recBytes * world, dtype=torch.uint8, device=dev)
+        self.shardNVars = int(self._lib.hzw_shard_nvars(self._ctx))
+
+    def pieces(self):
+        """[(witness index, count)] of the pieces this rank owns, in the order they are copied out."""
+        t = (ctypes.c_uint64 * 32)()
+        n = self._lib.hzw_shard_pieces(self._ctx, t, 16)
+        return [(int(t[2 * k]), int(t[2 * k + 1])) for k in range(n)]
+
+    def phase1(self, packed, sanityCheck=False):
+        """Own slots and fee txs; leaves this rank's exchange record in `self._rec`."""
+        err = _Error()
+        st = self._lib.hzw_shard_phase1(self._ctx, None if packed is None else _addr(packed), 1 if sanityCheck else 0,
+                                        self._rec.data_ptr(), ctypes.byref(err))
+        if st != 0:
+            self._raise(st, err)
+
+    def phase2(self, sanityCheck=False, out=None, resident=False):
+        """hasherInputs from the gathered records in `self._recs`; copies the own pieces out."""
+        err = _Error()
+        ms = ctypes.c_float()
+        buf = None if resident else (out if out is not None else bytearray(32 * self.shardNVars))
+        st = self._lib.hzw_shard_phase2(self._ctx, self._recs.data_ptr(), 1 if sanityCheck else 0,
+                                        None if buf is None else _addr(buf), ctypes.byref(ms), ctypes.byref(err))
+        if st != 0:
+            self._raise(st, err)
+        return buf, ms.value
+
+    def exchange(self):
+        """The one collective of a batch: all-gather of the per-rank records."""
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            if self._rec.is_cuda:
+                dist.all_gather_into_tensor(self._recs, self._rec, group=self.group)
+                torch.cuda.current_stream().synchronize()
+            else:
+                parts = list(self._recs.split(self.recBytes))
+                dist.all_gather(parts, self._rec, group=self.group)
+        else:
+            self._recs.copy_(self._rec)
+            if self._rec.is_cuda:
+                torch.cuda.current_stream().synchronize()
+
+    def calculateShard(self, packed, sanityCheck=False, out=None, resident=False):
+        """Both phases and the all-gather; returns (shard buffer, device ms of this rank's kernels)."""
+        self.phase1(packed, sanityCheck)
+        self.exchange()
+        return self.phase2(sanityCheck, out, resident)
+
+    @staticmethod
+    def assemble(nvars, shards):
+        """Full witness from [(pieces, shard bytes)] of all ranks (tests / single-host consumers)."""
+        w = bytearray(32 * nvars)
+        for pcs, data in shards:
+            off = 0
+            mv = memoryview(data)
+            for idx, cnt in pcs:
+                w[32 * idx:32 * (idx + cnt)] = mv[off:off + 32 * cnt]
+                off += 32 * cnt
+        return w
+
+
+def poseidon_pairs(inputs, reps=1, device=0, lib_path=None):
+    """Run Poseidon(2) on pairs of pairs of field elements on the GPU (`hzw_poseidon_bench`):
+    inputs = [(a, b, c, d), ...] -> ([(poseidon([a, b]), poseidon([c, d])), ...], device ms per repetition)."""
+    lib = load_library(lib_path)
+    lib.hzw_poseidon_bench.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.POINTER(ctypes.c_float)]
+    n = len(inputs)
+    buf = bytearray(b"".join(int(x % P).to_bytes(32, "little") for quad in inputs for x in quad))
+    out = bytearray(64 * n)
+    ms = ctypes.c_float()
+    st = lib.hzw_poseidon_bench(device, n, reps, _addr(buf), _addr(out), ctypes.byref(ms))
+    if st != 0:
+        raise WitnessError("hzw_poseidon_bench failed with code %d" % st)
+    dig = [(int.from_bytes(out[64 * i:64 * i + 32], "little"), int.from_bytes(out[64 * i + 32:64 * i + 64], "little"))
+           for i in range(n)]
+    return dig, ms.value

@@ -80,13 +80,44 @@ int hzw_get_signal(const hzw_ctx* ctx, const uint8_t* witness, const char* name,
 /* writes "index,name" lines (the `.sym` equivalent) for every signal whose name starts with prefix */
 int hzw_dump_sym(const hzw_ctx* ctx, const char* prefix, const char* path);
 /* sizes the layout walk derived, in witness entries: [0] nvars, [1] ninputs, [2] getAx, [3] sigVerifier,
- * [4] one sha256compression, [5] sha blocks, [6] feeTx[0], [7] decodeTx[1], [8] rollupTx[1] (0 if nTx < 2) */
-int hzw_plan_info(const hzw_ctx* ctx, uint64_t out[9]);
+ * [4] one sha256compression, [5] sha blocks, [6] feeTx[0], [7] decodeTx[1], [8] rollupTx[1] (0 if nTx < 3),
+ * [9] processor1 + s3 + processor2 + s4 + s5 of a RollupTx, [10] offset of processor2 in it, [11] head of hasherInputs */
+int hzw_plan_info(const hzw_ctx* ctx, uint64_t out[12]);
 /* device time of each kernel of the last calculate, in launch order; names are static strings.
  * Returns the number of kernels (<= cap). */
 int hzw_last_kernel_ms(const hzw_ctx* ctx, float* ms, const char** names, int cap);
 /* static description of what the last calculate launched: kernels and bytes, for the bench */
 int hzw_last_stats(const hzw_ctx* ctx, uint64_t* gpu_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
+
+/* ---- one batch on several GPUs -------------------------------------------------------------------
+ * The tx slots of a batch are independent given the intermediary inputs (`im*`,
+ * /root/reference/src/rollup-main.circom:93-99): the reference exploits this with one thread per
+ * RollupTx/DecodeTx/FeeTx component (`circom -n`, /root/reference/tools/helpers/actions.js:41); here a
+ * context per GPU evaluates a contiguous range of slots, fee txs and SHA blocks.  The only thing a
+ * rank needs from the others is what hasherInputs hashes: their slots' pre-image bits and the three
+ * chain ends (newLastIdx, newStateRoot, newExitRoot) -- one fixed-size record per rank, exchanged by
+ * the caller with ONE all-gather (NCCL in the Python binding) between the two phases.
+ *   hzw_set_shard      rank / world of this context (default 0 / 1: everything)
+ *   hzw_exchange_bytes size of one rank's record
+ *   hzw_shard_phase1   inputs -> own slots and fee txs; writes the own record to record_out
+ *   hzw_shard_phase2   records = world x exchange_bytes, gathered; hasherInputs, own SHA blocks; copies the
+ *                      witness pieces this rank owns to shard_out, back to back
+ *   hzw_shard_pieces   the (witness index, count) pairs of those pieces; hzw_shard_nvars their total
+ * record_out / records are DEVICE pointers for libhzwitness.so (the collective runs on device memory). */
+int hzw_set_shard(hzw_ctx* ctx, int32_t rank, int32_t world);
+uint64_t hzw_exchange_bytes(const hzw_ctx* ctx);
+int hzw_shard_pieces(const hzw_ctx* ctx, uint64_t* table /* 2 x cap */, int32_t cap);
+uint64_t hzw_shard_nvars(const hzw_ctx* ctx);
+int hzw_shard_phase1(hzw_ctx* ctx, const uint8_t* inputs_le32, int sanity_check, void* record_out, hzw_error* err);
+int hzw_shard_phase2(hzw_ctx* ctx, const void* records, int sanity_check, uint8_t* shard_out, float* kernel_ms, hzw_error* err);
+
+/* Poseidon alone, the second metric of the benchmark: `npairs` lane groups, each running two
+ * Poseidon(2) permutations (the old-path / new-path hash pair of an SMT level,
+ * circomlib smtprocessorlevel.circom via /root/reference/src/rollup-tx.circom:537) on the given
+ * inputs and storing all signals of both components, `reps` times; device ms per repetition. */
+int hzw_poseidon_bench(int device, uint64_t npairs, int reps, const uint8_t* inputs_le32 /* 4 x npairs x 32 B */,
+                       uint8_t* digests_le32 /* 2 x npairs x 32 B, nullable */, float* ms_per_rep);
 
 #ifdef __cplusplus
 }

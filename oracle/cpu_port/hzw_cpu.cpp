@@ -44,23 +44,24 @@ struct CpuBackend : HzBackend {
             if (counts[0] > HZ_CST_MAX || counts[1] != HZ_EDTAB_LEN) { fprintf(stderr, "hzw cpu port: hint table sizes %u %u\n", counts[0], counts[1]); abort(); }
         }
     }
-    int calculate(const uint8_t* inputs, int sanity, uint8_t* out, bool resident, float* ms, HzErrBuf* errs) override {
-        if (resident || !out) return HZW_E_PARAM;
-        (void)ms;
+    // ---- evaluation in two phases (a shard of the batch, or all of it) ---------------------------
+    HzShard sh;
+    std::vector<Fr> wbuf;                   // sharded runs keep a full-size witness of their own
+    std::vector<uint8_t> preb;
+    int stride = 1;
+    void phase1(Fr* w, const uint8_t* inputs, HzErrBuf* err) {
         const HzPlan& pl = L.plan;
-        const HzParams& P = pl.P;
-        Fr* w = reinterpret_cast<Fr*>(out);
         memset(&w[0], 0, 64);
         w[0].l[0] = 1;
         memcpy(&w[2], inputs, 32ull * pl.n_inputs);
-        HzErrBuf* err = sanity ? errs : nullptr;
         // bounded sample for the CPU-baseline timing: only every `stride`-th slot / fee tx / block
-        int stride = 1;
+        stride = 1;
         { const char* e = getenv("HZW_CPU_SAMPLE_STRIDE"); if (e && atoi(e) > 1) stride = atoi(e); }
-        std::vector<uint8_t> preb((size_t)pl.nblocks * 512, 0);
+        preb.assign((size_t)pl.nblocks * 512, 0);
         PreBits<MCompute> pre; pre.b = preb.data();
         SlotHook<MCompute> hook; hook.eddsa = nullptr; hook.smt = nullptr; hook.isExit = nullptr; hook.sz = &pl.sz;
-        hz_parallel_for(P.nTx, [&](int i) {
+        hz_parallel_for(sh.ns, [&](int q) {
+            int i = sh.s0 + q;
             if (i % stride) return;
             std::vector<Fr> scratch(use_hints ? HZ_HINT_SCRATCH : 0);
             HzHints h;
@@ -74,13 +75,18 @@ struct CpuBackend : HzBackend {
             RollupTxOut<MCompute> o;
             sec_rollup(c, pl, i, d, o, p2, hook);
         });
-        hz_parallel_for(P.maxFeeTx, [&](int i) {
+        hz_parallel_for(sh.nf, [&](int q) {
+            int i = sh.f0 + q;
             if (i % stride) return;
             Comp<MCompute> c(w, pl.off_fee[i], err);
             FeeHook<MCompute> fh; fh.smt = nullptr; fh.sib_idx = 0;
             sec_fee(c, pl, i, fh);
         });
-        Comp<MCompute> hc(w, pl.off_hasher, err);
+    }
+    void phase2(Fr* w, HzErrBuf* err) {
+        const HzPlan& pl = L.plan;
+        PreBits<MCompute> pre; pre.b = preb.data();
+        Comp<MCompute> hc(w, pl.off_hasher, sh.rank == 0 ? err : nullptr);
         uint32_t off_blocks = 0;
         W32<MCompute> ha[8];
         sec_hasher_head(hc, pl, pre, &off_blocks, ha);
@@ -98,22 +104,85 @@ struct CpuBackend : HzBackend {
             hz_sha256_compress(st, &msgw[(size_t)b * 16]);
             for (int j = 0; j < 8; j++) chain[(size_t)(b + 1) * 8 + j] = st[j];
         }
-        hz_parallel_for((int)pl.nblocks, [&](int b) {
+        hz_parallel_for((int)sh.nb, [&](int q) {
+            int b = (int)sh.b0 + q;
             if (b % stride) return;
-            Comp<MCompute> sh(w, off_blocks + (uint32_t)b * HZ_SZ_SHA_BLOCK, err);
+            Comp<MCompute> shc(w, off_blocks + (uint32_t)b * HZ_SZ_SHA_BLOCK, err);
             W32<MCompute> hin[8], msg[16], outw[8];
             for (int j = 0; j < 8; j++) hin[j].v = chain[(size_t)b * 8 + j];
             for (int t = 0; t < 16; t++) msg[t].v = msgw[(size_t)b * 16 + t];
-            sec_sha_block(sh, b, hin, msg, outw);
+            sec_sha_block(shc, b, hin, msg, outw);
         });
         W32<MCompute> dig[8];
         for (int j = 0; j < 8; j++) dig[j].v = chain[(size_t)pl.nblocks * 8 + j];
-        Comp<MCompute> tc(w, pl.off_hasher_tail, err);
-        Comp<MCompute> shc(w, pl.off_hasher_tail, err);
+        Comp<MCompute> tc(w, pl.off_hasher_tail, sh.rank == 0 ? err : nullptr);
+        Comp<MCompute> shc(w, pl.off_hasher_tail, nullptr);
         VC h = sec_hasher_tail(tc, shc, dig);
         w[1] = h.v;
+    }
+    int calculate(const uint8_t* inputs, int sanity, uint8_t* out, bool resident, float* ms, HzErrBuf* errs) override {
+        if (resident || !out || sh.world != 1) return HZW_E_PARAM;
+        (void)ms;
+        Fr* w = reinterpret_cast<Fr*>(out);
+        HzErrBuf* err = sanity ? errs : nullptr;
+        phase1(w, inputs, err);
+        phase2(w, err);
+        return 0;
+    }
+    // ---- shards: the same protocol as the CUDA library, records in host memory -------------------
+    int set_shard(int rank, int world) override { sh = hz_shard_ranges(L.plan, rank, world); return 0; }
+    uint64_t exchange_bytes() override { return hz_xrec_bytes(L.plan.P, sh.per); }
+    int pieces(uint64_t* table, int cap) override { return hz_shard_pieces(L, sh, table, cap); }
+    int shard_phase1(const uint8_t* inputs, int sanity, void* record_out, HzErrBuf* errs) override {
+        const HzPlan& pl = L.plan;
+        const HzParams& P = pl.P;
+        wbuf.assign(pl.nvars, fr_zero());
+        phase1(wbuf.data(), inputs, sanity ? errs : nullptr);
+        uint8_t* rec = static_cast<uint8_t*>(record_out);
+        memset(rec, 0, hz_xrec_bytes(P, sh.per));
+        const uint32_t sb = hz_xrec_slot_bytes(P), nL2 = sb - 624, p1 = hz_pre_pos_l1(P), p2 = hz_pre_pos_l2(P);
+        for (int q = 0; q < sh.ns; q++) {
+            uint32_t i = (uint32_t)(sh.s0 + q);
+            if ((int)i < P.maxL1Tx) memcpy(rec + (size_t)q * sb, &preb[p1 + i * 624], 624);
+            memcpy(rec + (size_t)q * sb + 624, &preb[p2 + i * nL2], nL2);
+        }
+        uint32_t* out = reinterpret_cast<uint32_t*>(rec + hz_xrec_vals_off(P, sh.per));
+        bool last_slot = sh.ns > 0 && sh.s0 + sh.ns == P.nTx, last_fee = sh.nf > 0 && sh.f0 + sh.nf == P.maxFeeTx;
+        if (last_slot) { memcpy(out, wbuf[pl.idx_newLastIdx].l, 32); memcpy(out + 16, wbuf[pl.idx_newExitRoot].l, 32); }
+        if (last_fee) memcpy(out + 8, wbuf[pl.idx_newStateRoot].l, 32);
+        out[24] = last_slot; out[25] = last_fee; out[26] = last_slot;
+        return 0;
+    }
+    int shard_phase2(const void* records, int sanity, uint8_t* shard_out, float* ms, HzErrBuf* errs) override {
+        (void)ms;
+        const HzPlan& pl = L.plan;
+        const HzParams& P = pl.P;
+        const uint8_t* recs = static_cast<const uint8_t*>(records);
+        const uint32_t sb = hz_xrec_slot_bytes(P), nL2 = sb - 624, p1 = hz_pre_pos_l1(P), p2 = hz_pre_pos_l2(P);
+        const size_t rb = hz_xrec_bytes(P, sh.per);
+        for (int r = 0; r < sh.world; r++) {
+            for (int q = 0; q < sh.per; q++) {
+                uint32_t i = (uint32_t)(r * sh.per + q);
+                if ((int)i >= P.nTx) break;
+                if ((int)i < P.maxL1Tx) memcpy(&preb[p1 + i * 624], recs + r * rb + (size_t)q * sb, 624);
+                memcpy(&preb[p2 + i * nL2], recs + r * rb + (size_t)q * sb + 624, nL2);
+            }
+            const uint32_t* in = reinterpret_cast<const uint32_t*>(recs + r * rb + hz_xrec_vals_off(P, sh.per));
+            if (in[24]) memcpy(wbuf[pl.idx_newLastIdx].l, in, 32);
+            if (in[25]) memcpy(wbuf[pl.idx_newStateRoot].l, in + 8, 32);
+            if (in[26]) memcpy(wbuf[pl.idx_newExitRoot].l, in + 16, 32);
+        }
+        phase2(wbuf.data(), sanity ? errs : nullptr);
+        if (shard_out) {
+            uint64_t t[32]; int n = hz_shard_pieces(L, sh, t, 16); size_t off = 0;
+            for (int k = 0; k < n; k++) { memcpy(shard_out + off, &wbuf[t[2 * k]], 32 * t[2 * k + 1]); off += 32 * t[2 * k + 1]; }
+        }
         return 0;
     }
 };
 
-HzBackend* hz_backend_create(const hzw_params&, const HzLayout& L, int*) { return new CpuBackend(L); }
+HzBackend* hz_backend_create(const hzw_params&, const HzLayout& L, int*) {
+    CpuBackend* b = new CpuBackend(L);
+    b->sh = hz_shard_ranges(L.plan, 0, 1);
+    return b;
+}

@@ -14,7 +14,7 @@ def test_cuda_library_exports_every_declared_symbol(built):
     """include/hzwitness.h <-> libhzwitness.so; no compute call (no GPU here)."""
     import re
     hdr = open(os.path.join(ROOT, "include", "hzwitness.h")).read()
-    declared = sorted(set(re.findall(r"\b(hzw_[a-z_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"\b(hzw_[a-z_0-9]+)\s*\(", hdr)))
     assert len(declared) >= 12
     lib = ctypes.CDLL(CUDA_LIB)
     for name in declared:

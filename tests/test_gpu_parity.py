@@ -67,3 +67,45 @@ def test_constraint_violation_on_gpu(built, small_bb):
         wc.calculateWitness(inp, True)
     assert "main.rollupTx[0].processor1.checkOldInput" in str(e.value)
     assert len(wc.calculateWitness(inp, False)) == wc.NVars
+
+
+def test_two_shards_on_one_gpu_equal_the_whole(built):
+    """The CUDA side of the multi-GPU protocol without a second GPU: two contexts (rank 0 and 1 of 2)
+    on this device, their exchange records concatenated by hand where NCCL's all-gather would be.
+    The assembled pieces must equal the single-context witness byte for byte."""
+    import torch
+    from circuits_b200.synth import bench_batch
+    from circuits_b200.witness_calculator import ShardedWitnessCalculator
+    prm = (24, 32, 8, 4)
+    bb = bench_batch(*prm, n_accounts=16)
+    whole = _cuda(*prm)
+    packed = whole.packInput(bb.getInput())
+    want = bytes(whole.calculateBinWitness(packed, True))
+    ranks = [ShardedWitnessCalculator(*prm, rank=r, world=2) for r in range(2)]
+    for wc in ranks:
+        wc.phase1(packed, True)
+    recs = torch.cat([wc._rec for wc in ranks])
+    shards = []
+    for wc in ranks:
+        wc._recs.copy_(recs)
+        torch.cuda.synchronize()
+        buf, _ = wc.phase2(True)
+        shards.append((wc.pieces(), bytes(buf)))
+    assert sum(c for pcs, _ in shards for _, c in pcs) == whole.NVars
+    assert bytes(ShardedWitnessCalculator.assemble(whole.NVars, shards)) == want
+
+
+def test_poseidon_lane_kernel_known_answers(built):
+    """The lane-parallel permutation on its own: circomlib's published vector poseidon([1, 2]) and
+    seeded random pairs against the oracle's big-integer Poseidon."""
+    import random
+    from circuits_b200.witness_calculator import poseidon_pairs
+    from oracle.poseidon_constants import poseidon_hash
+    from oracle.field import P
+    rng = random.Random(7)
+    quads = [(1, 2, 3, 4)] + [tuple(rng.randrange(P) for _ in range(4)) for _ in range(37)]
+    quads += [(0, 0, P - 1, P - 1)]
+    got, _ = poseidon_pairs(quads)
+    assert got[0][0] == 0x115cc0f5e7d690413df64c6b9662e9cf2a3617f2743245519e19607a4417189a
+    for (a, b, c, d), (x, y) in zip(quads, got):
+        assert x == poseidon_hash([a, b]) and y == poseidon_hash([c, d])
