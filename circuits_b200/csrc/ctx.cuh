@@ -89,10 +89,10 @@ HZ_HD VC operator*(const VC& a, const VC& b) { return vc(fr_mul(a.v, b.v)); }
 HZ_HD VC operator-(const VC& a) { return vc(fr_neg(a.v)); }
 HZ_HD VC operator+(const VC& a, uint64_t k) { return vc(fr_add(a.v, fr_from_u64(k))); }
 HZ_HD VC operator-(const VC& a, uint64_t k) { return vc(fr_sub(a.v, fr_from_u64(k))); }
-HZ_HD VC operator*(const VC& a, uint64_t k) { return vc(fr_mul(a.v, fr_from_u64(k))); }
+HZ_HD VC operator*(const VC& a, uint64_t k) { return vc(fr_mul_u64(a.v, k)); }
 HZ_HD VC operator-(uint64_t k, const VC& a) { return vc(fr_sub(fr_from_u64(k), a.v)); }
 HZ_HD VC operator+(uint64_t k, const VC& a) { return vc(fr_add(fr_from_u64(k), a.v)); }
-HZ_HD VC operator*(uint64_t k, const VC& a) { return vc(fr_mul(a.v, fr_from_u64(k))); }
+HZ_HD VC operator*(uint64_t k, const VC& a) { return vc(fr_mul_u64(a.v, k)); }
 HZ_HD VC vinv(const VC& a) { return vc(fr_inv(a.v)); }
 HZ_HD VC vdiv(const VC& a, const VC& b) { return vc(fr_mul(a.v, fr_inv(b.v))); }
 HZ_HD uint32_t vbit(const VC& a, int i) { return fr_bit(a.v, i); }
@@ -191,7 +191,11 @@ static inline std::string hz_nm(const Nm& n) {
 //            in projective Edwards coordinates and inverts all denominators with one inversion.
 // With no stream installed (CPU port by default, layout walk) a site inverts on the spot.  A wrong
 // hint cannot pass unnoticed: every such site is followed by its `===` check.
+#ifdef HZ_DEVICE_ONLY
+#define HZ_HINT_SCRATCH (4 * 600)
+#else
 #define HZ_HINT_SCRATCH (4 * 300)
+#endif
 #define HZ_HINT_MAX 300                    /* data hints of one component (SegmentMulAny(148): 294) */
 #define HZ_EDTAB_SEG1 (83 * 16 + 2)        /* window table: per window 8 points (u, v), then dblLast */
 #define HZ_EDTAB_LEN (HZ_EDTAB_SEG1 + 2 * 16 + 2)
@@ -203,6 +207,9 @@ struct HzHints {
     const Fr* edtab;                       // window entries of EscalarMulFix (affine Montgomery points)
     Fr* edrec; uint32_t ei;                // record mode for the table
     Fr* scratch;                           // HZ_HINT_SCRATCH entries owned by this lane group / thread
+    int lad_ok;                            // device: scratch[0 .. 588) holds the hints of all ladders (hints.cuh)
+    const Fr* cimg; uint32_t fix_shift;    // witness image of EscalarMulFix from the recording pass, and where the
+                                           // component being evaluated starts: its constant entries are copied
 };
 
 // ---- deferred inverses -----------------------------------------------------------------------
@@ -274,6 +281,14 @@ template <> struct Comp<MCompute> {
         Fr t = fr_inv(fr_mul(d1, d2));
         q1 = vc(z1 ? fr_zero() : fr_mul(a1.v, fr_mul(t, d2)));
         q2 = vc(z2 ? fr_zero() : fr_mul(a2.v, fr_mul(t, d1)));
+    }
+    // constant sub-components of EscalarMulFix (hint class 1): their entries do not depend on the
+    // inputs, so once recorded they are copied instead of recomputed
+    HZ_HD bool const_image() const { return hints && hints->cimg && !hints->rec; }
+    HZ_HD VC copy_const(const Nm&) {
+        VC r; r.v = hints->cimg[cur - hints->fix_shift]; r.sig = true;
+        put(cur, r.v); cur++;
+        return r;
     }
     // a / b at a division site of hint class `cls` (0: none)
     HZ_HD VC div(const VC& a, const VC& b, int cls) {
@@ -392,6 +407,8 @@ template <> struct Comp<MLayout> {
     VL own(const Nm& nm, const VL&) { name(nm, cur); VL r; r.idx = cur++; return r; }
     VL load(uint32_t idx) const { VL r; r.idx = idx; return r; }
     VL known(uint32_t idx, const VL&) const { VL r; r.idx = idx; return r; }
+    bool const_image() const { return false; }
+    VL copy_const(const Nm&) { return vl(); }
     VL iszero_inv(const Nm& nm, const VL&) { name(nm, cur); cur++; return vl(); }
     void flush_pending() {}
     VL div(const VL&, const VL&, int) { return vl(); }

@@ -251,7 +251,42 @@ template <int N> HZ_HD Fr fr_dot_mont_chain(const Fr* s, const Fr* cR) {
 }
 
 #ifdef HZ_DEVICE_ONLY
-HZ_HDN Fr fr_mul(const Fr& a, const Fr& b) { return fr_mul_chain(a, b); }
+// Most products in the glue of the circuits have a boolean signal on one side (selectors, state
+// machine flags, switchers): those are selections, not multiplications.
+HZ_HDN Fr fr_mul(const Fr& a, const Fr& b) {
+    const uint32_t bh = b.l[1] | b.l[2] | b.l[3] | b.l[4] | b.l[5] | b.l[6] | b.l[7];
+    if (bh == 0 && b.l[0] <= 1u) return b.l[0] ? a : b;
+    const uint32_t ah = a.l[1] | a.l[2] | a.l[3] | a.l[4] | a.l[5] | a.l[6] | a.l[7];
+    if (ah == 0 && a.l[0] <= 1u) return a.l[0] ? b : a;
+    return fr_mul_chain(a, b);
+}
+// k < 2^20: eight multiply-adds, the quotient from the top limbs, one conditional subtraction
+HZ_HD Fr fr_mul_small(const Fr& x, uint32_t k) {
+    uint32_t t[9];
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (uint64_t)x.l[i] * k; t[i] = (uint32_t)c; c >>= 32; }
+    t[8] = (uint32_t)c;
+    // q = floor(t / p) or one less: (t >> 224) * floor(2^288 / p) >> 64
+    const uint64_t thi = ((uint64_t)t[8] << 32) | t[7];
+    const uint32_t q = (uint32_t)__umul64hi(thi, 0x54a474626ull);
+    const uint32_t p1[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+    uint32_t qp[8];
+    c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (uint64_t)p1[i] * q; qp[i] = (uint32_t)c; c >>= 32; }
+    Fr r;
+    fr_sub8(r.l, t, qp);                     // the remainder is below 2p < 2^256: 8 limbs carry it
+    uint32_t d[8];
+    uint32_t b = fr_sub8(d, r.l, p1);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = b ? r.l[i] : d[i];
+    return r;
+}
+HZ_HDN Fr fr_mul_u64_dev(const Fr& a, uint64_t k) {
+    if (k < (1ull << 20)) return fr_mul_small(a, (uint32_t)k);
+    return fr_mul_chain(a, fr_from_u64(k));
+}
 #else
 HZ_HDN Fr fr_mul(const Fr& a, const Fr& b) {
     uint32_t t[16];
@@ -260,7 +295,11 @@ HZ_HDN Fr fr_mul(const Fr& a, const Fr& b) {
 }
 #endif
 HZ_HD Fr fr_sqr(const Fr& a) { return fr_mul(a, a); }
+#ifdef HZ_DEVICE_ONLY
+HZ_HD Fr fr_mul_u64(const Fr& a, uint64_t k) { return fr_mul_u64_dev(a, k); }
+#else
 HZ_HD Fr fr_mul_u64(const Fr& a, uint64_t k) { return fr_mul(a, fr_from_u64(k)); }
+#endif
 
 // ---- Montgomery row: sum_{j<n} s[j] * cR[j]  (cR = c * 2^256 mod p)  -> canonical -----------
 // n <= 7: the unreduced sum stays below 7 p^2 < 2^511.

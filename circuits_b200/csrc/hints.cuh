@@ -128,3 +128,145 @@ HZ_HD void hz_hints_record_point(HzHints* h, const Fr& u, const Fr& v) {
     h->edrec[h->ei++] = u;
     h->edrec[h->ei++] = v;
 }
+
+#ifdef HZ_DEVICE_ONLY
+// ---- the device's way: all ladders of one signature at once, spread over the lanes of a group ----
+// The doubling chain D_t = 2^t P runs through both segments of EscalarMulAny (Montgomery2Edwards
+// followed by Edwards2Montgomery at the segment boundary is the identity on (u, v)), 253 doublings
+// that nothing can shorten.  Everything else rides along in other lanes, one step behind:
+//   lane 0  D_{t+1} = double(D_t)                                  t = 0..252
+//   lane 1  segment 0 adder  (in1 = D_t, in2 = acc0), t = 1..147;  acc0 <- sum when e[t]
+//   lane 2  segment 1 adder  (in1 = D_t, in2 = acc1), t = 149..253; acc1 starts as D_148
+//   lane 3  EscalarMulFix segment 0 accumulating adder (in1 = accF, in2 = window_t[sel_t]), t = 0..82
+// A doubling and an addition differ only in how the slope lamda = N / Dn is formed; the rest of
+// MontgomeryAdd / MontgomeryDouble is the same map (u3 = lamda^2 - A - u1 - u2, v3 = lamda (u1 - u3) - v1),
+// so after a short role-specific head all lanes run ONE instruction stream.  The 588 denominators
+// are then inverted together: every lane takes a 74-element chunk of Montgomery's trick.
+#define HZ_LAD_N 588
+#define HZ_LAD_SCRATCH (4 * 600)
+struct MtOps { Fr N, Dn, W12, X1, X2, Y1; };
+__device__ __forceinline__ MtOps mt_head_dbl(const MtPt& p) {
+    MtOps o;
+    Fr UU = fr_mul_chain(p.U, p.U), UW = fr_mul_chain(p.U, p.W), WW = fr_mul_chain(p.W, p.W), VW = fr_mul_chain(p.V, p.W);
+    Fr AUW = fr_mul_small(UW, (uint32_t)HZ_MT_A);
+    o.N = fr_add(fr_add(fr_add(fr_add(UU, UU), UU), fr_add(AUW, AUW)), WW);
+    o.Dn = fr_add(VW, VW);
+    o.W12 = WW; o.X1 = UW; o.X2 = UW; o.Y1 = VW;
+    return o;
+}
+__device__ __forceinline__ MtOps mt_head_add(const MtPt& p1, const MtPt& p2) {
+    MtOps o;
+    o.X1 = fr_mul_chain(p1.U, p2.W); o.X2 = fr_mul_chain(p2.U, p1.W);
+    o.Y1 = fr_mul_chain(p1.V, p2.W);
+    Fr Y2 = fr_mul_chain(p2.V, p1.W);
+    o.W12 = fr_mul_chain(p1.W, p2.W);
+    o.N = fr_sub(Y2, o.Y1); o.Dn = fr_sub(o.X2, o.X1);
+    return o;
+}
+__device__ __forceinline__ MtPt mt_tail(const MtOps& o) {
+    Fr S = fr_mul_chain(o.Dn, o.Dn);
+    Fr NN = fr_mul_chain(o.N, o.N);
+    Fr G = fr_sub(fr_mul_chain(NN, o.W12), fr_mul_chain(fr_add(fr_add(fr_mul_small(o.W12, (uint32_t)HZ_MT_A), o.X1), o.X2), S));
+    Fr DS = fr_mul_chain(o.Dn, S);
+    MtPt r;
+    r.U = fr_mul_chain(G, o.Dn);
+    r.V = fr_sub(fr_mul_chain(o.N, fr_sub(fr_mul_chain(o.X1, S), G)), fr_mul_chain(o.Y1, DS));
+    r.W = fr_mul_chain(DS, o.W12);
+    return r;
+}
+__device__ __forceinline__ Fr hz_shfl8_fr(const Fr& v, int src) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], src, HZ_G);
+    return r;
+}
+// position of ladder element `el` in the hint array, which is in the order the templates consume:
+// [0, 294) segment 0 (doubler, adder per bit), [294] doublers[0], [295, 505) segment 1, [505, 588) fix adders
+__device__ __forceinline__ int hz_lad_pos(int el) {
+    if (el < 147) return 2 * el;
+    if (el == 147) return 294;
+    if (el < 253) return 295 + 2 * (el - 148);
+    if (el < 400) return 2 * (el - 253) + 1;
+    if (el < 505) return 295 + 2 * (el - 400) + 1;
+    return el;
+}
+// px, py: the Edwards input of EscalarMulAny (after its zero-point substitution); e: the 254 scalar
+// bits; s: the 253 bits of S.  Leaves h->lad_ok and, if set, the 588 hints in h->scratch[0 .. 588).
+__device__ __noinline__ void hz_hints_eddsa_lanes(HzHints* h, const Fr& px, const Fr& py, const BVT<MCompute, 8>& e,
+                                                 const BVT<MCompute, 8>& s) {
+    h->lad_ok = 0;
+    if (!h->scratch || !h->edtab) return;
+    __syncwarp();
+    Fr* hint = h->scratch; Fr* num = hint + 600; Fr* den = num + 600; Fr* pre = den + 600;
+    const int lane = (int)hz_glane();
+    MtPt D;
+    {
+        Fr y1 = fr_add(fr_one(), py);
+        D.U = fr_mul_chain(y1, px); D.V = y1; D.W = fr_mul_chain(fr_sub(fr_one(), py), px);
+    }
+    bool ok = !fr_is_zero(D.W);
+    MtPt acc = D;
+    const Fr* tab = h->edtab;
+    if (lane == 3) { acc.U = tab[83 * 16]; acc.V = tab[83 * 16 + 1]; acc.W = fr_one(); }
+    for (int t = 0; t <= 253; t++) {
+        if (lane == 2 && t == 148) acc = D;
+        bool active;
+        int el;
+        MtOps o;
+        Fr hn, hd;
+        if (lane == 0) {
+            active = t <= 252; el = t;
+            o = mt_head_dbl(D);
+            hn = D.W; hd = fr_add(D.V, D.V);
+        } else {
+            MtPt p1 = D, p2 = acc;
+            if (lane == 3) {
+                active = t < 83; el = 505 + t;
+                int tt = active ? t : 0;
+                int sel = (int)(s.bit(3 * tt) | (s.bit(3 * tt + 1) << 1) | (s.bit(3 * tt + 2) << 2));
+                p1 = acc; p2.U = tab[tt * 16 + 2 * sel]; p2.V = tab[tt * 16 + 2 * sel + 1]; p2.W = fr_one();
+            } else if (lane == 1) { active = t >= 1 && t <= 147; el = 253 + (t - 1); }
+            else if (lane == 2) { active = t >= 149; el = 400 + (t - 149); }
+            else { active = false; el = 0; }
+            o = mt_head_add(p1, p2);
+            hn = o.W12; hd = o.Dn;
+        }
+        MtPt r = mt_tail(o);
+        if (active) {
+            num[el] = hn; den[el] = hd;
+            if (fr_is_zero(hd)) ok = false;
+            if (lane == 0 || lane == 3) { if (lane == 0) D = r; else acc = r; }
+            else if (e.bit(t)) acc = r;
+        }
+        // every lane follows lane 0's point
+        D.U = hz_shfl8_fr(D.U, 0); D.V = hz_shfl8_fr(D.V, 0); D.W = hz_shfl8_fr(D.W, 0);
+    }
+    // any zero denominator in the group: no hints at all
+    {
+        unsigned bad = __ballot_sync(0xffffffffu, !ok);
+        unsigned mine = (bad >> ((threadIdx.x & 31u) & ~7u)) & 0xffu;
+        ok = mine == 0;
+    }
+    __syncwarp();
+    // Montgomery's trick, a 74-element chunk per lane
+    const int c0 = lane * 74, c1 = c0 + 74 < HZ_LAD_N ? c0 + 74 : HZ_LAD_N;
+    Fr tot = fr_one();
+    for (int k = c0; k < c1; k++) { pre[k] = tot; Fr dk = den[k]; tot = fr_mul_chain(tot, ok ? dk : fr_one()); }
+    // inverse of the own chunk total = inverse of the product of all chunk totals times the other totals
+    Fr all = fr_one(), others = fr_one();
+    for (int m = 0; m < HZ_G; m++) {
+        Fr tm = hz_shfl8_fr(tot, m);
+        all = fr_mul_chain(all, tm);
+        if (m != lane) others = fr_mul_chain(others, tm);
+    }
+    Fr inv = fr_mul_chain(fr_inv(all), others);
+    if (ok) {
+        for (int k = c1 - 1; k >= c0; k--) {
+            hint[hz_lad_pos(k)] = fr_mul_chain(num[k], fr_mul_chain(inv, pre[k]));
+            inv = fr_mul_chain(inv, den[k]);
+        }
+    }
+    __syncwarp();
+    h->lad_ok = ok ? 1 : 0;
+}
+#endif

@@ -39,6 +39,7 @@ struct HzCuda {
     Fr* isExit;                // nTx
     Fr* hint_cst;              // HZ_CST_MAX: constant inverses of EscalarMulFix (recorded at create)
     Fr* hint_tab;              // HZ_EDTAB_LEN: its window entries
+    Fr* hint_img;              // witness image of EscalarMulFix from the recording pass (constant entries are copied from it)
     Fr* hint_scratch;          // per lane group of k_eddsa: work area of the hint generators
     HzErrBuf* err;
     uint32_t *off_decode, *off_rollup, *off_fee;
@@ -117,12 +118,12 @@ __global__ void k_fix_consts(Fr* wtmp, Fr* cst, Fr* tab, uint32_t* counts) {
 }
 
 __global__ void __launch_bounds__(HZ_BLOCK, 3) k_eddsa(HzPlan pl, Fr* w, HzErrBuf* err, const HzEddsaJob* jobs,
-                                                    const Fr* cst, const Fr* tab, Fr* scratch, int s0, int ns) {
+                                                    const Fr* cst, const Fr* tab, const Fr* img, Fr* scratch, int s0, int ns) {
     bool real; int i = s0 + hz_item(ns, real);
     const HzEddsaJob& j = jobs[i];
     HzHints h;
     h.cst = cst; h.ci = 0; h.dat = nullptr; h.di = 0; h.rec = nullptr; h.ri = 0;
-    h.edtab = tab; h.edrec = nullptr; h.ei = 0; h.scratch = scratch + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) / HZ_G) * HZ_HINT_SCRATCH;   // per group, not per slot: padding groups redo a slot
+    h.edtab = tab; h.edrec = nullptr; h.ei = 0; h.lad_ok = 0; h.cimg = img; h.fix_shift = 0; h.scratch = scratch + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) / HZ_G) * HZ_HINT_SCRATCH;   // per group, not per slot: padding groups redo a slot
     HzPending pend; pend.n = 0;
     Comp<MCompute> c(w, j.cur, real ? err : nullptr, &h, &pend);
     VC vse, sgn, ay, s1Ay, S, R8x, R8y, Msg;
@@ -455,8 +456,9 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaDeviceSetLimit(cudaLimitStackSize, 80 * 1024) == cudaSuccess;
     if (ok) {
         // record the input-independent part of the EdDSA fixed-base multiplication once
-        Fr* wtmp = nullptr; uint32_t* counts = nullptr; uint32_t hc[2] = {0, 0};
-        ok = cudaMalloc(&wtmp, sizeof(Fr) * ((size_t)ph.sz.sigVerifier + 64)) == cudaSuccess && cudaMalloc(&counts, 8) == cudaSuccess;
+        uint32_t* counts = nullptr; uint32_t hc[2] = {0, 0};
+        ok = cudaMalloc(&d->hint_img, sizeof(Fr) * ((size_t)ph.sz.sigVerifier + 64)) == cudaSuccess && cudaMalloc(&counts, 8) == cudaSuccess;
+        Fr* wtmp = d->hint_img;
         if (ok) {
             k_fix_consts<<<1, 32, 0, d->stream>>>(wtmp, d->hint_cst, d->hint_tab, counts);
             ok = cudaMemcpyAsync(hc, counts, 8, cudaMemcpyDeviceToHost, d->stream) == cudaSuccess &&
@@ -466,7 +468,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
                 ok = false;
             }
         }
-        cudaFree(wtmp); cudaFree(counts);
+        cudaFree(counts);
     }
     if (!ok) {
         fprintf(stderr, "hzw: CUDA allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
@@ -483,7 +485,7 @@ void hz_cuda_destroy(HzCuda* d) {
     cudaSetDevice(d->device);
     cudaFree(d->w); cudaFree(d->pre); cudaFree(d->chain); cudaFree(d->msgw); cudaFree(d->jobs); cudaFree(d->err);
     cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit);
-    cudaFree(d->hint_cst); cudaFree(d->hint_tab); cudaFree(d->hint_scratch); cudaFree(d->recs);
+    cudaFree(d->hint_cst); cudaFree(d->hint_tab); cudaFree(d->hint_img); cudaFree(d->hint_scratch); cudaFree(d->recs);
     cudaFree(d->off_decode); cudaFree(d->off_rollup); cudaFree(d->off_fee); cudaFree(d->off_blocks);
     if (d->stream) cudaStreamDestroy(d->stream);
     if (d->stream2) cudaStreamDestroy(d->stream2);
@@ -535,7 +537,7 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     // the signatures run beside the merkle levels: neither fills the machine alone
     CK(cudaStreamWaitEvent(s2, d->ev_front, 0));
     CK(cudaEventRecord(d->kev[9], s2));
-    if (ns > 0) k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_scratch, s0, ns);
+    if (ns > 0) k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, s0, ns);
     CK(cudaEventRecord(d->kev[10], s2));
     CK(cudaEventRecord(d->ev_eddsa, s2));
     if (nf > 0) k_fee_front<<<hz_grid(nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt + 2 * pl.P.nTx, f0, nf);

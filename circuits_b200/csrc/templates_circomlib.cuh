@@ -814,16 +814,47 @@ HZ_HD Fr fr_base8_y() {
 
 TM struct HintGen;
 template <> struct HintGen<MCompute> {
-    static HZ_HD void seg_any(Comp<MCompute>& c, const VC& px, const VC& py, const BVC& e, int n) { hz_hints_segment_any(c.hints, px.v, py.v, e, n); }
+#ifdef HZ_DEVICE_ONLY
+    // device: one lane-parallel pass produces the hints of every ladder of the signature (hints.cuh)
+    static HZ_HD void ladder(Comp<MCompute>& c, const VC& px, const VC& py, const BVC& e, const BVC& s) {
+        if (!c.hints) return;
+        // EscalarMulAny's zero-point substitution (escalarmulany.circom): p.x == 0 -> BASE8
+        const bool zp = fr_is_zero(px.v);
+        hz_hints_eddsa_lanes(c.hints, zp ? fr_base8_x() : px.v, zp ? fr_base8_y() : py.v, e, s);
+    }
+    static HZ_HD void seg_any(Comp<MCompute>& c, const VC&, const VC&, const BVC&, int, int seg) {
+        if (!c.hints) return;
+        c.hints->dat = c.hints->lad_ok ? c.hints->scratch + (seg == 0 ? 0 : 295) : nullptr;
+        c.hints->di = 0;
+    }
+    static HZ_HD void mid(Comp<MCompute>& c) {
+        if (!c.hints) return;
+        c.hints->dat = c.hints->lad_ok ? c.hints->scratch + 294 : nullptr;
+        c.hints->di = 0;
+    }
+    static HZ_HD void seg_fix(Comp<MCompute>& c, const BVC& e, int nW, int seg) {
+        if (!c.hints) return;
+        if (seg == 0 && c.hints->lad_ok) { c.hints->dat = c.hints->scratch + 505; c.hints->di = 0; }
+        else hz_hints_segment_fix(c.hints, e, nW, seg);
+    }
+#else
+    static HZ_HD void ladder(Comp<MCompute>&, const VC&, const VC&, const BVC&, const BVC&) {}
+    static HZ_HD void seg_any(Comp<MCompute>& c, const VC& px, const VC& py, const BVC& e, int n, int) { hz_hints_segment_any(c.hints, px.v, py.v, e, n); }
+    static HZ_HD void mid(Comp<MCompute>&) {}
     static HZ_HD void seg_fix(Comp<MCompute>& c, const BVC& e, int nW, int seg) { hz_hints_segment_fix(c.hints, e, nW, seg); }
+#endif
     static HZ_HD void done(Comp<MCompute>& c) { hz_hints_done(c.hints); }
+    static HZ_HD void fix_begin(Comp<MCompute>& c) { if (c.hints) c.hints->fix_shift = c.cur; }
     static HZ_HD void record(Comp<MCompute>& c, const VC& u, const VC& v) { hz_hints_record_point(c.hints, u.v, v.v); }
 };
 #ifndef HZ_DEVICE_ONLY
 template <> struct HintGen<MLayout> {
-    static void seg_any(Comp<MLayout>&, const VL&, const VL&, const BVT<MLayout, 8>&, int) {}
+    static void ladder(Comp<MLayout>&, const VL&, const VL&, const BVT<MLayout, 8>&, const BVT<MLayout, 8>&) {}
+    static void seg_any(Comp<MLayout>&, const VL&, const VL&, const BVT<MLayout, 8>&, int, int) {}
+    static void mid(Comp<MLayout>&) {}
     static void seg_fix(Comp<MLayout>&, const BVT<MLayout, 8>&, int, int) {}
     static void done(Comp<MLayout>&) {}
+    static void fix_begin(Comp<MLayout>&) {}
     static void record(Comp<MLayout>&, const VL&, const VL&) {}
 };
 #endif
@@ -861,6 +892,7 @@ TM HZ_FN void BabyCheck(Comp<M>&& c, const V<M>& x, const V<M>& y) {
 TM HZ_FN PtV<M> Edwards2Montgomery(Comp<M>&& c, const V<M>& x, const V<M>& y, int hc = 0) {
     V<M> i0 = c.def(Nm("in", 0), x), i1 = c.def(Nm("in", 1), y);
     PtV<M> r;
+    if (hc == 1 && c.const_image()) { r.x = c.copy_const(Nm("out", 0)); r.y = c.copy_const(Nm("out", 1)); return r; }
     if (hc == 0) {
         // u = (1+y)/(1-y), v = u/x = (1+y)/((1-y) x): one inversion for both
         V<M> u, v;
@@ -878,6 +910,7 @@ TM HZ_FN PtV<M> Edwards2Montgomery(Comp<M>&& c, const V<M>& x, const V<M>& y, in
 TM HZ_FN PtV<M> Montgomery2Edwards(Comp<M>&& c, const V<M>& u, const V<M>& v, int hc = 0) {
     V<M> i0 = c.def(Nm("in", 0), u), i1 = c.def(Nm("in", 1), v);
     PtV<M> r;
+    if (hc == 1 && c.const_image()) { r.x = c.copy_const(Nm("out", 0)); r.y = c.copy_const(Nm("out", 1)); return r; }
     if (hc == 0) {
         V<M> x, y;
         c.div2(i0, i1, i0 - 1, i0 + 1, x, y);
@@ -894,6 +927,11 @@ TM HZ_FN PtV<M> Montgomery2Edwards(Comp<M>&& c, const V<M>& u, const V<M>& v, in
 TM HZ_FN PtV<M> MontgomeryAdd(Comp<M>&& c, const PtV<M>& p1, const PtV<M>& p2, int hc = 0) {
     V<M> a0 = c.def(Nm("in1", 0), p1.x), a1 = c.def(Nm("in1", 1), p1.y);
     V<M> b0 = c.def(Nm("in2", 0), p2.x), b1 = c.def(Nm("in2", 1), p2.y);
+    if (hc == 1 && c.const_image()) {
+        PtV<M> q;
+        q.x = c.copy_const(Nm("out", 0)); q.y = c.copy_const(Nm("out", 1)); c.copy_const("lamda");
+        return q;
+    }
     uint32_t out = c.sigs("out", 2);
     V<M> lam = c.def("lamda", c.div(b1 - a1, b0 - a0, hc));
     HZ_CHECK(c, lam * (b0 - a0), b1 - a1);
@@ -904,6 +942,11 @@ TM HZ_FN PtV<M> MontgomeryAdd(Comp<M>&& c, const PtV<M>& p1, const PtV<M>& p2, i
 }
 TM HZ_FN PtV<M> MontgomeryDouble(Comp<M>&& c, const PtV<M>& p, int hc = 0) {
     V<M> i0 = c.def(Nm("in", 0), p.x), i1 = c.def(Nm("in", 1), p.y);
+    if (hc == 1 && c.const_image()) {
+        PtV<M> q;
+        q.x = c.copy_const(Nm("out", 0)); q.y = c.copy_const(Nm("out", 1)); c.copy_const("lamda"); c.copy_const("x1_2");
+        return q;
+    }
     uint32_t out = c.sigs("out", 2);
     uint32_t lamda = c.sig("lamda");
     V<M> x1_2 = c.def("x1_2", i0 * i0);
@@ -942,14 +985,14 @@ TM HZ_FN void BitElementMulAny(Comp<M>&& c, const V<M>& sel, PtV<M>& dbl, PtV<M>
 }
 // wired size of SegmentMulAny(n) (e and p wired signals)
 #define HZ_SZ_SEGMENTMULANY(n) (13 + 9 * ((n) - 1))
-TM HZ_FN void SegmentMulAny(Comp<M>&& c, const BV<M>& e, int from, int n, const PtV<M>& p, PtV<M>& out, PtV<M>& dblOut) {
+TM HZ_FN void SegmentMulAny(Comp<M>&& c, const BV<M>& e, int from, int n, const PtV<M>& p, PtV<M>& out, PtV<M>& dblOut, int seg) {
     BV<M> e_; e_.clear(n);
     for (int i = 0; i < n; i++) e_.put(i, c.def(Nm("e", i), e.get(from + i)));
     PtV<M> p_;
     p_.x = c.def(Nm("p", 0), p.x); p_.y = c.def(Nm("p", 1), p.y);
     PtV<M> m = Edwards2Montgomery(c.sub("e2m"), p_.x, p_.y);
     PtV<M> d = m, a = m;
-    HintGen<M>::seg_any(c, p_.x, p_.y, e_, n);
+    HintGen<M>::seg_any(c, p_.x, p_.y, e_, n, seg);
     for (int i = 0; i < n - 1; i++) BitElementMulAny(c.sub(Nm("bits", i)), e_.get(i + 1), d, a);
     HintGen<M>::done(c);
     c.alias(Nm("dbl", 0), d.x); c.alias(Nm("dbl", 1), d.y);
@@ -972,13 +1015,15 @@ TM HZ_FN PtV<M> EscalarMulAny254(Comp<M>&& c, const BV<M>& e, const PtV<M>& p) {
     base.x = p_.x + (Ops<M>::KF(fr_base8_x()) - p_.x) * zp;
     base.y = p_.y + (Ops<M>::KF(fr_base8_y()) - p_.y) * zp;
     PtV<M> o0, d0, o1, d1;
-    SegmentMulAny(c.sub(Nm("segments", 0)), e_, 0, 148, base, o0, d0);
+    SegmentMulAny(c.sub(Nm("segments", 0)), e_, 0, 148, base, o0, d0, 0);
     (void)nsegments;
     Comp<M> seg1 = c.sub_reserve(Nm("segments", 1), HZ_SZ_SEGMENTMULANY(nlast));
-    PtV<M> dd = MontgomeryDouble(c.sub(Nm("doublers", 0)), d0);
+    HintGen<M>::mid(c);
+    PtV<M> dd = MontgomeryDouble(c.sub(Nm("doublers", 0)), d0, 2);
+    HintGen<M>::done(c);
     PtV<M> ed = Montgomery2Edwards(c.sub(Nm("m2e", 0)), dd.x, dd.y);
     Comp<M> add0 = c.sub_reserve(Nm("adders", 0), HZ_SZ_BABYADD_WIRED);
-    SegmentMulAny(HZ_MV(seg1), e_, 148, nlast, ed, o1, d1);
+    SegmentMulAny(HZ_MV(seg1), e_, 148, nlast, ed, o1, d1, 1);
     PtV<M> fin = BabyAdd(HZ_MV(add0), o0.x, o0.y, o1.x, o1.y);
     PtV<M> r;
     r.x = c.set(out, fin.x * (1 - zp));
@@ -1051,6 +1096,7 @@ TM HZ_FN void SegmentMulFix(Comp<M>&& c, const BV<M>& e, int nW, const PtV<M>& b
 
 // EscalarMulFix(253, BASE8): segment 0 = 249 bits (83 windows), segment 1 = 4 bits (2 windows)
 TM HZ_FN PtV<M> EscalarMulFix253(Comp<M>&& c, const BV<M>& e) {
+    HintGen<M>::fix_begin(c);
     BV<M> e_; e_.clear(253);
     for (int i = 0; i < 253; i++) e_.put(i, c.def(Nm("e", i), e.get(i)));
     PtV<M> B;
@@ -1081,7 +1127,7 @@ TM HZ_FN PtV<M> EscalarMulFix253(Comp<M>&& c, const BV<M>& e) {
 HZ_FN void hz_record_fix_consts(Fr* wtmp, Fr* cst, Fr* edtab, uint32_t* counts) {
     HzHints h;
     h.cst = nullptr; h.ci = 0; h.dat = nullptr; h.di = 0; h.rec = cst; h.ri = 0;
-    h.edtab = nullptr; h.edrec = edtab; h.ei = 0; h.scratch = nullptr;
+    h.edtab = nullptr; h.edrec = edtab; h.ei = 0; h.scratch = nullptr; h.lad_ok = 0; h.cimg = nullptr; h.fix_shift = 0;
     Comp<MCompute> c(wtmp, 0, nullptr, &h);
     BVC e; e.clear(253);
     VC z = vc(fr_zero()); z.sig = true;
@@ -1115,6 +1161,7 @@ TM HZ_FN void EdDSAPoseidonVerifier(Comp<M>&& c, const V<M>& enabled, const V<M>
     PtV<M> d3 = BabyDbl(c.sub("dbl3"), d2.x, d2.y);
     V<M> isz = IsZero(c.sub("isZero"), d2.x);        // dbl3.x is wired to dbl2.xout
     HZ_CHECK0(c, isz * en);
+    HintGen<M>::ladder(c, d3.x, d3.y, hbits, sbits);
     PtV<M> mulAny = EscalarMulAny254(c.sub("mulAny"), hbits, d3);
     PtV<M> right = BabyAdd(c.sub("addRight"), R8x_, R8y_, mulAny.x, mulAny.y);
     PtV<M> left = EscalarMulFix253(c.sub("mulFix"), sbits);

@@ -32,15 +32,15 @@ struct CpuBackend : HzBackend {
     // device's way) instead of one inversion per division (the reference's way, the default and
     // what the CPU baseline times); the tests run both and expect the same witness
     bool use_hints = false;
-    std::vector<Fr> cst, edtab;
+    std::vector<Fr> cst, edtab, cimg;
     explicit CpuBackend(const HzLayout& l) : L(l) {
         const char* e = getenv("HZW_CPU_HINTS");
         use_hints = e && atoi(e) > 0;
         if (use_hints) {
             cst.assign(HZ_CST_MAX, fr_zero()); edtab.assign(HZ_EDTAB_LEN, fr_zero());
-            std::vector<Fr> tmp((size_t)L.plan.sz.sigVerifier + 64);
+            cimg.assign((size_t)L.plan.sz.sigVerifier + 64, fr_zero());
             uint32_t counts[2];
-            hz_record_fix_consts(tmp.data(), cst.data(), edtab.data(), counts);
+            hz_record_fix_consts(cimg.data(), cst.data(), edtab.data(), counts);
             if (counts[0] > HZ_CST_MAX || counts[1] != HZ_EDTAB_LEN) { fprintf(stderr, "hzw cpu port: hint table sizes %u %u\n", counts[0], counts[1]); abort(); }
         }
     }
@@ -66,7 +66,7 @@ struct CpuBackend : HzBackend {
             std::vector<Fr> scratch(use_hints ? HZ_HINT_SCRATCH : 0);
             HzHints h;
             h.cst = cst.data(); h.ci = 0; h.dat = nullptr; h.di = 0; h.rec = nullptr; h.ri = 0;
-            h.edtab = edtab.data(); h.edrec = nullptr; h.ei = 0; h.scratch = scratch.data();
+            h.edtab = edtab.data(); h.edrec = nullptr; h.ei = 0; h.scratch = scratch.data(); h.lad_ok = 0; h.cimg = cimg.empty() ? nullptr : cimg.data(); h.fix_shift = 0;
             Comp<MCompute> c(w, pl.off_decode[i], err, use_hints ? &h : nullptr);
             DecodeOut<MCompute> d;
             PreBits<MCompute> p2 = pre;
