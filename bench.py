@@ -215,6 +215,20 @@ def poseidon_metric(device):
             "hbm_gbs": 2 * n * size * 32 / (ms.value * 1e-3) / 1e9}
 
 
+def poseidon_perm_products(t):
+    """32x32 limb products of one Poseidon permutation of width t as the kernels evaluate it."""
+    rp = {3: 57, 4: 56, 5: 60, 6: 60, 7: 63}[t]
+    return (8 * t + rp) * 3 * 153 + (8 + rp) * t * (64 * t + 100)
+
+
+def poseidon_products(cfg):
+    nTx, nLevels, _, F = cfg
+    per_proc = 2 * (nLevels + 1) * poseidon_perm_products(3) + 2 * poseidon_perm_products(4)
+    per_tx = 2 * per_proc + 4 * poseidon_perm_products(5) + poseidon_perm_products(6) + poseidon_perm_products(7)
+    per_fee = per_proc + 2 * poseidon_perm_products(5)
+    return nTx * per_tx + F * per_fee
+
+
 def committed_traffic(kernel, cfg_name):
     """dram bytes per launch of the dominant kernel, from the ncu --set full capture summarised under profiles/."""
     try:
@@ -364,6 +378,21 @@ def run_gpu(args, cfg, cfg_name):
         pm = poseidon_metric(local)
         if pm is not None:
             line["poseidon"] = pm
+        try:
+            peak = wcm.int_peak(local)
+            prod = poseidon_products(cfg)
+            line["int_roofline"] = {
+                "unit": "32x32->64 multiply-adds/s over all lanes", "peak": peak,
+                "peak_source": "measured live (hzw_int_peak: independent IMAD.WIDE.U32 chains, full occupancy)",
+                "achieved": prod / (ms_per_step * 1e-3), "frac": prod / (ms_per_step * 1e-3) / peak,
+                "algorithmic_products_per_step": prod,
+                "note": "Poseidon only (S-boxes: 153 limb products per modular multiplication; MDS rows: 64 t + 100 per row); "
+                        "EdDSA, SHA and glue not counted"}
+            if pm is not None:
+                pp = pm["perms_per_launch"] * poseidon_perm_products(3)
+                line["poseidon"]["int_frac"] = pp / (pm["ms_per_launch"] * 1e-3) / peak
+        except Exception as e:      # a measurement helper must not take the bench line down
+            log("[bench] int roofline skipped: %r" % (e,))
     if base is not None:
         line["cpu_baseline"] = base
     print(json.dumps(line))

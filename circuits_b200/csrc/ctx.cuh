@@ -231,11 +231,12 @@ template <> struct Comp<MCompute> {
     HzErrBuf* err;      // null = sanity check off
     HzHints* hints;     // null = every division inverts on the spot
     HzPending* pend;    // null = IsZero inverts on the spot
+    bool solo = false;  // device: this thread works alone (no lane group shares its stores)
     typedef VC Val;
 
     HZ_HD Comp(Fr* w_, uint32_t cur_, HzErrBuf* err_, HzHints* h_ = nullptr, HzPending* p_ = nullptr)
         : w(w_), cur(cur_), end(HZ_NOIDX), parent(nullptr), err(err_), hints(h_), pend(p_) {}
-    HZ_HD Comp(Comp* p, bool reserved, uint32_t size) : w(p->w), cur(p->cur), parent(reserved ? nullptr : p), err(p->err), hints(p->hints), pend(p->pend) {
+    HZ_HD Comp(Comp* p, bool reserved, uint32_t size) : w(p->w), cur(p->cur), parent(reserved ? nullptr : p), err(p->err), hints(p->hints), pend(p->pend), solo(p->solo) {
         if (reserved) { end = p->cur + size; p->cur += size; } else end = HZ_NOIDX;
     }
     HZ_HD ~Comp() {
@@ -245,7 +246,7 @@ template <> struct Comp<MCompute> {
 #endif
     }
     Comp(const Comp&) = delete;
-    HZ_HD Comp(Comp&& o) : w(o.w), cur(o.cur), end(o.end), parent(o.parent), err(o.err), hints(o.hints), pend(o.pend) { o.parent = nullptr; o.end = HZ_NOIDX; }
+    HZ_HD Comp(Comp&& o) : w(o.w), cur(o.cur), end(o.end), parent(o.parent), err(o.err), hints(o.hints), pend(o.pend), solo(o.solo) { o.parent = nullptr; o.end = HZ_NOIDX; }
     // the `inv` entry and the `out` value of IsZero(x) (comparators.circom): inv <-- x != 0 ? 1/x : 0
     HZ_HD VC iszero_inv(const Nm&, const VC& x) {
         const uint32_t slot = cur++;
@@ -308,10 +309,29 @@ template <> struct Comp<MCompute> {
     // the one place a witness entry is written
     HZ_HD void put(uint32_t slot, const Fr& v) {
 #ifdef HZ_DEVICE_ONLY
-        if (((slot ^ threadIdx.x) & (HZ_G - 1)) == 0) hz_store_fr(&w[slot], v);
+        if (solo || ((slot ^ threadIdx.x) & (HZ_G - 1)) == 0) hz_store_fr(&w[slot], v);
 #else
         w[slot] = v;
 #endif
+    }
+    // n consecutive entries holding the bits of `bits` (bit k -> entry cur + k, or reversed): on the
+    // device the lanes of a group take every 8th entry each
+    HZ_HD void put_bits(uint64_t bits, int n, bool msb_first = false) {
+        Fr f = fr_zero();
+#ifdef HZ_DEVICE_ONLY
+        const int step = solo ? 1 : HZ_G;
+        for (int k = solo ? 0 : (int)((threadIdx.x - cur) & (HZ_G - 1)); k < n; k += step) {
+#else
+        for (int k = 0; k < n; k++) {
+#endif
+            f.l[0] = (uint32_t)((bits >> (msb_first ? n - 1 - k : k)) & 1u);
+#ifdef HZ_DEVICE_ONLY
+            hz_store_fr(&w[cur + k], f);
+#else
+            w[cur + k] = f;
+#endif
+        }
+        cur += n;
     }
     HZ_HD uint32_t sig(const Nm&) { return cur++; }
     HZ_HD uint32_t sigs(const Nm&, int n) { uint32_t s = cur; cur += n; return s; }

@@ -3,6 +3,7 @@
 // signal names, and the `.wtns` writer.  No field arithmetic happens here.
 #pragma once
 #include "rollup_main.cuh"
+#include "withdraw.cuh"
 #include <string>
 #include <vector>
 #include <cstring>
@@ -112,6 +113,22 @@ static inline void hz_layout_walk(const HzParams& P, LayoutSink* sink, HzLayout&
     }
     pl.nvars = main.cur;
     pl.off_decode = R.off_decode.data(); pl.off_rollup = R.off_rollup.data(); pl.off_fee = R.off_fee.data();
+}
+
+// ---- Withdraw(nLevels): layout walk -------------------------------------------------------------
+struct HzWLayout { int nLevels = 0; uint32_t n_inputs = 0, nvars = 0; };
+static inline void hz_withdraw_walk(int nLevels, LayoutSink* sink, HzWLayout& R) {
+    R.nLevels = nLevels;
+    R.n_inputs = hz_withdraw_ninputs(nLevels);
+    Comp<MLayout> main(1, sink, "main");
+    main.sig("hashGlobalInputs");
+    if (main.named) {
+        for (int f = 0; f < WIN_siblingsState; f++) main.name(Nm(HZ_WITHDRAW_INPUT_NAMES[f]), main.cur + (uint32_t)f);
+        for (int k = 0; k < nLevels + 1; k++) main.name(Nm("siblingsState", k), main.cur + 7u + (uint32_t)k);
+    }
+    main.cur += R.n_inputs;
+    sec_withdraw(main, nLevels);
+    R.nvars = main.cur;
 }
 
 // `.wtns` container, snarkjs 0.3.59 wtns_utils.writeBin layout

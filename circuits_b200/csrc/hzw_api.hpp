@@ -18,6 +18,8 @@ struct HzBackend {
     virtual int pieces(uint64_t* table, int cap) = 0;
     virtual int shard_phase1(const uint8_t* inputs, int sanity, void* record_out, HzErrBuf* errs) = 0;
     virtual int shard_phase2(const void* records, int sanity, uint8_t* shard_out, float* kernel_ms, HzErrBuf* errs) = 0;
+    // Withdraw(nLevels): n independent instances, inputs n x ninputs x 32 B, witnesses n x nvars x 32 B
+    virtual int withdraw_batch(uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out, float* kernel_ms, HzErrBuf* errs) = 0;
     uint64_t launches = 0, h2d = 0, d2h = 0;
 };
 
@@ -61,12 +63,21 @@ static inline uint32_t hz_xrec_slot_bytes(const HzParams& P) { return 624u + 2u 
 static inline uint32_t hz_xrec_vals_off(const HzParams& P, int per) { return ((uint32_t)per * hz_xrec_slot_bytes(P) + 3u) & ~3u; }
 static inline uint32_t hz_xrec_bytes(const HzParams& P, int per) { return (hz_xrec_vals_off(P, per) + 3 * 32 + 3 * 4 + 15u) & ~15u; }
 HzBackend* hz_backend_create(const hzw_params& prm, const HzLayout& L, int* status);
+HzBackend* hz_backend_create_withdraw(const hzw_params& prm, const HzWLayout& WL, int* status);
 
 struct hzw_ctx {
     hzw_params prm;
     HzParams P;
-    HzLayout L;
+    HzLayout L;              // rollup-main
+    HzWLayout WL;            // withdraw
+    bool withdraw = false;
     std::unique_ptr<HzBackend> be;
+    uint64_t nvars() const { return withdraw ? WL.nvars : L.plan.nvars; }
+    uint64_t ninputs() const { return withdraw ? WL.n_inputs : L.plan.n_inputs; }
+    void walk(LayoutSink* sk) const {
+        if (withdraw) { HzWLayout t; hz_withdraw_walk(WL.nLevels, sk, t); }
+        else { HzLayout t; hz_layout_walk(P, sk, t); }
+    }
 };
 
 static inline void hz_fr_to_le32(const Fr& f, uint8_t* o) {
@@ -90,6 +101,17 @@ extern "C" {
 
 int hzw_create(const hzw_params* prm, const char* /*layout_map_path*/, hzw_ctx** out) {
     if (!prm || !out) return HZW_E_PARAM;
+    if (prm->circuit_kind == HZW_CIRCUIT_WITHDRAW) {
+        if (prm->nLevels < 1 || prm->nLevels > 48) return HZW_E_PARAM;
+        hzw_ctx* c = new hzw_ctx();
+        c->prm = *prm; c->withdraw = true;
+        hz_withdraw_walk(prm->nLevels, nullptr, c->WL);
+        int st = 0;
+        c->be.reset(hz_backend_create_withdraw(*prm, c->WL, &st));
+        if (!c->be) { delete c; return st ? st : HZW_E_DEVICE; }
+        *out = c;
+        return HZW_OK;
+    }
     if (prm->circuit_kind != HZW_CIRCUIT_ROLLUP_MAIN) return HZW_E_PARAM;
     HzParams P; P.nTx = prm->nTx; P.nLevels = prm->nLevels; P.maxL1Tx = prm->maxL1Tx; P.maxFeeTx = prm->maxFeeTx;
     if (!hz_params_ok(P)) return HZW_E_PARAM;
@@ -103,11 +125,20 @@ int hzw_create(const hzw_params* prm, const char* /*layout_map_path*/, hzw_ctx**
     return HZW_OK;
 }
 void hzw_destroy(hzw_ctx* ctx) { delete ctx; }
-uint64_t hzw_nvars(const hzw_ctx* ctx) { return ctx ? ctx->L.plan.nvars : 0; }
-uint64_t hzw_ninputs(const hzw_ctx* ctx) { return ctx ? ctx->L.plan.n_inputs : 0; }
+uint64_t hzw_nvars(const hzw_ctx* ctx) { return ctx ? ctx->nvars() : 0; }
+uint64_t hzw_ninputs(const hzw_ctx* ctx) { return ctx ? ctx->ninputs() : 0; }
 
 int hzw_input_index(const hzw_ctx* ctx, const char* name, uint64_t* offset, uint64_t* len) {
     if (!ctx || !name) return HZW_E_PARAM;
+    if (ctx->withdraw) {
+        for (int f = 0; f < WIN_COUNT; f++)
+            if (!strcmp(name, HZ_WITHDRAW_INPUT_NAMES[f])) {
+                if (offset) *offset = (uint64_t)f;
+                if (len) *len = f == WIN_siblingsState ? (uint64_t)ctx->WL.nLevels + 1 : 1;
+                return HZW_OK;
+            }
+        return HZW_E_NOSIGNAL;
+    }
     for (int f = 0; f < IN_COUNT; f++)
         if (!strcmp(name, HZ_INPUT_NAMES[f])) {
             if (offset) *offset = ctx->L.plan.in_off[f] - 2;
@@ -126,9 +157,9 @@ static int hz_report(hzw_ctx* ctx, HzErrBuf& eb, hzw_error* err) {
         err->code = HZW_E_CONSTRAINT; err->line = eb.rec[best].line; err->witness_index = eb.rec[best].cur;
         hz_fr_to_le32(eb.rec[best].lhs, err->lhs); hz_fr_to_le32(eb.rec[best].rhs, err->rhs);
         // component path: name of the last signal declared before the failing check
-        if (ctx->L.plan.nvars < 40000000u && eb.rec[best].cur > 1) {
+        if (ctx->nvars() < 40000000u && eb.rec[best].cur > 1) {
             LayoutSink sk; sk.want_names = true; sk.find_mode = true; sk.find_idx = eb.rec[best].cur - 1;
-            HzLayout tmp; hz_layout_walk(ctx->P, &sk, tmp);
+            ctx->walk(&sk);
             size_t dot = sk.found.rfind('.');
             std::string path = dot == std::string::npos ? sk.found : sk.found.substr(0, dot);
             snprintf(err->where, sizeof err->where, "%s", path.c_str());
@@ -140,12 +171,13 @@ static int hz_report(hzw_ctx* ctx, HzErrBuf& eb, hzw_error* err) {
 int hzw_calculate(hzw_ctx* ctx, const uint8_t* inputs, int sanity, uint8_t* witness_out, hzw_error* err) {
     if (!ctx || !inputs || !witness_out) return HZW_E_PARAM;
     HzErrBuf eb; memset(&eb, 0, sizeof eb);
-    int st = ctx->be->calculate(inputs, sanity, witness_out, false, nullptr, &eb);
+    int st = ctx->withdraw ? ctx->be->withdraw_batch(1, inputs, sanity, witness_out, nullptr, &eb)
+                           : ctx->be->calculate(inputs, sanity, witness_out, false, nullptr, &eb);
     if (st) { if (err) { memset(err, 0, sizeof *err); err->code = st; } return st; }
     return hz_report(ctx, eb, err);
 }
 int hzw_calculate_resident(hzw_ctx* ctx, const uint8_t* inputs, int sanity, float* kernel_ms, hzw_error* err) {
-    if (!ctx) return HZW_E_PARAM;
+    if (!ctx || ctx->withdraw) return HZW_E_PARAM;
     HzErrBuf eb; memset(&eb, 0, sizeof eb);
     int st = ctx->be->calculate(inputs, sanity, nullptr, true, kernel_ms, &eb);
     if (st) { if (err) { memset(err, 0, sizeof *err); err->code = st; } return st; }
@@ -153,6 +185,12 @@ int hzw_calculate_resident(hzw_ctx* ctx, const uint8_t* inputs, int sanity, floa
 }
 int hzw_calculate_batch(hzw_ctx* ctx, uint64_t n, const uint8_t* inputs, int sanity, uint8_t* witness_out, hzw_error* err) {
     if (!ctx || !inputs || !witness_out) return HZW_E_PARAM;
+    if (ctx->withdraw) {
+        HzErrBuf eb; memset(&eb, 0, sizeof eb);
+        int st = ctx->be->withdraw_batch(n, inputs, sanity, witness_out, nullptr, &eb);
+        if (st) { if (err) { memset(err, 0, sizeof *err); err->code = st; } return st; }
+        return hz_report(ctx, eb, err);
+    }
     for (uint64_t k = 0; k < n; k++) {
         int st = hzw_calculate(ctx, inputs + k * 32 * hzw_ninputs(ctx), sanity, witness_out + k * 32 * hzw_nvars(ctx), err);
         if (st) return st;
@@ -161,13 +199,13 @@ int hzw_calculate_batch(hzw_ctx* ctx, uint64_t n, const uint8_t* inputs, int san
 }
 int hzw_write_wtns(const hzw_ctx* ctx, const uint8_t* witness, const char* path) {
     if (!ctx || !witness || !path) return HZW_E_PARAM;
-    return hz_write_wtns(path, witness, ctx->L.plan.nvars) ? HZW_E_IO : HZW_OK;
+    return hz_write_wtns(path, witness, ctx->nvars()) ? HZW_E_IO : HZW_OK;
 }
 int hzw_get_signal(const hzw_ctx* ctx, const uint8_t* witness, const char* name, uint8_t out[32]) {
     if (!ctx || !witness || !name || !out) return HZW_E_PARAM;
     std::vector<std::pair<std::string, uint32_t> > v;
     LayoutSink sk; sk.want_names = true; sk.filter = name; sk.out = &v;
-    HzLayout tmp; hz_layout_walk(ctx->P, &sk, tmp);
+    ctx->walk(&sk);
     for (auto& e : v) if (e.first == name && e.second != HZ_NOIDX) { memcpy(out, witness + 32ull * e.second, 32); return HZW_OK; }
     return HZW_E_NOSIGNAL;
 }
@@ -175,7 +213,7 @@ int hzw_dump_sym(const hzw_ctx* ctx, const char* prefix, const char* path) {
     if (!ctx || !path) return HZW_E_PARAM;
     std::vector<std::pair<std::string, uint32_t> > v;
     LayoutSink sk; sk.want_names = true; sk.filter = prefix ? prefix : ""; sk.out = &v;
-    HzLayout tmp; hz_layout_walk(ctx->P, &sk, tmp);
+    ctx->walk(&sk);
     FILE* f = fopen(path, "w");
     if (!f) return HZW_E_IO;
     for (auto& e : v) fprintf(f, "%u,%s\n", e.second, e.first.c_str());
@@ -184,6 +222,7 @@ int hzw_dump_sym(const hzw_ctx* ctx, const char* prefix, const char* path) {
 }
 int hzw_plan_info(const hzw_ctx* ctx, uint64_t out[12]) {
     if (!ctx || !out) return HZW_E_PARAM;
+    if (ctx->withdraw) { for (int k = 0; k < 12; k++) out[k] = 0; out[0] = ctx->WL.nvars; out[1] = ctx->WL.n_inputs; out[4] = HZ_SZ_SHA_BLOCK; out[5] = 2; return HZW_OK; }
     const HzPlan& pl = ctx->L.plan;
     const HzParams& P = ctx->P;
     out[0] = pl.nvars; out[1] = pl.n_inputs; out[2] = pl.sz.getAx; out[3] = pl.sz.sigVerifier;
@@ -199,7 +238,7 @@ int hzw_last_kernel_ms(const hzw_ctx* ctx, float* ms, const char** names, int ca
     return ctx->be->kernel_ms(ms, names, cap);
 }
 int hzw_set_shard(hzw_ctx* ctx, int32_t rank, int32_t world) {
-    if (!ctx || world < 1 || rank < 0 || rank >= world) return HZW_E_PARAM;
+    if (!ctx || ctx->withdraw || world < 1 || rank < 0 || rank >= world) return HZW_E_PARAM;
     return ctx->be->set_shard(rank, world);
 }
 uint64_t hzw_exchange_bytes(const hzw_ctx* ctx) { return ctx ? ctx->be->exchange_bytes() : 0; }

@@ -2,6 +2,7 @@
 // CUDA half (hzw_kernels.cu: device memory, kernels, streams).
 #pragma once
 #include "rollup_main.cuh"
+#include "withdraw.cuh"
 
 struct HzCuda;   // device state of one context
 // returns null and sets *status (HZW_E_DEVICE) when no usable CUDA device / allocation failure
@@ -20,3 +21,8 @@ uint64_t hz_cuda_exchange_bytes(const HzCuda*);
 int hz_cuda_shard_phase1(HzCuda*, const uint8_t* inputs, int sanity, void* record_out_dev, HzErrBuf* errs);
 int hz_cuda_shard_phase2(HzCuda*, const void* records_dev, int sanity, uint8_t* shard_out, const uint64_t* pieces, int npieces,
                          float* kernel_ms, HzErrBuf* errs, uint64_t* d2h);
+
+// ---- Withdraw(nLevels) batches ---------------------------------------------------------------------
+int hz_cuda_probe(int device);       // 0 when the device exists, else HZW_E_DEVICE / HZW_E_PARAM
+int hz_cuda_withdraw(int device, int nLevels, uint32_t nvars, uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out,
+                     float* kernel_ms, HzErrBuf* errs);

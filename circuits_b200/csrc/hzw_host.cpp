@@ -26,6 +26,7 @@ struct CudaBackend : HzBackend {
         h2d = inputs ? 32ull * L->plan.n_inputs : 0;
         return hz_cuda_shard_phase1(d, inputs, sanity, record_out, errs);
     }
+    int withdraw_batch(uint64_t, const uint8_t*, int, uint8_t*, float*, HzErrBuf*) override { return HZW_E_PARAM; }
     int shard_phase2(const void* records, int sanity, uint8_t* shard_out, float* ms, HzErrBuf* errs) override {
         uint64_t t[32]; int n = hz_shard_pieces(*L, sh, t, 16);
         launches = 11;
@@ -39,5 +40,27 @@ HzBackend* hz_backend_create(const hzw_params& prm, const HzLayout& L, int* stat
     CudaBackend* b = new CudaBackend(d);
     b->L = &L;
     b->sh = hz_shard_ranges(L.plan, 0, 1);
+    return b;
+}
+
+// Withdraw(nLevels): instances are independent; the backend holds no per-circuit device state
+struct CudaWithdrawBackend : HzBackend {
+    int device; HzWLayout WL;
+    int calculate(const uint8_t*, int, uint8_t*, bool, float*, HzErrBuf*) override { return HZW_E_PARAM; }
+    int set_shard(int, int) override { return HZW_E_PARAM; }
+    uint64_t exchange_bytes() override { return 0; }
+    int pieces(uint64_t*, int) override { return 0; }
+    int shard_phase1(const uint8_t*, int, void*, HzErrBuf*) override { return HZW_E_PARAM; }
+    int shard_phase2(const void*, int, uint8_t*, float*, HzErrBuf*) override { return HZW_E_PARAM; }
+    int withdraw_batch(uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out, float* ms, HzErrBuf* errs) override {
+        launches = 1; h2d = 32ull * WL.n_inputs * n; d2h = 32ull * WL.nvars * n;
+        return hz_cuda_withdraw(device, WL.nLevels, WL.nvars, n, inputs, sanity, out, ms, errs);
+    }
+};
+HzBackend* hz_backend_create_withdraw(const hzw_params& prm, const HzWLayout& WL, int* status) {
+    int st = hz_cuda_probe(prm.device);
+    if (st) { *status = st; return nullptr; }
+    CudaWithdrawBackend* b = new CudaWithdrawBackend();
+    b->device = prm.device; b->WL = WL;
     return b;
 }

@@ -369,6 +369,7 @@ __global__ void __launch_bounds__(HZ_SHA_THREADS) k_sha_blocks(HzPlan pl, Fr* w,
 #pragma unroll
     for (int j = 0; j < 8; j++) hin[j] = chain[(size_t)b * 8 + j];
     Comp<MCompute> c(w, base, nullptr);
+    c.solo = true;                          // one thread per unit: it stores every entry of its unit
     if (u < 64) {
         uint32_t v[8];
 #pragma unroll
@@ -662,5 +663,104 @@ extern "C" int hzw_poseidon_bench(int device, uint64_t npairs, int reps, const u
     if (ms_per_rep) *ms_per_rep = ms / (reps > 0 ? reps : 1);
     if (digests_le32) CK(cudaMemcpy(digests_le32, dg, 64ull * npairs, cudaMemcpyDeviceToHost));
     cudaFree(in); cudaFree(sig); cudaFree(dg); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}
+
+// ---- measured ceiling of the pipe the field arithmetic runs on ------------------------------------
+// 32 x 32 -> 64-bit multiply-adds (IMAD.WIDE.U32) per second with nothing else in the way: 16 independent
+// accumulator chains per thread, full occupancy.  This is the denominator of the integer roofline in
+// bench.py (MEASURED_PEAKS.json only has HBM and bf16 figures).
+__global__ void __launch_bounds__(256) k_imad_peak(uint64_t* out, uint32_t a, uint32_t b, int iters) {
+    uint64_t acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc[k] = threadIdx.x + k;
+    uint32_t x = a + threadIdx.x, y = b + blockIdx.x;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(x + k), "r"(y));
+    }
+    uint64_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) r ^= acc[k];
+    if (r == 0x1234567ull) out[0] = r;          // keeps the chains alive
+}
+extern "C" int hzw_int_peak(int device, double* lane_products_per_s) {
+    int n = 0;
+    if (!lane_products_per_s) return HZW_E_PARAM;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return HZW_E_DEVICE;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    uint64_t* out = nullptr;
+    CK(cudaMalloc(&out, 8));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    k_imad_peak<<<blocks, 256>>>(out, 3, 5, 64);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(e0));
+        k_imad_peak<<<blocks, 256>>>(out, 3, 5, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    *lane_products_per_s = (double)blocks * 256.0 * 16.0 * iters / (best * 1e-3);
+    cudaFree(out); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}
+
+// ---- Withdraw(nLevels): one lane group per instance, each with its own witness range ----------------
+__global__ void __launch_bounds__(HZ_BLOCK, 3) k_withdraw(Fr* w, uint32_t nvars, int nLevels, int n, HzErrBuf* err) {
+    bool real; int i = hz_item(n, real);
+    HzPending pend; pend.n = 0;
+    Comp<MCompute> c(w + (size_t)i * nvars, 2 + hz_withdraw_ninputs(nLevels), real ? err : nullptr, nullptr, &pend);
+    VC h = sec_withdraw(c, nLevels);
+    c.put(1, h.v);
+    c.put(0, fr_one());
+    c.flush_pending();
+}
+int hz_cuda_probe(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        fprintf(stderr, "hzw: no CUDA device -- this library has no CPU path\n");
+        return HZW_E_DEVICE;
+    }
+    return device < 0 || device >= n ? HZW_E_PARAM : 0;
+}
+int hz_cuda_withdraw(int device, int nLevels, uint32_t nvars, uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out,
+                     float* kernel_ms, HzErrBuf* errs) {
+    CK(cudaSetDevice(device));
+    CK(cudaDeviceSetLimit(cudaLimitStackSize, 80 * 1024));
+    const uint32_t nin = 7u + (uint32_t)nLevels + 1u;          // hz_withdraw_ninputs (a device function in this translation unit)
+    const uint64_t chunk = 2048;                 // instances per launch: bounds the device witness buffer (~5.5 GB at nLevels 32)
+    const uint64_t cap = n < chunk ? n : chunk;
+    Fr* w = nullptr; HzErrBuf* err = nullptr;
+    cudaEvent_t e0, e1;
+    CK(cudaMalloc(&w, 32ull * nvars * cap));
+    CK(cudaMalloc(&err, sizeof(HzErrBuf)));
+    CK(cudaMemset(err, 0, sizeof(HzErrBuf)));
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float total = 0;
+    for (uint64_t k0 = 0; k0 < n; k0 += chunk) {
+        const uint64_t m = n - k0 < chunk ? n - k0 : chunk;
+        // inputs go to entries [2, 2 + nin) of each instance
+        CK(cudaMemcpy2D(reinterpret_cast<uint8_t*>(w) + 64, 32ull * nvars, inputs + 32ull * nin * k0, 32ull * nin, 32ull * nin, m, cudaMemcpyHostToDevice));
+        CK(cudaEventRecord(e0));
+        k_withdraw<<<hz_grid((int)m), HZ_BLOCK>>>(w, nvars, nLevels, (int)m, sanity ? err : nullptr);
+        CK(cudaEventRecord(e1));
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(out + 32ull * nvars * k0, w, 32ull * nvars * m, cudaMemcpyDeviceToHost));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        total += ms;
+    }
+    CK(cudaMemcpy(errs, err, sizeof(HzErrBuf), cudaMemcpyDeviceToHost));
+    if (kernel_ms) *kernel_ms = total;
+    cudaFree(w); cudaFree(err); cudaEventDestroy(e0); cudaEventDestroy(e1);
     return 0;
 }

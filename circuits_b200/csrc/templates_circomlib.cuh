@@ -1246,8 +1246,7 @@ template <> struct W32<MCompute> { uint32_t v; };
 template <> struct W32<MLayout> { uint32_t idx[32]; };
 
 HZ_HD W32<MCompute> w32_def(Comp<MCompute>& c, const char*, uint64_t value, int nout) {
-    Fr f = fr_zero();
-    for (int k = 0; k < nout; k++) { f.l[0] = (uint32_t)((value >> k) & 1u); c.w[c.cur++] = f; }
+    c.put_bits(value, nout);
     W32<MCompute> r; r.v = (uint32_t)value; return r;
 }
 HZ_HD void w32_alias(Comp<MCompute>&, const char*, const W32<MCompute>&) {}
@@ -1272,8 +1271,7 @@ HZ_HD void hz_binsum_names(Comp<MCompute>&, int, const W32<MCompute>&) {}
 HZ_HD void hz_sha_in_names(Comp<MCompute>&, const W32<MCompute>*, const W32<MCompute>*) {}
 // digest word j: entries out[32 j + k] = bit (31 - k) of v
 HZ_HD W32<MCompute> hz_sha_out_word(Comp<MCompute>& c, int, uint32_t v) {
-    Fr f = fr_zero();
-    for (int k = 0; k < 32; k++) { f.l[0] = (v >> (31 - k)) & 1u; c.w[c.cur++] = f; }
+    c.put_bits(v, 32, true);
     W32<MCompute> r; r.v = v; return r;
 }
 #ifndef HZ_DEVICE_ONLY
@@ -1300,8 +1298,7 @@ TM HZ_FN W32<M> RotR(Comp<M>&& c, const W32<M>& x, int r) {
 }
 // out[i] = in[i + r], zero (a constant entry) at the top r positions
 HZ_HD W32<MCompute> ShR(Comp<MCompute>&& c, const W32<MCompute>& x, int r) {
-    Fr z = fr_zero();
-    for (int i = 0; i < r; i++) c.w[c.cur++] = z;
+    c.put_bits(0, r);
     W32<MCompute> o; o.v = x.v >> r; return o;
 }
 #ifndef HZ_DEVICE_ONLY

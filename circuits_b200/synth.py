@@ -136,3 +136,35 @@ def bench_batch(nTx, nLevels, maxL1Tx, maxFeeTx, n_accounts=None, n_keys=64, see
     bb.addFeeIdx(idxs[rng.randrange(len(idxs))])
     bb.build()
     return bb
+
+
+def withdraw_inputs(nLevels, n, seed=SEED):
+    """`n` Withdraw(nLevels) inputs: the leaves of one exit tree (what `withdrawUtils` / `getExitTreeInfo`
+    produce in /root/reference/test/withdraw.test.js:60-103) with their inclusion proofs, plus the
+    hashGlobalInputs each must yield (SHA-256 of rootExit|ethAddr|tokenID|balance|idx, mod p:
+    src/withdraw.circom:84-176)."""
+    from .field import P
+    from .rollupdb import hash_state
+    from .smt import SMT, pad_siblings
+    rng = random.Random(seed)
+    tree, leaves = SMT(), []
+    used = set()
+    for k in range(n):
+        idx = rng.randrange(256, 1 << min(nLevels, 40))
+        while idx in used:
+            idx = rng.randrange(256, 1 << min(nLevels, 40))
+        used.add(idx)
+        st = dict(tokenID=rng.randrange(1 << 32), nonce=0, sign=rng.randrange(2), balance=rng.randrange(1 << 96),
+                  ay=rng.randrange(P), ethAddr=rng.randrange(1 << 160))
+        tree.insert(idx, hash_state(st))
+        leaves.append((idx, st))
+    out = []
+    for idx, st in leaves:
+        res = tree.find(idx)
+        assert res["found"]
+        inp = dict(rootExit=tree.root, ethAddr=st["ethAddr"], tokenID=st["tokenID"], balance=st["balance"], idx=idx,
+                   sign=st["sign"], ay=st["ay"], siblingsState=pad_siblings(res["siblings"], nLevels + 1))
+        pre = ((((tree.root << 160 | st["ethAddr"]) << 32 | st["tokenID"]) << 192 | st["balance"]) << 48) | idx
+        h = int.from_bytes(hashlib.sha256(pre.to_bytes(86, "big")).digest(), "big") % P
+        out.append((inp, h))
+    return out

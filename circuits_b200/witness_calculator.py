@@ -42,7 +42,7 @@ class _Error(ctypes.Structure):
 EXPORTS = ["hzw_create", "hzw_destroy", "hzw_nvars", "hzw_ninputs", "hzw_input_index", "hzw_calculate",
            "hzw_calculate_batch", "hzw_calculate_resident", "hzw_write_wtns", "hzw_get_signal", "hzw_dump_sym",
            "hzw_last_stats", "hzw_last_kernel_ms", "hzw_plan_info", "hzw_set_shard", "hzw_exchange_bytes",
-           "hzw_shard_pieces", "hzw_shard_nvars", "hzw_shard_phase1", "hzw_shard_phase2", "hzw_poseidon_bench"]
+           "hzw_shard_pieces", "hzw_shard_nvars", "hzw_shard_phase1", "hzw_shard_phase2", "hzw_poseidon_bench", "hzw_int_peak"]
 
 
 def load_library(path=None):
@@ -173,6 +173,17 @@ class WitnessCalculator:
         wit = out if out is not None else bytearray(32 * self.NVars)
         err = _Error()
         st = self._lib.hzw_calculate(self._ctx, _addr(packed), 1 if sanityCheck else 0, _addr(wit), ctypes.byref(err))
+        if st != 0:
+            self._raise(st, err)
+        return wit
+
+    def calculateBatch(self, n, packed, sanityCheck=False, out=None):
+        """`n` independent witnesses of one circuit in a single call (`hzw_calculate_batch`; Withdraw)."""
+        if isinstance(packed, bytes):
+            packed = bytearray(packed)
+        wit = out if out is not None else bytearray(32 * self.NVars * n)
+        err = _Error()
+        st = self._lib.hzw_calculate_batch(self._ctx, n, _addr(packed), 1 if sanityCheck else 0, _addr(wit), ctypes.byref(err))
         if st != 0:
             self._raise(st, err)
         return wit
@@ -361,3 +372,13 @@ def poseidon_pairs(inputs, reps=1, device=0, lib_path=None):
     dig = [(int.from_bytes(out[64 * i:64 * i + 32], "little"), int.from_bytes(out[64 * i + 32:64 * i + 64], "little"))
            for i in range(n)]
     return dig, ms.value
+
+
+def int_peak(device=0, lib_path=None):
+    """Measured 32x32->64 multiply-adds per second of the device (all lanes), `hzw_int_peak`."""
+    lib = load_library(lib_path)
+    lib.hzw_int_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    v = ctypes.c_double()
+    if lib.hzw_int_peak(device, ctypes.byref(v)) != 0:
+        raise WitnessError("hzw_int_peak failed")
+    return v.value

@@ -119,6 +119,10 @@ int hzw_shard_phase2(hzw_ctx* ctx, const void* records, int sanity_check, uint8_
 int hzw_poseidon_bench(int device, uint64_t npairs, int reps, const uint8_t* inputs_le32 /* 4 x npairs x 32 B */,
                        uint8_t* digests_le32 /* 2 x npairs x 32 B, nullable */, float* ms_per_rep);
 
+/* Measured ceiling of the integer-multiply pipe: 32 x 32 -> 64-bit multiply-adds per second over all
+ * lanes of the device (independent chains, full occupancy); the denominator of bench.py's integer roofline. */
+int hzw_int_peak(int device, double* lane_products_per_s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,7 @@ struct CpuBackend : HzBackend {
         phase2(w, err);
         return 0;
     }
+    int withdraw_batch(uint64_t, const uint8_t*, int, uint8_t*, float*, HzErrBuf*) override { return HZW_E_PARAM; }
     // ---- shards: the same protocol as the CUDA library, records in host memory -------------------
     int set_shard(int rank, int world) override { sh = hz_shard_ranges(L.plan, rank, world); return 0; }
     uint64_t exchange_bytes() override { return hz_xrec_bytes(L.plan.P, sh.per); }
@@ -184,5 +185,32 @@ struct CpuBackend : HzBackend {
 HzBackend* hz_backend_create(const hzw_params&, const HzLayout& L, int*) {
     CpuBackend* b = new CpuBackend(L);
     b->sh = hz_shard_ranges(L.plan, 0, 1);
+    return b;
+}
+
+struct CpuWithdrawBackend : HzBackend {
+    HzWLayout WL;
+    int calculate(const uint8_t*, int, uint8_t*, bool, float*, HzErrBuf*) override { return HZW_E_PARAM; }
+    int set_shard(int, int) override { return HZW_E_PARAM; }
+    uint64_t exchange_bytes() override { return 0; }
+    int pieces(uint64_t*, int) override { return 0; }
+    int shard_phase1(const uint8_t*, int, void*, HzErrBuf*) override { return HZW_E_PARAM; }
+    int shard_phase2(const void*, int, uint8_t*, float*, HzErrBuf*) override { return HZW_E_PARAM; }
+    int withdraw_batch(uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out, float*, HzErrBuf* errs) override {
+        hz_parallel_for((int)n, [&](int i) {
+            Fr* w = reinterpret_cast<Fr*>(out) + (size_t)i * WL.nvars;
+            memset(&w[0], 0, 64);
+            w[0].l[0] = 1;
+            memcpy(&w[2], inputs + 32ull * WL.n_inputs * i, 32ull * WL.n_inputs);
+            Comp<MCompute> c(w, 2 + WL.n_inputs, sanity ? errs : nullptr);
+            VC h = sec_withdraw(c, WL.nLevels);
+            w[1] = h.v;
+        });
+        return 0;
+    }
+};
+HzBackend* hz_backend_create_withdraw(const hzw_params&, const HzWLayout& WL, int*) {
+    CpuWithdrawBackend* b = new CpuWithdrawBackend();
+    b->WL = WL;
     return b;
 }
