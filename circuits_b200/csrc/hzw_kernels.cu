@@ -43,12 +43,14 @@ struct HzCuda {
     Fr* hint_scratch;          // per lane group of k_eddsa: work area of the hint generators
     HzErrBuf* err;
     uint32_t *off_decode, *off_rollup, *off_fee;
+    uint32_t h_off_decode0, h_off_rollup0, h_off_rollup_mid, h_off_fee0;   // host copies of the piece boundaries
     uint32_t* off_blocks;      // 1
     // shard of this context: rank / world and the ranges it evaluates (everything when world == 1)
     int rank, world, per, s0, ns, f0, nf;
     uint32_t b0, nb;
     uint8_t* recs;             // world x rec_bytes: the gathered exchange records (own one while packing)
-    cudaStream_t stream, stream2;
+    cudaStream_t stream, stream2, stream3;
+    cudaEvent_t ev_half[2], ev_ed[2], ev_done;
     cudaEvent_t ev0, ev1, ev_front, ev_eddsa;
     cudaEvent_t kev[HZ_NKERN + 2];
 };
@@ -449,6 +451,10 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaMemcpy(d->off_rollup, off_rollup, 4ull * P.nTx, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpy(d->off_fee, off_fee, 4ull * P.maxFeeTx, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaStreamCreate(&d->stream) == cudaSuccess && cudaStreamCreate(&d->stream2) == cudaSuccess;
+    ok = ok && cudaStreamCreate(&d->stream3) == cudaSuccess;
+    for (int k = 0; k < 2; k++) ok = ok && cudaEventCreateWithFlags(&d->ev_half[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&d->ev_ed[k], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming) == cudaSuccess;
+    d->h_off_decode0 = off_decode[0]; d->h_off_rollup0 = off_rollup[0]; d->h_off_rollup_mid = off_rollup[P.nTx / 2]; d->h_off_fee0 = off_fee[0];
     ok = ok && cudaEventCreate(&d->ev0) == cudaSuccess && cudaEventCreate(&d->ev1) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_front, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_eddsa, cudaEventDisableTiming) == cudaSuccess;
@@ -490,6 +496,9 @@ void hz_cuda_destroy(HzCuda* d) {
     cudaFree(d->off_decode); cudaFree(d->off_rollup); cudaFree(d->off_fee); cudaFree(d->off_blocks);
     if (d->stream) cudaStreamDestroy(d->stream);
     if (d->stream2) cudaStreamDestroy(d->stream2);
+    if (d->stream3) cudaStreamDestroy(d->stream3);
+    for (int k = 0; k < 2; k++) { if (d->ev_half[k]) cudaEventDestroy(d->ev_half[k]); if (d->ev_ed[k]) cudaEventDestroy(d->ev_ed[k]); }
+    if (d->ev_done) cudaEventDestroy(d->ev_done);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
     if (d->ev_front) cudaEventDestroy(d->ev_front);
@@ -569,21 +578,76 @@ static int hz_phase2(HzCuda* d, int sanity) {
     return 0;
 }
 
+// One batch end to end with the witness copied to the host WHILE it is computed.  The 8 GB copy over
+// PCIe (~150 ms) dwarfs the kernels, so pieces leave as soon as they are final: header, inputs and the
+// decodeTx ranges after k_front; the rollupTx ranges of the first half of the slots while the second
+// half is evaluated; the rest (second half, fee txs, hasherInputs) at the end.
+static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* out) {
+    const HzPlan& pl = d->plan;
+    const HzParams& P = pl.P;
+    cudaStream_t s = d->stream, s2 = d->stream2, s3 = d->stream3;
+    HzErrBuf* err = sanity ? d->err : nullptr;
+    const uint8_t* wb = reinterpret_cast<const uint8_t*>(d->w);
+    auto piece = [&](uint64_t a, uint64_t b) -> cudaError_t {
+        return b > a ? cudaMemcpyAsync(out + 32 * a, wb + 32 * a, 32 * (b - a), cudaMemcpyDeviceToHost, s3) : cudaSuccess;
+    };
+    CK(cudaMemsetAsync(d->err, 0, sizeof(HzErrBuf), s));
+    CK(cudaMemsetAsync(d->pre, 0, (size_t)pl.nblocks * 512, s));
+    CK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(d->w) + 64, inputs, 32ull * pl.n_inputs, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(d->ev0, s));
+    k_front<<<hz_grid(P.nTx), HZ_BLOCK, 0, s>>>(pl, d->w, d->pre, err, d->jobs, d->smt, d->isExit, 0, P.nTx);
+    CK(cudaEventRecord(d->ev_front, s));
+    CK(cudaStreamWaitEvent(s2, d->ev_front, 0));
+    CK(cudaStreamWaitEvent(s3, d->ev_front, 0));
+    const int F = P.maxFeeTx, h0 = P.nTx / 2;
+    k_fee_front<<<hz_grid(F), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt + 2 * P.nTx, 0, F);
+    // w[0], w[1] are written by the hasher at the end: entries [2, decodeTx[0]) and the decode ranges go now
+    CK(piece(2, d->h_off_rollup0));
+    for (int h = 0; h < 2; h++) {
+        const int s0 = h == 0 ? 0 : h0, ns = h == 0 ? h0 : P.nTx - h0, nf = h == 1 ? F : 0;
+        if (ns > 0) k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, s0, ns);
+        CK(cudaEventRecord(d->ev_ed[h], s2));
+        if (2 * ns + nf > 0) k_smt<<<hz_grid(2 * ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt, d->mids, s0, ns, 0, nf);
+        if (ns + nf > 0) k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->mids, d->isExit, s0, ns, 0, nf);
+        CK(cudaStreamWaitEvent(s, d->ev_ed[h], 0));
+        CK(cudaEventRecord(d->ev_half[h], s));
+        if (h == 0) {
+            CK(cudaStreamWaitEvent(s3, d->ev_half[0], 0));
+            CK(piece(d->h_off_rollup0, d->h_off_rollup_mid));
+        }
+    }
+    CK(cudaEventRecord(d->ev_eddsa, s2));
+    int st = hz_phase2(d, sanity);
+    if (st) return st;
+    CK(cudaEventRecord(d->ev_done, s));
+    CK(cudaStreamWaitEvent(s3, d->ev_done, 0));
+    CK(piece(d->h_off_rollup_mid, pl.nvars));
+    CK(piece(0, 2));
+    return 0;
+}
+
 int hz_cuda_calculate(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* witness_out, float* kernel_ms,
                       HzErrBuf* errs, uint64_t* launches, uint64_t* h2d, uint64_t* d2h) {
     CK(cudaSetDevice(d->device));
     if (d->world != 1) return HZW_E_PARAM;        // sharded contexts go through the two phases
     const HzPlan& pl = d->plan;
     cudaStream_t s = d->stream;
-    int st = hz_phase1(d, inputs, sanity);
-    if (st) return st;
-    st = hz_phase2(d, sanity);
-    if (st) return st;
-    if (witness_out) CK(cudaMemcpyAsync(witness_out, d->w, 32ull * pl.nvars, cudaMemcpyDeviceToHost, s));
+    const bool overlapped = witness_out && inputs && pl.P.nTx >= 8;
+    if (overlapped) {
+        int st = hz_calculate_overlapped(d, inputs, sanity, witness_out);
+        if (st) return st;
+    } else {
+        int st = hz_phase1(d, inputs, sanity);
+        if (st) return st;
+        st = hz_phase2(d, sanity);
+        if (st) return st;
+        if (witness_out) CK(cudaMemcpyAsync(witness_out, d->w, 32ull * pl.nvars, cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaMemcpyAsync(errs, d->err, sizeof(HzErrBuf), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (overlapped) CK(cudaStreamSynchronize(d->stream3));
     if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, d->ev0, d->ev1));
-    if (launches) *launches = HZ_NKERN;
+    if (launches) *launches = overlapped ? HZ_NKERN + 3 : HZ_NKERN;
     if (h2d) *h2d = inputs ? 32ull * pl.n_inputs : 0;
     if (d2h) *d2h = (witness_out ? 32ull * pl.nvars : 0) + sizeof(HzErrBuf);
     return 0;
