@@ -168,3 +168,49 @@ def withdraw_inputs(nLevels, n, seed=SEED):
         h = int.from_bytes(hashlib.sha256(pre.to_bytes(86, "big")).digest(), "big") % P
         out.append((inp, h))
     return out
+
+
+def mixed_batch(nLevels=16, nTx=12, maxL1Tx=7, maxFeeTx=3):
+    """One batch with every transaction type of the protocol, after the cases of
+    /root/reference/test/rollup-main.test.js:65-878 and rollup-main-L1.test.js:88-487: L1 createAccountDeposit,
+    deposit, createAccountDepositTransfer, depositTransfer, forceTransfer, forceExit, an L1 nullified by a wrong
+    token; L2 transfer, exit, a second exit of the same account (update of the exit leaf), transfer with
+    request-offset linkage left empty; NOP padding; two fee tokens and collectors."""
+    db = RollupDB(chain_id=0)
+    acc = [Account(k + 1) for k in range(4)]
+    bb = db.buildBatch(4, nLevels, 4, 1)
+    for a, amt, tok in ((acc[0], 10000, 1), (acc[1], 5000, 1), (acc[2], 7000, 2), (acc[3], 0, 1)):
+        bb.addTx(_deposit(a, amt, tok))
+    bb.build()
+    db.consolidate(bb)                      # accounts 256..259
+    bb = db.buildBatch(nTx, nLevels, maxL1Tx, maxFeeTx)
+    f = float40.fix2float
+    new = Account(9)
+    # L1 transactions
+    bb.addTx(_deposit(new, 300))                                                             # createAccountDeposit -> 260
+    bb.addTx(dict(fromIdx=256, loadAmountF=f(500), tokenID=1, fromBjjCompressed=[0] * 256,   # deposit
+                  fromEthAddr=acc[0].ethAddr, toIdx=0, onChain=1))
+    t = _deposit(Account(10), 800)                                                           # createAccountDepositTransfer -> 261
+    t.update(toIdx=257, amountF=f(100))
+    bb.addTx(t)
+    bb.addTx(dict(fromIdx=257, loadAmountF=f(200), amountF=f(50), tokenID=1, fromBjjCompressed=[0] * 256,   # depositTransfer
+                  fromEthAddr=acc[1].ethAddr, toIdx=256, onChain=1))
+    bb.addTx(dict(fromIdx=256, loadAmountF=0, amountF=f(70), tokenID=1, fromBjjCompressed=[0] * 256,        # forceTransfer
+                  fromEthAddr=acc[0].ethAddr, toIdx=259, onChain=1))
+    bb.addTx(dict(fromIdx=257, loadAmountF=0, amountF=f(30), tokenID=1, fromBjjCompressed=[0] * 256,        # forceExit
+                  fromEthAddr=acc[1].ethAddr, toIdx=1, onChain=1))
+    bb.addTx(dict(fromIdx=258, loadAmountF=f(40), amountF=0, tokenID=1, fromBjjCompressed=[0] * 256,        # deposit with the wrong token: nullified
+                  fromEthAddr=acc[2].ethAddr, toIdx=0, onChain=1))
+    # L2 transactions
+    tx = dict(fromIdx=256, toIdx=257, tokenID=1, amountF=f(150), nonce=0, userFee=126, onChain=0)
+    acc[0].sign_tx(tx, 0); bb.addTx(tx)
+    tx = dict(fromIdx=256, toIdx=1, tokenID=1, amountF=f(100), nonce=1, userFee=68, onChain=0)              # exit
+    acc[0].sign_tx(tx, 0); bb.addTx(tx)
+    tx = dict(fromIdx=256, toIdx=1, tokenID=1, amountF=f(20), nonce=2, userFee=0, onChain=0)                # second exit: exit leaf update
+    acc[0].sign_tx(tx, 0); bb.addTx(tx)
+    tx = dict(fromIdx=258, toIdx=258, tokenID=2, amountF=f(500), nonce=0, userFee=184, onChain=0)           # self transfer, other token
+    acc[2].sign_tx(tx, 0); bb.addTx(tx)
+    bb.addToken(1); bb.addFeeIdx(259)
+    bb.addToken(2); bb.addFeeIdx(258)
+    bb.build()
+    return bb
