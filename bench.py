@@ -206,13 +206,18 @@ def poseidon_metric(device):
     rng = random.Random(20261017)
     buf = bytearray(b"".join(rng.randrange(P).to_bytes(32, "little") for _ in range(4 * n)))
     ms = ctypes.c_float()
-    st = lib.hzw_poseidon_bench(device, n, 5, wcm._addr(buf), None, ctypes.byref(ms))
-    if st != 0:
-        return None
+    res = {}
+    for name, reps in (("transposed", 5), ("lane_groups", -5)):
+        st = lib.hzw_poseidon_bench(device, n, reps, wcm._addr(buf), None, ctypes.byref(ms))
+        if st != 0:
+            return None
+        res[name] = ms.value
     size = 634
-    return {"value": 2 * n / (ms.value * 1e-3), "unit": "perm/s", "t": 3, "perms_per_launch": 2 * n,
-            "ms_per_launch": ms.value, "signal_bytes_per_launch": 2 * n * size * 32,
-            "hbm_gbs": 2 * n * size * 32 / (ms.value * 1e-3) / 1e9}
+    best = min(res.values())
+    return {"value": 2 * n / (best * 1e-3), "unit": "perm/s", "t": 3, "perms_per_launch": 2 * n,
+            "ms_per_launch": best, "signal_bytes_per_launch": 2 * n * size * 32,
+            "hbm_gbs": 2 * n * size * 32 / (best * 1e-3) / 1e9,
+            "kernels_ms": res}
 
 
 def poseidon_perm_products(t):

@@ -702,6 +702,55 @@ int hz_cuda_kernel_ms(HzCuda* d, float* ms, const char** names, int cap) {
     return n;
 }
 
+// ---- the same permutations, transposed ------------------------------------------------------------
+// Thread (warp r, lane c) holds state element r of permutation c: a block of 3 warps runs 32 permutations.
+// A partial round's single S-box is then a full warp of 32 different permutations (warp 0) instead of one
+// active lane in eight, and the two other warps issue nothing while they wait for it; the state
+// elements meet in shared memory (word-major, conflict-free) once per round for the MDS rows, whose
+// constants are uniform per warp.  Same signals at the same indexes as the lane-group form.
+#define HZ_PT_CHAINS 32
+__global__ void __launch_bounds__(96) k_poseidon_t3(const Fr* in, Fr* sig, Fr* digests, int nperms) {
+    __shared__ uint32_t xch[2][3][8][HZ_PT_CHAINS];
+    const int r = (int)(threadIdx.x >> 5), c = (int)(threadIdx.x & 31);
+    int p = (int)blockIdx.x * HZ_PT_CHAINS + c;
+    const bool real = p < nperms;
+    if (!real) p = nperms - 1;
+    const uint32_t size = 1 + 2 * 3 * 65 + 3 * (8 * 3 + 57);
+    Fr* w = sig + (size_t)p * size;
+    // inputs are wires (no entries); entry 0 is ark[0].in[0] = 0
+    Fr s = r == 0 ? fr_zero() : in[2 * p + (r - 1)];
+    if (r == 0 && real) hz_store_fr(&w[0], s);
+    uint32_t cur = 1;
+    const Fr* C = &hz_poseidon_c(3, 0);
+    Fr m[3];
+    for (int k = 0; k < 3; k++) m[k] = hz_poseidon_mr(3, r)[k];
+    for (int i = 0; i < 65; i++) {
+        s = fr_add(s, C[3 * i + r]);
+        if (real) hz_store_fr(&w[cur + r], s);
+        const bool full = i < 4 || i >= 61;
+        const uint32_t sg = cur + 6;
+        if (full || r == 0) {                       // warp-uniform
+            Fr in2 = fr_mul_chain(s, s);
+            Fr in4 = fr_mul_chain(in2, in2);
+            s = fr_mul_chain(in4, s);
+            if (real) { hz_store_fr(&w[sg + 3 * r], s); hz_store_fr(&w[sg + 3 * r + 1], in2); hz_store_fr(&w[sg + 3 * r + 2], in4); }
+        }
+        uint32_t (*buf)[8][HZ_PT_CHAINS] = xch[i & 1];
+#pragma unroll
+        for (int k = 0; k < 8; k++) buf[r][k][c] = s.l[k];
+        __syncthreads();
+        Fr a[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) a[q].l[k] = buf[q][k][c];
+        s = fr_dot_mont_chain<3>(a, m);
+        if (real) hz_store_fr(&w[cur + 3 + r], s);
+        cur += 6 + (full ? 9 : 3);
+    }
+    if (r == 0 && real) digests[p] = s;
+}
+
 extern "C" int hzw_poseidon_bench(int device, uint64_t npairs, int reps, const uint8_t* inputs_le32 /* 4 x npairs */,
                                   uint8_t* digests_le32 /* 2 x npairs, nullable */, float* ms_per_rep) {
     if (npairs == 0 || npairs > (1u << 22) || !inputs_le32) return HZW_E_PARAM;
@@ -716,9 +765,18 @@ extern "C" int hzw_poseidon_bench(int device, uint64_t npairs, int reps, const u
     CK(cudaMalloc(&dg, 64ull * npairs));
     CK(cudaMemcpy(in, inputs_le32, 128ull * npairs, cudaMemcpyHostToDevice));
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    k_poseidon_pairs<<<hz_grid((int)npairs), HZ_BLOCK>>>(in, sig, dg, (int)npairs);      // warm-up
+    // reps < 0: the lane-group form (as inside k_smt); reps > 0: the transposed form
+    const bool lanes = reps < 0;
+    if (lanes) reps = -reps;
+    const int nperms = 2 * (int)npairs;
+    const unsigned tgrid = (unsigned)((nperms + HZ_PT_CHAINS - 1) / HZ_PT_CHAINS);
+    if (lanes) k_poseidon_pairs<<<hz_grid((int)npairs), HZ_BLOCK>>>(in, sig, dg, (int)npairs);      // warm-up
+    else k_poseidon_t3<<<tgrid, 96>>>(in, sig, dg, nperms);
     CK(cudaEventRecord(e0));
-    for (int r = 0; r < reps; r++) k_poseidon_pairs<<<hz_grid((int)npairs), HZ_BLOCK>>>(in, sig, dg, (int)npairs);
+    for (int r = 0; r < reps; r++) {
+        if (lanes) k_poseidon_pairs<<<hz_grid((int)npairs), HZ_BLOCK>>>(in, sig, dg, (int)npairs);
+        else k_poseidon_t3<<<tgrid, 96>>>(in, sig, dg, nperms);
+    }
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     CK(cudaGetLastError());

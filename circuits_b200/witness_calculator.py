@@ -356,9 +356,10 @@ class ShardedWitnessCalculator(WitnessCalculator):
         return w
 
 
-def poseidon_pairs(inputs, reps=1, device=0, lib_path=None):
+def poseidon_pairs(inputs, reps=1, device=0, lib_path=None, lanes=False):
     """Run Poseidon(2) on pairs of pairs of field elements on the GPU (`hzw_poseidon_bench`):
-    inputs = [(a, b, c, d), ...] -> ([(poseidon([a, b]), poseidon([c, d])), ...], device ms per repetition)."""
+    inputs = [(a, b, c, d), ...] -> ([(poseidon([a, b]), poseidon([c, d])), ...], device ms per repetition).
+    lanes=True uses the lane-group kernel (the form inside k_smt), else the transposed one."""
     lib = load_library(lib_path)
     lib.hzw_poseidon_bench.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.POINTER(ctypes.c_float)]
@@ -366,7 +367,7 @@ def poseidon_pairs(inputs, reps=1, device=0, lib_path=None):
     buf = bytearray(b"".join(int(x % P).to_bytes(32, "little") for quad in inputs for x in quad))
     out = bytearray(64 * n)
     ms = ctypes.c_float()
-    st = lib.hzw_poseidon_bench(device, n, reps, _addr(buf), _addr(out), ctypes.byref(ms))
+    st = lib.hzw_poseidon_bench(device, n, -reps if lanes else reps, _addr(buf), _addr(out), ctypes.byref(ms))
     if st != 0:
         raise WitnessError("hzw_poseidon_bench failed with code %d" % st)
     dig = [(int.from_bytes(out[64 * i:64 * i + 32], "little"), int.from_bytes(out[64 * i + 32:64 * i + 64], "little"))

@@ -115,7 +115,9 @@ int hzw_shard_phase2(hzw_ctx* ctx, const void* records, int sanity_check, uint8_
 /* Poseidon alone, the second metric of the benchmark: `npairs` lane groups, each running two
  * Poseidon(2) permutations (the old-path / new-path hash pair of an SMT level,
  * circomlib smtprocessorlevel.circom via /root/reference/src/rollup-tx.circom:537) on the given
- * inputs and storing all signals of both components, `reps` times; device ms per repetition. */
+ * inputs and storing all signals of both components, |reps| times; device ms per repetition.  reps > 0 runs the
+ * transposed kernel (thread = one state element of one permutation, 32 permutations per 3-warp block), reps < 0 the
+ * lane-group form used inside the SMT kernel; both store the same signals at the same indexes. */
 int hzw_poseidon_bench(int device, uint64_t npairs, int reps, const uint8_t* inputs_le32 /* 4 x npairs x 32 B */,
                        uint8_t* digests_le32 /* 2 x npairs x 32 B, nullable */, float* ms_per_rep);
 

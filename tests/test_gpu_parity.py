@@ -105,7 +105,8 @@ def test_poseidon_lane_kernel_known_answers(built):
     rng = random.Random(7)
     quads = [(1, 2, 3, 4)] + [tuple(rng.randrange(P) for _ in range(4)) for _ in range(37)]
     quads += [(0, 0, P - 1, P - 1)]
-    got, _ = poseidon_pairs(quads)
-    assert got[0][0] == 0x115cc0f5e7d690413df64c6b9662e9cf2a3617f2743245519e19607a4417189a
-    for (a, b, c, d), (x, y) in zip(quads, got):
-        assert x == poseidon_hash([a, b]) and y == poseidon_hash([c, d])
+    for lanes in (False, True):          # transposed kernel, lane-group kernel
+        got, _ = poseidon_pairs(quads, lanes=lanes)
+        assert got[0][0] == 0x115cc0f5e7d690413df64c6b9662e9cf2a3617f2743245519e19607a4417189a
+        for (a, b, c, d), (x, y) in zip(quads, got):
+            assert x == poseidon_hash([a, b]) and y == poseidon_hash([c, d])
