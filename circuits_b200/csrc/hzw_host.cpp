@@ -29,7 +29,7 @@ struct CudaBackend : HzBackend {
     int withdraw_batch(uint64_t, const uint8_t*, int, uint8_t*, float*, HzErrBuf*) override { return HZW_E_PARAM; }
     int shard_phase2(const void* records, int sanity, uint8_t* shard_out, float* ms, HzErrBuf* errs) override {
         uint64_t t[32]; int n = hz_shard_pieces(*L, sh, t, 16);
-        launches = 11;
+        launches = 12;
         return hz_cuda_shard_phase2(d, records, sanity, shard_out, t, n, ms, errs, &d2h);
     }
 };

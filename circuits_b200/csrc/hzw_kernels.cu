@@ -20,8 +20,9 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
-#define HZ_NKERN 9
+#define HZ_NKERN 9   /* timed intervals; k_smt's covers the head and the levels kernels */
 static const char* const HZ_KERN_NAMES[HZ_NKERN] = {"k_front", "k_fee_front", "k_smt", "k_tail", "k_hash_head",
                                                     "k_sha_chain", "k_sha_blocks", "k_hash_tail", "k_eddsa"};
 #define HZ_BLOCK 128                       /* 16 lane groups per block */
@@ -36,6 +37,8 @@ struct HzCuda {
     HzEddsaJob* jobs;          // nTx
     HzSmtJob* smt;             // 2 nTx + maxFeeTx
     HzSmtMid* mids;            // 2 nTx + maxFeeTx
+    HzLevJob* lev;             // 2 nTx + maxFeeTx: what k_smt leaves for k_smt_levels
+    Fr* smst;                  // per processor (nLevels + 1) x 6 state-machine values
     Fr* isExit;                // nTx
     Fr* hint_cst;              // HZ_CST_MAX: constant inverses of EscalarMulFix (recorded at create)
     Fr* hint_tab;              // HZ_EDTAB_LEN: its window entries
@@ -108,10 +111,120 @@ __global__ void __launch_bounds__(HZ_BLOCK) k_fee_front(HzPlan pl, Fr* w, HzErrB
 }
 
 // jobs of the shard: 2 per own slot, then 1 per own fee tx
-__global__ void __launch_bounds__(HZ_BLOCK, 3) k_smt(HzPlan pl, Fr* w, HzErrBuf* err, const HzSmtJob* smt, HzSmtMid* mids, int s0, int ns, int f0, int nf) {
+__device__ __forceinline__ int hz_smt_job_index(const HzPlan& pl, int q, int s0, int ns, int f0) {
+    return q < 2 * ns ? 2 * s0 + q : 2 * pl.P.nTx + f0 + (q - 2 * ns);
+}
+__global__ void __launch_bounds__(HZ_BLOCK, 3) k_smt(HzPlan pl, Fr* w, HzErrBuf* err, const HzSmtJob* smt, HzSmtMid* mids, HzLevJob* lev, Fr* smst,
+                                                  int s0, int ns, int f0, int nf) {
     bool real; int q = hz_item(2 * ns + nf, real);
-    q = q < 2 * ns ? 2 * s0 + q : 2 * pl.P.nTx + f0 + (q - 2 * ns);
-    sec_smt_body(w, real ? err : nullptr, pl.P.nLevels + 1, smt[q], mids[q]);
+    q = hz_smt_job_index(pl, q, s0, ns, f0);
+    const int L = pl.P.nLevels + 1;
+    sec_smt_head(w, real ? err : nullptr, L, smt[q], mids[q], lev[q], smst + (size_t)q * L * 6);
+}
+
+// ---- the levels of all SMT processors, transposed ------------------------------------------------------
+// 132 of the 142 Poseidon permutations of a transaction are the old-path / new-path hashes of the
+// 2 x 33 levels.  A chain = one path of one processor: 33 Poseidon(2) one after the other plus a few
+// selections per level.  Thread (warp r, lane c) holds state element r of chain c, a block of 3 warps
+// runs 32 chains (16 processors): the S-box of a partial round is one full warp, the MDS rows meet in
+// shared memory once per round (k_poseidon_t3 is this kernel without the level glue).  Warp 0 also
+// does the per-level glue of its chain (switcher in front of the hash, root behind it).  Entry
+// offsets inside a level follow SMTProcessorLevel (templates_circomlib.cuh): oldRoot, newRoot,
+// [oldChild, newChild: bottom level only], aux[4], oldProofHash (634), newProofHash (634),
+// oldSwitcher (outL, outR, aux), newSwitcher (L, R, outL, outR, aux).
+__global__ void __launch_bounds__(96) k_smt_levels(HzPlan pl, Fr* w, const HzLevJob* jobs, const Fr* smst, HzSmtMid* mids,
+                                                   int s0, int ns, int f0, int nf) {
+    __shared__ uint32_t xch[2][3][8][32];
+    __shared__ uint32_t hin[2][8][32];
+    const int r = (int)(threadIdx.x >> 5), c = (int)(threadIdx.x & 31);
+    const int njobs = 2 * ns + nf, L = pl.P.nLevels + 1;
+    int q = (int)blockIdx.x * 16 + (c >> 1);
+    if (q >= njobs) q = njobs - 1;                    // padding chains redo the last processor (identical stores)
+    const int job = hz_smt_job_index(pl, q, s0, ns, f0);
+    const int side = c & 1;                           // 0: old path, 1: new path
+    const HzLevJob& J = jobs[job];
+    const Fr* stj = smst + (size_t)job * L * 6;
+    const Fr o1 = J.o1, n1 = J.n1;
+    const uint32_t HS = HZ_SZ_SMTHASH2_WIRED;
+    const Fr* C = &hz_poseidon_c(3, 0);
+    Fr m[3];
+    for (int k = 0; k < 3; k++) m[k] = hz_poseidon_mr(3, r)[k];
+    Fr child = fr_zero();
+    for (int lev = L - 1; lev >= 0; lev--) {
+        const bool bottom = lev == L - 1;
+        const uint32_t lb = J.cur + (bottom ? 0u : 2u + (uint32_t)(L - 1 - lev) * HZ_SZ_SMT_LEVEL);
+        const uint32_t o_aux = lb + 2 + (bottom ? 2u : 0u), o_oph = o_aux + 4, o_nph = o_oph + HS, o_osw = o_nph + HS, o_nsw = o_osw + 3;
+        Fr st_top, st_old0, st_bot, st_new1, st_upd;
+        if (r == 0) {
+            st_top = stj[lev * 6 + 0]; st_old0 = stj[lev * 6 + 1]; st_bot = stj[lev * 6 + 2]; st_new1 = stj[lev * 6 + 3]; st_upd = stj[lev * 6 + 5];
+            const Fr sib = w[J.sib + lev];
+            const Fr lr = fr_from_u64((J.lrbits >> lev) & 1ull);
+            Fr hL, hR;
+            if (side == 0) {
+                if (bottom) hz_store_fr(&w[lb + 2], fr_zero());
+                Fr aux = fr_mul(fr_sub(sib, child), lr);
+                hL = fr_add(aux, child); hR = fr_sub(sib, aux);
+                hz_store_fr(&w[o_osw], hL); hz_store_fr(&w[o_osw + 1], hR); hz_store_fr(&w[o_osw + 2], aux);
+            } else {
+                if (bottom) hz_store_fr(&w[lb + 3], fr_zero());
+                Fr a1 = fr_mul(child, fr_add(st_top, st_bot)), a2 = fr_mul(sib, st_top);
+                Fr Ln = fr_add(a1, fr_mul(n1, st_new1)), Rn = fr_add(a2, fr_mul(o1, st_new1));
+                Fr aux = fr_mul(fr_sub(Rn, Ln), lr);
+                hL = fr_add(aux, Ln); hR = fr_sub(Rn, aux);
+                hz_store_fr(&w[o_aux + 1], a1); hz_store_fr(&w[o_aux + 2], a2);
+                hz_store_fr(&w[o_nsw], Ln); hz_store_fr(&w[o_nsw + 1], Rn); hz_store_fr(&w[o_nsw + 2], hL);
+                hz_store_fr(&w[o_nsw + 3], hR); hz_store_fr(&w[o_nsw + 4], aux);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) { hin[0][k][c] = hL.l[k]; hin[1][k][c] = hR.l[k]; }
+        }
+        __syncthreads();
+        Fr s = fr_zero();
+        if (r > 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) s.l[k] = hin[r - 1][k][c];
+        }
+        // SMTHash2 (wired L, R) -> Poseidon(2): entry 0 is ark[0].in[0] = 0
+        Fr* hw = w + (side == 0 ? o_oph : o_nph);
+        if (r == 0) hz_store_fr(&hw[0], s);
+        uint32_t cur = 1;
+        for (int i = 0; i < 65; i++) {
+            s = fr_add(s, C[3 * i + r]);
+            hz_store_fr(&hw[cur + r], s);
+            const bool full = i < 4 || i >= 61;
+            const uint32_t sg = cur + 6;
+            if (full || r == 0) {                       // warp-uniform
+                Fr in2 = fr_mul_chain(s, s);
+                Fr in4 = fr_mul_chain(in2, in2);
+                s = fr_mul_chain(in4, s);
+                hz_store_fr(&hw[sg + 3 * r], s); hz_store_fr(&hw[sg + 3 * r + 1], in2); hz_store_fr(&hw[sg + 3 * r + 2], in4);
+            }
+            uint32_t (*buf)[8][32] = xch[i & 1];
+#pragma unroll
+            for (int k = 0; k < 8; k++) buf[r][k][c] = s.l[k];
+            __syncthreads();
+            Fr a[3];
+#pragma unroll
+            for (int qq = 0; qq < 3; qq++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) a[qq].l[k] = buf[qq][k][c];
+            s = fr_dot_mont_chain<3>(a, m);
+            hz_store_fr(&hw[cur + 3 + r], s);
+            cur += 6 + (full ? 9 : 3);
+        }
+        if (r == 0) {
+            if (side == 0) {
+                Fr a0 = fr_mul(o1, fr_add(fr_add(st_bot, st_new1), st_upd));
+                child = fr_add(a0, fr_mul(s, st_top));
+                hz_store_fr(&w[o_aux], a0); hz_store_fr(&w[lb], child);
+            } else {
+                Fr a3 = fr_mul(s, fr_add(fr_add(st_top, st_bot), st_new1));
+                child = fr_add(a3, fr_mul(n1, fr_add(st_old0, st_upd)));
+                hz_store_fr(&w[o_aux + 3], a3); hz_store_fr(&w[lb + 1], child);
+            }
+        }
+    }
+    if (r == 0) { if (side == 0) mids[job].oc = child; else mids[job].nc = child; }
 }
 
 // one-time: the constant division sites and window entries of EscalarMulFix(253, BASE8)
@@ -438,6 +551,8 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaMalloc(&d->jobs, sizeof(HzEddsaJob) * P.nTx) == cudaSuccess;
     ok = ok && cudaMalloc(&d->smt, sizeof(HzSmtJob) * (2 * P.nTx + P.maxFeeTx)) == cudaSuccess;
     ok = ok && cudaMalloc(&d->mids, sizeof(HzSmtMid) * (2 * P.nTx + P.maxFeeTx)) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->lev, sizeof(HzLevJob) * (2 * P.nTx + P.maxFeeTx)) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->smst, sizeof(Fr) * 6 * (size_t)(P.nLevels + 1) * (2 * P.nTx + P.maxFeeTx)) == cudaSuccess;
     ok = ok && cudaMalloc(&d->isExit, sizeof(Fr) * P.nTx) == cudaSuccess;
     ok = ok && cudaMalloc(&d->hint_cst, sizeof(Fr) * HZ_CST_MAX) == cudaSuccess;
     ok = ok && cudaMalloc(&d->hint_tab, sizeof(Fr) * HZ_EDTAB_LEN) == cudaSuccess;
@@ -459,6 +574,18 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaEventCreateWithFlags(&d->ev_front, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_eddsa, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; k < HZ_NKERN + 2; k++) ok = ok && cudaEventCreate(&d->kev[k]) == cudaSuccess;
+    // kernels that are to share an SM must agree on its L1 / shared-memory split: k_smt_levels stages the MDS
+    // exchange in shared memory, k_eddsa (running beside it on the second stream) uses none -- without a common
+    // carve-out the second kernel only gets SMs the first has left
+    {
+        const int carve = 15;    // percent of the 228 KB: room for four k_smt_levels blocks
+        cudaFuncSetAttribute(k_front, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_fee_front, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_eddsa, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_smt, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_smt_levels, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_tail, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    }
     // the per-thread frames of the circuit templates are large (sibling arrays, state machines)
     ok = ok && cudaDeviceSetLimit(cudaLimitStackSize, 80 * 1024) == cudaSuccess;
     if (ok) {
@@ -491,7 +618,7 @@ void hz_cuda_destroy(HzCuda* d) {
     if (!d) return;
     cudaSetDevice(d->device);
     cudaFree(d->w); cudaFree(d->pre); cudaFree(d->chain); cudaFree(d->msgw); cudaFree(d->jobs); cudaFree(d->err);
-    cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit);
+    cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit); cudaFree(d->lev); cudaFree(d->smst);
     cudaFree(d->hint_cst); cudaFree(d->hint_tab); cudaFree(d->hint_img); cudaFree(d->hint_scratch); cudaFree(d->recs);
     cudaFree(d->off_decode); cudaFree(d->off_rollup); cudaFree(d->off_fee); cudaFree(d->off_blocks);
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -533,7 +660,7 @@ uint64_t hz_cuda_exchange_bytes(const HzCuda* d) { return hz_rec_bytes(d->plan.P
 // phase 1: inputs to the device, then everything per slot / fee tx of the shard
 static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     const HzPlan& pl = d->plan;
-    cudaStream_t s = d->stream, s2 = d->stream2;
+    cudaStream_t s = d->stream, s2 = getenv("HZW_SERIAL_STREAMS") ? d->stream : d->stream2;    // (measurement switch)
     HzErrBuf* err = sanity ? d->err : nullptr;
     CK(cudaMemsetAsync(d->err, 0, sizeof(HzErrBuf), s));
     CK(cudaMemsetAsync(d->pre, 0, (size_t)pl.nblocks * 512, s));
@@ -552,7 +679,10 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     CK(cudaEventRecord(d->ev_eddsa, s2));
     if (nf > 0) k_fee_front<<<hz_grid(nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt + 2 * pl.P.nTx, f0, nf);
     CK(cudaEventRecord(d->kev[2], s));
-    if (2 * ns + nf > 0) k_smt<<<hz_grid(2 * ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt, d->mids, s0, ns, f0, nf);
+    if (2 * ns + nf > 0) {
+        k_smt<<<hz_grid(2 * ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, f0, nf);
+        k_smt_levels<<<(unsigned)((2 * ns + nf + 15) / 16), 96, 0, s>>>(pl, d->w, d->lev, d->smst, d->mids, s0, ns, f0, nf);
+    }
     CK(cudaEventRecord(d->kev[3], s));
     if (ns + nf > 0) k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->mids, d->isExit, s0, ns, f0, nf);
     CK(cudaEventRecord(d->kev[4], s));
@@ -607,7 +737,10 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
         const int s0 = h == 0 ? 0 : h0, ns = h == 0 ? h0 : P.nTx - h0, nf = h == 1 ? F : 0;
         if (ns > 0) k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, s0, ns);
         CK(cudaEventRecord(d->ev_ed[h], s2));
-        if (2 * ns + nf > 0) k_smt<<<hz_grid(2 * ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt, d->mids, s0, ns, 0, nf);
+        if (2 * ns + nf > 0) {
+            k_smt<<<hz_grid(2 * ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, 0, nf);
+            k_smt_levels<<<(unsigned)((2 * ns + nf + 15) / 16), 96, 0, s>>>(pl, d->w, d->lev, d->smst, d->mids, s0, ns, 0, nf);
+        }
         if (ns + nf > 0) k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->mids, d->isExit, s0, ns, 0, nf);
         CK(cudaStreamWaitEvent(s, d->ev_ed[h], 0));
         CK(cudaEventRecord(d->ev_half[h], s));
@@ -647,7 +780,7 @@ int hz_cuda_calculate(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* wit
     CK(cudaStreamSynchronize(s));
     if (overlapped) CK(cudaStreamSynchronize(d->stream3));
     if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, d->ev0, d->ev1));
-    if (launches) *launches = overlapped ? HZ_NKERN + 3 : HZ_NKERN;
+    if (launches) *launches = overlapped ? 14 : 10;        // kernels of ours per batch (see the launch sequences above)
     if (h2d) *h2d = inputs ? 32ull * pl.n_inputs : 0;
     if (d2h) *d2h = (witness_out ? 32ull * pl.nvars : 0) + sizeof(HzErrBuf);
     return 0;

@@ -221,28 +221,35 @@ TM HZ_FN V<M> sec_fee(Comp<M>& c, const HzPlan& pl, int i, const FeeHook<M>& hoo
 // ---- device only: bodies and tops of the SMT processors as their own sections -------------------
 __device__ __forceinline__ VC hz_sigv(const Fr& f, bool sig) { VC r; r.v = f; r.sig = sig; return r; }
 
-// one SMTProcessor body from its job record (k_smt)
-__device__ __noinline__ void sec_smt_body(Fr* w, HzErrBuf* err, int nLevels1, const HzSmtJob& j, HzSmtMid& out) {
+// head of one SMTProcessor body from its job record (k_smt): everything before the levels; the levels
+// themselves are evaluated by k_smt_levels from the HzLevJob and the state-machine tuples left here
+__device__ __noinline__ void sec_smt_head(Fr* w, HzErrBuf* err, int nLevels1, const HzSmtJob& j, HzSmtMid& out, HzLevJob& lev, Fr* smst) {
     Comp<MCompute> c(w, j.cur, err);
     VC sib[HZ_MAX_LEVELS];
     for (int k = 0; k < nLevels1; k++) sib[k] = c.load(j.sib + k);
     VC f[2];
     f[0] = hz_sigv(j.fnc0, j.sigmask & 32u); f[1] = hz_sigv(j.fnc1, j.sigmask & 64u);
     SMTMid<MCompute> mid;
+    SMTHead<MCompute> hd;
     // the old root is not needed by the body (wired signal: no entry); the top gets the real one
-    SMTProcessorBody<MCompute>(c, nLevels1, hz_sigv(fr_zero(), true), sib, hz_sigv(j.oldKey, j.sigmask & 1u),
+    SMTProcessorHead<MCompute>(c, nLevels1, hz_sigv(fr_zero(), true), sib, hz_sigv(j.oldKey, j.sigmask & 1u),
                                hz_sigv(j.oldValue, j.sigmask & 2u), hz_sigv(j.isOld0, j.sigmask & 4u),
-                               hz_sigv(j.newKey, j.sigmask & 8u), hz_sigv(j.newValue, j.sigmask & 16u), f, mid);
-    if (hz_glane() == 0) {
+                               hz_sigv(j.newKey, j.sigmask & 8u), hz_sigv(j.newValue, j.sigmask & 16u), f, mid, hd);
+    const uint32_t lane = hz_glane();
+    for (int k = (int)lane; k < nLevels1 * 6; k += HZ_G) smst[k] = hd.sm[k / 6][k % 6].v;
+    if (lane == 0) {
+        uint64_t bits = 0;
+        for (int k = 0; k < nLevels1; k++) bits |= (uint64_t)hd.n2bNew.bit(k) << k;
+        lev.o1 = hd.hash1Old.v; lev.n1 = hd.hash1New.v; lev.lrbits = bits; lev.cur = c.cur; lev.sib = j.sib;
         out.enabled = mid.enabled.v; out.oldKey = mid.oldKey.v; out.newKey = mid.newKey.v; out.fnc0 = mid.fnc0.v;
-        out.fnc1 = mid.fnc1.v; out.tL = mid.tL.v; out.tR = mid.tR.v; out.cur = c.cur; out.newRootIdx = mid.newRootIdx;
+        out.fnc1 = mid.fnc1.v; out.cur = c.cur + hz_smt_levels_size(nLevels1); out.newRootIdx = mid.newRootIdx;
     }
 }
 __device__ __forceinline__ VC hz_smt_top(Comp<MCompute>& c, const HzSmtMid& m, const VC& oldRoot) {
     SMTMid<MCompute> mid;
     mid.oldRoot = oldRoot; mid.enabled = hz_sigv(m.enabled, true); mid.oldKey = hz_sigv(m.oldKey, true);
     mid.newKey = hz_sigv(m.newKey, true); mid.fnc0 = hz_sigv(m.fnc0, true); mid.fnc1 = hz_sigv(m.fnc1, true);
-    mid.tL = hz_sigv(m.tL, true); mid.tR = hz_sigv(m.tR, true); mid.newRootIdx = m.newRootIdx;
+    mid.oc = hz_sigv(m.oc, true); mid.nc = hz_sigv(m.nc, true); mid.newRootIdx = m.newRootIdx;
     c.cur = m.cur;
     return SMTProcessorTop<MCompute>(c, mid);
 }

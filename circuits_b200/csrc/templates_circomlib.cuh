@@ -637,15 +637,21 @@ TM HZ_FN void SMTProcessorLevel(Comp<M>&& c, const V<M>* st, const V<M>& sibling
 // does.  The device evaluates the bodies of all processors of a batch at once and the tops
 // afterwards, when processor 2's old root (= processor 1's new root, src/rollup-tx.circom:553-560)
 // is known; everywhere else the two run back to back.
-TM struct SMTMid { V<M> oldRoot, enabled, oldKey, newKey, fnc0, fnc1, tL, tR; uint32_t newRootIdx; };
+TM struct SMTMid { V<M> oldRoot, enabled, oldKey, newKey, fnc0, fnc1, oc, nc; uint32_t newRootIdx; };
+// what the head of the body leaves for the levels
+TM struct SMTHead { V<M> sib[HZ_MAX_LEVELS]; V<M> hash1Old, hash1New; V<M> sm[HZ_MAX_LEVELS][6]; BV<M> n2bNew; };
+// witness entries of the nLevels level components: 1282 each (oldRoot, newRoot, aux[4], two wired SMTHash2, the
+// two switchers), the bottom one (instantiated first) with two more for its constant children
+#define HZ_SZ_SMT_LEVEL (2 + 4 + 2 * HZ_SZ_SMTHASH2_WIRED + 3 + 5)
+HZ_HD uint32_t hz_smt_levels_size(int nLevels) { return (uint32_t)nLevels * HZ_SZ_SMT_LEVEL + 2; }
 
-TM HZ_FN void SMTProcessorBody(Comp<M>& c, int nLevels, const V<M>& oldRoot, const V<M>* siblings,
+// everything of the body before the levels: leaf hashes, key bits, level-insert flags, state machine
+TM HZ_FN void SMTProcessorHead(Comp<M>& c, int nLevels, const V<M>& oldRoot, const V<M>* siblings,
                                const V<M>& oldKey, const V<M>& oldValue, const V<M>& isOld0,
-                               const V<M>& newKey, const V<M>& newValue, const V<M>* fnc, SMTMid<M>& mid) {
+                               const V<M>& newKey, const V<M>& newValue, const V<M>* fnc, SMTMid<M>& mid, SMTHead<M>& hd) {
     mid.oldRoot = c.def("oldRoot", oldRoot);
     mid.newRootIdx = c.sig("newRoot");
-    V<M> sib[HZ_MAX_LEVELS];
-    for (int i = 0; i < nLevels; i++) sib[i] = c.def(Nm("siblings", i), siblings[i]);
+    for (int i = 0; i < nLevels; i++) hd.sib[i] = c.def(Nm("siblings", i), siblings[i]);
     V<M> oldKey_ = c.def("oldKey", oldKey);
     V<M> oldValue_ = c.def("oldValue", oldValue);
     V<M> isOld0_ = c.def("isOld0", isOld0);
@@ -655,44 +661,52 @@ TM HZ_FN void SMTProcessorBody(Comp<M>& c, int nLevels, const V<M>& oldRoot, con
     f[0] = c.def(Nm("fnc", 0), fnc[0]);
     f[1] = c.def(Nm("fnc", 1), fnc[1]);
     V<M> enabled = c.def("enabled", f[0] + f[1] - f[0] * f[1]);
-    V<M> hash1Old, hash1New;
     {
         Comp<M> h1o = c.sub_reserve("hash1Old", HZ_SZ_SMTHASH1_WIRED);
         Comp<M> h1n = c.sub_reserve("hash1New", HZ_SZ_SMTHASH1_WIRED);
-        SMTHash1Pair<M>(HZ_MV(h1o), oldKey_, oldValue_, HZ_MV(h1n), newKey_, newValue_, hash1Old, hash1New);
+        SMTHash1Pair<M>(HZ_MV(h1o), oldKey_, oldValue_, HZ_MV(h1n), newKey_, newValue_, hd.hash1Old, hd.hash1New);
     }
     BV<M> n2bOld = Num2Bits_strict(c.sub("n2bOld"), oldKey_);
-    BV<M> n2bNew = Num2Bits_strict(c.sub("n2bNew"), newKey_);
+    hd.n2bNew = Num2Bits_strict(c.sub("n2bNew"), newKey_);
     V<M> levIns[HZ_MAX_LEVELS];
-    SMTLevIns(c.sub("smtLevIns"), nLevels, enabled, sib, levIns);
+    SMTLevIns(c.sub("smtLevIns"), nLevels, enabled, hd.sib, levIns);
     V<M> xors[HZ_MAX_LEVELS];
-    for (int i = 0; i < nLevels; i++) xors[i] = XOR(c.sub(Nm("xors", i)), n2bOld.get(i), n2bNew.get(i));
-    // state machine; sm[i] tuples kept for the levels
-    V<M> sm[HZ_MAX_LEVELS][6];
+    for (int i = 0; i < nLevels; i++) xors[i] = XOR(c.sub(Nm("xors", i)), n2bOld.get(i), hd.n2bNew.get(i));
     for (int i = 0; i < nLevels; i++) {
         V<M> prev[6];
         if (i == 0) {
             prev[0] = enabled; prev[1] = Ops<M>::K(0); prev[2] = Ops<M>::K(0); prev[3] = Ops<M>::K(0);
             prev[4] = 1 - enabled; prev[5] = Ops<M>::K(0);
         } else {
-            for (int k = 0; k < 6; k++) prev[k] = sm[i - 1][k];
+            for (int k = 0; k < 6; k++) prev[k] = hd.sm[i - 1][k];
         }
-        SMTProcessorSM(c.sub(Nm("sm", i)), xors[i], isOld0_, levIns[i], f, prev, sm[i]);
+        SMTProcessorSM(c.sub(Nm("sm", i)), xors[i], isOld0_, levIns[i], f, prev, hd.sm[i]);
     }
-    HZ_CHECK(c, sm[nLevels - 1][4] + sm[nLevels - 1][3] + sm[nLevels - 1][1] + sm[nLevels - 1][5], Ops<M>::K(1));
-    V<M> oc = Ops<M>::K(0), nc = Ops<M>::K(0);
+    HZ_CHECK(c, hd.sm[nLevels - 1][4] + hd.sm[nLevels - 1][3] + hd.sm[nLevels - 1][1] + hd.sm[nLevels - 1][5], Ops<M>::K(1));
+    mid.enabled = enabled; mid.oldKey = oldKey_; mid.newKey = newKey_; mid.fnc0 = f[0]; mid.fnc1 = f[1];
+}
+// the levels, bottom up: old-path and new-path roots of level 0
+TM HZ_FN void SMTProcessorLevels(Comp<M>& c, int nLevels, const SMTHead<M>& hd, V<M>& oc, V<M>& nc) {
+    oc = Ops<M>::K(0); nc = Ops<M>::K(0);
     for (int i = nLevels - 1; i >= 0; i--) {
         V<M> o, n;
-        SMTProcessorLevel(c.sub(Nm("levels", i)), sm[i], sib[i], hash1Old, hash1New, n2bNew.get(i), oc, nc, o, n);
+        SMTProcessorLevel(c.sub(Nm("levels", i)), hd.sm[i], hd.sib[i], hd.hash1Old, hd.hash1New, hd.n2bNew.get(i), oc, nc, o, n);
         oc = o; nc = n;
     }
-    Switcher(c.sub("topSwitcher"), f[0] * f[1], oc, nc, mid.tL, mid.tR);
-    mid.enabled = enabled; mid.oldKey = oldKey_; mid.newKey = newKey_; mid.fnc0 = f[0]; mid.fnc1 = f[1];
+}
+TM HZ_FN void SMTProcessorBody(Comp<M>& c, int nLevels, const V<M>& oldRoot, const V<M>* siblings,
+                               const V<M>& oldKey, const V<M>& oldValue, const V<M>& isOld0,
+                               const V<M>& newKey, const V<M>& newValue, const V<M>* fnc, SMTMid<M>& mid) {
+    SMTHead<M> hd;
+    SMTProcessorHead<M>(c, nLevels, oldRoot, siblings, oldKey, oldValue, isOld0, newKey, newValue, fnc, mid, hd);
+    SMTProcessorLevels<M>(c, nLevels, hd, mid.oc, mid.nc);
 }
 
 TM HZ_FN V<M> SMTProcessorTop(Comp<M>& c, const SMTMid<M>& mid) {
-    ForceEqualIfEnabled(c.sub("checkOldInput"), mid.enabled, mid.oldRoot, mid.tL);
-    V<M> nr = c.set(mid.newRootIdx, mid.enabled * (mid.tR - mid.oldRoot) + mid.oldRoot);
+    V<M> tL, tR;
+    Switcher(c.sub("topSwitcher"), mid.fnc0 * mid.fnc1, mid.oc, mid.nc, tL, tR);
+    ForceEqualIfEnabled(c.sub("checkOldInput"), mid.enabled, mid.oldRoot, tL);
+    V<M> nr = c.set(mid.newRootIdx, mid.enabled * (tR - mid.oldRoot) + mid.oldRoot);
     V<M> eq = IsEqual(c.sub("areKeyEquals"), mid.oldKey, mid.newKey);
     V<M> xs[3];
     xs[0] = 1 - mid.fnc0; xs[1] = mid.fnc1; xs[2] = 1 - eq;

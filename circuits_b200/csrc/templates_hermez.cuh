@@ -482,7 +482,10 @@ struct HzEddsaJob { Fr aySignature, signSignature, enabled, s1Ay, S, R8x, R8y, M
 // own), k: 0 oldKey, 1 oldValue, 2 isOld0, 3 newKey, 4 newValue, 5 fnc[0], 6 fnc[1]
 struct HzSmtJob { Fr oldKey, oldValue, isOld0, newKey, newValue, fnc0, fnc1; uint32_t cur, sib, sigmask, pad[5]; };
 // what a body leaves for its top; cur = witness cursor where the top continues
-struct HzSmtMid { Fr enabled, oldKey, newKey, fnc0, fnc1, tL, tR; uint32_t cur, newRootIdx, pad[6]; };
+struct HzSmtMid { Fr enabled, oldKey, newKey, fnc0, fnc1, oc, nc; uint32_t cur, newRootIdx, pad[6]; };
+// what the head of a body leaves for the levels kernel: leaf hashes, the level bits of the new key, where the
+// level components start, where the siblings are; the state-machine tuples go to a scratch array
+struct HzLevJob { Fr o1, n1; uint64_t lrbits; uint32_t cur, sib, pad[4]; };
 struct HzSizes { uint32_t getAx, sigVerifier, phaseJK, p2_off; };   // p2_off: processor2 start within phases J-K
 
 TM struct SlotHook;
