@@ -33,8 +33,20 @@ METRIC = "rollup-main(2048,32) witness tx/sec"
 CPU_PORT = os.path.join(ROOT, "oracle", "_ref", "libhzw_cpu_port.so")
 
 
+_REAL_STDOUT = None
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def make_input(cfg):
@@ -181,7 +193,7 @@ def run_reference(args, cfg, cfg_name):
     os.environ.pop("HZW_CPU_SAMPLE_STRIDE", None)
     val = n_s / dt
     base["value"] = val
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "tx/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (BN254 Fr, 254-bit modular)",
@@ -189,7 +201,7 @@ def run_reference(args, cfg, cfg_name):
                                          "maxFeeTx": cfg[3], "l2_flush": "n/a (CPU)"},
         "cpu_baseline": base,
         "e2e": {"value": val, "unit": "tx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
 
 
 def poseidon_metric(device):
@@ -400,10 +412,15 @@ def run_gpu(args, cfg, cfg_name):
             log("[bench] int roofline skipped: %r" % (e,))
     if base is not None:
         line["cpu_baseline"] = base
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
+    # the driver reads ONE JSON line from stdout: libraries that print there (NCCL's version banner) go to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -17,6 +17,7 @@
 #define HZ_BASE8_Y_LIMBS {0x872d7d8bu, 0x4b3c257au, 0xb9e13377u, 0xfce0051fu, 0xd16bf9edu, 0x25572e1cu, 0xf7a0b249u, 0x25797203u}
 #define HZ_TONELLI_C_LIMBS {0x725b19f0u, 0x9bd61b6eu, 0x41112ed4u, 0x402d111eu, 0x8ef62abcu, 0x00e0a7ebu, 0xa58a7e85u, 0x2a3c09f0u}
 #define HZ_TONELLI_T_LIMBS {0x3e1f593fu, 0x9b970914u, 0x833e8487u, 0x181585d2u, 0x85045b68u, 0x131a029bu, 0x0644e72eu, 0x00000003u}
+#define HZ_TONELLI_TM1H_LIMBS {0x1f0fac9fu, 0xcdcb848au, 0x419f4243u, 0x0c0ac2e9u, 0xc2822db4u, 0x098d014du, 0x83227397u, 0x00000001u}
 #define HZ_TONELLI_T1H_LIMBS {0x1f0faca0u, 0xcdcb848au, 0x419f4243u, 0x0c0ac2e9u, 0xc2822db4u, 0x098d014du, 0x83227397u, 0x00000001u}
 #define TM template <class M>
 typedef BVT<MCompute, 8> BVC;
@@ -1189,18 +1190,22 @@ TM HZ_FN void EdDSAPoseidonVerifier(Comp<M>&& c, const V<M>& enabled, const V<M>
 // circomlib `sqrt()`: Tonelli-Shanks, 0 for non-residues, result normalised to <= (p-1)/2
 HZ_HDN Fr fr_sqrt(const Fr& n) {
     if (fr_is_zero(n)) return n;
-    // (p-1)/2
-    Fr half = fr_const_half();
     Fr one = fr_one();
-    if (!fr_eq(fr_pow(n, half.l, 253), one)) return fr_zero();
+    // p - 1 = t 2^28, t odd.  One exponentiation gives everything: x = n^((t-1)/2), r = x n = n^((t+1)/2),
+    // tt = r x = n^t, and Euler's criterion n^((p-1)/2) = tt^(2^27) (circomlib evaluates three separate powers;
+    // the values are the same)
+    const uint32_t e_l[8] = HZ_TONELLI_TM1H_LIMBS;      // (t-1)/2
+    const uint32_t cst_l[8] = HZ_TONELLI_C_LIMBS;       // c = 5^t
+    Fr x = fr_pow(n, e_l, 225);
+    Fr r = fr_mul(x, n);
+    Fr t = fr_mul(r, x);
+    {
+        Fr s = t;
+        for (int k = 0; k < 27; k++) s = fr_sqr(s);
+        if (!fr_eq(s, one)) return fr_zero();
+    }
     int m = 28;
-    // c = 5^t, t = (p-1)/2^28
-    const uint32_t cst_l[8] = HZ_TONELLI_C_LIMBS;
-    const uint32_t t_l[8] = HZ_TONELLI_T_LIMBS;
-    const uint32_t t1_l[8] = HZ_TONELLI_T1H_LIMBS;     // (t+1)/2
     Fr cst; for (int i = 0; i < 8; i++) cst.l[i] = cst_l[i];
-    Fr t = fr_pow(n, t_l, 226);
-    Fr r = fr_pow(n, t1_l, 226);
     while (!fr_is_zero(r) && !fr_eq(t, one)) {
         Fr sq = fr_sqr(t);
         int i = 1;
