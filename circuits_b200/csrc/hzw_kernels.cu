@@ -34,7 +34,9 @@ struct HzCuda {
     uint8_t* pre;              // SHA pre-image bits, nblocks*512
     uint32_t* chain;           // (nblocks+1) x 8
     uint32_t* msgw;            // nblocks x 16
-    HzEddsaJob* jobs;          // nTx
+    HzEddsaJob* jobs;          // nTx: from k_edjob, read by k_eddsa
+    HzEddsaJob* jobs_front;    // nTx: the same as the templates of k_front arrive at them (k_tail compares)
+    uint32_t* off_eddsa;       // nTx: where phase F of each slot starts
     HzSmtJob* smt;             // 2 nTx + maxFeeTx
     HzSmtMid* mids;            // 2 nTx + maxFeeTx
     HzLevJob* lev;             // 2 nTx + maxFeeTx: what k_smt leaves for k_smt_levels
@@ -59,6 +61,7 @@ struct HzCuda {
 };
 
 static void hz_set_ranges(HzCuda* d, int rank, int world);
+__device__ __forceinline__ void hz_head_err(HzErrBuf* err, uint32_t cur, uint32_t line, const Fr& lhs);
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "hzw: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return HZW_E_DEVICE; } } while (0)
 
@@ -98,6 +101,62 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_front(HzPlan pl, Fr* w, uint8_t
     RollupTxOut<MCompute> o;
     sec_rollup(c, pl, i, d, o, pre, hook);
     c.flush_pending();
+}
+
+// ---- the EdDSA job of a slot straight from the main inputs -------------------------------------------
+// The signature is the longest chain of a slot, and what it needs from the rest of the slot is little:
+// the message hash (src/decode-tx.circom:254-283: Poseidon(6) over inputs and one repacked element),
+// the signer's key (state 1, or the compressed key of an account being created:
+// src/rollup-tx.circom:331-343,454-482) and verifySignEnabled (src/rollup-tx-states.circom:98-103,222).
+// This kernel derives them from the inputs with the formulas of those templates, so k_eddsa starts at
+// once instead of after k_front.  k_front still records the job the templates arrive at; k_tail compares
+// the two when the sanity check is on.
+__global__ void __launch_bounds__(HZ_BLOCK, 3) k_edjob(HzPlan pl, const Fr* w, HzEddsaJob* jobs, const uint32_t* off_eddsa, int s0, int ns) {
+    bool real; int i = s0 + hz_item(ns, real);
+    const int lane = (int)hz_glane();
+    auto in = [&](int f) -> Fr { return w[pl.in_off[f] + (uint32_t)i * pl.in_d1[f]]; };
+    const Fr txc = in(IN_txCompressedData), oc = in(IN_onChain), na = in(IN_newAccount);
+    // states: finalFromIdx = Mux1(fromIdx, auxFromIdx, onChain * newAccount), fromIdx = bits 48..95 of txCompressedData
+    Fr fromIdx = fr_zero();
+    fromIdx.l[0] = (txc.l[1] >> 16) | (txc.l[2] << 16);
+    fromIdx.l[1] = txc.l[2] >> 16;
+    const Fr ins1 = fr_mul(oc, na);                                   // isP1Insert
+    const Fr fin = fr_add(fr_mul(fr_sub(in(IN_auxFromIdx), fromIdx), ins1), fromIdx);
+    const Fr vse = fr_mul(fr_sub(fr_one(), oc), fr_is_zero(fin) ? fr_zero() : fr_one());
+    // decodeTx: element 1 of the message = toEthAddr (160 bits) | amountF (40) << 160 | maxNumBatch (32) << 200
+    const Fr eth = in(IN_toEthAddr), am = in(IN_amountF), mnb = in(IN_maxNumBatch);
+    Fr e1;
+#pragma unroll
+    for (int k = 0; k < 5; k++) e1.l[k] = eth.l[k];
+    e1.l[5] = am.l[0]; e1.l[6] = (am.l[1] & 0xffu) | (mnb.l[0] << 8); e1.l[7] = mnb.l[0] >> 24;
+    Fr hs = fr_zero();
+    if (lane == 1) hs = txc; else if (lane == 2) hs = e1; else if (lane == 3) hs = in(IN_toBjjAy);
+    else if (lane == 4) hs = in(IN_rqTxCompressedDataV2); else if (lane == 5) hs = in(IN_rqToEthAddr); else if (lane == 6) hs = in(IN_rqToBjjAy);
+    const Fr M = hz_poseidon_lanes<7, true>(nullptr, 0, hs, 0);
+    // decodeFromBjj: ay = bits 0..253 (mod p), sign = bit 255; the lanes read every 8th bit each
+    uint32_t bl[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) bl[k] = 0;
+    const uint32_t bjj0 = pl.in_off[IN_fromBjjCompressed] + (uint32_t)i * pl.in_d1[IN_fromBjjCompressed];
+    for (int k = lane; k < 256; k += HZ_G) bl[k >> 5] |= (w[bjj0 + k].l[0] & 1u) << (k & 31);
+#pragma unroll
+    for (int o = 1; o < HZ_G; o <<= 1)
+#pragma unroll
+        for (int k = 0; k < 8; k++) bl[k] |= __shfl_xor_sync(0xffffffffu, bl[k], o, HZ_G);
+    Fr bay;
+#pragma unroll
+    for (int k = 0; k < 8; k++) bay.l[k] = bl[k];
+    const Fr bsign = fr_from_u64(bl[7] >> 31);
+    bay.l[7] &= 0x3fffffffu;
+    if (fr_geq_p(bay)) fr_sub_p(bay);
+    const Fr sign1 = in(IN_sign1), ay1 = in(IN_ay1);
+    const Fr s1Sign = fr_add(fr_mul(fr_sub(bsign, sign1), ins1), sign1);
+    const Fr s1Ay = fr_add(fr_mul(fr_sub(bay, ay1), ins1), ay1);
+    if (lane == 0) {
+        HzEddsaJob& j = jobs[i];
+        j.aySignature = fr_mul(s1Ay, vse); j.signSignature = fr_mul(s1Sign, vse); j.enabled = vse; j.s1Ay = s1Ay;
+        j.S = in(IN_s); j.R8x = in(IN_r8x); j.R8y = in(IN_r8y); j.M = M; j.cur = off_eddsa[i];
+    }
 }
 
 __global__ void __launch_bounds__(HZ_BLOCK) k_fee_front(HzPlan pl, Fr* w, HzErrBuf* err, HzSmtJob* smt, int f0, int nf) {
@@ -249,9 +308,20 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_eddsa(HzPlan pl, Fr* w, HzErrBu
     c.flush_pending();
 }
 
-__global__ void __launch_bounds__(HZ_BLOCK) k_tail(HzPlan pl, Fr* w, HzErrBuf* err, const HzSmtMid* mids, const Fr* isExit, int s0, int ns, int f0, int nf) {
+__global__ void __launch_bounds__(HZ_BLOCK) k_tail(HzPlan pl, Fr* w, HzErrBuf* err, const HzSmtMid* mids, const Fr* isExit,
+                                                  const HzEddsaJob* jobs, const HzEddsaJob* jobs_front, int s0, int ns, int f0, int nf) {
     bool real; int q = hz_item(ns + nf, real);
-    if (q < ns) { int i = s0 + q; sec_rollup_tail(w, real ? err : nullptr, pl, i, &mids[2 * i], isExit[i]); }
+    if (q < ns) {
+        int i = s0 + q;
+        sec_rollup_tail(w, real ? err : nullptr, pl, i, &mids[2 * i], isExit[i]);
+        // the signature job k_edjob derived from the inputs against the one the templates of k_front arrived at
+        if (err && real && hz_glane() == 0) {
+            const HzEddsaJob &a = jobs[i], &b = jobs_front[i];
+            const bool same = fr_eq(a.aySignature, b.aySignature) && fr_eq(a.signSignature, b.signSignature) && fr_eq(a.enabled, b.enabled) &&
+                              fr_eq(a.s1Ay, b.s1Ay) && fr_eq(a.S, b.S) && fr_eq(a.R8x, b.R8x) && fr_eq(a.R8y, b.R8y) && fr_eq(a.M, b.M) && a.cur == b.cur;
+            if (!same) hz_head_err(err, b.cur, __LINE__, a.M);
+        }
+    }
     else { int i = f0 + (q - ns); sec_fee_tail(w, real ? err : nullptr, pl, i, mids[2 * pl.P.nTx + i]); }
 }
 
@@ -524,7 +594,7 @@ __global__ void k_hash_tail(HzPlan pl, Fr* w, HzErrBuf* err, const uint32_t* cha
 }
 
 HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode, const uint32_t* off_rollup,
-                       const uint32_t* off_fee, int* status) {
+                       const uint32_t* off_fee, const uint32_t* off_eddsa, int* status) {
     *status = HZW_E_DEVICE;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -549,6 +619,9 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaMalloc(&d->chain, (size_t)(ph.nblocks + 1) * 8 * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&d->msgw, (size_t)ph.nblocks * 16 * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&d->jobs, sizeof(HzEddsaJob) * P.nTx) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->jobs_front, sizeof(HzEddsaJob) * P.nTx) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->off_eddsa, 4ull * P.nTx) == cudaSuccess;
+    ok = ok && cudaMemcpy(d->off_eddsa, off_eddsa, 4ull * P.nTx, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMalloc(&d->smt, sizeof(HzSmtJob) * (2 * P.nTx + P.maxFeeTx)) == cudaSuccess;
     ok = ok && cudaMalloc(&d->mids, sizeof(HzSmtMid) * (2 * P.nTx + P.maxFeeTx)) == cudaSuccess;
     ok = ok && cudaMalloc(&d->lev, sizeof(HzLevJob) * (2 * P.nTx + P.maxFeeTx)) == cudaSuccess;
@@ -581,6 +654,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
         const int carve = 15;    // percent of the 228 KB: room for four k_smt_levels blocks
         cudaFuncSetAttribute(k_front, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_fee_front, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_edjob, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_eddsa, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_smt, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_smt_levels, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
@@ -617,7 +691,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
 void hz_cuda_destroy(HzCuda* d) {
     if (!d) return;
     cudaSetDevice(d->device);
-    cudaFree(d->w); cudaFree(d->pre); cudaFree(d->chain); cudaFree(d->msgw); cudaFree(d->jobs); cudaFree(d->err);
+    cudaFree(d->w); cudaFree(d->pre); cudaFree(d->chain); cudaFree(d->msgw); cudaFree(d->jobs); cudaFree(d->jobs_front); cudaFree(d->off_eddsa); cudaFree(d->err);
     cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit); cudaFree(d->lev); cudaFree(d->smst);
     cudaFree(d->hint_cst); cudaFree(d->hint_tab); cudaFree(d->hint_img); cudaFree(d->hint_scratch); cudaFree(d->recs);
     cudaFree(d->off_decode); cudaFree(d->off_rollup); cudaFree(d->off_fee); cudaFree(d->off_blocks);
@@ -667,16 +741,21 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     if (inputs) CK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(d->w) + 64, inputs, 32ull * pl.n_inputs, cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(d->ev0, s));
     const int s0 = d->s0, ns = d->ns, f0 = d->f0, nf = d->nf;
-    CK(cudaEventRecord(d->kev[0], s));
-    if (ns > 0) k_front<<<hz_grid(ns), HZ_BLOCK, 0, s>>>(pl, d->w, d->pre, err, d->jobs, d->smt, d->isExit, s0, ns);
-    CK(cudaEventRecord(d->kev[1], s));
-    CK(cudaEventRecord(d->ev_front, s));
-    // the signatures run beside the merkle levels: neither fills the machine alone
-    CK(cudaStreamWaitEvent(s2, d->ev_front, 0));
+    // the signatures are the longest chain of a slot and need little from the rest of it: their jobs come
+    // straight from the inputs (k_edjob) and they run on the second stream from the start, beside k_front
+    // and the merkle levels -- no kernel fills the machine alone
+    CK(cudaStreamWaitEvent(s2, d->ev0, 0));
     CK(cudaEventRecord(d->kev[9], s2));
-    if (ns > 0) k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, s0, ns);
+    if (ns > 0) {
+        k_edjob<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, d->jobs, d->off_eddsa, s0, ns);
+        k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, s0, ns);
+    }
     CK(cudaEventRecord(d->kev[10], s2));
     CK(cudaEventRecord(d->ev_eddsa, s2));
+    CK(cudaEventRecord(d->kev[0], s));
+    if (ns > 0) k_front<<<hz_grid(ns), HZ_BLOCK, 0, s>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt, d->isExit, s0, ns);
+    CK(cudaEventRecord(d->kev[1], s));
+    CK(cudaEventRecord(d->ev_front, s));
     if (nf > 0) k_fee_front<<<hz_grid(nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt + 2 * pl.P.nTx, f0, nf);
     CK(cudaEventRecord(d->kev[2], s));
     if (2 * ns + nf > 0) {
@@ -684,7 +763,7 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
         k_smt_levels<<<(unsigned)((2 * ns + nf + 15) / 16), 96, 0, s>>>(pl, d->w, d->lev, d->smst, d->mids, s0, ns, f0, nf);
     }
     CK(cudaEventRecord(d->kev[3], s));
-    if (ns + nf > 0) k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->mids, d->isExit, s0, ns, f0, nf);
+    if (ns + nf > 0) k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->mids, d->isExit, d->jobs, d->jobs_front, s0, ns, f0, nf);
     CK(cudaEventRecord(d->kev[4], s));
     return 0;
 }
@@ -725,9 +804,10 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
     CK(cudaMemsetAsync(d->pre, 0, (size_t)pl.nblocks * 512, s));
     CK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(d->w) + 64, inputs, 32ull * pl.n_inputs, cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(d->ev0, s));
-    k_front<<<hz_grid(P.nTx), HZ_BLOCK, 0, s>>>(pl, d->w, d->pre, err, d->jobs, d->smt, d->isExit, 0, P.nTx);
+    CK(cudaStreamWaitEvent(s2, d->ev0, 0));
+    k_edjob<<<hz_grid(P.nTx), HZ_BLOCK, 0, s2>>>(pl, d->w, d->jobs, d->off_eddsa, 0, P.nTx);
+    k_front<<<hz_grid(P.nTx), HZ_BLOCK, 0, s>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt, d->isExit, 0, P.nTx);
     CK(cudaEventRecord(d->ev_front, s));
-    CK(cudaStreamWaitEvent(s2, d->ev_front, 0));
     CK(cudaStreamWaitEvent(s3, d->ev_front, 0));
     const int F = P.maxFeeTx, h0 = P.nTx / 2;
     k_fee_front<<<hz_grid(F), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt + 2 * P.nTx, 0, F);
@@ -741,7 +821,7 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
             k_smt<<<hz_grid(2 * ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, 0, nf);
             k_smt_levels<<<(unsigned)((2 * ns + nf + 15) / 16), 96, 0, s>>>(pl, d->w, d->lev, d->smst, d->mids, s0, ns, 0, nf);
         }
-        if (ns + nf > 0) k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->mids, d->isExit, s0, ns, 0, nf);
+        if (ns + nf > 0) k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->mids, d->isExit, d->jobs, d->jobs_front, s0, ns, 0, nf);
         CK(cudaStreamWaitEvent(s, d->ev_ed[h], 0));
         CK(cudaEventRecord(d->ev_half[h], s));
         if (h == 0) {
@@ -780,7 +860,7 @@ int hz_cuda_calculate(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* wit
     CK(cudaStreamSynchronize(s));
     if (overlapped) CK(cudaStreamSynchronize(d->stream3));
     if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, d->ev0, d->ev1));
-    if (launches) *launches = overlapped ? 14 : 10;        // kernels of ours per batch (see the launch sequences above)
+    if (launches) *launches = overlapped ? 15 : 11;        // kernels of ours per batch (see the launch sequences above)
     if (h2d) *h2d = inputs ? 32ull * pl.n_inputs : 0;
     if (d2h) *d2h = (witness_out ? 32ull * pl.nvars : 0) + sizeof(HzErrBuf);
     return 0;

@@ -391,7 +391,8 @@ __device__ __forceinline__ Fr hz_shfl_fr(const Fr& v, int src) {
     for (int i = 0; i < 8; i++) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], src, HZ_G);
     return r;
 }
-template <int T> __device__ __noinline__ Fr hz_poseidon_lanes(Fr* w, uint32_t cur, Fr s, int base) {
+// DRY: the digest only, no entry is stored (k_edjob: the message hash of a signature before its slot is evaluated)
+template <int T, bool DRY = false> __device__ __noinline__ Fr hz_poseidon_lanes(Fr* w, uint32_t cur, Fr s, int base) {
     const int rp = poseidon_rp(T), R = 8 + rp;
     const int lane = (int)hz_glane();
     const int j = lane - base;
@@ -406,22 +407,24 @@ template <int T> __device__ __noinline__ Fr hz_poseidon_lanes(Fr* w, uint32_t cu
     }
     for (int i = 0; i < R; i++) {
         s = fr_add(s, C[T * i + jj]);
-        if (mine) hz_store_fr(&w[cur + jj], s);
+        if (!DRY && mine) hz_store_fr(&w[cur + jj], s);
         const bool full = i < 4 || i >= rp + 4;
         const uint32_t sg = cur + 2 * T;
         if (mine && (full || j == 0)) {
             Fr in2 = fr_mul_chain(s, s);
             Fr in4 = fr_mul_chain(in2, in2);
             s = fr_mul_chain(in4, s);
-            hz_store_fr(&w[sg + 3 * jj], s);
-            hz_store_fr(&w[sg + 3 * jj + 1], in2);
-            hz_store_fr(&w[sg + 3 * jj + 2], in4);
+            if (!DRY) {
+                hz_store_fr(&w[sg + 3 * jj], s);
+                hz_store_fr(&w[sg + 3 * jj + 1], in2);
+                hz_store_fr(&w[sg + 3 * jj + 2], in4);
+            }
         }
         Fr a[T];
 #pragma unroll
         for (int k = 0; k < T; k++) a[k] = hz_shfl_fr(s, base + k);
         s = fr_dot_mont_chain<T>(a, T <= 4 ? mreg : Mrow);
-        if (mine) hz_store_fr(&w[cur + T + jj], s);
+        if (!DRY && mine) hz_store_fr(&w[cur + T + jj], s);
         cur += 2 * T + (full ? 3 * T : 3);
     }
     return hz_shfl_fr(s, base);

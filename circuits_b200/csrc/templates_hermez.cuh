@@ -4,12 +4,23 @@
 #pragma once
 #include "templates_circomlib.cuh"
 
-HZ_HD uint64_t hz_fee_shift(int i) {
-    // feeShiftTable, src/compute-fee.circom:105-109 (protocol constants, copied as data)
-    const uint64_t T[256] = {
+// feeShiftTable, src/compute-fee.circom:105-109 (protocol constants, copied as data).  The device reads
+// its own copy in global memory: a table local to the function is rebuilt on the thread's stack at
+// every call (it was a fifth of k_front's time).
+static const uint64_t hz_fee_table_host[256] = {
 #include "fee_table.inc"
-    };
-    return T[i];
+};
+#if defined(__CUDACC__)
+__device__ const uint64_t hz_fee_table_dev[256] = {
+#include "fee_table.inc"
+};
+#endif
+HZ_HD uint64_t hz_fee_shift(int i) {
+#if defined(__CUDA_ARCH__)
+    return hz_fee_table_dev[i];
+#else
+    return hz_fee_table_host[i];
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -497,6 +508,7 @@ template <> struct SlotHook<MCompute> {
 };
 template <> struct SlotHook<MLayout> {
     HzSizes* sz_out;                // sizes recorded by the layout walk (may be null)
+    uint32_t* ed_cur = nullptr;     // where phase F of the slot being walked starts (may be null)
 };
 
 TM HZ_FN void hz_phaseF(Comp<M>& c, const V<M>& vse, const V<M>& signSignature, const V<M>& aySignature,
@@ -520,6 +532,7 @@ inline void hz_phaseF_hook(Comp<MLayout>& c, const SlotHook<MLayout>& hk, const 
     uint32_t c1 = c.cur;
     EdDSAPoseidonVerifier(c.sub("sigVerifier"), vse, ax, s1Ay, S, R8x, R8y, Msg);
     if (hk.sz_out) { hk.sz_out->getAx = c1 - c0; hk.sz_out->sigVerifier = c.cur - c1; }
+    if (hk.ed_cur) *hk.ed_cur = c0;
 }
 #endif
 
