@@ -192,7 +192,7 @@ static inline std::string hz_nm(const Nm& n) {
 // With no stream installed (CPU port by default, layout walk) a site inverts on the spot.  A wrong
 // hint cannot pass unnoticed: every such site is followed by its `===` check.
 #ifdef HZ_DEVICE_ONLY
-#define HZ_HINT_SCRATCH (4 * 600)
+#define HZ_HINT_SCRATCH 3104               /* hints.cuh: hint / num / den / pre arrays, captured points, fill record */
 #else
 #define HZ_HINT_SCRATCH (4 * 300)
 #endif
@@ -208,6 +208,7 @@ struct HzHints {
     Fr* edrec; uint32_t ei;                // record mode for the table
     Fr* scratch;                           // HZ_HINT_SCRATCH entries owned by this lane group / thread
     int lad_ok;                            // device: scratch[0 .. 588) holds the hints of all ladders (hints.cuh)
+    int fill;                              // device: the entries of the ladder steps are left to k_ed_fill
     const Fr* cimg; uint32_t fix_shift;    // witness image of EscalarMulFix from the recording pass, and where the
                                            // component being evaluated starts: its constant entries are copied
 };

@@ -106,10 +106,10 @@ template <int W> HZ_HD void hz_hints_segment_any(HzHints* h, const Fr& px, const
 // the accumulating adders of SegmentMulFix(nW) of segment `seg`: acc_0 = dblLast, acc_{i+1} =
 // MontgomeryAdd(in1 = acc_i, in2 = window_i[sel_i]); the window entries (affine Montgomery points)
 // come from the table recorded with the constants
-template <int W> HZ_HD void hz_hints_segment_fix(HzHints* h, const BVT<MCompute, W>& e, int nW, int seg) {
+template <int W> HZ_HD void hz_hints_segment_fix(HzHints* h, const BVT<MCompute, W>& e, int nW, int seg, Fr* area = nullptr) {
     if (!h || !h->scratch || !h->edtab || nW > HZ_HINT_MAX) return;
     hz_hints_sync();
-    Fr* hint = h->scratch; Fr* out = hint + HZ_HINT_MAX; Fr* den = out + HZ_HINT_MAX; Fr* pre = den + HZ_HINT_MAX;
+    Fr* hint = area ? area : h->scratch; Fr* out = hint + HZ_HINT_MAX; Fr* den = out + HZ_HINT_MAX; Fr* pre = den + HZ_HINT_MAX;
     const Fr* tab = h->edtab + (seg == 0 ? 0 : HZ_EDTAB_SEG1);
     MtPt acc; acc.U = tab[nW * 16]; acc.V = tab[nW * 16 + 1]; acc.W = fr_one();
     h->dat = nullptr; h->di = 0;
@@ -143,7 +143,32 @@ HZ_HD void hz_hints_record_point(HzHints* h, const Fr& u, const Fr& v) {
 // so after a short role-specific head all lanes run ONE instruction stream.  The 588 denominators
 // are then inverted together: every lane takes a 74-element chunk of Montgomery's trick.
 #define HZ_LAD_N 588
-#define HZ_LAD_SCRATCH (4 * 600)
+// ---- what the ladder leaves for k_ed_fill ---------------------------------------------------------------
+// The witness entries of the ladder steps (BitElementMulAny x 252, the 83 accumulating adders of
+// EscalarMulFix) are a fixed function of the step's input points and its two hints, so once the ladder has
+// run they can be written by independent threads instead of by the lane group that walked it: k_ed_fill
+// gives every CHUNK of HZ_FILL_CH consecutive steps to one thread.  A chunk starts from affine points, so
+// the ladder also records the projective points at the chunk starts (and the final ones, which the
+// templates continue from) and their W join the one batched inversion: "extra" element ex holds 1/W.
+//   ex  0..18  D at the chunk starts of segment 0        19..37  its accumulator there
+//      38..51  D at the chunk starts of segment 1        52..65  its accumulator there
+//      66..76  accumulator of the fixed-base adders at their chunk starts
+//      77 D_147 (dbl of segment 0)   78, 79 final accumulators of segments 0, 1   80 final fixed-base accumulator
+#define HZ_FILL_CH 8
+#define HZ_FILL_C0 19                      /* chunks of segment 0: 147 steps */
+#define HZ_FILL_C1 14                      /* chunks of segment 1: 105 steps */
+#define HZ_FILL_CF 11                      /* chunks of the 83 fixed-base adders */
+#define HZ_FILL_CHUNKS (HZ_FILL_C0 + HZ_FILL_C1 + HZ_FILL_CF)
+#define HZ_LAD_EX 81
+#define HZ_LAD_TOT (HZ_LAD_N + HZ_LAD_EX)
+// scratch of a lane group: hint[704] num[704] den[704] pre[704] vv[96] aff[176], then the fill record
+#define HZ_SCR_ARR 704
+#define HZ_SCR_VV (4 * HZ_SCR_ARR)
+#define HZ_SCR_AFF (HZ_SCR_VV + 96)
+#define HZ_SCR_REC (HZ_SCR_AFF + 176)
+// per signature, written by lane 0 of k_eddsa: whether the ladder data is usable, where the three runs of
+// step entries start in the witness, the scalar bits
+struct HzFillRec { uint32_t ok, base_seg0, base_seg1, base_fix; uint32_t e[8]; uint32_t s[8]; uint32_t pad[12]; };
 struct MtOps { Fr N, Dn, W12, X1, X2, Y1; };
 __device__ __forceinline__ MtOps mt_head_dbl(const MtPt& p) {
     MtOps o;
@@ -190,14 +215,71 @@ __device__ __forceinline__ int hz_lad_pos(int el) {
     if (el < 505) return 295 + 2 * (el - 400) + 1;
     return el;
 }
+// ---- captures for k_ed_fill and the one batched inversion ------------------------------------------------
+__device__ __forceinline__ void hz_lad_capture(Fr* num, Fr* den, Fr* vv, int ex, const MtPt& P, bool& ok) {
+    num[HZ_LAD_N + ex] = P.U; vv[ex] = P.V; den[HZ_LAD_N + ex] = P.W;
+    if (fr_is_zero(P.W)) ok = false;
+}
+// loop-start captures of iteration t: D_t for the doubling role, the accumulators for the others
+__device__ __forceinline__ void hz_lad_captures(int role, int t, Fr* num, Fr* den, Fr* vv, const MtPt& D, const MtPt& acc, bool& ok) {
+    if (role == 0) {
+        if (t <= 144 && (t & 7) == 0) hz_lad_capture(num, den, vv, t >> 3, D, ok);
+        if (t >= 148 && t <= 252 && ((t - 148) & 7) == 0) hz_lad_capture(num, den, vv, 38 + ((t - 148) >> 3), D, ok);
+        if (t == 147) hz_lad_capture(num, den, vv, 77, D, ok);
+    } else if (role == 1) {
+        if (t >= 1 && t <= 145 && ((t - 1) & 7) == 0) hz_lad_capture(num, den, vv, 19 + ((t - 1) >> 3), acc, ok);
+    } else if (role == 2) {
+        if (t >= 149 && ((t - 149) & 7) == 0) hz_lad_capture(num, den, vv, 52 + ((t - 149) >> 3), acc, ok);
+    } else {
+        if (t < 83 && (t & 7) == 0) hz_lad_capture(num, den, vv, 66 + (t >> 3), acc, ok);
+    }
+}
+// Montgomery's trick over the 588 hint denominators and the 81 captured W, a chunk per lane; leaves the hints
+// in template order in hint[], the affine captured points in aff[] and h->lad_ok
+__device__ __forceinline__ void hz_lad_finish(HzHints* h, bool ok) {
+    Fr* hint = h->scratch; Fr* num = hint + HZ_SCR_ARR; Fr* den = num + HZ_SCR_ARR; Fr* pre = den + HZ_SCR_ARR;
+    Fr* vv = h->scratch + HZ_SCR_VV; Fr* aff = h->scratch + HZ_SCR_AFF;
+    const int lane = (int)hz_glane();
+    // any zero denominator in the group: no hints at all
+    {
+        unsigned bad = __ballot_sync(0xffffffffu, !ok);
+        unsigned mine = (bad >> ((threadIdx.x & 31u) & ~7u)) & 0xffu;
+        ok = mine == 0;
+    }
+    __syncwarp();
+    const int per = (HZ_LAD_TOT + HZ_G - 1) / HZ_G;
+    const int c0 = lane * per, c1 = c0 + per < HZ_LAD_TOT ? c0 + per : HZ_LAD_TOT;
+    Fr tot = fr_one();
+    for (int k = c0; k < c1; k++) { pre[k] = tot; Fr dk = den[k]; tot = fr_mul_chain(tot, ok ? dk : fr_one()); }
+    // inverse of the own chunk total = inverse of the product of all chunk totals times the other totals
+    Fr all = fr_one(), others = fr_one();
+    for (int m = 0; m < HZ_G; m++) {
+        Fr tm = hz_shfl8_fr(tot, m);
+        all = fr_mul_chain(all, tm);
+        if (m != lane) others = fr_mul_chain(others, tm);
+    }
+    Fr inv = fr_mul_chain(fr_inv(all), others);
+    if (ok) {
+        for (int k = c1 - 1; k >= c0; k--) {
+            const Fr x = fr_mul_chain(inv, pre[k]);
+            if (k < HZ_LAD_N) hint[hz_lad_pos(k)] = fr_mul_chain(num[k], x);
+            else { aff[2 * (k - HZ_LAD_N)] = fr_mul_chain(num[k], x); aff[2 * (k - HZ_LAD_N) + 1] = fr_mul_chain(vv[k - HZ_LAD_N], x); }
+            inv = fr_mul_chain(inv, den[k]);
+        }
+    }
+    __syncwarp();
+    h->lad_ok = ok ? 1 : 0;
+}
+
 // px, py: the Edwards input of EscalarMulAny (after its zero-point substitution); e: the 254 scalar
 // bits; s: the 253 bits of S.  Leaves h->lad_ok and, if set, the 588 hints in h->scratch[0 .. 588).
+#ifndef HZ_WIDE_LADDER
 __device__ __noinline__ void hz_hints_eddsa_lanes(HzHints* h, const Fr& px, const Fr& py, const BVT<MCompute, 8>& e,
                                                  const BVT<MCompute, 8>& s) {
     h->lad_ok = 0;
     if (!h->scratch || !h->edtab) return;
     __syncwarp();
-    Fr* hint = h->scratch; Fr* num = hint + 600; Fr* den = num + 600; Fr* pre = den + 600;
+    Fr* hint = h->scratch; Fr* num = hint + HZ_SCR_ARR; Fr* den = num + HZ_SCR_ARR; Fr* vv = h->scratch + HZ_SCR_VV;
     const int lane = (int)hz_glane();
     MtPt D;
     {
@@ -210,6 +292,7 @@ __device__ __noinline__ void hz_hints_eddsa_lanes(HzHints* h, const Fr& px, cons
     if (lane == 3) { acc.U = tab[83 * 16]; acc.V = tab[83 * 16 + 1]; acc.W = fr_one(); }
     for (int t = 0; t <= 253; t++) {
         if (lane == 2 && t == 148) acc = D;
+        if (lane < 4) hz_lad_captures(lane, t, num, den, vv, D, acc, ok);
         bool active;
         int el;
         MtOps o;
@@ -241,32 +324,173 @@ __device__ __noinline__ void hz_hints_eddsa_lanes(HzHints* h, const Fr& px, cons
         // every lane follows lane 0's point
         D.U = hz_shfl8_fr(D.U, 0); D.V = hz_shfl8_fr(D.V, 0); D.W = hz_shfl8_fr(D.W, 0);
     }
-    // any zero denominator in the group: no hints at all
+    if (lane >= 1 && lane <= 3) hz_lad_capture(num, den, vv, 77 + lane, acc, ok);
+    hz_lad_finish(h, ok);
+}
+#else
+// The same walk with TWO lanes per role (lanes 2r, 2r+1 of the group; r = 0 doubling, 1 / 2 the adders of the
+// two segments, 3 the fixed-base adder): the 14 products of a point operation are split between the pair and
+// exchanged with lane-pair shuffles, 8 multiplication times per step instead of 18 (a doubling is the addition
+// of a point to itself with another slope, so all pairs run one instruction stream):
+//   head     half 0: X1 = U1 W2, Y1 = V1 W2, W12 = W1 W2       half 1: X2 = U2 W1, Y2 = V2 W1, Z = U1 U2
+//   slope    add: N = Y2 - Y1, Dn = X2 - X1                     double: N = 3 Z + 2 A X1 + W12, Dn = 2 Y1
+//   stage 1  half 0: S = Dn^2                                    half 1: NN = N^2
+//   stage 2  half 0: NN W12, X1 S                                half 1: (A W12 + X1 + X2) S, DS = Dn S
+//   stage 3  half 0: U3 = G Dn, W3 = DS W12                      half 1: N (X1 S - G), Y1 DS  (V3 = their difference)
+__device__ __forceinline__ Fr hz_swap1_fr(const Fr& v) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_xor_sync(0xffffffffu, v.l[i], 1, HZ_G);
+    return r;
+}
+__device__ __forceinline__ Fr hz_sel_fr(bool c, const Fr& a, const Fr& b) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = c ? a.l[i] : b.l[i];
+    return r;
+}
+__device__ __noinline__ void hz_hints_eddsa_lanes(HzHints* h, const Fr& px, const Fr& py, const BVT<MCompute, 8>& e,
+                                                 const BVT<MCompute, 8>& s) {
+    h->lad_ok = 0;
+    if (!h->scratch || !h->edtab) return;
+    __syncwarp();
+    Fr* hint = h->scratch; Fr* num = hint + HZ_SCR_ARR; Fr* den = num + HZ_SCR_ARR; Fr* vv = h->scratch + HZ_SCR_VV;
+    const int lane = (int)hz_glane(), role = lane >> 1;
+    const bool half = (lane & 1) != 0;
+    MtPt D;
     {
-        unsigned bad = __ballot_sync(0xffffffffu, !ok);
-        unsigned mine = (bad >> ((threadIdx.x & 31u) & ~7u)) & 0xffu;
-        ok = mine == 0;
+        Fr y1 = fr_add(fr_one(), py);
+        D.U = fr_mul_chain(y1, px); D.V = y1; D.W = fr_mul_chain(fr_sub(fr_one(), py), px);
     }
-    __syncwarp();
-    // Montgomery's trick, a 74-element chunk per lane
-    const int c0 = lane * 74, c1 = c0 + 74 < HZ_LAD_N ? c0 + 74 : HZ_LAD_N;
-    Fr tot = fr_one();
-    for (int k = c0; k < c1; k++) { pre[k] = tot; Fr dk = den[k]; tot = fr_mul_chain(tot, ok ? dk : fr_one()); }
-    // inverse of the own chunk total = inverse of the product of all chunk totals times the other totals
-    Fr all = fr_one(), others = fr_one();
-    for (int m = 0; m < HZ_G; m++) {
-        Fr tm = hz_shfl8_fr(tot, m);
-        all = fr_mul_chain(all, tm);
-        if (m != lane) others = fr_mul_chain(others, tm);
-    }
-    Fr inv = fr_mul_chain(fr_inv(all), others);
-    if (ok) {
-        for (int k = c1 - 1; k >= c0; k--) {
-            hint[hz_lad_pos(k)] = fr_mul_chain(num[k], fr_mul_chain(inv, pre[k]));
-            inv = fr_mul_chain(inv, den[k]);
+    bool ok = !fr_is_zero(D.W);
+    MtPt acc = D;
+    const Fr* tab = h->edtab;
+    if (role == 3) { acc.U = tab[83 * 16]; acc.V = tab[83 * 16 + 1]; acc.W = fr_one(); }
+    for (int t = 0; t <= 253; t++) {
+        if (role == 2 && t == 148) acc = D;
+        if (!half) hz_lad_captures(role, t, num, den, vv, D, acc, ok);
+        bool active;
+        int el;
+        MtPt p1 = D, p2 = acc;
+        if (role == 0) { active = t <= 252; el = t; p2 = D; }
+        else if (role == 1) { active = t >= 1 && t <= 147; el = 253 + (t - 1); }
+        else if (role == 2) { active = t >= 149; el = 400 + (t - 149); }
+        else {
+            active = t < 83; el = 505 + t;
+            int tt = active ? t : 0;
+            int sel = (int)(s.bit(3 * tt) | (s.bit(3 * tt + 1) << 1) | (s.bit(3 * tt + 2) << 2));
+            p1 = acc; p2.U = tab[tt * 16 + 2 * sel]; p2.V = tab[tt * 16 + 2 * sel + 1]; p2.W = fr_one();
         }
+        // head
+        const Fr b01 = hz_sel_fr(half, p1.W, p2.W);
+        const Fr m0 = fr_mul_chain(hz_sel_fr(half, p2.U, p1.U), b01);
+        const Fr m1 = fr_mul_chain(hz_sel_fr(half, p2.V, p1.V), b01);
+        const Fr m2 = fr_mul_chain(hz_sel_fr(half, p1.U, p1.W), hz_sel_fr(half, p2.U, p2.W));
+        const Fr o0 = hz_swap1_fr(m0), o1 = hz_swap1_fr(m1), o2 = hz_swap1_fr(m2);
+        const Fr X1 = hz_sel_fr(half, o0, m0), X2 = hz_sel_fr(half, m0, o0);
+        const Fr Y1 = hz_sel_fr(half, o1, m1), Y2 = hz_sel_fr(half, m1, o1);
+        const Fr W12 = hz_sel_fr(half, o2, m2), Z = hz_sel_fr(half, m2, o2);
+        Fr N, Dn, hn, hd;
+        if (role == 0) {
+            const Fr AX = fr_mul_small(X1, (uint32_t)HZ_MT_A);
+            N = fr_add(fr_add(fr_add(fr_add(Z, Z), Z), fr_add(AX, AX)), W12);
+            Dn = fr_add(Y1, Y1);
+            hn = D.W; hd = fr_add(D.V, D.V);
+        } else {
+            N = fr_sub(Y2, Y1); Dn = fr_sub(X2, X1);
+            hn = W12; hd = Dn;
+        }
+        // stage 1
+        const Fr q = half ? fr_mul_chain(N, N) : fr_mul_chain(Dn, Dn);
+        const Fr qo = hz_swap1_fr(q);
+        const Fr S = hz_sel_fr(half, qo, q), NN = hz_sel_fr(half, q, qo);
+        const Fr T = fr_add(fr_add(fr_mul_small(W12, (uint32_t)HZ_MT_A), X1), X2);
+        // stage 2
+        const Fr r0 = fr_mul_chain(hz_sel_fr(half, T, NN), hz_sel_fr(half, S, W12));
+        const Fr r1 = fr_mul_chain(hz_sel_fr(half, Dn, X1), S);
+        const Fr r0o = hz_swap1_fr(r0), r1o = hz_swap1_fr(r1);
+        const Fr G = fr_sub(hz_sel_fr(half, r0o, r0), hz_sel_fr(half, r0, r0o));
+        const Fr P2 = hz_sel_fr(half, r1o, r1), DS = hz_sel_fr(half, r1, r1o);
+        // stage 3
+        const Fr s0 = fr_mul_chain(hz_sel_fr(half, N, G), hz_sel_fr(half, fr_sub(P2, G), Dn));
+        const Fr s1 = fr_mul_chain(hz_sel_fr(half, Y1, DS), hz_sel_fr(half, DS, W12));
+        const Fr s0o = hz_swap1_fr(s0), s1o = hz_swap1_fr(s1);
+        MtPt r;
+        r.U = hz_sel_fr(half, s0o, s0); r.W = hz_sel_fr(half, s1o, s1);
+        r.V = fr_sub(hz_sel_fr(half, s0, s0o), hz_sel_fr(half, s1, s1o));
+        if (active) {
+            if (!half) { num[el] = hn; den[el] = hd; }
+            if (fr_is_zero(hd)) ok = false;
+            if (role == 0) D = r; else if (role == 3) acc = r; else if (e.bit(t)) acc = r;
+        }
+        // every lane follows the doubling pair's point
+        D.U = hz_shfl8_fr(D.U, 0); D.V = hz_shfl8_fr(D.V, 0); D.W = hz_shfl8_fr(D.W, 0);
     }
-    __syncwarp();
-    h->lad_ok = ok ? 1 : 0;
+    if (!half && role >= 1) hz_lad_capture(num, den, vv, 77 + role, acc, ok);
+    hz_lad_finish(h, ok);
+}
+#endif
+
+// ---- k_ed_fill: the entries of the ladder steps from the ladder's data ------------------------------------
+// One thread per chunk of HZ_FILL_CH consecutive steps.  Entries per step (templates_circomlib.cuh):
+//   BitElementMulAny: doubler.out[2], doubler.lamda, doubler.x1_2, adder.out[2], adder.lamda, selector.out[2]
+//   accumulating adder of SegmentMulFix: out[2], lamda
+// computed with the formulas of MontgomeryDouble / MontgomeryAdd / Multiplexor2, the divisions taking the
+// ladder's hints (each keeps its `===` check when the sanity check is on).
+struct AffPt { Fr u, v; };
+__device__ __forceinline__ void hz_fill_err(HzErrBuf* err, uint32_t cur, uint32_t line, const Fr& lhs, const Fr& rhs) {
+    uint32_t k = atomicAdd(&err->count, 1u);
+    if (k < HZ_MAX_ERR) { err->rec[k].cur = cur; err->rec[k].line = line; err->rec[k].lhs = lhs; err->rec[k].rhs = rhs; }
+}
+// in1 = a, in2 = b, hint = 1 / (b.u - a.u); stores out[2], lamda at w[0..3)
+__device__ __forceinline__ AffPt hz_fill_madd(Fr* w, uint32_t at, HzErrBuf* err, const AffPt& a, const AffPt& b, const Fr& hint) {
+    const Fr dy = fr_sub(b.v, a.v);
+    const Fr lam = fr_mul_chain(dy, hint);
+    if (err) { const Fr lhs = fr_mul_chain(lam, fr_sub(b.u, a.u)); if (!fr_eq(lhs, dy)) hz_fill_err(err, at + 3, __LINE__, lhs, dy); }
+    AffPt r;
+    r.u = fr_sub(fr_sub(fr_sub(fr_mul_chain(lam, lam), fr_from_u64(HZ_MT_A)), a.u), b.u);
+    r.v = fr_sub(fr_mul_chain(lam, fr_sub(a.u, r.u)), a.v);
+    hz_store_fr(&w[at], r.u); hz_store_fr(&w[at + 1], r.v); hz_store_fr(&w[at + 2], lam);
+    return r;
+}
+__device__ __forceinline__ void hz_fill_seg(Fr* w, HzErrBuf* err, const Fr* hint, const Fr* aff, const HzFillRec& rec, int sg, int k) {
+    const int nsteps = sg == 0 ? 147 : 105, from = sg == 0 ? 0 : 148;
+    const int i0 = k * HZ_FILL_CH, i1 = i0 + HZ_FILL_CH < nsteps ? i0 + HZ_FILL_CH : nsteps;
+    const Fr* hp = hint + (sg == 0 ? 0 : 295);
+    const int exD = sg == 0 ? k : 38 + k, exA = sg == 0 ? 19 + k : 52 + k;
+    AffPt D, acc;
+    D.u = aff[2 * exD]; D.v = aff[2 * exD + 1]; acc.u = aff[2 * exA]; acc.v = aff[2 * exA + 1];
+    uint32_t at = (sg == 0 ? rec.base_seg0 : rec.base_seg1) + 9u * (uint32_t)i0;
+    for (int i = i0; i < i1; i++, at += 9) {
+        const int eb = from + i + 1;
+        const bool sel = ((rec.e[eb >> 5] >> (eb & 31)) & 1u) != 0;
+        // doubler
+        const Fr x1_2 = fr_mul_chain(D.u, D.u);
+        const Fr num = fr_add(fr_add(fr_add(fr_add(x1_2, x1_2), x1_2), fr_mul_small(D.u, (uint32_t)(2 * HZ_MT_A))), fr_one());
+        const Fr lam = fr_mul_chain(num, hp[2 * i]);
+        if (err) { const Fr lhs = fr_mul_chain(lam, fr_add(D.v, D.v)); if (!fr_eq(lhs, num)) hz_fill_err(err, at + 4, __LINE__, lhs, num); }
+        AffPt dd;
+        dd.u = fr_sub(fr_sub(fr_mul_chain(lam, lam), fr_from_u64(HZ_MT_A)), fr_add(D.u, D.u));
+        dd.v = fr_sub(fr_mul_chain(lam, fr_sub(D.u, dd.u)), D.v);
+        hz_store_fr(&w[at], dd.u); hz_store_fr(&w[at + 1], dd.v); hz_store_fr(&w[at + 2], lam); hz_store_fr(&w[at + 3], x1_2);
+        // adder (in1 = the doubled point, in2 = the accumulator), selector
+        const AffPt ad = hz_fill_madd(w, at + 4, err, dd, acc, hp[2 * i + 1]);
+        if (sel) acc = ad;
+        hz_store_fr(&w[at + 7], acc.u); hz_store_fr(&w[at + 8], acc.v);
+        D = dd;
+    }
+}
+__device__ __forceinline__ void hz_fill_fix(Fr* w, HzErrBuf* err, const Fr* hint, const Fr* aff, const Fr* tab, const HzFillRec& rec, int k) {
+    const int i0 = k * HZ_FILL_CH, i1 = i0 + HZ_FILL_CH < 83 ? i0 + HZ_FILL_CH : 83;
+    AffPt acc;
+    acc.u = aff[2 * (66 + k)]; acc.v = aff[2 * (66 + k) + 1];
+    uint32_t at = rec.base_fix + 3u * (uint32_t)i0;
+    for (int i = i0; i < i1; i++, at += 3) {
+        int sel = 0;
+        for (int b = 0; b < 3; b++) sel |= (int)((rec.s[(3 * i + b) >> 5] >> ((3 * i + b) & 31)) & 1u) << b;
+        AffPt win;
+        win.u = tab[i * 16 + 2 * sel]; win.v = tab[i * 16 + 2 * sel + 1];
+        acc = hz_fill_madd(w, at, err, acc, win, hint[505 + i]);
+    }
 }
 #endif

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_eddsa(HzPlan pl, Fr* w, HzErrBu
     const HzEddsaJob& j = jobs[i];
     HzHints h;
     h.cst = cst; h.ci = 0; h.dat = nullptr; h.di = 0; h.rec = nullptr; h.ri = 0;
-    h.edtab = tab; h.edrec = nullptr; h.ei = 0; h.lad_ok = 0; h.cimg = img; h.fix_shift = 0; h.scratch = scratch + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) / HZ_G) * HZ_HINT_SCRATCH;   // per group, not per slot: padding groups redo a slot
+    h.edtab = tab; h.edrec = nullptr; h.ei = 0; h.lad_ok = 0; h.fill = 1; h.cimg = img; h.fix_shift = 0; h.scratch = scratch + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) / HZ_G) * HZ_HINT_SCRATCH;   // per group, not per slot: padding groups redo a slot
     HzPending pend; pend.n = 0;
     Comp<MCompute> c(w, j.cur, real ? err : nullptr, &h, &pend);
     VC vse, sgn, ay, s1Ay, S, R8x, R8y, Msg;
@@ -306,6 +306,23 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_eddsa(HzPlan pl, Fr* w, HzErrBu
     vse.sig = sgn.sig = ay.sig = s1Ay.sig = S.sig = R8x.sig = R8y.sig = Msg.sig = true;
     hz_phaseF(c, vse, sgn, ay, s1Ay, S, R8x, R8y, Msg);
     c.flush_pending();
+}
+
+// the entries of the ladder steps of the signatures k_eddsa walked (hints.cuh): a thread per chunk of steps;
+// first the 33 chunks of the two EscalarMulAny segments of every signature, then the 11 of the fixed-base adders
+__global__ void __launch_bounds__(128) k_ed_fill(Fr* w, HzErrBuf* err, const Fr* tab, const Fr* scratch, int ns) {
+    const int gid = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int nseg = HZ_FILL_C0 + HZ_FILL_C1;
+    const bool fix = gid >= nseg * ns;
+    const int g2 = fix ? gid - nseg * ns : gid;
+    const int g = fix ? g2 / HZ_FILL_CF : g2 / nseg, k = fix ? g2 % HZ_FILL_CF : g2 % nseg;
+    if (g >= ns) return;
+    const Fr* scr = scratch + (size_t)g * HZ_HINT_SCRATCH;          // group g of k_eddsa evaluated slot s0 + g
+    const HzFillRec rec = *reinterpret_cast<const HzFillRec*>(scr + HZ_SCR_REC);
+    if (!rec.ok) return;                                            // degenerate input: the templates divided on the spot
+    if (fix) hz_fill_fix(w, err, scr, scr + HZ_SCR_AFF, tab, rec, k);
+    else if (k < HZ_FILL_C0) hz_fill_seg(w, err, scr, scr + HZ_SCR_AFF, rec, 0, k);
+    else hz_fill_seg(w, err, scr, scr + HZ_SCR_AFF, rec, 1, k - HZ_FILL_C0);
 }
 
 __global__ void __launch_bounds__(HZ_BLOCK) k_tail(HzPlan pl, Fr* w, HzErrBuf* err, const HzSmtMid* mids, const Fr* isExit,
@@ -749,6 +766,7 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     if (ns > 0) {
         k_edjob<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, d->jobs, d->off_eddsa, s0, ns);
         k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, s0, ns);
+        k_ed_fill<<<(unsigned)((HZ_FILL_CHUNKS * ns + 127) / 128), 128, 0, s2>>>(d->w, err, d->hint_tab, d->hint_scratch, ns);
     }
     CK(cudaEventRecord(d->kev[10], s2));
     CK(cudaEventRecord(d->ev_eddsa, s2));
@@ -815,7 +833,10 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
     CK(piece(2, d->h_off_rollup0));
     for (int h = 0; h < 2; h++) {
         const int s0 = h == 0 ? 0 : h0, ns = h == 0 ? h0 : P.nTx - h0, nf = h == 1 ? F : 0;
-        if (ns > 0) k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, s0, ns);
+        if (ns > 0) {
+            k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, s0, ns);
+            k_ed_fill<<<(unsigned)((HZ_FILL_CHUNKS * ns + 127) / 128), 128, 0, s2>>>(d->w, err, d->hint_tab, d->hint_scratch, ns);
+        }
         CK(cudaEventRecord(d->ev_ed[h], s2));
         if (2 * ns + nf > 0) {
             k_smt<<<hz_grid(2 * ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, 0, nf);
@@ -860,7 +881,7 @@ int hz_cuda_calculate(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* wit
     CK(cudaStreamSynchronize(s));
     if (overlapped) CK(cudaStreamSynchronize(d->stream3));
     if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, d->ev0, d->ev1));
-    if (launches) *launches = overlapped ? 15 : 11;        // kernels of ours per batch (see the launch sequences above)
+    if (launches) *launches = overlapped ? 17 : 12;        // kernels of ours per batch (see the launch sequences above)
     if (h2d) *h2d = inputs ? 32ull * pl.n_inputs : 0;
     if (d2h) *d2h = (witness_out ? 32ull * pl.nvars : 0) + sizeof(HzErrBuf);
     return 0;

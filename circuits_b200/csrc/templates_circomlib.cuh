@@ -839,6 +839,11 @@ template <> struct HintGen<MCompute> {
         // EscalarMulAny's zero-point substitution (escalarmulany.circom): p.x == 0 -> BASE8
         const bool zp = fr_is_zero(px.v);
         hz_hints_eddsa_lanes(c.hints, zp ? fr_base8_x() : px.v, zp ? fr_base8_y() : py.v, e, s);
+        if (c.hints->fill && c.hints->scratch && hz_glane() == 0) {
+            HzFillRec* rec = reinterpret_cast<HzFillRec*>(c.hints->scratch + HZ_SCR_REC);
+            rec->ok = (uint32_t)c.hints->lad_ok;
+            for (int k = 0; k < 8; k++) { rec->e[k] = e.val[k]; rec->s[k] = s.val[k]; }
+        }
     }
     static HZ_HD void seg_any(Comp<MCompute>& c, const VC&, const VC&, const BVC&, int, int seg) {
         if (!c.hints) return;
@@ -853,9 +858,32 @@ template <> struct HintGen<MCompute> {
     static HZ_HD void seg_fix(Comp<MCompute>& c, const BVC& e, int nW, int seg) {
         if (!c.hints) return;
         if (seg == 0 && c.hints->lad_ok) { c.hints->dat = c.hints->scratch + 505; c.hints->di = 0; }
-        else hz_hints_segment_fix(c.hints, e, nW, seg);
+        else hz_hints_segment_fix(c.hints, e, nW, seg, c.hints->scratch + HZ_SCR_ARR);   // the ladder's hints stay for k_ed_fill
+    }
+    // the steps of a ladder are left to k_ed_fill: reserve their entries, note where they start and go on from
+    // the points the ladder ended at
+    static HZ_HD bool fill_on(const Comp<MCompute>& c) { return c.hints && c.hints->fill && c.hints->lad_ok; }
+    static HZ_HD VC aff(const Comp<MCompute>& c, int k) { VC r; r.v = c.hints->scratch[HZ_SCR_AFF + k]; r.sig = true; return r; }
+    static HZ_HD bool fill_any(Comp<MCompute>& c, int n, int seg, PtV<MCompute>& d, PtV<MCompute>& a) {
+        if (!fill_on(c)) return false;
+        HzFillRec* rec = reinterpret_cast<HzFillRec*>(c.hints->scratch + HZ_SCR_REC);
+        if (hz_glane() == 0) { if (seg == 0) rec->base_seg0 = c.cur; else rec->base_seg1 = c.cur; }
+        c.cur += 9u * (uint32_t)(n - 1);
+        if (seg == 0) { d.x = aff(c, 2 * 77); d.y = aff(c, 2 * 77 + 1); }      // segment 1's dbl output is wired nowhere
+        a.x = aff(c, 2 * (78 + seg)); a.y = aff(c, 2 * (78 + seg) + 1);
+        return true;
+    }
+    static HZ_HD bool fill_fix(Comp<MCompute>& c, int nW, int seg, PtV<MCompute>& acc) {
+        if (seg != 0 || !fill_on(c)) return false;
+        HzFillRec* rec = reinterpret_cast<HzFillRec*>(c.hints->scratch + HZ_SCR_REC);
+        if (hz_glane() == 0) rec->base_fix = c.cur;
+        c.cur += 3u * (uint32_t)nW;
+        acc.x = aff(c, 2 * 80); acc.y = aff(c, 2 * 80 + 1);
+        return true;
     }
 #else
+    static HZ_HD bool fill_any(Comp<MCompute>&, int, int, PtV<MCompute>&, PtV<MCompute>&) { return false; }
+    static HZ_HD bool fill_fix(Comp<MCompute>&, int, int, PtV<MCompute>&) { return false; }
     static HZ_HD void ladder(Comp<MCompute>&, const VC&, const VC&, const BVC&, const BVC&) {}
     static HZ_HD void seg_any(Comp<MCompute>& c, const VC& px, const VC& py, const BVC& e, int n, int) { hz_hints_segment_any(c.hints, px.v, py.v, e, n); }
     static HZ_HD void mid(Comp<MCompute>&) {}
@@ -871,6 +899,8 @@ template <> struct HintGen<MLayout> {
     static void seg_any(Comp<MLayout>&, const VL&, const VL&, const BVT<MLayout, 8>&, int, int) {}
     static void mid(Comp<MLayout>&) {}
     static void seg_fix(Comp<MLayout>&, const BVT<MLayout, 8>&, int, int) {}
+    static bool fill_any(Comp<MLayout>&, int, int, PtV<MLayout>&, PtV<MLayout>&) { return false; }
+    static bool fill_fix(Comp<MLayout>&, int, int, PtV<MLayout>&) { return false; }
     static void done(Comp<MLayout>&) {}
     static void fix_begin(Comp<MLayout>&) {}
     static void record(Comp<MLayout>&, const VL&, const VL&) {}
@@ -1011,7 +1041,8 @@ TM HZ_FN void SegmentMulAny(Comp<M>&& c, const BV<M>& e, int from, int n, const 
     PtV<M> m = Edwards2Montgomery(c.sub("e2m"), p_.x, p_.y);
     PtV<M> d = m, a = m;
     HintGen<M>::seg_any(c, p_.x, p_.y, e_, n, seg);
-    for (int i = 0; i < n - 1; i++) BitElementMulAny(c.sub(Nm("bits", i)), e_.get(i + 1), d, a);
+    if (!HintGen<M>::fill_any(c, n, seg, d, a))
+        for (int i = 0; i < n - 1; i++) BitElementMulAny(c.sub(Nm("bits", i)), e_.get(i + 1), d, a);
     HintGen<M>::done(c);
     c.alias(Nm("dbl", 0), d.x); c.alias(Nm("dbl", 1), d.y);
     PtV<M> ed = Montgomery2Edwards(c.sub("m2e"), a.x, a.y);
@@ -1102,7 +1133,8 @@ TM HZ_FN void SegmentMulFix(Comp<M>&& c, const BV<M>& e, int nW, const PtV<M>& b
     // the accumulating adders depend on the scalar: data stream
     HintGen<M>::seg_fix(c, e_, nW, seg);
     PtV<M> acc = dblLast;
-    for (int i = 0; i < nW; i++) acc = MontgomeryAdd(c.sub(Nm("adders", i)), acc, win_out[i], 2);
+    if (!HintGen<M>::fill_fix(c, nW, seg, acc))
+        for (int i = 0; i < nW; i++) acc = MontgomeryAdd(c.sub(Nm("adders", i)), acc, win_out[i], 2);
     HintGen<M>::done(c);
     PtV<M> ed = Montgomery2Edwards(c.sub("m2e"), acc.x, acc.y);
     PtV<M> ced = Montgomery2Edwards(c.sub("cm2e"), cad.x, cad.y, 1);
@@ -1145,7 +1177,7 @@ TM HZ_FN PtV<M> EscalarMulFix253(Comp<M>&& c, const BV<M>& e) {
 HZ_FN void hz_record_fix_consts(Fr* wtmp, Fr* cst, Fr* edtab, uint32_t* counts) {
     HzHints h;
     h.cst = nullptr; h.ci = 0; h.dat = nullptr; h.di = 0; h.rec = cst; h.ri = 0;
-    h.edtab = nullptr; h.edrec = edtab; h.ei = 0; h.scratch = nullptr; h.lad_ok = 0; h.cimg = nullptr; h.fix_shift = 0;
+    h.edtab = nullptr; h.edrec = edtab; h.ei = 0; h.scratch = nullptr; h.lad_ok = 0; h.fill = 0; h.cimg = nullptr; h.fix_shift = 0;
     Comp<MCompute> c(wtmp, 0, nullptr, &h);
     BVC e; e.clear(253);
     VC z = vc(fr_zero()); z.sig = true;
