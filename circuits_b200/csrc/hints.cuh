@@ -142,6 +142,7 @@ HZ_HD void hz_hints_record_point(HzHints* h, const Fr& u, const Fr& v) {
 // MontgomeryAdd / MontgomeryDouble is the same map (u3 = lamda^2 - A - u1 - u2, v3 = lamda (u1 - u3) - v1),
 // so after a short role-specific head all lanes run ONE instruction stream.  The 588 denominators
 // are then inverted together: every lane takes a 74-element chunk of Montgomery's trick.
+#define HZ_WIDE_LADDER 1
 #define HZ_LAD_N 588
 // ---- what the ladder leaves for k_ed_fill ---------------------------------------------------------------
 // The witness entries of the ladder steps (BitElementMulAny x 252, the 83 accumulating adders of
