@@ -41,6 +41,8 @@ struct HzCuda {
     HzSmtMid* mids;            // 2 nTx + maxFeeTx
     HzLevJob* lev;             // 2 nTx + maxFeeTx: what k_smt leaves for k_smt_levels
     Fr* smst;                  // per processor (nLevels + 1) x 6 state-machine values
+    Fr* img00;                 // the 634 entries of SMTHash2(0, 0) and, at [HZ_IMG00_DIGEST], its digest
+    uint8_t* zflag;            // per block of k_smt_levels and level: the level hashed (0, 0) in every chain of the block
     Fr* isExit;                // nTx
     Fr* hint_cst;              // HZ_CST_MAX: constant inverses of EscalarMulFix (recorded at create)
     Fr* hint_tab;              // HZ_EDTAB_LEN: its window entries
@@ -56,12 +58,13 @@ struct HzCuda {
     uint8_t* recs;             // world x rec_bytes: the gathered exchange records (own one while packing)
     cudaStream_t stream, stream2, stream3;
     cudaEvent_t ev_half[2], ev_ed[2], ev_done;
-    cudaEvent_t ev0, ev1, ev_front, ev_eddsa;
+    cudaEvent_t ev0, ev1, ev_front, ev_eddsa, ev_lev, ev_zero, ev_fee;
     cudaEvent_t kev[HZ_NKERN + 2];
 };
 
 static void hz_set_ranges(HzCuda* d, int rank, int world);
 __device__ __forceinline__ void hz_head_err(HzErrBuf* err, uint32_t cur, uint32_t line, const Fr& lhs);
+__global__ void k_poseidon_t3(const Fr* in, Fr* sig, Fr* digests, int nperms);
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "hzw: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return HZW_E_DEVICE; } } while (0)
 
@@ -191,8 +194,14 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_smt(HzPlan pl, Fr* w, HzErrBuf*
 // offsets inside a level follow SMTProcessorLevel (templates_circomlib.cuh): oldRoot, newRoot,
 // [oldChild, newChild: bottom level only], aux[4], oldProofHash (634), newProofHash (634),
 // oldSwitcher (outL, outR, aux), newSwitcher (L, R, outL, outR, aux).
+// Levels below the leaf of a sparse tree hash (0, 0): child and sibling are both zero there, on the old path
+// and on the new one.  With 2^12 accounts in a tree of depth 32 that is some 19 of the 33 levels of every
+// processor.  Their 634 entries do not depend on anything, so when a level is (0, 0) in EVERY chain of the
+// block the 65 rounds are skipped, the digest is the constant, and the entries are copied from an image
+// recorded at context creation by k_smt_zero (a wide copy, off the critical chain of the levels).
+#define HZ_IMG00_DIGEST 640
 __global__ void __launch_bounds__(96) k_smt_levels(HzPlan pl, Fr* w, const HzLevJob* jobs, const Fr* smst, HzSmtMid* mids,
-                                                   int s0, int ns, int f0, int nf) {
+                                                   const Fr* img00, uint8_t* zflag, int s0, int ns, int f0, int nf) {
     __shared__ uint32_t xch[2][3][8][32];
     __shared__ uint32_t hin[2][8][32];
     const int r = (int)(threadIdx.x >> 5), c = (int)(threadIdx.x & 31);
@@ -243,11 +252,14 @@ __global__ void __launch_bounds__(96) k_smt_levels(HzPlan pl, Fr* w, const HzLev
 #pragma unroll
             for (int k = 0; k < 8; k++) s.l[k] = hin[r - 1][k][c];
         }
+        const int allz = __syncthreads_and(fr_is_zero(s) ? 1 : 0);
+        if (threadIdx.x == 0) zflag[(size_t)blockIdx.x * L + lev] = allz ? 1 : 0;
         // SMTHash2 (wired L, R) -> Poseidon(2): entry 0 is ark[0].in[0] = 0
         Fr* hw = w + (side == 0 ? o_oph : o_nph);
-        if (r == 0) hz_store_fr(&hw[0], s);
+        if (allz) s = img00[HZ_IMG00_DIGEST];
+        else if (r == 0) hz_store_fr(&hw[0], s);
         uint32_t cur = 1;
-        for (int i = 0; i < 65; i++) {
+        for (int i = 0; i < (allz ? 0 : 65); i++) {
             s = fr_add(s, C[3 * i + r]);
             hz_store_fr(&hw[cur + r], s);
             const bool full = i < 4 || i >= 61;
@@ -284,6 +296,28 @@ __global__ void __launch_bounds__(96) k_smt_levels(HzPlan pl, Fr* w, const HzLev
         }
     }
     if (r == 0) { if (side == 0) mids[job].oc = child; else mids[job].nc = child; }
+}
+
+// the entries of the (0, 0) levels k_smt_levels skipped: block (b, lev) copies the image into the 32 chains of
+// levels-block b when that level was flagged, a warp per 4 chains
+__global__ void __launch_bounds__(256) k_smt_zero(HzPlan pl, Fr* w, const HzLevJob* jobs, const Fr* img00, const uint8_t* zflag,
+                                                  int s0, int ns, int f0, int nf) {
+    const int njobs = 2 * ns + nf, L = pl.P.nLevels + 1;
+    const int b = (int)blockIdx.x, lev = (int)blockIdx.y;
+    if (!zflag[(size_t)b * L + lev]) return;
+    const int wi = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+    const uint32_t HS = HZ_SZ_SMTHASH2_WIRED;
+    const uint4* src = reinterpret_cast<const uint4*>(img00);
+    for (int c = wi * 4; c < wi * 4 + 4; c++) {
+        int q = b * 16 + (c >> 1);
+        if (q >= njobs) q = njobs - 1;
+        const HzLevJob& J = jobs[hz_smt_job_index(pl, q, s0, ns, f0)];
+        const bool bottom = lev == L - 1;
+        const uint32_t lb = J.cur + (bottom ? 0u : 2u + (uint32_t)(L - 1 - lev) * HZ_SZ_SMT_LEVEL);
+        const uint32_t o_oph = lb + 2 + (bottom ? 2u : 0u) + 4;
+        uint4* dst = reinterpret_cast<uint4*>(w + ((c & 1) == 0 ? o_oph : o_oph + HS));
+        for (uint32_t e = (uint32_t)lane; e < 2 * HS; e += 32) __stcs(&dst[e], src[e]);
+    }
 }
 
 // one-time: the constant division sites and window entries of EscalarMulFix(253, BASE8)
@@ -644,6 +678,8 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaMalloc(&d->lev, sizeof(HzLevJob) * (2 * P.nTx + P.maxFeeTx)) == cudaSuccess;
     ok = ok && cudaMalloc(&d->smst, sizeof(Fr) * 6 * (size_t)(P.nLevels + 1) * (2 * P.nTx + P.maxFeeTx)) == cudaSuccess;
     ok = ok && cudaMalloc(&d->isExit, sizeof(Fr) * P.nTx) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->img00, sizeof(Fr) * (HZ_IMG00_DIGEST + 1)) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->zflag, (size_t)((2 * P.nTx + P.maxFeeTx + 15) / 16) * (P.nLevels + 1)) == cudaSuccess;
     ok = ok && cudaMalloc(&d->hint_cst, sizeof(Fr) * HZ_CST_MAX) == cudaSuccess;
     ok = ok && cudaMalloc(&d->hint_tab, sizeof(Fr) * HZ_EDTAB_LEN) == cudaSuccess;
     ok = ok && cudaMalloc(&d->hint_scratch, sizeof(Fr) * HZ_HINT_SCRATCH * (size_t)hz_grid(P.nTx) * (HZ_BLOCK / HZ_G)) == cudaSuccess;
@@ -663,6 +699,9 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaEventCreate(&d->ev0) == cudaSuccess && cudaEventCreate(&d->ev1) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_front, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_eddsa, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&d->ev_lev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&d->ev_fee, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&d->ev_zero, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; k < HZ_NKERN + 2; k++) ok = ok && cudaEventCreate(&d->kev[k]) == cudaSuccess;
     // kernels that are to share an SM must agree on its L1 / shared-memory split: k_smt_levels stages the MDS
     // exchange in shared memory, k_eddsa (running beside it on the second stream) uses none -- without a common
@@ -679,6 +718,16 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     }
     // the per-thread frames of the circuit templates are large (sibling arrays, state machines)
     ok = ok && cudaDeviceSetLimit(cudaLimitStackSize, 80 * 1024) == cudaSuccess;
+    if (ok) {
+        // the entries and the digest of SMTHash2(0, 0), once (k_poseidon_t3 on one permutation of two zero inputs)
+        Fr* zin = nullptr;
+        ok = cudaMalloc(&zin, sizeof(Fr) * 2) == cudaSuccess && cudaMemset(zin, 0, sizeof(Fr) * 2) == cudaSuccess;
+        if (ok) {
+            k_poseidon_t3<<<1, 96, 0, d->stream>>>(zin, d->img00, d->img00 + HZ_IMG00_DIGEST, 1);
+            ok = cudaStreamSynchronize(d->stream) == cudaSuccess;
+        }
+        cudaFree(zin);
+    }
     if (ok) {
         // record the input-independent part of the EdDSA fixed-base multiplication once
         uint32_t* counts = nullptr; uint32_t hc[2] = {0, 0};
@@ -709,7 +758,7 @@ void hz_cuda_destroy(HzCuda* d) {
     if (!d) return;
     cudaSetDevice(d->device);
     cudaFree(d->w); cudaFree(d->pre); cudaFree(d->chain); cudaFree(d->msgw); cudaFree(d->jobs); cudaFree(d->jobs_front); cudaFree(d->off_eddsa); cudaFree(d->err);
-    cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit); cudaFree(d->lev); cudaFree(d->smst);
+    cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit); cudaFree(d->lev); cudaFree(d->smst); cudaFree(d->img00); cudaFree(d->zflag);
     cudaFree(d->hint_cst); cudaFree(d->hint_tab); cudaFree(d->hint_img); cudaFree(d->hint_scratch); cudaFree(d->recs);
     cudaFree(d->off_decode); cudaFree(d->off_rollup); cudaFree(d->off_fee); cudaFree(d->off_blocks);
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -721,6 +770,9 @@ void hz_cuda_destroy(HzCuda* d) {
     if (d->ev1) cudaEventDestroy(d->ev1);
     if (d->ev_front) cudaEventDestroy(d->ev_front);
     if (d->ev_eddsa) cudaEventDestroy(d->ev_eddsa);
+    if (d->ev_lev) cudaEventDestroy(d->ev_lev);
+    if (d->ev_fee) cudaEventDestroy(d->ev_fee);
+    if (d->ev_zero) cudaEventDestroy(d->ev_zero);
     for (int k = 0; k < HZ_NKERN + 2; k++) if (d->kev[k]) cudaEventDestroy(d->kev[k]);
     delete d;
 }
@@ -770,16 +822,26 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     }
     CK(cudaEventRecord(d->kev[10], s2));
     CK(cudaEventRecord(d->ev_eddsa, s2));
+    // the fee transactions need nothing but inputs either: third stream, joined before the merkle kernels
+    CK(cudaStreamWaitEvent(d->stream3, d->ev0, 0));
+    if (nf > 0) k_fee_front<<<hz_grid(nf), HZ_BLOCK, 0, d->stream3>>>(pl, d->w, err, d->smt + 2 * pl.P.nTx, f0, nf);
+    CK(cudaEventRecord(d->ev_fee, d->stream3));
     CK(cudaEventRecord(d->kev[0], s));
     if (ns > 0) k_front<<<hz_grid(ns), HZ_BLOCK, 0, s>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt, d->isExit, s0, ns);
     CK(cudaEventRecord(d->kev[1], s));
     CK(cudaEventRecord(d->ev_front, s));
-    if (nf > 0) k_fee_front<<<hz_grid(nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt + 2 * pl.P.nTx, f0, nf);
+    CK(cudaStreamWaitEvent(s, d->ev_fee, 0));
     CK(cudaEventRecord(d->kev[2], s));
     if (2 * ns + nf > 0) {
         k_smt<<<hz_grid(2 * ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, f0, nf);
-        k_smt_levels<<<(unsigned)((2 * ns + nf + 15) / 16), 96, 0, s>>>(pl, d->w, d->lev, d->smst, d->mids, s0, ns, f0, nf);
+        const unsigned lb = (unsigned)((2 * ns + nf + 15) / 16);
+        k_smt_levels<<<lb, 96, 0, s>>>(pl, d->w, d->lev, d->smst, d->mids, d->img00, d->zflag, s0, ns, f0, nf);
+        // the skipped (0, 0) levels are filled in beside the tail and the hash of the inputs
+        CK(cudaEventRecord(d->ev_lev, s));
+        CK(cudaStreamWaitEvent(d->stream3, d->ev_lev, 0));
+        k_smt_zero<<<dim3(lb, (unsigned)(pl.P.nLevels + 1)), 256, 0, d->stream3>>>(pl, d->w, d->lev, d->img00, d->zflag, s0, ns, f0, nf);
     }
+    CK(cudaEventRecord(d->ev_zero, d->stream3));
     CK(cudaEventRecord(d->kev[3], s));
     if (ns + nf > 0) k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->mids, d->isExit, d->jobs, d->jobs_front, s0, ns, f0, nf);
     CK(cudaEventRecord(d->kev[4], s));
@@ -800,6 +862,7 @@ static int hz_phase2(HzCuda* d, int sanity) {
     k_hash_tail<<<1, 32, 0, s>>>(pl, d->w, d->rank == 0 ? err : nullptr, d->chain);
     CK(cudaEventRecord(d->kev[8], s));
     CK(cudaStreamWaitEvent(s, d->ev_eddsa, 0));
+    CK(cudaStreamWaitEvent(s, d->ev_zero, 0));
     CK(cudaGetLastError());
     CK(cudaEventRecord(d->ev1, s));
     return 0;
@@ -840,7 +903,9 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
         CK(cudaEventRecord(d->ev_ed[h], s2));
         if (2 * ns + nf > 0) {
             k_smt<<<hz_grid(2 * ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, 0, nf);
-            k_smt_levels<<<(unsigned)((2 * ns + nf + 15) / 16), 96, 0, s>>>(pl, d->w, d->lev, d->smst, d->mids, s0, ns, 0, nf);
+            const unsigned lb = (unsigned)((2 * ns + nf + 15) / 16);
+            k_smt_levels<<<lb, 96, 0, s>>>(pl, d->w, d->lev, d->smst, d->mids, d->img00, d->zflag, s0, ns, 0, nf);
+            k_smt_zero<<<dim3(lb, (unsigned)(P.nLevels + 1)), 256, 0, s>>>(pl, d->w, d->lev, d->img00, d->zflag, s0, ns, 0, nf);
         }
         if (ns + nf > 0) k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->mids, d->isExit, d->jobs, d->jobs_front, s0, ns, 0, nf);
         CK(cudaStreamWaitEvent(s, d->ev_ed[h], 0));
@@ -881,7 +946,7 @@ int hz_cuda_calculate(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* wit
     CK(cudaStreamSynchronize(s));
     if (overlapped) CK(cudaStreamSynchronize(d->stream3));
     if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, d->ev0, d->ev1));
-    if (launches) *launches = overlapped ? 17 : 12;        // kernels of ours per batch (see the launch sequences above)
+    if (launches) *launches = overlapped ? 19 : 13;        // kernels of ours per batch (see the launch sequences above)
     if (h2d) *h2d = inputs ? 32ull * pl.n_inputs : 0;
     if (d2h) *d2h = (witness_out ? 32ull * pl.nvars : 0) + sizeof(HzErrBuf);
     return 0;
