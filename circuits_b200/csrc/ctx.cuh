@@ -209,6 +209,8 @@ struct HzHints {
     Fr* scratch;                           // HZ_HINT_SCRATCH entries owned by this lane group / thread
     int lad_ok;                            // device: scratch[0 .. 588) holds the hints of all ladders (hints.cuh)
     int fill;                              // device: the entries of the ladder steps are left to k_ed_fill
+    int prefilled;                         // device: the constant entries of EscalarMulFix are already in the witness (k_ed_const)
+    uint32_t win_c0, win_size;             // the windows / carry adders of its segment 0: where they start (record mode: measured) and their size
     const Fr* cimg; uint32_t fix_shift;    // witness image of EscalarMulFix from the recording pass, and where the
                                            // component being evaluated starts: its constant entries are copied
 };
@@ -289,7 +291,8 @@ template <> struct Comp<MCompute> {
     HZ_HD bool const_image() const { return hints && hints->cimg && !hints->rec; }
     HZ_HD VC copy_const(const Nm&) {
         VC r; r.v = hints->cimg[cur - hints->fix_shift]; r.sig = true;
-        put(cur, r.v); cur++;
+        if (!hints->prefilled) put(cur, r.v);
+        cur++;
         return r;
     }
     // a / b at a division site of hint class `cls` (0: none)

@@ -169,7 +169,7 @@ HZ_HD void hz_hints_record_point(HzHints* h, const Fr& u, const Fr& v) {
 #define HZ_SCR_REC (HZ_SCR_AFF + 176)
 // per signature, written by lane 0 of k_eddsa: whether the ladder data is usable, where the three runs of
 // step entries start in the witness, the scalar bits
-struct HzFillRec { uint32_t ok, base_seg0, base_seg1, base_fix; uint32_t e[8]; uint32_t s[8]; uint32_t pad[12]; };
+struct HzFillRec { uint32_t ok, base_seg0, base_seg1, base_fix; uint32_t e[8]; uint32_t s[8]; uint32_t base_win; uint32_t pad[11]; };
 struct MtOps { Fr N, Dn, W12, X1, X2, Y1; };
 __device__ __forceinline__ MtOps mt_head_dbl(const MtPt& p) {
     MtOps o;
@@ -367,6 +367,9 @@ __device__ __noinline__ void hz_hints_eddsa_lanes(HzHints* h, const Fr& px, cons
     MtPt acc = D;
     const Fr* tab = h->edtab;
     if (role == 3) { acc.U = tab[83 * 16]; acc.V = tab[83 * 16 + 1]; acc.W = fr_one(); }
+    // the window entry of the fixed-base adder is read one step ahead: the load is off the step's critical path
+    Fr wnU = fr_zero(), wnV = fr_zero();
+    if (role == 3) { int sel = (int)(s.bit(0) | (s.bit(1) << 1) | (s.bit(2) << 2)); wnU = tab[2 * sel]; wnV = tab[2 * sel + 1]; }
     for (int t = 0; t <= 253; t++) {
         if (role == 2 && t == 148) acc = D;
         if (!half) hz_lad_captures(role, t, num, den, vv, D, acc, ok);
@@ -378,9 +381,10 @@ __device__ __noinline__ void hz_hints_eddsa_lanes(HzHints* h, const Fr& px, cons
         else if (role == 2) { active = t >= 149; el = 400 + (t - 149); }
         else {
             active = t < 83; el = 505 + t;
-            int tt = active ? t : 0;
+            p1 = acc; p2.U = wnU; p2.V = wnV; p2.W = fr_one();
+            int tt = t + 1 < 83 ? t + 1 : 0;
             int sel = (int)(s.bit(3 * tt) | (s.bit(3 * tt + 1) << 1) | (s.bit(3 * tt + 2) << 2));
-            p1 = acc; p2.U = tab[tt * 16 + 2 * sel]; p2.V = tab[tt * 16 + 2 * sel + 1]; p2.W = fr_one();
+            wnU = tab[tt * 16 + 2 * sel]; wnV = tab[tt * 16 + 2 * sel + 1];
         }
         // head
         const Fr b01 = hz_sel_fr(half, p1.W, p2.W);
@@ -493,5 +497,32 @@ __device__ __forceinline__ void hz_fill_fix(Fr* w, HzErrBuf* err, const Fr* hint
         win.u = tab[i * 16 + 2 * sel]; win.v = tab[i * 16 + 2 * sel + 1];
         acc = hz_fill_madd(w, at, err, acc, win, hint[505 + i]);
     }
+}
+// the multiplexer of window i of EscalarMulFix segment 0 (MultiMux3 with two outputs over the window's eight
+// constant points, selected by three bits of S): out[2], a210[2], a21[2], a20[2], a2[2], a10[2], a1[2], a0[2], s10
+__device__ __forceinline__ void hz_fill_winmux(Fr* w, const Fr* tab, const HzFillRec& rec, uint32_t stride, int i) {
+    uint32_t b[3];
+    for (int k = 0; k < 3; k++) b[k] = (rec.s[(3 * i + k) >> 5] >> ((3 * i + k) & 31)) & 1u;
+    const bool s0 = b[0] != 0, s1 = b[1] != 0, s2 = b[2] != 0, s10 = s0 && s1;
+    const Fr z = fr_zero();
+    const uint32_t at = rec.base_win + stride * (uint32_t)i;
+    for (int o = 0; o < 2; o++) {
+        Fr q[8];
+        for (int j = 0; j < 8; j++) q[j] = tab[i * 16 + 2 * j + o];
+        const Fr d210 = fr_sub(fr_add(fr_add(fr_sub(fr_add(fr_sub(fr_sub(q[7], q[6]), q[5]), q[4]), q[3]), q[2]), q[1]), q[0]);
+        const Fr v210 = s10 ? d210 : z;
+        const Fr v21 = s1 ? fr_add(fr_sub(fr_sub(q[6], q[4]), q[2]), q[0]) : z;
+        const Fr v20 = s0 ? fr_add(fr_sub(fr_sub(q[5], q[4]), q[1]), q[0]) : z;
+        const Fr v2 = fr_sub(q[4], q[0]);
+        const Fr v10 = s10 ? fr_add(fr_sub(fr_sub(q[3], q[2]), q[1]), q[0]) : z;
+        const Fr v1 = s1 ? fr_sub(q[2], q[0]) : z;
+        const Fr v0 = s0 ? fr_sub(q[1], q[0]) : z;
+        const Fr hi = fr_add(fr_add(fr_add(v210, v21), v20), v2);
+        const Fr out = fr_add(s2 ? hi : z, fr_add(fr_add(fr_add(v10, v1), v0), q[0]));
+        hz_store_fr(&w[at + o], out); hz_store_fr(&w[at + 2 + o], v210); hz_store_fr(&w[at + 4 + o], v21);
+        hz_store_fr(&w[at + 6 + o], v20); hz_store_fr(&w[at + 8 + o], v2); hz_store_fr(&w[at + 10 + o], v10);
+        hz_store_fr(&w[at + 12 + o], v1); hz_store_fr(&w[at + 14 + o], v0);
+    }
+    hz_store_fr(&w[at + 16], fr_from_u64(s10 ? 1u : 0u));
 }
 #endif

@@ -48,6 +48,7 @@ struct HzCuda {
     Fr* hint_tab;              // HZ_EDTAB_LEN: its window entries
     Fr* hint_img;              // witness image of EscalarMulFix from the recording pass (constant entries are copied from it)
     Fr* hint_scratch;          // per lane group of k_eddsa: work area of the hint generators
+    uint32_t fix_size, win_size, win_stride;   // entries of EscalarMulFix; of the windows + carry adders of its segment 0; per window
     HzErrBuf* err;
     uint32_t *off_decode, *off_rollup, *off_fee;
     uint32_t h_off_decode0, h_off_rollup0, h_off_rollup_mid, h_off_fee0;   // host copies of the piece boundaries
@@ -325,13 +326,26 @@ __global__ void k_fix_consts(Fr* wtmp, Fr* cst, Fr* tab, uint32_t* counts) {
     hz_record_fix_consts(wtmp, cst, tab, counts);
 }
 
+// the constant entries of EscalarMulFix(253, BASE8) for every signature of the shard: its recorded image copied
+// to sigVerifier.mulFix of each slot before k_eddsa runs (which then only writes the entries that depend on S)
+__global__ void __launch_bounds__(256) k_ed_const(HzPlan pl, Fr* w, const uint32_t* off_eddsa, const Fr* img, uint32_t fix_size, int s0, int ns) {
+    const uint32_t per = 2 * fix_size;                                  // uint4 pieces per signature
+    const uint64_t total = (uint64_t)per * (uint64_t)ns;
+    const uint4* src = reinterpret_cast<const uint4*>(img);
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t g = (uint32_t)(e / per), k = (uint32_t)(e % per);
+        uint4* dst = reinterpret_cast<uint4*>(w + off_eddsa[s0 + (int)g] + pl.sz.mulfix_off);
+        __stcs(&dst[k], src[k]);
+    }
+}
+
 __global__ void __launch_bounds__(HZ_BLOCK, 3) k_eddsa(HzPlan pl, Fr* w, HzErrBuf* err, const HzEddsaJob* jobs,
-                                                    const Fr* cst, const Fr* tab, const Fr* img, Fr* scratch, int s0, int ns) {
+                                                    const Fr* cst, const Fr* tab, const Fr* img, Fr* scratch, uint32_t win_size, int s0, int ns) {
     bool real; int i = s0 + hz_item(ns, real);
     const HzEddsaJob& j = jobs[i];
     HzHints h;
     h.cst = cst; h.ci = 0; h.dat = nullptr; h.di = 0; h.rec = nullptr; h.ri = 0;
-    h.edtab = tab; h.edrec = nullptr; h.ei = 0; h.lad_ok = 0; h.fill = 1; h.cimg = img; h.fix_shift = 0; h.scratch = scratch + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) / HZ_G) * HZ_HINT_SCRATCH;   // per group, not per slot: padding groups redo a slot
+    h.edtab = tab; h.edrec = nullptr; h.ei = 0; h.lad_ok = 0; h.fill = 1; h.prefilled = 1; h.win_c0 = 0; h.win_size = win_size; h.cimg = img; h.fix_shift = 0; h.scratch = scratch + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) / HZ_G) * HZ_HINT_SCRATCH;   // per group, not per slot: padding groups redo a slot
     HzPending pend; pend.n = 0;
     Comp<MCompute> c(w, j.cur, real ? err : nullptr, &h, &pend);
     VC vse, sgn, ay, s1Ay, S, R8x, R8y, Msg;
@@ -344,9 +358,19 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_eddsa(HzPlan pl, Fr* w, HzErrBu
 
 // the entries of the ladder steps of the signatures k_eddsa walked (hints.cuh): a thread per chunk of steps;
 // first the 33 chunks of the two EscalarMulAny segments of every signature, then the 11 of the fixed-base adders
-__global__ void __launch_bounds__(128) k_ed_fill(Fr* w, HzErrBuf* err, const Fr* tab, const Fr* scratch, int ns) {
+#define HZ_FILL_PER_SIG (HZ_FILL_CHUNKS + 83)
+__global__ void __launch_bounds__(128) k_ed_fill(Fr* w, HzErrBuf* err, const Fr* tab, const Fr* scratch, uint32_t win_stride, int ns) {
     const int gid = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const int nseg = HZ_FILL_C0 + HZ_FILL_C1;
+    if (gid >= (nseg + HZ_FILL_CF) * ns) {
+        // the 83 window multiplexers of every signature
+        const int g3 = gid - (nseg + HZ_FILL_CF) * ns, gw = g3 / 83;
+        if (gw >= ns) return;
+        const Fr* scw = scratch + (size_t)gw * HZ_HINT_SCRATCH;
+        const HzFillRec recw = *reinterpret_cast<const HzFillRec*>(scw + HZ_SCR_REC);
+        if (recw.ok) hz_fill_winmux(w, tab, recw, win_stride, g3 % 83);
+        return;
+    }
     const bool fix = gid >= nseg * ns;
     const int g2 = fix ? gid - nseg * ns : gid;
     const int g = fix ? g2 / HZ_FILL_CF : g2 / nseg, k = fix ? g2 % HZ_FILL_CF : g2 % nseg;
@@ -730,15 +754,20 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     }
     if (ok) {
         // record the input-independent part of the EdDSA fixed-base multiplication once
-        uint32_t* counts = nullptr; uint32_t hc[2] = {0, 0};
-        ok = cudaMalloc(&d->hint_img, sizeof(Fr) * ((size_t)ph.sz.sigVerifier + 64)) == cudaSuccess && cudaMalloc(&counts, 8) == cudaSuccess;
+        uint32_t* counts = nullptr; uint32_t hc[5] = {0, 0, 0, 0, 0};
+        ok = cudaMalloc(&d->hint_img, sizeof(Fr) * ((size_t)ph.sz.sigVerifier + 64)) == cudaSuccess && cudaMalloc(&counts, 20) == cudaSuccess;
         Fr* wtmp = d->hint_img;
         if (ok) {
             k_fix_consts<<<1, 32, 0, d->stream>>>(wtmp, d->hint_cst, d->hint_tab, counts);
-            ok = cudaMemcpyAsync(hc, counts, 8, cudaMemcpyDeviceToHost, d->stream) == cudaSuccess &&
+            ok = cudaMemcpyAsync(hc, counts, 20, cudaMemcpyDeviceToHost, d->stream) == cudaSuccess &&
                  cudaStreamSynchronize(d->stream) == cudaSuccess;
             if (ok && (hc[0] > HZ_CST_MAX || hc[1] != HZ_EDTAB_LEN)) {
                 fprintf(stderr, "hzw: hint table sizes %u / %u do not match the templates\n", hc[0], hc[1]);
+                ok = false;
+            }
+            d->fix_size = hc[4]; d->win_size = hc[3]; d->win_stride = hc[3] / 83;
+            if (ok && (hc[3] == 0 || hc[3] % 83 != 0 || hc[4] > ph.sz.sigVerifier || ph.sz.mulfix_off + hc[4] > ph.sz.getAx + ph.sz.sigVerifier)) {
+                fprintf(stderr, "hzw: EscalarMulFix image (%u entries, windows %u) does not fit the layout\n", hc[4], hc[3]);
                 ok = false;
             }
         }
@@ -817,8 +846,9 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     CK(cudaEventRecord(d->kev[9], s2));
     if (ns > 0) {
         k_edjob<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, d->jobs, d->off_eddsa, s0, ns);
-        k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, s0, ns);
-        k_ed_fill<<<(unsigned)((HZ_FILL_CHUNKS * ns + 127) / 128), 128, 0, s2>>>(d->w, err, d->hint_tab, d->hint_scratch, ns);
+        k_ed_const<<<592, 256, 0, s2>>>(pl, d->w, d->off_eddsa, d->hint_img, d->fix_size, s0, ns);
+            k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, s0, ns);
+        k_ed_fill<<<(unsigned)((HZ_FILL_PER_SIG * ns + 127) / 128), 128, 0, s2>>>(d->w, err, d->hint_tab, d->hint_scratch, d->win_stride, ns);
     }
     CK(cudaEventRecord(d->kev[10], s2));
     CK(cudaEventRecord(d->ev_eddsa, s2));
@@ -897,8 +927,9 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
     for (int h = 0; h < 2; h++) {
         const int s0 = h == 0 ? 0 : h0, ns = h == 0 ? h0 : P.nTx - h0, nf = h == 1 ? F : 0;
         if (ns > 0) {
-            k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, s0, ns);
-            k_ed_fill<<<(unsigned)((HZ_FILL_CHUNKS * ns + 127) / 128), 128, 0, s2>>>(d->w, err, d->hint_tab, d->hint_scratch, ns);
+            k_ed_const<<<592, 256, 0, s2>>>(pl, d->w, d->off_eddsa, d->hint_img, d->fix_size, s0, ns);
+            k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, s0, ns);
+            k_ed_fill<<<(unsigned)((HZ_FILL_PER_SIG * ns + 127) / 128), 128, 0, s2>>>(d->w, err, d->hint_tab, d->hint_scratch, d->win_stride, ns);
         }
         CK(cudaEventRecord(d->ev_ed[h], s2));
         if (2 * ns + nf > 0) {
@@ -946,7 +977,7 @@ int hz_cuda_calculate(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* wit
     CK(cudaStreamSynchronize(s));
     if (overlapped) CK(cudaStreamSynchronize(d->stream3));
     if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, d->ev0, d->ev1));
-    if (launches) *launches = overlapped ? 19 : 13;        // kernels of ours per batch (see the launch sequences above)
+    if (launches) *launches = overlapped ? 21 : 14;        // kernels of ours per batch (see the launch sequences above)
     if (h2d) *h2d = inputs ? 32ull * pl.n_inputs : 0;
     if (d2h) *d2h = (witness_out ? 32ull * pl.nvars : 0) + sizeof(HzErrBuf);
     return 0;

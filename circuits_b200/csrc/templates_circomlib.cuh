@@ -873,6 +873,17 @@ template <> struct HintGen<MCompute> {
         a.x = aff(c, 2 * (78 + seg)); a.y = aff(c, 2 * (78 + seg) + 1);
         return true;
     }
+    // windows and carry adders of segment 0: constants (prefilled by k_ed_const) and the window multiplexers,
+    // which only depend on the scalar bits (k_ed_fill); nothing of them is needed here
+    static HZ_HD bool fill_windows(Comp<MCompute>& c, int seg, PtV<MCompute>& wbase, PtV<MCompute>& cad, PtV<MCompute>& dblLast) {
+        if (seg != 0 || !fill_on(c) || !c.hints->prefilled || c.hints->win_size == 0) return false;
+        HzFillRec* rec = reinterpret_cast<HzFillRec*>(c.hints->scratch + HZ_SCR_REC);
+        if (hz_glane() == 0) rec->base_win = c.cur;
+        c.cur += c.hints->win_size;
+        VC z; z.v = fr_zero(); z.sig = true;          // wired signals whose values nothing downstream reads
+        wbase.x = wbase.y = cad.x = cad.y = dblLast.x = dblLast.y = z;
+        return true;
+    }
     static HZ_HD bool fill_fix(Comp<MCompute>& c, int nW, int seg, PtV<MCompute>& acc) {
         if (seg != 0 || !fill_on(c)) return false;
         HzFillRec* rec = reinterpret_cast<HzFillRec*>(c.hints->scratch + HZ_SCR_REC);
@@ -884,11 +895,15 @@ template <> struct HintGen<MCompute> {
 #else
     static HZ_HD bool fill_any(Comp<MCompute>&, int, int, PtV<MCompute>&, PtV<MCompute>&) { return false; }
     static HZ_HD bool fill_fix(Comp<MCompute>&, int, int, PtV<MCompute>&) { return false; }
+    static HZ_HD bool fill_windows(Comp<MCompute>&, int, PtV<MCompute>&, PtV<MCompute>&, PtV<MCompute>&) { return false; }
     static HZ_HD void ladder(Comp<MCompute>&, const VC&, const VC&, const BVC&, const BVC&) {}
     static HZ_HD void seg_any(Comp<MCompute>& c, const VC& px, const VC& py, const BVC& e, int n, int) { hz_hints_segment_any(c.hints, px.v, py.v, e, n); }
     static HZ_HD void mid(Comp<MCompute>&) {}
     static HZ_HD void seg_fix(Comp<MCompute>& c, const BVC& e, int nW, int seg) { hz_hints_segment_fix(c.hints, e, nW, seg); }
 #endif
+    // record mode: where the windows / carry adders of segment 0 start and how many entries they take
+    static HZ_HD void win_begin(Comp<MCompute>& c, int seg) { if (c.hints && c.hints->rec && seg == 0) c.hints->win_c0 = c.cur; }
+    static HZ_HD void win_end(Comp<MCompute>& c, int seg) { if (c.hints && c.hints->rec && seg == 0) c.hints->win_size = c.cur - c.hints->win_c0; }
     static HZ_HD void done(Comp<MCompute>& c) { hz_hints_done(c.hints); }
     static HZ_HD void fix_begin(Comp<MCompute>& c) { if (c.hints) c.hints->fix_shift = c.cur; }
     static HZ_HD void record(Comp<MCompute>& c, const VC& u, const VC& v) { hz_hints_record_point(c.hints, u.v, v.v); }
@@ -901,8 +916,12 @@ template <> struct HintGen<MLayout> {
     static void seg_fix(Comp<MLayout>&, const BVT<MLayout, 8>&, int, int) {}
     static bool fill_any(Comp<MLayout>&, int, int, PtV<MLayout>&, PtV<MLayout>&) { return false; }
     static bool fill_fix(Comp<MLayout>&, int, int, PtV<MLayout>&) { return false; }
+    static bool fill_windows(Comp<MLayout>&, int, PtV<MLayout>&, PtV<MLayout>&, PtV<MLayout>&) { return false; }
+    static void win_begin(Comp<MLayout>&, int) {}
+    static void win_end(Comp<MLayout>&, int) {}
     static void done(Comp<MLayout>&) {}
-    static void fix_begin(Comp<MLayout>&) {}
+    static uint32_t& last_fix_begin() { static uint32_t v = 0; return v; }     // where the last mulFix walked starts
+    static void fix_begin(Comp<MLayout>& c) { last_fix_begin() = c.cur; }
     static void record(Comp<MLayout>&, const VL&, const VL&) {}
 };
 #endif
@@ -1117,6 +1136,8 @@ TM HZ_FN void SegmentMulFix(Comp<M>&& c, const BV<M>& e, int nW, const PtV<M>& b
     // window outputs are kept: read them back from the witness when accumulating
     PtV<M> wbase = m, cad = m, dblLast, o8;
     PtV<M> win_out[85];
+    HintGen<M>::win_begin(c, seg);
+    if (!HintGen<M>::fill_windows(c, seg, wbase, cad, dblLast))
     for (int i = 0; i < nW; i++) {
         V<M> in3[3];
         for (int k = 0; k < 3; k++) in3[k] = e_.get(3 * i + k);
@@ -1130,6 +1151,7 @@ TM HZ_FN void SegmentMulFix(Comp<M>&& c, const BV<M>& e, int nW, const PtV<M>& b
             cad = MontgomeryAdd(c.sub(Nm("cadders", i)), cad, dblLast, 1);
         }
     }
+    HintGen<M>::win_end(c, seg);
     // the accumulating adders depend on the scalar: data stream
     HintGen<M>::seg_fix(c, e_, nW, seg);
     PtV<M> acc = dblLast;
@@ -1177,13 +1199,13 @@ TM HZ_FN PtV<M> EscalarMulFix253(Comp<M>&& c, const BV<M>& e) {
 HZ_FN void hz_record_fix_consts(Fr* wtmp, Fr* cst, Fr* edtab, uint32_t* counts) {
     HzHints h;
     h.cst = nullptr; h.ci = 0; h.dat = nullptr; h.di = 0; h.rec = cst; h.ri = 0;
-    h.edtab = nullptr; h.edrec = edtab; h.ei = 0; h.scratch = nullptr; h.lad_ok = 0; h.fill = 0; h.cimg = nullptr; h.fix_shift = 0;
+    h.edtab = nullptr; h.edrec = edtab; h.ei = 0; h.scratch = nullptr; h.lad_ok = 0; h.fill = 0; h.prefilled = 0; h.win_c0 = 0; h.win_size = 0; h.cimg = nullptr; h.fix_shift = 0;
     Comp<MCompute> c(wtmp, 0, nullptr, &h);
     BVC e; e.clear(253);
     VC z = vc(fr_zero()); z.sig = true;
     for (int i = 0; i < 253; i++) e.put(i, z);
     EscalarMulFix253<MCompute>(c.sub("mulFix"), e);
-    counts[0] = h.ri; counts[1] = h.ei;
+    counts[0] = h.ri; counts[1] = h.ei; counts[2] = h.win_c0; counts[3] = h.win_size; counts[4] = c.cur;
 }
 
 // ---------------------------------------------------------------------------

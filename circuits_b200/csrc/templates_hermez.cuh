@@ -497,7 +497,7 @@ struct HzSmtMid { Fr enabled, oldKey, newKey, fnc0, fnc1, oc, nc; uint32_t cur, 
 // what the head of a body leaves for the levels kernel: leaf hashes, the level bits of the new key, where the
 // level components start, where the siblings are; the state-machine tuples go to a scratch array
 struct HzLevJob { Fr o1, n1; uint64_t lrbits; uint32_t cur, sib, pad[4]; };
-struct HzSizes { uint32_t getAx, sigVerifier, phaseJK, p2_off; };   // p2_off: processor2 start within phases J-K
+struct HzSizes { uint32_t getAx, sigVerifier, phaseJK, p2_off, mulfix_off; };   // p2_off: processor2 start within phases J-K; mulfix_off: sigVerifier.mulFix from the start of phase F
 
 TM struct SlotHook;
 template <> struct SlotHook<MCompute> {
@@ -531,7 +531,7 @@ inline void hz_phaseF_hook(Comp<MLayout>& c, const SlotHook<MLayout>& hk, const 
     V<MLayout> ax = AySign2Ax(c.sub("getAx"), aySignature, signSignature);
     uint32_t c1 = c.cur;
     EdDSAPoseidonVerifier(c.sub("sigVerifier"), vse, ax, s1Ay, S, R8x, R8y, Msg);
-    if (hk.sz_out) { hk.sz_out->getAx = c1 - c0; hk.sz_out->sigVerifier = c.cur - c1; }
+    if (hk.sz_out) { hk.sz_out->getAx = c1 - c0; hk.sz_out->sigVerifier = c.cur - c1; hk.sz_out->mulfix_off = HintGen<MLayout>::last_fix_begin() - c0; }
     if (hk.ed_cur) *hk.ed_cur = c0;
 }
 #endif

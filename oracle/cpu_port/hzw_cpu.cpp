@@ -66,7 +66,7 @@ struct CpuBackend : HzBackend {
             std::vector<Fr> scratch(use_hints ? HZ_HINT_SCRATCH : 0);
             HzHints h;
             h.cst = cst.data(); h.ci = 0; h.dat = nullptr; h.di = 0; h.rec = nullptr; h.ri = 0;
-            h.edtab = edtab.data(); h.edrec = nullptr; h.ei = 0; h.scratch = scratch.data(); h.lad_ok = 0; h.fill = 0; h.cimg = cimg.empty() ? nullptr : cimg.data(); h.fix_shift = 0;
+            h.edtab = edtab.data(); h.edrec = nullptr; h.ei = 0; h.scratch = scratch.data(); h.lad_ok = 0; h.fill = 0; h.prefilled = 0; h.win_c0 = 0; h.win_size = 0; h.cimg = cimg.empty() ? nullptr : cimg.data(); h.fix_shift = 0;
             Comp<MCompute> c(w, pl.off_decode[i], err, use_hints ? &h : nullptr);
             DecodeOut<MCompute> d;
             PreBits<MCompute> p2 = pre;
