@@ -235,11 +235,13 @@ template <> struct Comp<MCompute> {
     HzHints* hints;     // null = every division inverts on the spot
     HzPending* pend;    // null = IsZero inverts on the spot
     bool solo = false;  // device: this thread works alone (no lane group shares its stores)
+    bool dry = false;   // values only: nothing is stored, no inverse is queued (k_smtjob derives the SMT jobs of a
+                        // slot ahead of k_front by running the same templates this way)
     typedef VC Val;
 
     HZ_HD Comp(Fr* w_, uint32_t cur_, HzErrBuf* err_, HzHints* h_ = nullptr, HzPending* p_ = nullptr)
         : w(w_), cur(cur_), end(HZ_NOIDX), parent(nullptr), err(err_), hints(h_), pend(p_) {}
-    HZ_HD Comp(Comp* p, bool reserved, uint32_t size) : w(p->w), cur(p->cur), parent(reserved ? nullptr : p), err(p->err), hints(p->hints), pend(p->pend), solo(p->solo) {
+    HZ_HD Comp(Comp* p, bool reserved, uint32_t size) : w(p->w), cur(p->cur), parent(reserved ? nullptr : p), err(p->err), hints(p->hints), pend(p->pend), solo(p->solo), dry(p->dry) {
         if (reserved) { end = p->cur + size; p->cur += size; } else end = HZ_NOIDX;
     }
     HZ_HD ~Comp() {
@@ -249,11 +251,12 @@ template <> struct Comp<MCompute> {
 #endif
     }
     Comp(const Comp&) = delete;
-    HZ_HD Comp(Comp&& o) : w(o.w), cur(o.cur), end(o.end), parent(o.parent), err(o.err), hints(o.hints), pend(o.pend), solo(o.solo) { o.parent = nullptr; o.end = HZ_NOIDX; }
+    HZ_HD Comp(Comp&& o) : w(o.w), cur(o.cur), end(o.end), parent(o.parent), err(o.err), hints(o.hints), pend(o.pend), solo(o.solo), dry(o.dry) { o.parent = nullptr; o.end = HZ_NOIDX; }
     // the `inv` entry and the `out` value of IsZero(x) (comparators.circom): inv <-- x != 0 ? 1/x : 0
     HZ_HD VC iszero_inv(const Nm&, const VC& x) {
         const uint32_t slot = cur++;
         const bool z = fr_is_zero(x.v);
+        if (dry) return vc(z ? fr_one() : fr_zero());
         if (pend) {
             if (pend->n == HZ_PEND_CAP) flush_pending();
             pend->idx[pend->n] = slot; pend->val[pend->n] = x.v; pend->n++;
@@ -312,6 +315,7 @@ template <> struct Comp<MCompute> {
 
     // the one place a witness entry is written
     HZ_HD void put(uint32_t slot, const Fr& v) {
+        if (dry) return;
 #ifdef HZ_DEVICE_ONLY
         if (solo || ((slot ^ threadIdx.x) & (HZ_G - 1)) == 0) hz_store_fr(&w[slot], v);
 #else
@@ -321,6 +325,7 @@ template <> struct Comp<MCompute> {
     // n consecutive entries holding the bits of `bits` (bit k -> entry cur + k, or reversed): on the
     // device the lanes of a group take every 8th entry each
     HZ_HD void put_bits(uint64_t bits, int n, bool msb_first = false) {
+        if (dry) { cur += n; return; }
         Fr f = fr_zero();
 #ifdef HZ_DEVICE_ONLY
         const int step = solo ? 1 : HZ_G;

@@ -45,7 +45,7 @@ static inline void hz_input_shape(const HzParams& P, int f, int& rank, uint32_t&
 
 struct HzLayout {
     HzPlan plan;
-    std::vector<uint32_t> off_decode, off_rollup, off_fee, off_eddsa;   // off_eddsa: start of phase F (getAx) per slot
+    std::vector<uint32_t> off_decode, off_rollup, off_fee, off_eddsa, off_jk;   // off_eddsa: start of phase F (getAx) per slot; off_jk: of phases J-K (processor1)
 };
 
 static inline bool hz_params_ok(const HzParams& P) {
@@ -78,13 +78,14 @@ static inline void hz_layout_walk(const HzParams& P, LayoutSink* sink, HzLayout&
     std::vector<uint32_t> preidx((size_t)pl.nblocks * 512, HZ_NOIDX);
     PreBits<MLayout> pre; pre.idx = preidx.data();
     std::vector<DecodeOut<MLayout> > dec(P.nTx);
-    R.off_decode.resize(P.nTx); R.off_rollup.resize(P.nTx); R.off_fee.resize(P.maxFeeTx); R.off_eddsa.resize(P.nTx);
+    R.off_decode.resize(P.nTx); R.off_rollup.resize(P.nTx); R.off_fee.resize(P.maxFeeTx); R.off_eddsa.resize(P.nTx); R.off_jk.resize(P.nTx);
     for (int i = 0; i < P.nTx; i++) { R.off_decode[i] = main.cur; sec_decode(main, pl, i, dec[i], pre); }
     pl.idx_newLastIdx = dec[P.nTx - 1].outIdx.idx;
     SlotHook<MLayout> hook; hook.sz_out = &pl.sz;
     for (int i = 0; i < P.nTx; i++) {
         R.off_rollup[i] = main.cur;
         hook.ed_cur = &R.off_eddsa[i];
+        hook.jk_cur = &R.off_jk[i];
         RollupTxOut<MLayout> o;
         sec_rollup(main, pl, i, dec[i], o, pre, hook);
         if (i == P.nTx - 1) pl.idx_newExitRoot = o.newExitRoot.idx;

@@ -149,6 +149,12 @@ int hzw_input_index(const hzw_ctx* ctx, const char* name, uint64_t* offset, uint
 }
 
 static int hz_report(hzw_ctx* ctx, HzErrBuf& eb, hzw_error* err) {
+    if (eb.pad != 0) {
+        // the jobs derived ahead of k_front differ from the ones its templates arrive at: a bug, never a property of the input
+        fprintf(stderr, "hzw: internal error: %u slot(s) with job records that do not match\n", eb.pad);
+        if (err) { memset(err, 0, sizeof *err); err->code = HZW_E_DEVICE; }
+        return HZW_E_DEVICE;
+    }
     if (eb.count == 0) { if (err) memset(err, 0, sizeof *err); return HZW_OK; }
     uint32_t n = eb.count < HZ_MAX_ERR ? eb.count : HZ_MAX_ERR, best = 0;
     for (uint32_t k = 1; k < n; k++) if (eb.rec[k].cur < eb.rec[best].cur) best = k;

@@ -22,9 +22,9 @@
 #include <cstring>
 #include <cstdlib>
 
-#define HZ_NKERN 9   /* timed intervals; k_smt's covers the head and the levels kernels */
-static const char* const HZ_KERN_NAMES[HZ_NKERN] = {"k_front", "k_fee_front", "k_smt", "k_tail", "k_hash_head",
-                                                    "k_sha_chain", "k_sha_blocks", "k_hash_tail", "k_eddsa"};
+#define HZ_NKERN 10  /* timed intervals; k_smt's covers the head and the levels kernels */
+static const char* const HZ_KERN_NAMES[HZ_NKERN] = {"k_smtjob", "k_fee_front", "k_smt", "k_tail", "k_hash_head",
+                                                    "k_sha_chain", "k_sha_blocks", "k_hash_tail", "k_eddsa", "k_front"};
 #define HZ_BLOCK 128                       /* 16 lane groups per block */
 
 struct HzCuda {
@@ -37,13 +37,16 @@ struct HzCuda {
     HzEddsaJob* jobs;          // nTx: from k_edjob, read by k_eddsa
     HzEddsaJob* jobs_front;    // nTx: the same as the templates of k_front arrive at them (k_tail compares)
     uint32_t* off_eddsa;       // nTx: where phase F of each slot starts
-    HzSmtJob* smt;             // 2 nTx + maxFeeTx
+    HzSmtJob* smt;             // 2 nTx + maxFeeTx: from k_smtjob (slots) and k_fee_front
+    HzSmtJob* smt_front;       // 2 nTx: the same as k_front arrives at them (k_tail compares)
+    uint32_t* off_jk;          // nTx: where phases J-K of each slot start
     HzSmtMid* mids;            // 2 nTx + maxFeeTx
     HzLevJob* lev;             // 2 nTx + maxFeeTx: what k_smt leaves for k_smt_levels
     Fr* smst;                  // per processor (nLevels + 1) x 6 state-machine values
     Fr* img00;                 // the 634 entries of SMTHash2(0, 0) and, at [HZ_IMG00_DIGEST], its digest
     uint8_t* zflag;            // per block of k_smt_levels and level: the level hashed (0, 0) in every chain of the block
     Fr* isExit;                // nTx
+    Fr* isExit_front;          // nTx: k_front's copy
     Fr* hint_cst;              // HZ_CST_MAX: constant inverses of EscalarMulFix (recorded at create)
     Fr* hint_tab;              // HZ_EDTAB_LEN: its window entries
     Fr* hint_img;              // witness image of EscalarMulFix from the recording pass (constant entries are copied from it)
@@ -57,10 +60,10 @@ struct HzCuda {
     int rank, world, per, s0, ns, f0, nf;
     uint32_t b0, nb;
     uint8_t* recs;             // world x rec_bytes: the gathered exchange records (own one while packing)
-    cudaStream_t stream, stream2, stream3;
+    cudaStream_t stream, stream2, stream3, stream4;
     cudaEvent_t ev_half[2], ev_ed[2], ev_done;
     cudaEvent_t ev0, ev1, ev_front, ev_eddsa, ev_lev, ev_zero, ev_fee;
-    cudaEvent_t kev[HZ_NKERN + 2];
+    cudaEvent_t kev[HZ_NKERN + 3];
 };
 
 static void hz_set_ranges(HzCuda* d, int rank, int world);
@@ -105,6 +108,28 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_front(HzPlan pl, Fr* w, uint8_t
     RollupTxOut<MCompute> o;
     sec_rollup(c, pl, i, d, o, pre, hook);
     c.flush_pending();
+}
+
+// ---- the SMT jobs of a slot ahead of k_front --------------------------------------------------------------
+// The merkle kernels are the other long chain of a slot, and what they need from rollupTx[i] are the two job
+// records (keys, old / new state hashes, function selectors).  This kernel runs the SAME templates as k_front on
+// a dry context -- values only: no entry stored, no inverse queued, the signature and the fee accumulator
+// skipped, decodeTx reduced to the fields rollupTx reads -- so the merkle kernels start after a fraction of
+// k_front's time, and k_front itself runs beside them.  k_front still records the jobs it arrives at; k_tail
+// compares the two (always: a difference is an internal error, HzErrBuf.pad).
+__global__ void __launch_bounds__(HZ_BLOCK, 3) k_smtjob(HzPlan pl, Fr* w, HzSmtJob* smt, Fr* isExit, const uint32_t* off_jk, int s0, int ns) {
+    bool real; int i = s0 + hz_item(ns, real);
+    Comp<MCompute> c(w, pl.off_rollup[i], nullptr);
+    c.dry = true;
+    DecodeOut<MCompute> d;
+    hz_decode_lite(c, pl, i, d);
+    PreBits<MCompute> pre; pre.b = nullptr;
+    SlotHook<MCompute> hook; hook.eddsa = nullptr; hook.smt = &smt[2 * i]; hook.isExit = &isExit[i]; hook.sz = &pl.sz; hook.jobs_only = true;
+    RollupTxOut<MCompute> o;
+    sec_rollup(c, pl, i, d, o, pre, hook);
+    __syncwarp();
+    // the dry walk does not keep the witness cursor: the processors start where the layout walk put them
+    if (hz_glane() == 0) { smt[2 * i].cur = off_jk[i]; smt[2 * i + 1].cur = off_jk[i] + pl.sz.p2_off; }
 }
 
 // ---- the EdDSA job of a slot straight from the main inputs -------------------------------------------
@@ -383,18 +408,25 @@ __global__ void __launch_bounds__(128) k_ed_fill(Fr* w, HzErrBuf* err, const Fr*
     else hz_fill_seg(w, err, scr, scr + HZ_SCR_AFF, rec, 1, k - HZ_FILL_C0);
 }
 
-__global__ void __launch_bounds__(HZ_BLOCK) k_tail(HzPlan pl, Fr* w, HzErrBuf* err, const HzSmtMid* mids, const Fr* isExit,
-                                                  const HzEddsaJob* jobs, const HzEddsaJob* jobs_front, int s0, int ns, int f0, int nf) {
+__global__ void __launch_bounds__(HZ_BLOCK) k_tail(HzPlan pl, Fr* w, HzErrBuf* err, HzErrBuf* ebuf, const HzSmtMid* mids, const Fr* isExit, const Fr* isExit_front,
+                                                  const HzEddsaJob* jobs, const HzEddsaJob* jobs_front, const HzSmtJob* smt, const HzSmtJob* smt_front,
+                                                  int s0, int ns, int f0, int nf) {
     bool real; int q = hz_item(ns + nf, real);
     if (q < ns) {
         int i = s0 + q;
         sec_rollup_tail(w, real ? err : nullptr, pl, i, &mids[2 * i], isExit[i]);
-        // the signature job k_edjob derived from the inputs against the one the templates of k_front arrived at
-        if (err && real && hz_glane() == 0) {
+        // the jobs k_edjob / k_smtjob derived ahead of k_front against the ones its templates arrived at
+        if (real && hz_glane() == 0) {
             const HzEddsaJob &a = jobs[i], &b = jobs_front[i];
-            const bool same = fr_eq(a.aySignature, b.aySignature) && fr_eq(a.signSignature, b.signSignature) && fr_eq(a.enabled, b.enabled) &&
-                              fr_eq(a.s1Ay, b.s1Ay) && fr_eq(a.S, b.S) && fr_eq(a.R8x, b.R8x) && fr_eq(a.R8y, b.R8y) && fr_eq(a.M, b.M) && a.cur == b.cur;
-            if (!same) hz_head_err(err, b.cur, __LINE__, a.M);
+            bool same = fr_eq(a.aySignature, b.aySignature) && fr_eq(a.signSignature, b.signSignature) && fr_eq(a.enabled, b.enabled) &&
+                        fr_eq(a.s1Ay, b.s1Ay) && fr_eq(a.S, b.S) && fr_eq(a.R8x, b.R8x) && fr_eq(a.R8y, b.R8y) && fr_eq(a.M, b.M) && a.cur == b.cur;
+            for (int k = 0; k < 2; k++) {
+                const HzSmtJob &p = smt[2 * i + k], &q2 = smt_front[2 * i + k];
+                same = same && fr_eq(p.oldKey, q2.oldKey) && fr_eq(p.oldValue, q2.oldValue) && fr_eq(p.isOld0, q2.isOld0) && fr_eq(p.newKey, q2.newKey) &&
+                       fr_eq(p.newValue, q2.newValue) && fr_eq(p.fnc0, q2.fnc0) && fr_eq(p.fnc1, q2.fnc1) && p.cur == q2.cur && p.sib == q2.sib && p.sigmask == q2.sigmask;
+            }
+            same = same && fr_eq(isExit[i], isExit_front[i]);
+            if (!same) atomicAdd(&ebuf->pad, 1u);
         }
     }
     else { int i = f0 + (q - ns); sec_fee_tail(w, real ? err : nullptr, pl, i, mids[2 * pl.P.nTx + i]); }
@@ -669,7 +701,7 @@ __global__ void k_hash_tail(HzPlan pl, Fr* w, HzErrBuf* err, const uint32_t* cha
 }
 
 HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode, const uint32_t* off_rollup,
-                       const uint32_t* off_fee, const uint32_t* off_eddsa, int* status) {
+                       const uint32_t* off_fee, const uint32_t* off_eddsa, const uint32_t* off_jk, int* status) {
     *status = HZW_E_DEVICE;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -696,6 +728,10 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaMalloc(&d->jobs, sizeof(HzEddsaJob) * P.nTx) == cudaSuccess;
     ok = ok && cudaMalloc(&d->jobs_front, sizeof(HzEddsaJob) * P.nTx) == cudaSuccess;
     ok = ok && cudaMalloc(&d->off_eddsa, 4ull * P.nTx) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->off_jk, 4ull * P.nTx) == cudaSuccess;
+    ok = ok && cudaMemcpy(d->off_jk, off_jk, 4ull * P.nTx, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->smt_front, sizeof(HzSmtJob) * 2 * P.nTx) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->isExit_front, sizeof(Fr) * P.nTx) == cudaSuccess;
     ok = ok && cudaMemcpy(d->off_eddsa, off_eddsa, 4ull * P.nTx, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMalloc(&d->smt, sizeof(HzSmtJob) * (2 * P.nTx + P.maxFeeTx)) == cudaSuccess;
     ok = ok && cudaMalloc(&d->mids, sizeof(HzSmtMid) * (2 * P.nTx + P.maxFeeTx)) == cudaSuccess;
@@ -716,7 +752,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaMemcpy(d->off_rollup, off_rollup, 4ull * P.nTx, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpy(d->off_fee, off_fee, 4ull * P.maxFeeTx, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaStreamCreate(&d->stream) == cudaSuccess && cudaStreamCreate(&d->stream2) == cudaSuccess;
-    ok = ok && cudaStreamCreate(&d->stream3) == cudaSuccess;
+    ok = ok && cudaStreamCreate(&d->stream3) == cudaSuccess && cudaStreamCreate(&d->stream4) == cudaSuccess;
     for (int k = 0; k < 2; k++) ok = ok && cudaEventCreateWithFlags(&d->ev_half[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&d->ev_ed[k], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming) == cudaSuccess;
     d->h_off_decode0 = off_decode[0]; d->h_off_rollup0 = off_rollup[0]; d->h_off_rollup_mid = off_rollup[P.nTx / 2]; d->h_off_fee0 = off_fee[0];
@@ -726,7 +762,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaEventCreateWithFlags(&d->ev_lev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_fee, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_zero, cudaEventDisableTiming) == cudaSuccess;
-    for (int k = 0; k < HZ_NKERN + 2; k++) ok = ok && cudaEventCreate(&d->kev[k]) == cudaSuccess;
+    for (int k = 0; k < HZ_NKERN + 3; k++) ok = ok && cudaEventCreate(&d->kev[k]) == cudaSuccess;
     // kernels that are to share an SM must agree on its L1 / shared-memory split: k_smt_levels stages the MDS
     // exchange in shared memory, k_eddsa (running beside it on the second stream) uses none -- without a common
     // carve-out the second kernel only gets SMs the first has left
@@ -735,6 +771,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
         cudaFuncSetAttribute(k_front, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_fee_front, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_edjob, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_smtjob, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_eddsa, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_smt, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_smt_levels, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
@@ -786,13 +823,14 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
 void hz_cuda_destroy(HzCuda* d) {
     if (!d) return;
     cudaSetDevice(d->device);
-    cudaFree(d->w); cudaFree(d->pre); cudaFree(d->chain); cudaFree(d->msgw); cudaFree(d->jobs); cudaFree(d->jobs_front); cudaFree(d->off_eddsa); cudaFree(d->err);
+    cudaFree(d->w); cudaFree(d->pre); cudaFree(d->chain); cudaFree(d->msgw); cudaFree(d->jobs); cudaFree(d->jobs_front); cudaFree(d->off_eddsa); cudaFree(d->off_jk); cudaFree(d->smt_front); cudaFree(d->isExit_front); cudaFree(d->err);
     cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit); cudaFree(d->lev); cudaFree(d->smst); cudaFree(d->img00); cudaFree(d->zflag);
     cudaFree(d->hint_cst); cudaFree(d->hint_tab); cudaFree(d->hint_img); cudaFree(d->hint_scratch); cudaFree(d->recs);
     cudaFree(d->off_decode); cudaFree(d->off_rollup); cudaFree(d->off_fee); cudaFree(d->off_blocks);
     if (d->stream) cudaStreamDestroy(d->stream);
     if (d->stream2) cudaStreamDestroy(d->stream2);
     if (d->stream3) cudaStreamDestroy(d->stream3);
+    if (d->stream4) cudaStreamDestroy(d->stream4);
     for (int k = 0; k < 2; k++) { if (d->ev_half[k]) cudaEventDestroy(d->ev_half[k]); if (d->ev_ed[k]) cudaEventDestroy(d->ev_ed[k]); }
     if (d->ev_done) cudaEventDestroy(d->ev_done);
     if (d->ev0) cudaEventDestroy(d->ev0);
@@ -802,7 +840,7 @@ void hz_cuda_destroy(HzCuda* d) {
     if (d->ev_lev) cudaEventDestroy(d->ev_lev);
     if (d->ev_fee) cudaEventDestroy(d->ev_fee);
     if (d->ev_zero) cudaEventDestroy(d->ev_zero);
-    for (int k = 0; k < HZ_NKERN + 2; k++) if (d->kev[k]) cudaEventDestroy(d->kev[k]);
+    for (int k = 0; k < HZ_NKERN + 3; k++) if (d->kev[k]) cudaEventDestroy(d->kev[k]);
     delete d;
 }
 
@@ -856,10 +894,15 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     CK(cudaStreamWaitEvent(d->stream3, d->ev0, 0));
     if (nf > 0) k_fee_front<<<hz_grid(nf), HZ_BLOCK, 0, d->stream3>>>(pl, d->w, err, d->smt + 2 * pl.P.nTx, f0, nf);
     CK(cudaEventRecord(d->ev_fee, d->stream3));
+    // k_front on a stream of its own: the merkle kernels take their jobs from k_smtjob
+    CK(cudaStreamWaitEvent(d->stream4, d->ev0, 0));
+    CK(cudaEventRecord(d->kev[11], d->stream4));
+    if (ns > 0) k_front<<<hz_grid(ns), HZ_BLOCK, 0, d->stream4>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt_front, d->isExit_front, s0, ns);
+    CK(cudaEventRecord(d->kev[12], d->stream4));
+    CK(cudaEventRecord(d->ev_front, d->stream4));
     CK(cudaEventRecord(d->kev[0], s));
-    if (ns > 0) k_front<<<hz_grid(ns), HZ_BLOCK, 0, s>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt, d->isExit, s0, ns);
+    if (ns > 0) k_smtjob<<<hz_grid(ns), HZ_BLOCK, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, s0, ns);
     CK(cudaEventRecord(d->kev[1], s));
-    CK(cudaEventRecord(d->ev_front, s));
     CK(cudaStreamWaitEvent(s, d->ev_fee, 0));
     CK(cudaEventRecord(d->kev[2], s));
     if (2 * ns + nf > 0) {
@@ -873,7 +916,8 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     }
     CK(cudaEventRecord(d->ev_zero, d->stream3));
     CK(cudaEventRecord(d->kev[3], s));
-    if (ns + nf > 0) k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->mids, d->isExit, d->jobs, d->jobs_front, s0, ns, f0, nf);
+    CK(cudaStreamWaitEvent(s, d->ev_front, 0));       // the tail compares the jobs, the hash of the inputs reads k_front's pre-image bits
+    if (ns + nf > 0) k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->err, d->mids, d->isExit, d->isExit_front, d->jobs, d->jobs_front, d->smt, d->smt_front, s0, ns, f0, nf);
     CK(cudaEventRecord(d->kev[4], s));
     return 0;
 }
@@ -917,8 +961,10 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
     CK(cudaEventRecord(d->ev0, s));
     CK(cudaStreamWaitEvent(s2, d->ev0, 0));
     k_edjob<<<hz_grid(P.nTx), HZ_BLOCK, 0, s2>>>(pl, d->w, d->jobs, d->off_eddsa, 0, P.nTx);
-    k_front<<<hz_grid(P.nTx), HZ_BLOCK, 0, s>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt, d->isExit, 0, P.nTx);
-    CK(cudaEventRecord(d->ev_front, s));
+    CK(cudaStreamWaitEvent(d->stream4, d->ev0, 0));
+    k_front<<<hz_grid(P.nTx), HZ_BLOCK, 0, d->stream4>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt_front, d->isExit_front, 0, P.nTx);
+    CK(cudaEventRecord(d->ev_front, d->stream4));
+    k_smtjob<<<hz_grid(P.nTx), HZ_BLOCK, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, 0, P.nTx);
     CK(cudaStreamWaitEvent(s3, d->ev_front, 0));
     const int F = P.maxFeeTx, h0 = P.nTx / 2;
     k_fee_front<<<hz_grid(F), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt + 2 * P.nTx, 0, F);
@@ -938,7 +984,8 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
             k_smt_levels<<<lb, 96, 0, s>>>(pl, d->w, d->lev, d->smst, d->mids, d->img00, d->zflag, s0, ns, 0, nf);
             k_smt_zero<<<dim3(lb, (unsigned)(P.nLevels + 1)), 256, 0, s>>>(pl, d->w, d->lev, d->img00, d->zflag, s0, ns, 0, nf);
         }
-        if (ns + nf > 0) k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->mids, d->isExit, d->jobs, d->jobs_front, s0, ns, 0, nf);
+        if (h == 0) CK(cudaStreamWaitEvent(s, d->ev_front, 0));
+        if (ns + nf > 0) k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->err, d->mids, d->isExit, d->isExit_front, d->jobs, d->jobs_front, d->smt, d->smt_front, s0, ns, 0, nf);
         CK(cudaStreamWaitEvent(s, d->ev_ed[h], 0));
         CK(cudaEventRecord(d->ev_half[h], s));
         if (h == 0) {
@@ -977,7 +1024,7 @@ int hz_cuda_calculate(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* wit
     CK(cudaStreamSynchronize(s));
     if (overlapped) CK(cudaStreamSynchronize(d->stream3));
     if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, d->ev0, d->ev1));
-    if (launches) *launches = overlapped ? 21 : 14;        // kernels of ours per batch (see the launch sequences above)
+    if (launches) *launches = overlapped ? 22 : 15;        // kernels of ours per batch (see the launch sequences above)
     if (h2d) *h2d = inputs ? 32ull * pl.n_inputs : 0;
     if (d2h) *d2h = (witness_out ? 32ull * pl.nvars : 0) + sizeof(HzErrBuf);
     return 0;
@@ -1025,7 +1072,7 @@ int hz_cuda_kernel_ms(HzCuda* d, float* ms, const char** names, int cap) {
     int n = cap < HZ_NKERN ? cap : HZ_NKERN;
     for (int k = 0; k < n; k++) {
         // kernels 0..7 are bracketed by kev[k], kev[k+1] on the main stream; k_eddsa by kev[9], kev[10]
-        cudaEvent_t a = k < 8 ? d->kev[k] : d->kev[9], b = k < 8 ? d->kev[k + 1] : d->kev[10];
+        cudaEvent_t a = k < 8 ? d->kev[k] : (k == 8 ? d->kev[9] : d->kev[11]), b = k < 8 ? d->kev[k + 1] : (k == 8 ? d->kev[10] : d->kev[12]);
         if (cudaEventElapsedTime(&ms[k], a, b) != cudaSuccess) return HZW_E_DEVICE;
         if (names) names[k] = HZ_KERN_NAMES[k];
     }

@@ -194,6 +194,7 @@ TM HZ_FN void sec_rollup(Comp<M>& c, const HzPlan& pl, int i, const DecodeOut<M>
         for (int k = 0; k < P.maxFeeTx; k++)
             c.check(o.accFeeOut[k], i < nTx - 1 ? hz_in(c, pl, IN_imAccFeeOut, i, k) : hz_in(c, pl, IN_imFinalAccFee, k), __LINE__);
     }
+    if (hz_jobs_only(hook)) return;
     // H - L1L2TxData with the amount nullified (:452-461): what hasherInputs.L1L2TxsData[] holds
     const int nL2 = 2 * P.nLevels + 48;
     uint32_t p0 = hz_pre_pos_l2(P) + (uint32_t)i * nL2;
@@ -218,6 +219,27 @@ TM HZ_FN V<M> sec_fee(Comp<M>& c, const HzPlan& pl, int i, const FeeHook<M>& hoo
 }
 
 #ifdef HZ_DEVICE_ONLY
+// ---- device only: what sec_rollup needs of decodeTx[i], values only (k_smtjob) ----------------------
+// The fields DecodeTx cuts out of txCompressedData (src/decode-tx.circom:96-162) and the decoded amount
+// (:166-172, through the same DecodeFloatBin template on a dry context); every one is a signal there.
+__device__ __forceinline__ Fr hz_fr_field(const Fr& x, int from, int n) {
+    Fr r = fr_zero();
+    for (int k = 0; k < n; k++) r.l[k >> 5] |= fr_bit(x, from + k) << (k & 31);
+    return r;
+}
+__device__ __noinline__ void hz_decode_lite(Comp<MCompute>& c, const HzPlan& pl, int i, DecodeOut<MCompute>& o) {
+    const Fr txc = hz_in(c, pl, IN_txCompressedData, i).v;
+    auto sigv = [](const Fr& f) { VC r; r.v = f; r.sig = true; return r; };
+    o.fromIdx = sigv(hz_fr_field(txc, 48, 48)); o.toIdx = sigv(hz_fr_field(txc, 96, 48));
+    o.tokenID = sigv(hz_fr_field(txc, 144, 32)); o.nonce = sigv(hz_fr_field(txc, 176, 40));
+    o.userFee = sigv(hz_fr_field(txc, 216, 8)); o.toBjjSign = sigv(hz_fr_field(txc, 224, 1));
+    BV<MCompute> am = Num2Bits(c.sub("n2bAmount"), 40, hz_in(c, pl, IN_amountF, i));
+    o.amount = DecodeFloatBin(c.sub("dfAmount"), am);
+    o.sigL2Hash = sigv(fr_zero());                  // only the signature reads it (k_edjob)
+    o.L1L2TxData.clear(2 * pl.P.nLevels + 48); o.L1TxFullData.clear(624);
+    o.txCompressedDataV2 = o.outIdx = o.onChain = sigv(fr_zero());
+}
+
 // ---- device only: bodies and tops of the SMT processors as their own sections -------------------
 __device__ __forceinline__ VC hz_sigv(const Fr& f, bool sig) { VC r; r.v = f; r.sig = sig; return r; }
 

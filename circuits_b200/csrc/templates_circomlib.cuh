@@ -429,6 +429,15 @@ template <int T, bool DRY = false> __device__ __noinline__ Fr hz_poseidon_lanes(
     }
     return hz_shfl_fr(s, base);
 }
+__device__ __forceinline__ Fr hz_poseidon_dispatch_dry(int t, const Fr& s) {
+    switch (t) {
+        case 3: return hz_poseidon_lanes<3, true>(nullptr, 0, s, 0);
+        case 4: return hz_poseidon_lanes<4, true>(nullptr, 0, s, 0);
+        case 5: return hz_poseidon_lanes<5, true>(nullptr, 0, s, 0);
+        case 6: return hz_poseidon_lanes<6, true>(nullptr, 0, s, 0);
+        default: return hz_poseidon_lanes<7, true>(nullptr, 0, s, 0);
+    }
+}
 __device__ __forceinline__ Fr hz_poseidon_dispatch(Fr* w, int t, uint32_t cur, const Fr& s, int base) {
     switch (t) {
         case 3: return hz_poseidon_lanes<3>(w, cur, s, base);
@@ -453,7 +462,7 @@ template <> __device__ __noinline__ VC Poseidon<MCompute>(Comp<MCompute>&& c, co
     uint32_t cur = hz_poseidon_head(c, inputs, n);
     const int lane = (int)hz_glane();
     Fr s = (lane >= 1 && lane <= n) ? inputs[lane - 1].v : fr_zero();
-    Fr o = hz_poseidon_dispatch(c.w, t, cur, s, 0);
+    Fr o = c.dry ? hz_poseidon_dispatch_dry(t, s) : hz_poseidon_dispatch(c.w, t, cur, s, 0);
     c.cur = c0 + n_own + poseidon_size(t);
     VC r; r.v = o; r.sig = true;
     return r;

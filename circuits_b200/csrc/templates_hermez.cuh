@@ -51,7 +51,18 @@ TM HZ_FN V<M> DecodeFloat(Comp<M>&& c, const V<M>& x) {
 // src/lib/mux256.circom:10-51 -- table inputs are the constants of feeShiftTable
 // ---------------------------------------------------------------------------
 #define HZ_SZ_MUX256_FEE (8 + 256 + 17 * HZ_SZ_MUX4_WIRED)
+HZ_HD bool hz_is_dry(const Comp<MCompute>& c) { return c.dry; }
+#ifndef HZ_DEVICE_ONLY
+inline bool hz_is_dry(const Comp<MLayout>&) { return false; }
+#endif
 TM HZ_FN V<M> Mux256Fee(Comp<M>&& c, const V<M>* s) {
+    if (hz_is_dry(c)) {
+        // values only: the table entry the eight selector bits point at
+        uint32_t idx = 0;
+        for (int i = 0; i < 8; i++) idx |= vlsb(s[i]) << i;
+        V<M> r = Ops<M>::K(hz_fee_shift((int)idx));
+        return c.known(0, r);
+    }
     V<M> s_[8];
     for (int i = 0; i < 8; i++) s_[i] = c.def(Nm("s", i), s[i]);
     uint32_t in0 = c.cur;
@@ -505,11 +516,17 @@ template <> struct SlotHook<MCompute> {
     HzSmtJob* smt;                  // null: evaluate phases J, K in place; else 2 jobs (processor 1, 2)
     Fr* isExit;                     // with smt: the selector the tail needs
     const HzSizes* sz;
+    bool jobs_only = false;         // dry evaluation for the SMT jobs alone (k_smtjob): the fee accumulator is skipped
 };
 template <> struct SlotHook<MLayout> {
     HzSizes* sz_out;                // sizes recorded by the layout walk (may be null)
     uint32_t* ed_cur = nullptr;     // where phase F of the slot being walked starts (may be null)
+    uint32_t* jk_cur = nullptr;     // where phases J-K (processor1) of the slot being walked start (may be null)
 };
+HZ_HD bool hz_jobs_only(const SlotHook<MCompute>& hk) { return hk.jobs_only; }
+#ifndef HZ_DEVICE_ONLY
+inline bool hz_jobs_only(const SlotHook<MLayout>&) { return false; }
+#endif
 
 TM HZ_FN void hz_phaseF(Comp<M>& c, const V<M>& vse, const V<M>& signSignature, const V<M>& aySignature,
                         const V<M>& s1Ay, const V<M>& S, const V<M>& R8x, const V<M>& R8y, const V<M>& Msg) {
@@ -518,6 +535,7 @@ TM HZ_FN void hz_phaseF(Comp<M>& c, const V<M>& vse, const V<M>& signSignature, 
 }
 HZ_HD void hz_phaseF_hook(Comp<MCompute>& c, const SlotHook<MCompute>& hk, const VC& vse, const VC& signSignature,
                           const VC& aySignature, const VC& s1Ay, const VC& S, const VC& R8x, const VC& R8y, const VC& Msg) {
+    if (hk.jobs_only) { c.cur += hk.sz->getAx + hk.sz->sigVerifier; return; }
     if (!hk.eddsa) { hz_phaseF(c, vse, signSignature, aySignature, s1Ay, S, R8x, R8y, Msg); return; }
     HzEddsaJob* j = hk.eddsa;
     j->aySignature = aySignature.v; j->signSignature = signSignature.v; j->enabled = vse.v; j->s1Ay = s1Ay.v;
@@ -581,6 +599,7 @@ inline void hz_phaseJK_hook(Comp<MLayout>& c, const SlotHook<MLayout>& hk, int n
     uint32_t c0 = c.cur, p2 = 0;
     hz_phaseJK(c, nLevels, in, newStateRoot, newExitRoot, &p2);
     if (hk.sz_out) { hk.sz_out->phaseJK = c.cur - c0; hk.sz_out->p2_off = p2 - c0; }
+    if (hk.jk_cur) *hk.jk_cur = c0;
 }
 #endif
 
@@ -674,8 +693,10 @@ TM HZ_FN void RollupTx(Comp<M>&& c, int nLevels, int maxFeeTx, const RollupTxIn<
                                       oc, st.nop, st.nullifyLoadAmount, st.nullifyAmount);
     o.isAmountNullified = c.alias("isAmountNullified", bo.isAmountNullified);
     // H - accumulate fees (:501-512)
-    FeeAccumulator(c.sub("feeAccumulator"), maxFeeTx, tokenID, bo.fee2Charge, feePlanTokens, accFeeIn, o.accFeeOut);
-    for (int k = 0; k < maxFeeTx; k++) c.alias(Nm("accFeeOut", k), o.accFeeOut[k]);
+    if (!hz_jobs_only(hook)) {
+        FeeAccumulator(c.sub("feeAccumulator"), maxFeeTx, tokenID, bo.fee2Charge, feePlanTokens, accFeeIn, o.accFeeOut);
+        for (int k = 0; k < maxFeeTx; k++) c.alias(Nm("accFeeOut", k), o.accFeeOut[k]);
+    }
     // I - compute hash new states (:517-532)
     V<M> newSt1Hash = HashState(c.sub("newSt1Hash"), s1TokenID, s1Nonce + (1 - oc), s1Sign, bo.newS, s1Ay, s1EthAddr);
     V<M> newSt2Hash = HashState(c.sub("newSt2Hash"), s2TokenID, s2Nonce, s2Sign, bo.newR, s2Ay, s2EthAddr);
