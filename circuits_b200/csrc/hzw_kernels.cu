@@ -34,6 +34,7 @@ struct HzCuda {
     uint8_t* pre;              // SHA pre-image bits, nblocks*512
     uint32_t* chain;           // (nblocks+1) x 8
     uint32_t* msgw;            // nblocks x 16
+    uint32_t* shawk;           // nblocks x 64: message schedule + round constants
     HzEddsaJob* jobs;          // nTx: from k_edjob, read by k_eddsa
     HzEddsaJob* jobs_front;    // nTx: the same as the templates of k_front arrive at them (k_tail compares)
     uint32_t* off_eddsa;       // nTx: where phase F of each slot starts
@@ -605,10 +606,20 @@ __device__ __forceinline__ uint32_t hz_sha_sched(uint32_t w2, uint32_t w7, uint3
     return w16 + s0 + w7 + s1;
 }
 
-// chaining values of all blocks.  The chain is serial (block b needs the digest of block b-1), so
-// one thread walks it, with the message schedule in a 16-word register window; the other threads
-// only pack the pre-image bits into words first.
-__global__ void __launch_bounds__(256) k_sha_chain(HzPlan pl, const uint8_t* preb, uint32_t* chain, uint32_t* msgw) {
+// chaining values of all blocks.  The chain is serial (block b needs the digest of block b-1), so one thread
+// walks it -- but only the 64 rounds: the message schedule does not depend on the chaining value, so all
+// threads of the block first expand it for every SHA block (W[t] + K[t], 64 words per block), and the walking
+// thread reads the next block's words while it works on the current one.
+__device__ __forceinline__ void hz_sha_round_wk(uint32_t* v, uint32_t wk) {
+    uint32_t S1 = hz_rr(v[4], 6) ^ hz_rr(v[4], 11) ^ hz_rr(v[4], 25);
+    uint32_t ch = (v[4] & v[5]) ^ (~v[4] & v[6]);
+    uint32_t t1 = (v[7] + wk) + (S1 + ch);
+    uint32_t S0 = hz_rr(v[0], 2) ^ hz_rr(v[0], 13) ^ hz_rr(v[0], 22);
+    uint32_t mj = (v[0] & v[1]) ^ (v[0] & v[2]) ^ (v[1] & v[2]);
+    uint32_t t2 = S0 + mj;
+    v[7] = v[6]; v[6] = v[5]; v[5] = v[4]; v[4] = v[3] + t1; v[3] = v[2]; v[2] = v[1]; v[1] = v[0]; v[0] = t1 + t2;
+}
+__global__ void __launch_bounds__(256) k_sha_chain(HzPlan pl, const uint8_t* preb, uint32_t* chain, uint32_t* msgw, uint32_t* wk) {
     uint32_t nw = pl.nblocks * 16;
     for (uint32_t t = threadIdx.x; t < nw; t += blockDim.x) {
         const uint4* p = reinterpret_cast<const uint4*>(preb + (size_t)t * 32);
@@ -625,19 +636,37 @@ __global__ void __launch_bounds__(256) k_sha_chain(HzPlan pl, const uint8_t* pre
         msgw[t] = v;
     }
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    uint32_t st[8];
-    for (int j = 0; j < 8; j++) { st[j] = hz_sha_h(j); chain[j] = st[j]; }
-    for (uint32_t b = 0; b < pl.nblocks; b++) {
-        uint32_t wv[16], v[8];
+    for (uint32_t b = threadIdx.x; b < pl.nblocks; b += blockDim.x) {
+        uint32_t wv[16];
 #pragma unroll
         for (int t = 0; t < 16; t++) wv[t] = msgw[(size_t)b * 16 + t];
 #pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = st[j];
-#pragma unroll
         for (int t = 0; t < 64; t++) {
             if (t >= 16) wv[t & 15] = hz_sha_sched(wv[(t - 2) & 15], wv[(t - 7) & 15], wv[(t - 15) & 15], wv[t & 15]);
-            hz_sha_round(v, wv[t & 15], t);
+            wk[(size_t)b * 64 + t] = wv[t & 15] + HZ_SHA_K_DEV[t];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    uint32_t st[8];
+    for (int j = 0; j < 8; j++) { st[j] = hz_sha_h(j); chain[j] = st[j]; }
+    const uint4* wk4 = reinterpret_cast<const uint4*>(wk);
+    uint4 nxt[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) nxt[q] = wk4[q];
+    for (uint32_t b = 0; b < pl.nblocks; b++) {
+        uint4 cur[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) cur[q] = nxt[q];
+        const uint32_t bn = b + 1 < pl.nblocks ? b + 1 : b;
+#pragma unroll
+        for (int q = 0; q < 16; q++) nxt[q] = wk4[(size_t)bn * 16 + q];
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = st[j];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            hz_sha_round_wk(v, cur[q].x); hz_sha_round_wk(v, cur[q].y); hz_sha_round_wk(v, cur[q].z); hz_sha_round_wk(v, cur[q].w);
         }
 #pragma unroll
         for (int j = 0; j < 8; j++) { st[j] += v[j]; chain[(size_t)(b + 1) * 8 + j] = st[j]; }
@@ -725,6 +754,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaMalloc(&d->pre, (size_t)ph.nblocks * 512) == cudaSuccess;
     ok = ok && cudaMalloc(&d->chain, (size_t)(ph.nblocks + 1) * 8 * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&d->msgw, (size_t)ph.nblocks * 16 * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->shawk, (size_t)ph.nblocks * 64 * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&d->jobs, sizeof(HzEddsaJob) * P.nTx) == cudaSuccess;
     ok = ok && cudaMalloc(&d->jobs_front, sizeof(HzEddsaJob) * P.nTx) == cudaSuccess;
     ok = ok && cudaMalloc(&d->off_eddsa, 4ull * P.nTx) == cudaSuccess;
@@ -823,7 +853,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
 void hz_cuda_destroy(HzCuda* d) {
     if (!d) return;
     cudaSetDevice(d->device);
-    cudaFree(d->w); cudaFree(d->pre); cudaFree(d->chain); cudaFree(d->msgw); cudaFree(d->jobs); cudaFree(d->jobs_front); cudaFree(d->off_eddsa); cudaFree(d->off_jk); cudaFree(d->smt_front); cudaFree(d->isExit_front); cudaFree(d->err);
+    cudaFree(d->w); cudaFree(d->pre); cudaFree(d->chain); cudaFree(d->msgw); cudaFree(d->shawk); cudaFree(d->jobs); cudaFree(d->jobs_front); cudaFree(d->off_eddsa); cudaFree(d->off_jk); cudaFree(d->smt_front); cudaFree(d->isExit_front); cudaFree(d->err);
     cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit); cudaFree(d->lev); cudaFree(d->smst); cudaFree(d->img00); cudaFree(d->zflag);
     cudaFree(d->hint_cst); cudaFree(d->hint_tab); cudaFree(d->hint_img); cudaFree(d->hint_scratch); cudaFree(d->recs);
     cudaFree(d->off_decode); cudaFree(d->off_rollup); cudaFree(d->off_fee); cudaFree(d->off_blocks);
@@ -929,7 +959,7 @@ static int hz_phase2(HzCuda* d, int sanity) {
     HzErrBuf* err = sanity ? d->err : nullptr;
     k_hash_head<<<148, 256, 0, s>>>(pl, d->w, d->pre, d->rank == 0 ? err : nullptr, d->off_blocks);
     CK(cudaEventRecord(d->kev[5], s));
-    k_sha_chain<<<1, 256, 0, s>>>(pl, d->pre, d->chain, d->msgw);
+    k_sha_chain<<<1, 256, 0, s>>>(pl, d->pre, d->chain, d->msgw, d->shawk);
     CK(cudaEventRecord(d->kev[6], s));
     if (d->nb > 0) k_sha_blocks<<<d->nb, HZ_SHA_THREADS, 0, s>>>(pl, d->w, err, d->chain, d->msgw, d->off_blocks, d->b0);
     CK(cudaEventRecord(d->kev[7], s));
