@@ -417,8 +417,64 @@ __device__ __forceinline__ void hz_submod8(uint32_t* x, const uint32_t* y) {
 __device__ __forceinline__ bool hz_is_one8(const uint32_t* a) {
     return (a[0] == 1u) && ((a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7]) == 0u);
 }
-// a != 0
+// 2^-k mod p, k = 0..512: turns Kaliski's almost inverse a^-1 2^k into the inverse with one multiplication
+__device__ const Fr hz_inv2k_dev[513] = {
+#include "fr_inv2k.inc"
+};
+__device__ __forceinline__ void hz_shl8(uint32_t* a) {
+#pragma unroll
+    for (int i = 7; i > 0; i--) a[i] = __funnelshift_l(a[i - 1], a[i], 1);
+    a[0] <<= 1;
+}
+// a != 0, a < p.  Kaliski's almost Montgomery inverse (1995): the same subtract-and-halve walk on (u, v) as the
+// binary extended Euclid, but the cofactors are only doubled and added -- plain 256-bit shifts and additions
+// (r, s < 2p < 2^255) instead of a modular halving / modular subtraction per step -- and the 2^k they pick up
+// (254 <= k <= 508) is divided out at the end: a^-1 = (p - r) 2^-k.
 __device__ __noinline__ Fr fr_inv_euclid(const Fr& a) {
+    const uint32_t p1[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+    uint32_t u[8], v[8], r[8], sv[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { u[i] = p1[i]; v[i] = a.l[i]; r[i] = 0u; sv[i] = i == 0 ? 1u : 0u; }
+    int k = 0;
+    while ((v[0] | v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7]) != 0u) {
+        if (!(u[0] & 1u)) { hz_shr8(u, 0); hz_shl8(sv); }
+        else if (!(v[0] & 1u)) { hz_shr8(v, 0); hz_shl8(r); }
+        else {
+            uint32_t d[8], t[8];
+            const uint32_t b = fr_sub8(d, u, v);
+            const uint32_t dz = d[0] | d[1] | d[2] | d[3] | d[4] | d[5] | d[6] | d[7];
+            if (!b && dz != 0u) {                    // u > v
+                hz_shr8(d, 0);
+#pragma unroll
+                for (int i = 0; i < 8; i++) u[i] = d[i];
+                hz_add8(t, r, sv);
+#pragma unroll
+                for (int i = 0; i < 8; i++) r[i] = t[i];
+                hz_shl8(sv);
+            } else {                                 // v >= u
+                fr_sub8(d, v, u);
+                hz_shr8(d, 0);
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = d[i];
+                hz_add8(t, sv, r);
+#pragma unroll
+                for (int i = 0; i < 8; i++) sv[i] = t[i];
+                hz_shl8(r);
+            }
+        }
+        k++;
+    }
+    uint32_t d[8];
+    if (!fr_sub8(d, r, p1)) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) r[i] = d[i];
+    }
+    Fr x;
+    fr_sub8(x.l, p1, r);
+    return fr_mul_chain(x, hz_inv2k_dev[k]);
+}
+// a != 0: the binary extended Euclid it replaces (kept for reference)
+__device__ __noinline__ Fr fr_inv_euclid_binary(const Fr& a) {
     uint32_t u[8], v[8], x1[8], x2[8];
     const uint32_t p1[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
 #pragma unroll
