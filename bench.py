@@ -86,7 +86,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -306,10 +306,12 @@ def run_gpu(args, cfg, cfg_name):
             wc.calculateBinWitness(pin_in, False, out=pin_out)
 
     # -- device-resident runs: inputs already in HBM, witness left in HBM ------------------------
+    # clocks / throttle reasons are sampled from the warm-up to the end of the end-to-end loop: nvidia-smi needs a
+    # few hundred ms to start and the device-resident timed region alone is only steps x ~13 ms long
+    sampler = ClockSampler(local) if rank == 0 else None
     resident_step(first=True)                      # uploads the inputs once
     for _ in range(max(args.warmup - 1, 0)):
         resident_step()
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     step_ms, kern = [], {}
     for _ in range(args.steps):
@@ -320,7 +322,6 @@ def run_gpu(args, cfg, cfg_name):
         for name, kms in wc.lastKernelMs():
             kern.setdefault(name, []).append(kms)
     barrier()
-    clocks = sampler.stop() if sampler else None
     t_dev = torch.tensor([sum(step_ms) / len(step_ms)], device="cuda")
     if dist is not None:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
@@ -335,6 +336,7 @@ def run_gpu(args, cfg, cfg_name):
         e2e_step()
         e2e_t.append(time.perf_counter() - t)
     barrier()
+    clocks = sampler.stop() if sampler else None
     stats = wc.lastStats()
     t_e2e = torch.tensor([sum(e2e_t) / len(e2e_t)], device="cuda")
     io = torch.tensor([float(stats["h2d_bytes"]), float(stats["d2h_bytes"])], device="cuda", dtype=torch.float64)
@@ -360,6 +362,7 @@ def run_gpu(args, cfg, cfg_name):
     alg_bytes = {
         # written signals + the main inputs the kernel reads, 32 B each
         "k_front": 32 * n_slots * (front_entries + 362 + 2 * F),
+        "k_smtjob": 32 * n_slots * (362 + 2 * F),      # reads only: a dry run for the SMT job records
         "k_eddsa": 32 * n_slots * (info["getAx"] + info["sigVerifier"] + 8),
         "k_smt": 32 * (n_slots * (info["processors"] + 2 * L1 + 14) + n_fee * (fee_proc + L1 + 7)),
         "k_sha_blocks": 32 * ((info["sha_blocks"] + world - 1) // world) * info["sha_block"],
@@ -371,7 +374,10 @@ def run_gpu(args, cfg, cfg_name):
                 "peak_source": src + " (copy bandwidth)",
                 "kernel_ms": kmean, "algorithmic_bytes": alg_bytes,
                 "note": "254-bit modular arithmetic: the kernels are bound by dependent integer issue (IMAD.WIDE carry "
-                        "chains), not by HBM; the HBM fraction is reported as the contract asks, see DESIGN.md"}
+                        "chains), not by HBM; the HBM fraction is reported as the contract asks, see DESIGN.md.  Timed "
+                        "intervals (CUDA events on the launching stream, four streams run together): k_eddsa = k_edjob + "
+                        "k_ed_const + k_eddsa + k_ed_fill, k_smt = k_smt + k_smt_levels; serialised per-launch times in "
+                        "profiles/r1_launches_2048_v15.csv"}
     base = None
     if world == 1 and not args.no_cpu_baseline:
         if not os.path.exists(CPU_PORT):

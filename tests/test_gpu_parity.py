@@ -69,6 +69,37 @@ def test_constraint_violation_on_gpu(built, small_bb):
     assert len(wc.calculateWitness(inp, False)) == wc.NVars
 
 
+def test_tampered_signature_on_gpu(built, small_bb):
+    """A wrong `s` walks the whole signature path (ladder walk, k_ed_fill, prefilled constants) with consistent
+    values and only fails at the final comparison: same error as the CPU port with the sanity check on, the same
+    witness byte for byte with it off."""
+    from circuits_b200.witness_calculator import WitnessError
+    wc, ref = _cuda(3, 16, 2, 2), cpu_port_calculator(3, 16, 2, 2)
+    inp = dict(small_bb.getInput())
+    inp["s"] = list(inp["s"])
+    inp["s"][0] = int(inp["s"][0]) + 1
+    with pytest.raises(WitnessError, match="Constraint doesn't match") as eg:
+        wc.calculateWitness(inp, True)
+    with pytest.raises(WitnessError, match="Constraint doesn't match") as ec:
+        ref.calculateWitness(inp, True)
+    assert "main.rollupTx[0].sigVerifier.eqCheck" in str(eg.value)
+    assert str(eg.value) == str(ec.value)
+    packed = wc.packInput(inp)
+    assert bytes(wc.calculateBinWitness(packed, False)) == bytes(ref.calculateBinWitness(packed, False))
+
+
+def test_repeated_batches_on_one_context(built, small_bb):
+    """Scratch areas, job records and level flags are reused between batches: a context gives the same witness
+    for the same input after it has evaluated a different one."""
+    wc = _cuda(3, 16, 2, 2)
+    inp = small_bb.getInput()
+    first = bytes(wc.calculateBinWitness(wc.packInput(inp), True))
+    other = dict(inp)
+    other["s"] = list(inp["s"]); other["s"][0] = int(inp["s"][0]) + 7
+    wc.calculateBinWitness(wc.packInput(other), False)
+    assert bytes(wc.calculateBinWitness(wc.packInput(inp), True)) == first
+
+
 def test_two_shards_on_one_gpu_equal_the_whole(built):
     """The CUDA side of the multi-GPU protocol without a second GPU: two contexts (rank 0 and 1 of 2)
     on this device, their exchange records concatenated by hand where NCCL's all-gather would be.
