@@ -21,6 +21,8 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <thread>
+#include <vector>
 
 #define HZ_NKERN 10  /* timed intervals; k_smt's covers the head and the levels kernels */
 static const char* const HZ_KERN_NAMES[HZ_NKERN] = {"k_smtjob", "k_fee_front", "k_smt", "k_tail", "k_hash_head",
@@ -46,6 +48,13 @@ struct HzCuda {
     Fr* smst;                  // per processor (nLevels + 1) x 6 state-machine values
     Fr* img00;                 // the 634 entries of SMTHash2(0, 0) and, at [HZ_IMG00_DIGEST], its digest
     uint8_t* zflag;            // per block of k_smt_levels and level: the level hashed (0, 0) in every chain of the block
+    // end-to-end path: the (0, 0) levels at the bottom of every processor are not copied to the host but rebuilt there
+    struct HzHole* holes; struct HzHole* h_holes;   // per job: where its levels start, how many bottom levels are (0, 0) images
+    Fr* gl; Fr* h_gl;          // per job: the entries between those images (level headers, switchers), compact
+    Fr* h_img00;               // host copy of the image
+    cudaStream_t stream5;
+    cudaEvent_t ev_pack[2], ev_info[2];
+    uint64_t last_d2h;
     Fr* isExit;                // nTx
     Fr* isExit_front;          // nTx: k_front's copy
     Fr* hint_cst;              // HZ_CST_MAX: constant inverses of EscalarMulFix (recorded at create)
@@ -323,6 +332,41 @@ __global__ void __launch_bounds__(96) k_smt_levels(HzPlan pl, Fr* w, const HzLev
         }
     }
     if (r == 0) { if (side == 0) mids[job].oc = child; else mids[job].nc = child; }
+}
+
+// ---- end-to-end path: the bottom (0, 0) levels stay on the device ---------------------------------------------
+// Those levels are 40 % of the witness of a sparse tree and all alike: instead of crossing PCIe they are rebuilt in
+// the caller's buffer by host threads from one copy of the image (computed on the device at context creation),
+// while the rest of the witness is copied around them.  What the host needs per processor: where its levels
+// start, how many bottom levels are images (`nz`: the leading run of flagged levels of its block), and the few
+// entries between the images (level headers and switchers), which k_hole_pack gathers into a compact array.
+struct HzHole { uint32_t cur, nz; };
+#define HZ_HS 634u                          /* poseidon_size(3): entries of SMTHash2 (checked at context creation) */
+#define HZ_SZL (2u + 4u + 2u * HZ_HS + 3u + 5u)   /* HZ_SZ_SMT_LEVEL */
+#define HZ_GL_STRIDE(L) (2u + 14u * (uint32_t)(L))
+// level k from the bottom of a processor whose levels start at cur: its first entry, its old-path hash
+__host__ __device__ static inline uint32_t hz_lev_base(uint32_t cur, uint32_t k) { return k == 0 ? cur : cur + 2u + k * HZ_SZL; }
+__host__ __device__ static inline uint32_t hz_lev_oph(uint32_t cur, uint32_t k) { return hz_lev_base(cur, k) + (k == 0 ? 8u : 6u); }
+// witness index of glue entry j of the hole: the bottom header (8), then per level its switchers (8) and the next header (6)
+__host__ __device__ static inline uint32_t hz_hole_glue_index(uint32_t cur, uint32_t j) {
+    if (j < 8u) return cur + j;
+    const uint32_t p = j - 8u, k = p / 14u, r = p % 14u;
+    return hz_lev_oph(cur, k) + 2u * HZ_HS + r;          // switchers of level k, running on into the header of level k + 1
+}
+__global__ void __launch_bounds__(128) k_hole_pack(HzPlan pl, const Fr* w, const HzLevJob* jobs, const uint8_t* zflag, HzHole* holes, Fr* gl,
+                                                   int s0, int ns, int f0, int nf) {
+    const int njobs = 2 * ns + nf, L = pl.P.nLevels + 1;
+    const int q = (int)blockIdx.x;
+    if (q >= njobs) return;
+    const int job = hz_smt_job_index(pl, q, s0, ns, f0);
+    const int b = q / 16;
+    int nz = 0;
+    while (nz < L && zflag[(size_t)b * L + (L - 1 - nz)]) nz++;
+    const uint32_t cur = jobs[job].cur;
+    if (threadIdx.x == 0) { holes[job].cur = cur; holes[job].nz = (uint32_t)nz; }
+    const uint32_t G = nz ? 2u + 14u * (uint32_t)nz : 0u;
+    Fr* dst = gl + (size_t)job * HZ_GL_STRIDE(L);
+    for (uint32_t j = threadIdx.x; j < G; j += blockDim.x) dst[j] = w[hz_hole_glue_index(cur, j)];
 }
 
 // the entries of the (0, 0) levels k_smt_levels skipped: block (b, lev) copies the image into the 32 chains of
@@ -769,7 +813,15 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaMalloc(&d->smst, sizeof(Fr) * 6 * (size_t)(P.nLevels + 1) * (2 * P.nTx + P.maxFeeTx)) == cudaSuccess;
     ok = ok && cudaMalloc(&d->isExit, sizeof(Fr) * P.nTx) == cudaSuccess;
     ok = ok && cudaMalloc(&d->img00, sizeof(Fr) * (HZ_IMG00_DIGEST + 1)) == cudaSuccess;
-    ok = ok && cudaMalloc(&d->zflag, (size_t)((2 * P.nTx + P.maxFeeTx + 15) / 16) * (P.nLevels + 1)) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->zflag, (size_t)((2 * P.nTx + P.maxFeeTx + 15) / 16 + 1) * (P.nLevels + 1)) == cudaSuccess;
+    {
+        const size_t nj = (size_t)2 * P.nTx + P.maxFeeTx, gs = HZ_GL_STRIDE(P.nLevels + 1);
+        ok = ok && cudaMalloc(&d->holes, sizeof(HzHole) * nj) == cudaSuccess && cudaMallocHost(&d->h_holes, sizeof(HzHole) * nj) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->gl, sizeof(Fr) * gs * nj) == cudaSuccess && cudaMallocHost(&d->h_gl, sizeof(Fr) * gs * nj) == cudaSuccess;
+        ok = ok && cudaMallocHost(&d->h_img00, sizeof(Fr) * HZ_HS) == cudaSuccess;
+        ok = ok && cudaStreamCreate(&d->stream5) == cudaSuccess;
+        for (int k = 0; k < 2; k++) ok = ok && cudaEventCreateWithFlags(&d->ev_pack[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&d->ev_info[k], cudaEventDisableTiming) == cudaSuccess;
+    }
     ok = ok && cudaMalloc(&d->hint_cst, sizeof(Fr) * HZ_CST_MAX) == cudaSuccess;
     ok = ok && cudaMalloc(&d->hint_tab, sizeof(Fr) * HZ_EDTAB_LEN) == cudaSuccess;
     ok = ok && cudaMalloc(&d->hint_scratch, sizeof(Fr) * HZ_HINT_SCRATCH * (size_t)hz_grid(P.nTx) * (HZ_BLOCK / HZ_G)) == cudaSuccess;
@@ -816,6 +868,8 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
         if (ok) {
             k_poseidon_t3<<<1, 96, 0, d->stream>>>(zin, d->img00, d->img00 + HZ_IMG00_DIGEST, 1);
             ok = cudaStreamSynchronize(d->stream) == cudaSuccess;
+            ok = ok && cudaMemcpy(d->h_img00, d->img00, sizeof(Fr) * HZ_HS, cudaMemcpyDeviceToHost) == cudaSuccess;
+            if (ok && (ph.sz.phaseJK == 0 || HZ_HS != 1u + 2u * 3u * 65u + 3u * (8u * 3u + 57u))) ok = false;
         }
         cudaFree(zin);
     }
@@ -854,13 +908,15 @@ void hz_cuda_destroy(HzCuda* d) {
     if (!d) return;
     cudaSetDevice(d->device);
     cudaFree(d->w); cudaFree(d->pre); cudaFree(d->chain); cudaFree(d->msgw); cudaFree(d->shawk); cudaFree(d->jobs); cudaFree(d->jobs_front); cudaFree(d->off_eddsa); cudaFree(d->off_jk); cudaFree(d->smt_front); cudaFree(d->isExit_front); cudaFree(d->err);
-    cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit); cudaFree(d->lev); cudaFree(d->smst); cudaFree(d->img00); cudaFree(d->zflag);
+    cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit); cudaFree(d->lev); cudaFree(d->smst); cudaFree(d->img00); cudaFree(d->zflag); cudaFree(d->holes); cudaFree(d->gl); cudaFreeHost(d->h_holes); cudaFreeHost(d->h_gl); cudaFreeHost(d->h_img00);
     cudaFree(d->hint_cst); cudaFree(d->hint_tab); cudaFree(d->hint_img); cudaFree(d->hint_scratch); cudaFree(d->recs);
     cudaFree(d->off_decode); cudaFree(d->off_rollup); cudaFree(d->off_fee); cudaFree(d->off_blocks);
     if (d->stream) cudaStreamDestroy(d->stream);
     if (d->stream2) cudaStreamDestroy(d->stream2);
     if (d->stream3) cudaStreamDestroy(d->stream3);
     if (d->stream4) cudaStreamDestroy(d->stream4);
+    if (d->stream5) cudaStreamDestroy(d->stream5);
+    for (int k = 0; k < 2; k++) { if (d->ev_pack[k]) cudaEventDestroy(d->ev_pack[k]); if (d->ev_info[k]) cudaEventDestroy(d->ev_info[k]); }
     for (int k = 0; k < 2; k++) { if (d->ev_half[k]) cudaEventDestroy(d->ev_half[k]); if (d->ev_ed[k]) cudaEventDestroy(d->ev_ed[k]); }
     if (d->ev_done) cudaEventDestroy(d->ev_done);
     if (d->ev0) cudaEventDestroy(d->ev0);
@@ -976,15 +1032,50 @@ static int hz_phase2(HzCuda* d, int sanity) {
 // PCIe (~150 ms) dwarfs the kernels, so pieces leave as soon as they are final: header, inputs and the
 // decodeTx ranges after k_front; the rollupTx ranges of the first half of the slots while the second
 // half is evaluated; the rest (second half, fee txs, hasherInputs) at the end.
+// host side of the holes: the images and the glue entries of jobs [j0, j1) written into the caller's buffer
+static void hz_fill_holes(const HzCuda* d, uint8_t* out, int j0, int j1, int part, int parts) {
+    const uint32_t gs = HZ_GL_STRIDE(d->plan.P.nLevels + 1);
+    for (int job = j0 + part; job < j1; job += parts) {
+        const HzHole h = d->h_holes[job];
+        if (h.nz == 0) continue;
+        const uint8_t* g = reinterpret_cast<const uint8_t*>(d->h_gl + (size_t)job * gs);
+        memcpy(out + 32ull * h.cur, g, 8 * 32);
+        for (uint32_t k = 0; k < h.nz; k++) {
+            const uint32_t oph = hz_lev_oph(h.cur, k);
+            memcpy(out + 32ull * oph, d->h_img00, 32ull * HZ_HS);
+            memcpy(out + 32ull * (oph + HZ_HS), d->h_img00, 32ull * HZ_HS);
+            // switchers of level k and, unless it is the last image level, the header of level k + 1
+            memcpy(out + 32ull * (oph + 2 * HZ_HS), g + 32ull * (8 + 14 * k), (k + 1 < h.nz ? 14 : 8) * 32);
+        }
+    }
+}
 static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* out) {
     const HzPlan& pl = d->plan;
     const HzParams& P = pl.P;
-    cudaStream_t s = d->stream, s2 = d->stream2, s3 = d->stream3;
+    cudaStream_t s = d->stream, s2 = d->stream2, s3 = d->stream3, s5 = d->stream5;
     HzErrBuf* err = sanity ? d->err : nullptr;
     const uint8_t* wb = reinterpret_cast<const uint8_t*>(d->w);
+    d->last_d2h = 0;
     auto piece = [&](uint64_t a, uint64_t b) -> cudaError_t {
-        return b > a ? cudaMemcpyAsync(out + 32 * a, wb + 32 * a, 32 * (b - a), cudaMemcpyDeviceToHost, s3) : cudaSuccess;
+        if (b <= a) return cudaSuccess;
+        d->last_d2h += 32 * (b - a);
+        return cudaMemcpyAsync(out + 32 * a, wb + 32 * a, 32 * (b - a), cudaMemcpyDeviceToHost, s3);
     };
+    // [a, b) of the witness around the holes of jobs [j0, j1) (in memory order)
+    auto pieces_around = [&](uint64_t a, uint64_t b, int j0, int j1) -> cudaError_t {
+        uint64_t at = a;
+        for (int job = j0; job < j1; job++) {
+            const HzHole h = d->h_holes[job];
+            if (h.nz == 0) continue;
+            const uint64_t h0 = h.cur, h1 = (uint64_t)h.cur + 2u + (uint64_t)h.nz * HZ_SZL;
+            if (h0 < at || h1 > b) continue;                       // not inside this range
+            cudaError_t e = piece(at, h0);
+            if (e != cudaSuccess) return e;
+            at = h1;
+        }
+        return piece(at, b);
+    };
+    const uint32_t gs = HZ_GL_STRIDE(P.nLevels + 1);
     CK(cudaMemsetAsync(d->err, 0, sizeof(HzErrBuf), s));
     CK(cudaMemsetAsync(d->pre, 0, (size_t)pl.nblocks * 512, s));
     CK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(d->w) + 64, inputs, 32ull * pl.n_inputs, cudaMemcpyHostToDevice, s));
@@ -1012,24 +1103,47 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
             k_smt<<<hz_grid(2 * ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, 0, nf);
             const unsigned lb = (unsigned)((2 * ns + nf + 15) / 16);
             k_smt_levels<<<lb, 96, 0, s>>>(pl, d->w, d->lev, d->smst, d->mids, d->img00, d->zflag, s0, ns, 0, nf);
+            k_hole_pack<<<(unsigned)(2 * ns + nf), 128, 0, s>>>(pl, d->w, d->lev, d->zflag, d->holes, d->gl, s0, ns, 0, nf);
+            CK(cudaEventRecord(d->ev_pack[h], s));
             k_smt_zero<<<dim3(lb, (unsigned)(P.nLevels + 1)), 256, 0, s>>>(pl, d->w, d->lev, d->img00, d->zflag, s0, ns, 0, nf);
+            // the hole records and glue entries of this half's jobs to the host, on a stream of their own
+            CK(cudaStreamWaitEvent(s5, d->ev_pack[h], 0));
+            CK(cudaMemcpyAsync(d->h_holes + 2 * s0, d->holes + 2 * s0, sizeof(HzHole) * 2 * ns, cudaMemcpyDeviceToHost, s5));
+            CK(cudaMemcpyAsync(d->h_gl + (size_t)2 * s0 * gs, d->gl + (size_t)2 * s0 * gs, sizeof(Fr) * gs * 2 * ns, cudaMemcpyDeviceToHost, s5));
+            if (nf > 0) {
+                CK(cudaMemcpyAsync(d->h_holes + 2 * P.nTx, d->holes + 2 * P.nTx, sizeof(HzHole) * nf, cudaMemcpyDeviceToHost, s5));
+                CK(cudaMemcpyAsync(d->h_gl + (size_t)2 * P.nTx * gs, d->gl + (size_t)2 * P.nTx * gs, sizeof(Fr) * gs * nf, cudaMemcpyDeviceToHost, s5));
+            }
+            d->last_d2h += (sizeof(HzHole) + sizeof(Fr) * gs) * (size_t)(2 * ns + nf);
         }
+        CK(cudaEventRecord(d->ev_info[h], s5));
         if (h == 0) CK(cudaStreamWaitEvent(s, d->ev_front, 0));
         if (ns + nf > 0) k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->err, d->mids, d->isExit, d->isExit_front, d->jobs, d->jobs_front, d->smt, d->smt_front, s0, ns, 0, nf);
         CK(cudaStreamWaitEvent(s, d->ev_ed[h], 0));
         CK(cudaEventRecord(d->ev_half[h], s));
-        if (h == 0) {
-            CK(cudaStreamWaitEvent(s3, d->ev_half[0], 0));
-            CK(piece(d->h_off_rollup0, d->h_off_rollup_mid));
-        }
     }
     CK(cudaEventRecord(d->ev_eddsa, s2));
     int st = hz_phase2(d, sanity);
     if (st) return st;
     CK(cudaEventRecord(d->ev_done, s));
-    CK(cudaStreamWaitEvent(s3, d->ev_done, 0));
-    CK(piece(d->h_off_rollup_mid, pl.nvars));
-    CK(piece(0, 2));
+    // everything is queued; from here the host follows the device.  Half 0: its hole records, then host threads
+    // rebuild its images while the copy engine moves the rest of its range around them
+    unsigned nthr = std::thread::hardware_concurrency();
+    nthr = nthr == 0 ? 4 : (nthr > 16 ? 16 : nthr);
+    std::vector<std::thread> workers;
+    CK(cudaEventSynchronize(d->ev_info[0]));
+    for (unsigned t = 0; t < nthr; t++) workers.emplace_back(hz_fill_holes, d, out, 0, 2 * h0, (int)t, (int)nthr);
+    CK(cudaStreamWaitEvent(s3, d->ev_half[0], 0));
+    cudaError_t ce = pieces_around(d->h_off_rollup0, d->h_off_rollup_mid, 0, 2 * h0);
+    if (ce == cudaSuccess) ce = cudaEventSynchronize(d->ev_info[1]);
+    if (ce == cudaSuccess) {
+        for (unsigned t = 0; t < nthr; t++) workers.emplace_back(hz_fill_holes, d, out, 2 * h0, 2 * P.nTx + F, (int)t, (int)nthr);
+        ce = cudaStreamWaitEvent(s3, d->ev_done, 0);
+    }
+    if (ce == cudaSuccess) ce = pieces_around(d->h_off_rollup_mid, pl.nvars, 2 * h0, 2 * P.nTx + F);
+    if (ce == cudaSuccess) ce = piece(0, 2);
+    for (auto& t : workers) t.join();
+    CK(ce);
     return 0;
 }
 
@@ -1054,9 +1168,9 @@ int hz_cuda_calculate(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* wit
     CK(cudaStreamSynchronize(s));
     if (overlapped) CK(cudaStreamSynchronize(d->stream3));
     if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, d->ev0, d->ev1));
-    if (launches) *launches = overlapped ? 22 : 15;        // kernels of ours per batch (see the launch sequences above)
+    if (launches) *launches = overlapped ? 24 : 15;        // kernels of ours per batch (see the launch sequences above)
     if (h2d) *h2d = inputs ? 32ull * pl.n_inputs : 0;
-    if (d2h) *d2h = (witness_out ? 32ull * pl.nvars : 0) + sizeof(HzErrBuf);
+    if (d2h) *d2h = (overlapped ? d->last_d2h : (witness_out ? 32ull * pl.nvars : 0)) + sizeof(HzErrBuf);
     return 0;
 }
 
