@@ -64,3 +64,18 @@ HzBackend* hz_backend_create_withdraw(const hzw_params& prm, const HzWLayout& WL
     b->device = prm.device; b->WL = WL;
     return b;
 }
+
+// ---- streaming copy for the host side of the end-to-end path (hzw_kernels.cu: hz_fill_holes) -----------------
+// The rebuilt images are written once and not read again by this process: non-temporal stores keep them out of
+// the caches and spare the read-for-ownership of every line.  n is a multiple of 32, dst is 32-byte aligned.
+#include <immintrin.h>
+__attribute__((target("avx2"))) static void hz_copy_nt_avx2(uint8_t* dst, const uint8_t* src, size_t n) {
+    for (size_t i = 0; i < n; i += 32)
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i)));
+}
+void hz_host_copy_stream(uint8_t* dst, const uint8_t* src, size_t n) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2 && (reinterpret_cast<uintptr_t>(dst) & 31u) == 0 && (n & 31u) == 0) hz_copy_nt_avx2(dst, src, n);
+    else memcpy(dst, src, n);
+}
+void hz_host_copy_fence() { _mm_sfence(); }

@@ -22,6 +22,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <thread>
+#include <chrono>
 #include <vector>
 
 #define HZ_NKERN 10  /* timed intervals; k_smt's covers the head and the levels kernels */
@@ -52,9 +53,10 @@ struct HzCuda {
     struct HzHole* holes; struct HzHole* h_holes;   // per job: where its levels start, how many bottom levels are (0, 0) images
     Fr* gl; Fr* h_gl;          // per job: the entries between those images (level headers, switchers), compact
     Fr* h_img00;               // host copy of the image
-    cudaStream_t stream5;
+    cudaStream_t stream5, stream6;
     cudaEvent_t ev_pack[2], ev_info[2];
     uint64_t last_d2h;
+    std::vector<uint32_t>* h_off_rollup;   // host copy of the slot offsets (plus the end of the last slot)
     Fr* isExit;                // nTx
     Fr* isExit_front;          // nTx: k_front's copy
     Fr* hint_cst;              // HZ_CST_MAX: constant inverses of EscalarMulFix (recorded at create)
@@ -819,7 +821,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
         ok = ok && cudaMalloc(&d->holes, sizeof(HzHole) * nj) == cudaSuccess && cudaMallocHost(&d->h_holes, sizeof(HzHole) * nj) == cudaSuccess;
         ok = ok && cudaMalloc(&d->gl, sizeof(Fr) * gs * nj) == cudaSuccess && cudaMallocHost(&d->h_gl, sizeof(Fr) * gs * nj) == cudaSuccess;
         ok = ok && cudaMallocHost(&d->h_img00, sizeof(Fr) * HZ_HS) == cudaSuccess;
-        ok = ok && cudaStreamCreate(&d->stream5) == cudaSuccess;
+        ok = ok && cudaStreamCreate(&d->stream5) == cudaSuccess && cudaStreamCreate(&d->stream6) == cudaSuccess;
         for (int k = 0; k < 2; k++) ok = ok && cudaEventCreateWithFlags(&d->ev_pack[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&d->ev_info[k], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaMalloc(&d->hint_cst, sizeof(Fr) * HZ_CST_MAX) == cudaSuccess;
@@ -837,6 +839,8 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaStreamCreate(&d->stream3) == cudaSuccess && cudaStreamCreate(&d->stream4) == cudaSuccess;
     for (int k = 0; k < 2; k++) ok = ok && cudaEventCreateWithFlags(&d->ev_half[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&d->ev_ed[k], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming) == cudaSuccess;
+    d->h_off_rollup = new std::vector<uint32_t>(off_rollup, off_rollup + P.nTx);
+    d->h_off_rollup->push_back(off_fee[0]);
     d->h_off_decode0 = off_decode[0]; d->h_off_rollup0 = off_rollup[0]; d->h_off_rollup_mid = off_rollup[P.nTx / 2]; d->h_off_fee0 = off_fee[0];
     ok = ok && cudaEventCreate(&d->ev0) == cudaSuccess && cudaEventCreate(&d->ev1) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_front, cudaEventDisableTiming) == cudaSuccess;
@@ -916,6 +920,7 @@ void hz_cuda_destroy(HzCuda* d) {
     if (d->stream3) cudaStreamDestroy(d->stream3);
     if (d->stream4) cudaStreamDestroy(d->stream4);
     if (d->stream5) cudaStreamDestroy(d->stream5);
+    if (d->stream6) cudaStreamDestroy(d->stream6);
     for (int k = 0; k < 2; k++) { if (d->ev_pack[k]) cudaEventDestroy(d->ev_pack[k]); if (d->ev_info[k]) cudaEventDestroy(d->ev_info[k]); }
     for (int k = 0; k < 2; k++) { if (d->ev_half[k]) cudaEventDestroy(d->ev_half[k]); if (d->ev_ed[k]) cudaEventDestroy(d->ev_ed[k]); }
     if (d->ev_done) cudaEventDestroy(d->ev_done);
@@ -927,6 +932,7 @@ void hz_cuda_destroy(HzCuda* d) {
     if (d->ev_fee) cudaEventDestroy(d->ev_fee);
     if (d->ev_zero) cudaEventDestroy(d->ev_zero);
     for (int k = 0; k < HZ_NKERN + 3; k++) if (d->kev[k]) cudaEventDestroy(d->kev[k]);
+    delete d->h_off_rollup;
     delete d;
 }
 
@@ -1032,6 +1038,8 @@ static int hz_phase2(HzCuda* d, int sanity) {
 // PCIe (~150 ms) dwarfs the kernels, so pieces leave as soon as they are final: header, inputs and the
 // decodeTx ranges after k_front; the rollupTx ranges of the first half of the slots while the second
 // half is evaluated; the rest (second half, fee txs, hasherInputs) at the end.
+void hz_host_copy_stream(uint8_t* dst, const uint8_t* src, size_t n);   // hzw_host.cpp: non-temporal stores
+void hz_host_copy_fence();
 // host side of the holes: the images and the glue entries of jobs [j0, j1) written into the caller's buffer
 static void hz_fill_holes(const HzCuda* d, uint8_t* out, int j0, int j1, int part, int parts) {
     const uint32_t gs = HZ_GL_STRIDE(d->plan.P.nLevels + 1);
@@ -1042,12 +1050,13 @@ static void hz_fill_holes(const HzCuda* d, uint8_t* out, int j0, int j1, int par
         memcpy(out + 32ull * h.cur, g, 8 * 32);
         for (uint32_t k = 0; k < h.nz; k++) {
             const uint32_t oph = hz_lev_oph(h.cur, k);
-            memcpy(out + 32ull * oph, d->h_img00, 32ull * HZ_HS);
-            memcpy(out + 32ull * (oph + HZ_HS), d->h_img00, 32ull * HZ_HS);
+            hz_host_copy_stream(out + 32ull * oph, reinterpret_cast<const uint8_t*>(d->h_img00), 32ull * HZ_HS);
+            hz_host_copy_stream(out + 32ull * (oph + HZ_HS), reinterpret_cast<const uint8_t*>(d->h_img00), 32ull * HZ_HS);
             // switchers of level k and, unless it is the last image level, the header of level k + 1
             memcpy(out + 32ull * (oph + 2 * HZ_HS), g + 32ull * (8 + 14 * k), (k + 1 < h.nz ? 14 : 8) * 32);
         }
     }
+    hz_host_copy_fence();
 }
 static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* out) {
     const HzPlan& pl = d->plan;
@@ -1056,10 +1065,13 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
     HzErrBuf* err = sanity ? d->err : nullptr;
     const uint8_t* wb = reinterpret_cast<const uint8_t*>(d->w);
     d->last_d2h = 0;
+    // the pieces alternate between two copy streams: one stream leaves the link idle between two copies
+    const cudaStream_t s6 = d->stream6;
+    unsigned npiece = 0;
     auto piece = [&](uint64_t a, uint64_t b) -> cudaError_t {
         if (b <= a) return cudaSuccess;
         d->last_d2h += 32 * (b - a);
-        return cudaMemcpyAsync(out + 32 * a, wb + 32 * a, 32 * (b - a), cudaMemcpyDeviceToHost, s3);
+        return cudaMemcpyAsync(out + 32 * a, wb + 32 * a, 32 * (b - a), cudaMemcpyDeviceToHost, (npiece++ & 1u) ? s6 : s3);
     };
     // [a, b) of the witness around the holes of jobs [j0, j1) (in memory order)
     auto pieces_around = [&](uint64_t a, uint64_t b, int j0, int j1) -> cudaError_t {
@@ -1075,6 +1087,40 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
         }
         return piece(at, b);
     };
+    // the slots [i0, i1) of a half around the holes of their processors.  Eight consecutive slots share a block of
+    // k_smt_levels and so the number of image levels; slots in the middle of the batch are laid out alike.  Such a
+    // group goes as three pitched copies (before, between and after the two holes, one row per slot) instead of
+    // 24 pieces: the copy engine spends microseconds per copy whatever its size.
+    auto slots_around = [&](int i0, int i1) -> cudaError_t {
+        const std::vector<uint32_t>& off = *d->h_off_rollup;
+        for (int g0 = i0; g0 < i1; g0 += 8) {
+            const int g1 = g0 + 8 < i1 ? g0 + 8 : i1, n = g1 - g0;
+            const uint64_t pitch = (uint64_t)off[g0 + 1] - off[g0];
+            const HzHole a0 = d->h_holes[2 * g0], b0 = d->h_holes[2 * g0 + 1];
+            bool uniform = n > 1 && a0.nz > 0 && b0.nz > 0;
+            for (int i = g0; i < g1 && uniform; i++) {
+                const HzHole a = d->h_holes[2 * i], b = d->h_holes[2 * i + 1];
+                uniform = (uint64_t)off[i + 1] - off[i] == pitch && a.nz == a0.nz && b.nz == b0.nz &&
+                          a.cur - off[i] == a0.cur - off[g0] && b.cur - off[i] == b0.cur - off[g0];
+            }
+            if (!uniform) {
+                cudaError_t e = pieces_around(off[g0], off[g1], 2 * g0, 2 * g1);
+                if (e != cudaSuccess) return e;
+                continue;
+            }
+            const uint64_t base = off[g0];
+            const uint64_t r1s = a0.cur - base, r1e = r1s + 2u + (uint64_t)a0.nz * HZ_SZL, r2s = b0.cur - base, r2e = r2s + 2u + (uint64_t)b0.nz * HZ_SZL;
+            const uint64_t seg[3][2] = {{0, r1s}, {r1e, r2s}, {r2e, pitch}};
+            for (int k = 0; k < 3; k++) {
+                if (seg[k][1] <= seg[k][0]) continue;
+                const uint64_t at = 32 * (base + seg[k][0]), wdt = 32 * (seg[k][1] - seg[k][0]);
+                d->last_d2h += wdt * (uint64_t)n;
+                cudaError_t e = cudaMemcpy2DAsync(out + at, 32 * pitch, wb + at, 32 * pitch, wdt, (size_t)n, cudaMemcpyDeviceToHost, (npiece++ & 1u) ? s6 : s3);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        return cudaSuccess;
+    };
     const uint32_t gs = HZ_GL_STRIDE(P.nLevels + 1);
     CK(cudaMemsetAsync(d->err, 0, sizeof(HzErrBuf), s));
     CK(cudaMemsetAsync(d->pre, 0, (size_t)pl.nblocks * 512, s));
@@ -1087,6 +1133,7 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
     CK(cudaEventRecord(d->ev_front, d->stream4));
     k_smtjob<<<hz_grid(P.nTx), HZ_BLOCK, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, 0, P.nTx);
     CK(cudaStreamWaitEvent(s3, d->ev_front, 0));
+    CK(cudaStreamWaitEvent(s6, d->ev_front, 0));
     const int F = P.maxFeeTx, h0 = P.nTx / 2;
     k_fee_front<<<hz_grid(F), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt + 2 * P.nTx, 0, F);
     // w[0], w[1] are written by the hasher at the end: entries [2, decodeTx[0]) and the decode ranges go now
@@ -1128,21 +1175,37 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
     CK(cudaEventRecord(d->ev_done, s));
     // everything is queued; from here the host follows the device.  Half 0: its hole records, then host threads
     // rebuild its images while the copy engine moves the rest of its range around them
+    const bool trace = getenv("HZW_TRACE") != nullptr;           // (measurement switch) host-side timeline on stderr
+    const auto t00 = std::chrono::steady_clock::now();
+    auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t00).count(); };
     unsigned nthr = std::thread::hardware_concurrency();
-    nthr = nthr == 0 ? 4 : (nthr > 16 ? 16 : nthr);
+    // two cores stay free for this thread (it issues a few thousand copies while the workers run) and the driver's
+    nthr = nthr == 0 ? 4 : (nthr > 18 ? 16 : (nthr > 3 ? nthr - 2 : 1));
+    if (getenv("HZW_FILL_THREADS")) nthr = (unsigned)atoi(getenv("HZW_FILL_THREADS")) > 0 ? (unsigned)atoi(getenv("HZW_FILL_THREADS")) : nthr;
     std::vector<std::thread> workers;
     CK(cudaEventSynchronize(d->ev_info[0]));
+    const double t_info0 = ms_since();
     for (unsigned t = 0; t < nthr; t++) workers.emplace_back(hz_fill_holes, d, out, 0, 2 * h0, (int)t, (int)nthr);
     CK(cudaStreamWaitEvent(s3, d->ev_half[0], 0));
-    cudaError_t ce = pieces_around(d->h_off_rollup0, d->h_off_rollup_mid, 0, 2 * h0);
+    CK(cudaStreamWaitEvent(s6, d->ev_half[0], 0));
+    cudaError_t ce = slots_around(0, h0);
     if (ce == cudaSuccess) ce = cudaEventSynchronize(d->ev_info[1]);
     if (ce == cudaSuccess) {
         for (unsigned t = 0; t < nthr; t++) workers.emplace_back(hz_fill_holes, d, out, 2 * h0, 2 * P.nTx + F, (int)t, (int)nthr);
         ce = cudaStreamWaitEvent(s3, d->ev_done, 0);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s6, d->ev_done, 0);
     }
-    if (ce == cudaSuccess) ce = pieces_around(d->h_off_rollup_mid, pl.nvars, 2 * h0, 2 * P.nTx + F);
+    if (ce == cudaSuccess) ce = slots_around(h0, P.nTx);
+    if (ce == cudaSuccess) ce = pieces_around(d->h_off_fee0, pl.nvars, 2 * P.nTx, 2 * P.nTx + F);
     if (ce == cudaSuccess) ce = piece(0, 2);
+    const double t_issued = ms_since();
     for (auto& t : workers) t.join();
+    const double t_filled = ms_since();
+    if (trace) {
+        cudaStreamSynchronize(s3); cudaStreamSynchronize(s6);
+        fprintf(stderr, "hzw trace: hole records of half 0 at %.1f ms, copies issued at %.1f, host fill done at %.1f, copies done at %.1f (%u threads, %.2f GB copied)\n",
+                t_info0, t_issued, t_filled, ms_since(), nthr, d->last_d2h / 1e9);
+    }
     CK(ce);
     return 0;
 }
@@ -1166,7 +1229,7 @@ int hz_cuda_calculate(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* wit
     }
     CK(cudaMemcpyAsync(errs, d->err, sizeof(HzErrBuf), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (overlapped) CK(cudaStreamSynchronize(d->stream3));
+    if (overlapped) { CK(cudaStreamSynchronize(d->stream3)); CK(cudaStreamSynchronize(d->stream6)); }
     if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, d->ev0, d->ev1));
     if (launches) *launches = overlapped ? 24 : 15;        // kernels of ours per batch (see the launch sequences above)
     if (h2d) *h2d = inputs ? 32ull * pl.n_inputs : 0;
