@@ -1005,6 +1005,23 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
         CK(cudaEventRecord(d->ev_lev, s));
         CK(cudaStreamWaitEvent(d->stream3, d->ev_lev, 0));
         k_smt_zero<<<dim3(lb, (unsigned)(pl.P.nLevels + 1)), 256, 0, d->stream3>>>(pl, d->w, d->lev, d->img00, d->zflag, s0, ns, f0, nf);
+        if (d->world > 1) {
+            // a shard's pieces are copied around the image levels too (hz_cuda_shard_phase2): their records go to the host now
+            const uint32_t gs = HZ_GL_STRIDE(pl.P.nLevels + 1);
+            k_hole_pack<<<(unsigned)(2 * ns + nf), 128, 0, s>>>(pl, d->w, d->lev, d->zflag, d->holes, d->gl, s0, ns, f0, nf);
+            CK(cudaEventRecord(d->ev_pack[0], s));
+            CK(cudaStreamWaitEvent(d->stream5, d->ev_pack[0], 0));
+            if (ns > 0) {
+                CK(cudaMemcpyAsync(d->h_holes + 2 * s0, d->holes + 2 * s0, sizeof(HzHole) * 2 * ns, cudaMemcpyDeviceToHost, d->stream5));
+                CK(cudaMemcpyAsync(d->h_gl + (size_t)2 * s0 * gs, d->gl + (size_t)2 * s0 * gs, sizeof(Fr) * gs * 2 * ns, cudaMemcpyDeviceToHost, d->stream5));
+            }
+            if (nf > 0) {
+                const size_t j = (size_t)2 * pl.P.nTx + f0;
+                CK(cudaMemcpyAsync(d->h_holes + j, d->holes + j, sizeof(HzHole) * nf, cudaMemcpyDeviceToHost, d->stream5));
+                CK(cudaMemcpyAsync(d->h_gl + j * gs, d->gl + j * gs, sizeof(Fr) * gs * nf, cudaMemcpyDeviceToHost, d->stream5));
+            }
+            CK(cudaEventRecord(d->ev_info[0], d->stream5));
+        }
     }
     CK(cudaEventRecord(d->ev_zero, d->stream3));
     CK(cudaEventRecord(d->kev[3], s));
@@ -1058,23 +1075,19 @@ static void hz_fill_holes(const HzCuda* d, uint8_t* out, int j0, int j1, int par
     }
     hz_host_copy_fence();
 }
-static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* out) {
-    const HzPlan& pl = d->plan;
-    const HzParams& P = pl.P;
-    cudaStream_t s = d->stream, s2 = d->stream2, s3 = d->stream3, s5 = d->stream5;
-    HzErrBuf* err = sanity ? d->err : nullptr;
-    const uint8_t* wb = reinterpret_cast<const uint8_t*>(d->w);
-    d->last_d2h = 0;
+// device-to-host copies of witness ranges around the holes (the image levels the host rebuilds itself).  `out` is
+// where witness entry 0 would be: the end-to-end path passes the caller's buffer, the sharded path a pointer
+// shifted so that the piece being copied lands at its place in the shard buffer.
+struct HzCopier {
+    HzCuda* d; uint8_t* out; const uint8_t* wb; unsigned npiece;
     // the pieces alternate between two copy streams: one stream leaves the link idle between two copies
-    const cudaStream_t s6 = d->stream6;
-    unsigned npiece = 0;
-    auto piece = [&](uint64_t a, uint64_t b) -> cudaError_t {
+    cudaError_t piece(uint64_t a, uint64_t b) {
         if (b <= a) return cudaSuccess;
         d->last_d2h += 32 * (b - a);
-        return cudaMemcpyAsync(out + 32 * a, wb + 32 * a, 32 * (b - a), cudaMemcpyDeviceToHost, (npiece++ & 1u) ? s6 : s3);
-    };
+        return cudaMemcpyAsync(out + 32 * a, wb + 32 * a, 32 * (b - a), cudaMemcpyDeviceToHost, (npiece++ & 1u) ? d->stream6 : d->stream3);
+    }
     // [a, b) of the witness around the holes of jobs [j0, j1) (in memory order)
-    auto pieces_around = [&](uint64_t a, uint64_t b, int j0, int j1) -> cudaError_t {
+    cudaError_t pieces_around(uint64_t a, uint64_t b, int j0, int j1) {
         uint64_t at = a;
         for (int job = j0; job < j1; job++) {
             const HzHole h = d->h_holes[job];
@@ -1086,12 +1099,12 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
             at = h1;
         }
         return piece(at, b);
-    };
-    // the slots [i0, i1) of a half around the holes of their processors.  Eight consecutive slots share a block of
+    }
+    // the slots [i0, i1) around the holes of their processors.  Eight consecutive slots share a block of
     // k_smt_levels and so the number of image levels; slots in the middle of the batch are laid out alike.  Such a
     // group goes as three pitched copies (before, between and after the two holes, one row per slot) instead of
     // 24 pieces: the copy engine spends microseconds per copy whatever its size.
-    auto slots_around = [&](int i0, int i1) -> cudaError_t {
+    cudaError_t slots_around(int i0, int i1) {
         const std::vector<uint32_t>& off = *d->h_off_rollup;
         for (int g0 = i0; g0 < i1; g0 += 8) {
             const int g1 = g0 + 8 < i1 ? g0 + 8 : i1, n = g1 - g0;
@@ -1115,12 +1128,25 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
                 if (seg[k][1] <= seg[k][0]) continue;
                 const uint64_t at = 32 * (base + seg[k][0]), wdt = 32 * (seg[k][1] - seg[k][0]);
                 d->last_d2h += wdt * (uint64_t)n;
-                cudaError_t e = cudaMemcpy2DAsync(out + at, 32 * pitch, wb + at, 32 * pitch, wdt, (size_t)n, cudaMemcpyDeviceToHost, (npiece++ & 1u) ? s6 : s3);
+                cudaError_t e = cudaMemcpy2DAsync(out + at, 32 * pitch, wb + at, 32 * pitch, wdt, (size_t)n, cudaMemcpyDeviceToHost, (npiece++ & 1u) ? d->stream6 : d->stream3);
                 if (e != cudaSuccess) return e;
             }
         }
         return cudaSuccess;
-    };
+    }
+};
+static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* out) {
+    const HzPlan& pl = d->plan;
+    const HzParams& P = pl.P;
+    cudaStream_t s = d->stream, s2 = d->stream2, s3 = d->stream3, s5 = d->stream5;
+    HzErrBuf* err = sanity ? d->err : nullptr;
+    const uint8_t* wb = reinterpret_cast<const uint8_t*>(d->w);
+    d->last_d2h = 0;
+    const cudaStream_t s6 = d->stream6;
+    HzCopier cp{d, out, wb, 0};
+    auto piece = [&](uint64_t a, uint64_t b) { return cp.piece(a, b); };
+    auto pieces_around = [&](uint64_t a, uint64_t b, int j0, int j1) { return cp.pieces_around(a, b, j0, j1); };
+    auto slots_around = [&](int i0, int i1) { return cp.slots_around(i0, i1); };
     const uint32_t gs = HZ_GL_STRIDE(P.nLevels + 1);
     CK(cudaMemsetAsync(d->err, 0, sizeof(HzErrBuf), s));
     CK(cudaMemsetAsync(d->pre, 0, (size_t)pl.nblocks * 512, s));
@@ -1262,16 +1288,58 @@ int hz_cuda_shard_phase2(HzCuda* d, const void* records, int sanity, uint8_t* sh
     int st = hz_phase2(d, sanity);
     if (st) return st;
     uint64_t bytes = 0;
-    if (shard_out)
-        for (int k = 0; k < npieces; k++) {
-            CK(cudaMemcpyAsync(shard_out + bytes, reinterpret_cast<const uint8_t*>(d->w) + 32ull * pieces[2 * k], 32ull * pieces[2 * k + 1], cudaMemcpyDeviceToHost, s));
-            bytes += 32ull * pieces[2 * k + 1];
+    std::vector<std::thread> workers;
+    d->last_d2h = 0;
+    if (shard_out) {
+        // as on the end-to-end path of one GPU: the image levels of the shard's processors are rebuilt in the shard
+        // buffer by host threads, the pieces are copied around them
+        const HzParams& P = d->plan.P;
+        const bool holes = d->ns + d->nf > 0;
+        unsigned nthr = std::thread::hardware_concurrency();
+        nthr = nthr == 0 ? 4 : (nthr > 18 ? 16 : (nthr > 3 ? nthr - 2 : 1));
+        nthr = nthr / (unsigned)(d->world < 8 ? d->world : 8) > 0 ? nthr / (unsigned)(d->world < 8 ? d->world : 8) : 1;   // the ranks of a box share its cores
+        CK(cudaEventRecord(d->ev_done, s));
+        CK(cudaStreamWaitEvent(d->stream3, d->ev_done, 0));
+        CK(cudaStreamWaitEvent(d->stream6, d->ev_done, 0));
+        if (holes) CK(cudaEventSynchronize(d->ev_info[0]));
+        const uint32_t r0 = d->ns > 0 ? (*d->h_off_rollup)[d->s0] : 0xffffffffu;
+        const int fj0 = 2 * P.nTx + d->f0, fj1 = fj0 + d->nf;
+        cudaError_t ce = cudaSuccess;
+        for (int k = 0; k < npieces && ce == cudaSuccess; k++) {
+            const uint64_t a = pieces[2 * k], n = pieces[2 * k + 1];
+            uint8_t* out_v = shard_out + bytes - 32ull * a;          // where witness entry 0 would be for this piece
+            HzCopier cp{d, out_v, reinterpret_cast<const uint8_t*>(d->w), (unsigned)k};
+            if (holes && d->ns > 0 && a == r0 && n == (uint64_t)(*d->h_off_rollup)[d->s0 + d->ns] - r0) {
+                for (unsigned t = 0; t < nthr; t++) workers.emplace_back(hz_fill_holes, d, out_v, 2 * d->s0, 2 * (d->s0 + d->ns), (int)t, (int)nthr);
+                ce = cp.slots_around(d->s0, d->s0 + d->ns);
+            } else if (holes && d->nf > 0) {
+                // fee transactions' processors, if they lie in this piece
+                bool inside = false;
+                for (int j = fj0; j < fj1; j++) inside = inside || (d->h_holes[j].nz > 0 && d->h_holes[j].cur >= a && d->h_holes[j].cur < a + n);
+                if (inside) {
+                    // only the holes inside [a, a + n) are skipped by the copies; the fill must match: all of them lie in the fee range
+                    bool all_in = true;
+                    for (int j = fj0; j < fj1; j++)
+                        if (d->h_holes[j].nz > 0) all_in = all_in && d->h_holes[j].cur >= a && (uint64_t)d->h_holes[j].cur + 2u + (uint64_t)d->h_holes[j].nz * HZ_SZL <= a + n;
+                    if (all_in) {
+                        workers.emplace_back(hz_fill_holes, d, out_v, fj0, fj1, 0, 1);
+                        ce = cp.pieces_around(a, a + n, fj0, fj1);
+                    } else ce = cp.piece(a, a + n);
+                } else ce = cp.piece(a, a + n);
+            } else ce = cp.piece(a, a + n);
+            bytes += 32ull * n;
         }
+        for (auto& t : workers) t.join();
+        CK(ce);
+        if (holes) d->last_d2h += (sizeof(HzHole) + sizeof(Fr) * HZ_GL_STRIDE(P.nLevels + 1)) * (size_t)(2 * d->ns + d->nf);
+    }
     CK(cudaMemcpyAsync(errs, d->err, sizeof(HzErrBuf), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaStreamSynchronize(d->stream2));
+    CK(cudaStreamSynchronize(d->stream3));
+    CK(cudaStreamSynchronize(d->stream6));
     if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, d->ev0, d->ev1));
-    if (d2h) *d2h = bytes + sizeof(HzErrBuf);
+    if (d2h) *d2h = (shard_out ? d->last_d2h : 0) + sizeof(HzErrBuf);
     return 0;
 }
 
