@@ -440,6 +440,12 @@ def main():
         run_reference(args, cfg, args.config)
     else:
         run_gpu(args, cfg, args.config)
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 if __name__ == "__main__":
