@@ -56,6 +56,7 @@ struct HzCuda {
     cudaStream_t stream5, stream6;
     cudaEvent_t ev_pack[2], ev_info[2];
     uint64_t last_d2h;
+    bool no_holes;             // HZW_NO_HOLES (tests / measurement): copy every entry, rebuild nothing on the host
     std::vector<uint32_t>* h_off_rollup;   // host copy of the slot offsets (plus the end of the last slot)
     Fr* isExit;                // nTx
     Fr* isExit_front;          // nTx: k_front's copy
@@ -839,6 +840,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaStreamCreate(&d->stream3) == cudaSuccess && cudaStreamCreate(&d->stream4) == cudaSuccess;
     for (int k = 0; k < 2; k++) ok = ok && cudaEventCreateWithFlags(&d->ev_half[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&d->ev_ed[k], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming) == cudaSuccess;
+    d->no_holes = getenv("HZW_NO_HOLES") != nullptr;
     d->h_off_rollup = new std::vector<uint32_t>(off_rollup, off_rollup + P.nTx);
     d->h_off_rollup->push_back(off_fee[0]);
     d->h_off_decode0 = off_decode[0]; d->h_off_rollup0 = off_rollup[0]; d->h_off_rollup_mid = off_rollup[P.nTx / 2]; d->h_off_fee0 = off_fee[0];
@@ -1007,7 +1009,7 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
         k_smt_zero<<<dim3(lb, (unsigned)(pl.P.nLevels + 1)), 256, 0, d->stream3>>>(pl, d->w, d->lev, d->img00, d->zflag, s0, ns, f0, nf);
         unsigned cores = std::thread::hardware_concurrency();
         cores = cores == 0 ? 4 : (cores > 18 ? 16 : (cores > 3 ? cores - 2 : 1));
-        if (d->world > 1 && cores / (unsigned)d->world >= 4) {
+        if (d->world > 1 && cores / (unsigned)d->world >= 4 && !d->no_holes) {
             // a shard's pieces are copied around the image levels too (hz_cuda_shard_phase2): their records go to the host now
             const uint32_t gs = HZ_GL_STRIDE(pl.P.nLevels + 1);
             k_hole_pack<<<(unsigned)(2 * ns + nf), 128, 0, s>>>(pl, d->w, d->lev, d->zflag, d->holes, d->gl, s0, ns, f0, nf);
@@ -1212,6 +1214,7 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
     if (getenv("HZW_FILL_THREADS")) nthr = (unsigned)atoi(getenv("HZW_FILL_THREADS")) > 0 ? (unsigned)atoi(getenv("HZW_FILL_THREADS")) : nthr;
     std::vector<std::thread> workers;
     CK(cudaEventSynchronize(d->ev_info[0]));
+    if (d->no_holes) for (int j = 0; j < 2 * h0; j++) d->h_holes[j].nz = 0;
     const double t_info0 = ms_since();
     for (unsigned t = 0; t < nthr; t++) workers.emplace_back(hz_fill_holes, d, out, 0, 2 * h0, (int)t, (int)nthr);
     CK(cudaStreamWaitEvent(s3, d->ev_half[0], 0));
@@ -1219,6 +1222,7 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
     cudaError_t ce = slots_around(0, h0);
     if (ce == cudaSuccess) ce = cudaEventSynchronize(d->ev_info[1]);
     if (ce == cudaSuccess) {
+        if (d->no_holes) for (int j = 2 * h0; j < 2 * P.nTx + F; j++) d->h_holes[j].nz = 0;
         for (unsigned t = 0; t < nthr; t++) workers.emplace_back(hz_fill_holes, d, out, 2 * h0, 2 * P.nTx + F, (int)t, (int)nthr);
         ce = cudaStreamWaitEvent(s3, d->ev_done, 0);
         if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s6, d->ev_done, 0);
@@ -1302,7 +1306,7 @@ int hz_cuda_shard_phase2(HzCuda* d, const void* records, int sanity, uint8_t* sh
         // rebuilding the images pays while a rank's link is the bottleneck (few ranks: gigabytes per link) and the
         // rank has threads to do it with; with eight ranks on a 16-core host one thread per rank would take longer
         // to write its 0.4 GB of images than the link takes to carry them (measured: 79 ms per batch at 8 GPUs)
-        const bool holes = d->ns + d->nf > 0 && nthr >= 4;
+        const bool holes = d->ns + d->nf > 0 && nthr >= 4 && !d->no_holes;
         CK(cudaEventRecord(d->ev_done, s));
         CK(cudaStreamWaitEvent(d->stream3, d->ev_done, 0));
         CK(cudaStreamWaitEvent(d->stream6, d->ev_done, 0));

@@ -126,6 +126,14 @@ def test_two_shards_on_one_gpu_equal_the_whole(built):
     assert bytes(ShardedWitnessCalculator.assemble(whole.NVars, shards)) == want
 
 
+def test_copy_paths_without_rebuilt_images(built, monkeypatch):
+    """With many ranks per host the image levels are copied like everything else (a rank has no threads to
+    rebuild them with): the same witnesses from the end-to-end path and from two shards with HZW_NO_HOLES set."""
+    monkeypatch.setenv("HZW_NO_HOLES", "1")
+    test_nlevels32_batch_equals_cpu_port_and_hashlib(built)
+    test_two_shards_on_one_gpu_equal_the_whole(built)
+
+
 def test_poseidon_lane_kernel_known_answers(built):
     """The lane-parallel permutation on its own: circomlib's published vector poseidon([1, 2]) and
     seeded random pairs against the oracle's big-integer Poseidon."""
