@@ -54,7 +54,7 @@ struct HzCuda {
     Fr* gl; Fr* h_gl;          // per job: the entries between those images (level headers, switchers), compact
     Fr* h_img00;               // host copy of the image
     cudaStream_t stream5, stream6;
-    cudaEvent_t ev_pack[2], ev_info[2];
+    cudaEvent_t ev_pack[2], ev_info[2], ev_sha[2];
     uint64_t last_d2h;
     bool no_holes;             // HZW_NO_HOLES (tests / measurement): copy every entry, rebuild nothing on the host
     std::vector<uint32_t>* h_off_rollup;   // host copy of the slot offsets (plus the end of the last slot)
@@ -666,7 +666,11 @@ __device__ __forceinline__ void hz_sha_round_wk(uint32_t* v, uint32_t wk) {
     uint32_t t2 = S0 + mj;
     v[7] = v[6]; v[6] = v[5]; v[5] = v[4]; v[4] = v[3] + t1; v[3] = v[2]; v[2] = v[1]; v[1] = v[0]; v[0] = t1 + t2;
 }
-__global__ void __launch_bounds__(256) k_sha_chain(HzPlan pl, const uint8_t* preb, uint32_t* chain, uint32_t* msgw, uint32_t* wk) {
+// Launched twice per batch, [0, nblocks / 2) (with the expansion of every block's schedule) and the rest, so that
+// the bit signals of the first half's blocks (k_sha_blocks) are written while the second half is walked.
+__global__ void __launch_bounds__(256) k_sha_chain(HzPlan pl, const uint8_t* preb, uint32_t* chain, uint32_t* msgw, uint32_t* wk,
+                                                   uint32_t b_begin, uint32_t b_end) {
+    if (b_begin == 0) {
     uint32_t nw = pl.nblocks * 16;
     for (uint32_t t = threadIdx.x; t < nw; t += blockDim.x) {
         const uint4* p = reinterpret_cast<const uint4*>(preb + (size_t)t * 32);
@@ -694,14 +698,16 @@ __global__ void __launch_bounds__(256) k_sha_chain(HzPlan pl, const uint8_t* pre
         }
     }
     __syncthreads();
+    }
     if (threadIdx.x != 0) return;
     uint32_t st[8];
-    for (int j = 0; j < 8; j++) { st[j] = hz_sha_h(j); chain[j] = st[j]; }
+    if (b_begin == 0) { for (int j = 0; j < 8; j++) { st[j] = hz_sha_h(j); chain[j] = st[j]; } }
+    else { for (int j = 0; j < 8; j++) st[j] = chain[(size_t)b_begin * 8 + j]; }
     const uint4* wk4 = reinterpret_cast<const uint4*>(wk);
     uint4 nxt[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) nxt[q] = wk4[q];
-    for (uint32_t b = 0; b < pl.nblocks; b++) {
+    for (int q = 0; q < 16; q++) nxt[q] = wk4[(size_t)b_begin * 16 + q];
+    for (uint32_t b = b_begin; b < b_end; b++) {
         uint4 cur[16];
 #pragma unroll
         for (int q = 0; q < 16; q++) cur[q] = nxt[q];
@@ -823,7 +829,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
         ok = ok && cudaMalloc(&d->gl, sizeof(Fr) * gs * nj) == cudaSuccess && cudaMallocHost(&d->h_gl, sizeof(Fr) * gs * nj) == cudaSuccess;
         ok = ok && cudaMallocHost(&d->h_img00, sizeof(Fr) * HZ_HS) == cudaSuccess;
         ok = ok && cudaStreamCreate(&d->stream5) == cudaSuccess && cudaStreamCreate(&d->stream6) == cudaSuccess;
-        for (int k = 0; k < 2; k++) ok = ok && cudaEventCreateWithFlags(&d->ev_pack[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&d->ev_info[k], cudaEventDisableTiming) == cudaSuccess;
+        for (int k = 0; k < 2; k++) ok = ok && cudaEventCreateWithFlags(&d->ev_pack[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&d->ev_info[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&d->ev_sha[k], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaMalloc(&d->hint_cst, sizeof(Fr) * HZ_CST_MAX) == cudaSuccess;
     ok = ok && cudaMalloc(&d->hint_tab, sizeof(Fr) * HZ_EDTAB_LEN) == cudaSuccess;
@@ -923,7 +929,7 @@ void hz_cuda_destroy(HzCuda* d) {
     if (d->stream4) cudaStreamDestroy(d->stream4);
     if (d->stream5) cudaStreamDestroy(d->stream5);
     if (d->stream6) cudaStreamDestroy(d->stream6);
-    for (int k = 0; k < 2; k++) { if (d->ev_pack[k]) cudaEventDestroy(d->ev_pack[k]); if (d->ev_info[k]) cudaEventDestroy(d->ev_info[k]); }
+    for (int k = 0; k < 2; k++) { if (d->ev_pack[k]) cudaEventDestroy(d->ev_pack[k]); if (d->ev_info[k]) cudaEventDestroy(d->ev_info[k]); if (d->ev_sha[k]) cudaEventDestroy(d->ev_sha[k]); }
     for (int k = 0; k < 2; k++) { if (d->ev_half[k]) cudaEventDestroy(d->ev_half[k]); if (d->ev_ed[k]) cudaEventDestroy(d->ev_ed[k]); }
     if (d->ev_done) cudaEventDestroy(d->ev_done);
     if (d->ev0) cudaEventDestroy(d->ev0);
@@ -1042,9 +1048,20 @@ static int hz_phase2(HzCuda* d, int sanity) {
     HzErrBuf* err = sanity ? d->err : nullptr;
     k_hash_head<<<148, 256, 0, s>>>(pl, d->w, d->pre, d->rank == 0 ? err : nullptr, d->off_blocks);
     CK(cudaEventRecord(d->kev[5], s));
-    k_sha_chain<<<1, 256, 0, s>>>(pl, d->pre, d->chain, d->msgw, d->shawk);
+    // the chain in two halves: the blocks of the first half are expanded (stream 5) while the second half is walked
+    const uint32_t mid = pl.nblocks / 2, bend = d->b0 + d->nb;
+    k_sha_chain<<<1, 256, 0, s>>>(pl, d->pre, d->chain, d->msgw, d->shawk, 0, mid);
+    const uint32_t n1 = d->b0 < mid ? (bend < mid ? bend : mid) - d->b0 : 0;       // own blocks below mid
+    if (n1 > 0) {
+        CK(cudaEventRecord(d->ev_sha[0], s));
+        CK(cudaStreamWaitEvent(d->stream5, d->ev_sha[0], 0));
+        k_sha_blocks<<<n1, HZ_SHA_THREADS, 0, d->stream5>>>(pl, d->w, err, d->chain, d->msgw, d->off_blocks, d->b0);
+        CK(cudaEventRecord(d->ev_sha[1], d->stream5));
+    }
+    k_sha_chain<<<1, 256, 0, s>>>(pl, d->pre, d->chain, d->msgw, d->shawk, mid, pl.nblocks);
     CK(cudaEventRecord(d->kev[6], s));
-    if (d->nb > 0) k_sha_blocks<<<d->nb, HZ_SHA_THREADS, 0, s>>>(pl, d->w, err, d->chain, d->msgw, d->off_blocks, d->b0);
+    if (d->nb > n1) k_sha_blocks<<<d->nb - n1, HZ_SHA_THREADS, 0, s>>>(pl, d->w, err, d->chain, d->msgw, d->off_blocks, d->b0 + n1);
+    if (n1 > 0) CK(cudaStreamWaitEvent(s, d->ev_sha[1], 0));
     CK(cudaEventRecord(d->kev[7], s));
     k_hash_tail<<<1, 32, 0, s>>>(pl, d->w, d->rank == 0 ? err : nullptr, d->chain);
     CK(cudaEventRecord(d->kev[8], s));
