@@ -16,8 +16,8 @@
 #if defined(__CUDACC__) && defined(HZ_DEVICE_ONLY)
 // CUDA translation unit: device code only (the host half of the library is compiled by g++)
 #define HZ_HD __device__ __forceinline__
-#define HZ_HDN __device__ __noinline__
-#define HZ_FN __device__ __noinline__
+#define HZ_HDN static __device__ __noinline__
+#define HZ_FN static __device__ __noinline__
 #elif defined(__CUDACC__)
 #define HZ_HD __host__ __device__ __forceinline__
 #define HZ_HDN __host__ __device__ __noinline__
@@ -430,7 +430,7 @@ __device__ __forceinline__ void hz_shl8(uint32_t* a) {
 // binary extended Euclid, but the cofactors are only doubled and added -- plain 256-bit shifts and additions
 // (r, s < 2p < 2^255) instead of a modular halving / modular subtraction per step -- and the 2^k they pick up
 // (254 <= k <= 508) is divided out at the end: a^-1 = (p - r) 2^-k.
-__device__ __noinline__ Fr fr_inv_euclid(const Fr& a) {
+static __device__ __noinline__ Fr fr_inv_euclid(const Fr& a) {
     const uint32_t p1[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
     uint32_t u[8], v[8], r[8], sv[8];
 #pragma unroll
@@ -474,7 +474,7 @@ __device__ __noinline__ Fr fr_inv_euclid(const Fr& a) {
     return fr_mul_chain(x, hz_inv2k_dev[k]);
 }
 // a != 0: the binary extended Euclid it replaces (kept for reference)
-__device__ __noinline__ Fr fr_inv_euclid_binary(const Fr& a) {
+static __device__ __noinline__ Fr fr_inv_euclid_binary(const Fr& a) {
     uint32_t u[8], v[8], x1[8], x2[8];
     const uint32_t p1[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
 #pragma unroll
@@ -509,7 +509,7 @@ __device__ __forceinline__ Fr hz_shfl_xor_fr(const Fr& v, int m) {
     for (int i = 0; i < 8; i++) r.l[i] = __shfl_xor_sync(0xffffffffu, v.l[i], m);
     return r;
 }
-__device__ __noinline__ Fr fr_inv(const Fr& a) {
+static __device__ __noinline__ Fr fr_inv(const Fr& a) {
     const bool z = fr_is_zero(a);
     Fr x = a;
     if (z) x.l[0] = 1u;

@@ -275,7 +275,7 @@ __device__ __forceinline__ void hz_lad_finish(HzHints* h, bool ok) {
 // px, py: the Edwards input of EscalarMulAny (after its zero-point substitution); e: the 254 scalar
 // bits; s: the 253 bits of S.  Leaves h->lad_ok and, if set, the 588 hints in h->scratch[0 .. 588).
 #ifndef HZ_WIDE_LADDER
-__device__ __noinline__ void hz_hints_eddsa_lanes(HzHints* h, const Fr& px, const Fr& py, const BVT<MCompute, 8>& e,
+static __device__ __noinline__ void hz_hints_eddsa_lanes(HzHints* h, const Fr& px, const Fr& py, const BVT<MCompute, 8>& e,
                                                  const BVT<MCompute, 8>& s) {
     h->lad_ok = 0;
     if (!h->scratch || !h->edtab) return;
@@ -350,7 +350,7 @@ __device__ __forceinline__ Fr hz_sel_fr(bool c, const Fr& a, const Fr& b) {
     for (int i = 0; i < 8; i++) r.l[i] = c ? a.l[i] : b.l[i];
     return r;
 }
-__device__ __noinline__ void hz_hints_eddsa_lanes(HzHints* h, const Fr& px, const Fr& py, const BVT<MCompute, 8>& e,
+static __device__ __noinline__ void hz_hints_eddsa_lanes(HzHints* h, const Fr& px, const Fr& py, const BVT<MCompute, 8>& e,
                                                  const BVT<MCompute, 8>& s) {
     h->lad_ok = 0;
     if (!h->scratch || !h->edtab) return;

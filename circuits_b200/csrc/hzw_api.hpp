@@ -20,6 +20,9 @@ struct HzBackend {
     virtual int shard_phase2(const void* records, int sanity, uint8_t* shard_out, float* kernel_ms, HzErrBuf* errs) = 0;
     // Withdraw(nLevels): n independent instances, inputs n x ninputs x 32 B, witnesses n x nvars x 32 B
     virtual int withdraw_batch(uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out, float* kernel_ms, HzErrBuf* errs) = 0;
+    // device-resident witness (null / HZW_E_PARAM for a backend without device memory)
+    virtual int witness_device(void** ptr, int32_t* device, void** stream) { (void)ptr; (void)device; (void)stream; return HZW_E_PARAM; }
+    virtual int witness_read(uint64_t first, uint64_t count, uint8_t* out) { (void)first; (void)count; (void)out; return HZW_E_PARAM; }
     uint64_t launches = 0, h2d = 0, d2h = 0;
 };
 
@@ -99,8 +102,9 @@ static inline std::string hz_dec(const Fr& f) {
 
 extern "C" {
 
-int hzw_create(const hzw_params* prm, const char* /*layout_map_path*/, hzw_ctx** out) {
+int hzw_create(const hzw_params* prm, const char* layout_map_path, hzw_ctx** out) {
     if (!prm || !out) return HZW_E_PARAM;
+    if (layout_map_path) return HZW_E_PARAM;      // a circom .sym map is not applied yet: refuse rather than ignore it
     if (prm->circuit_kind == HZW_CIRCUIT_WITHDRAW) {
         if (prm->nLevels < 1 || prm->nLevels > 48) return HZW_E_PARAM;
         hzw_ctx* c = new hzw_ctx();
@@ -206,6 +210,22 @@ int hzw_calculate_batch(hzw_ctx* ctx, uint64_t n, const uint8_t* inputs, int san
 int hzw_write_wtns(const hzw_ctx* ctx, const uint8_t* witness, const char* path) {
     if (!ctx || !witness || !path) return HZW_E_PARAM;
     return hz_write_wtns(path, witness, ctx->nvars()) ? HZW_E_IO : HZW_OK;
+}
+int hzw_witness_device(const hzw_ctx* ctx, void** dev_ptr, int32_t* device, void** stream) {
+    if (!ctx || !dev_ptr) return HZW_E_PARAM;
+    return ctx->be->witness_device(dev_ptr, device, stream);
+}
+int hzw_witness_read(hzw_ctx* ctx, uint64_t first, uint64_t count, uint8_t* out) {
+    if (!ctx || !out || first + count > ctx->nvars()) return HZW_E_PARAM;
+    return ctx->be->witness_read(first, count, out);
+}
+int hzw_signal_index(const hzw_ctx* ctx, const char* name, uint64_t* index) {
+    if (!ctx || !name || !index) return HZW_E_PARAM;
+    std::vector<std::pair<std::string, uint32_t> > v;
+    LayoutSink sk; sk.want_names = true; sk.filter = name; sk.out = &v;
+    ctx->walk(&sk);
+    for (auto& e : v) if (e.first == name && e.second != HZ_NOIDX) { *index = e.second; return HZW_OK; }
+    return HZW_E_NOSIGNAL;
 }
 int hzw_get_signal(const hzw_ctx* ctx, const uint8_t* witness, const char* name, uint8_t out[32]) {
     if (!ctx || !witness || !name || !out) return HZW_E_PARAM;

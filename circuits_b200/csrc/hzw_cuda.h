@@ -12,12 +12,16 @@ void hz_cuda_destroy(HzCuda*);
 // inputs: n_inputs x 32 B host; witness_out: nvars x 32 B host or null (resident)
 int hz_cuda_calculate(HzCuda*, const uint8_t* inputs, int sanity, uint8_t* witness_out, float* kernel_ms,
                       HzErrBuf* errs, uint64_t* launches, uint64_t* h2d, uint64_t* d2h);
+// device-resident hand-off: base of the witness in HBM, its device and the stream its kernels were ordered on
+int hz_cuda_witness_device(HzCuda*, void** ptr, int32_t* device, void** stream);
+int hz_cuda_witness_read(HzCuda*, uint64_t first, uint64_t count, uint8_t* out);
 // per-kernel device times of the last calculate
 int hz_cuda_kernel_ms(HzCuda*, float* ms, const char** names, int cap);
 
 // ---- sharded evaluation (one context per GPU; include/hzwitness.h, hzw_shard_*) -------------------
 int hz_cuda_set_shard(HzCuda*, int rank, int world);
 uint64_t hz_cuda_exchange_bytes(const HzCuda*);
+uint64_t hz_cuda_launches(const HzCuda*);     // kernels launched since the start of the current calculate / shard phase 1
 int hz_cuda_shard_phase1(HzCuda*, const uint8_t* inputs, int sanity, void* record_out_dev, HzErrBuf* errs);
 int hz_cuda_shard_phase2(HzCuda*, const void* records_dev, int sanity, uint8_t* shard_out, const uint64_t* pieces, int npieces,
                          float* kernel_ms, HzErrBuf* errs, uint64_t* d2h);

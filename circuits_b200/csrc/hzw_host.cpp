@@ -13,6 +13,8 @@ struct CudaBackend : HzBackend {
         return hz_cuda_calculate(d, inputs, sanity, resident ? nullptr : out, ms, errs, &launches, &h2d, &d2h);
     }
     int kernel_ms(float* ms, const char** names, int cap) override { return hz_cuda_kernel_ms(d, ms, names, cap); }
+    int witness_device(void** ptr, int32_t* device, void** stream) override { return hz_cuda_witness_device(d, ptr, device, stream); }
+    int witness_read(uint64_t first, uint64_t count, uint8_t* out) override { return hz_cuda_witness_read(d, first, count, out); }
     const HzLayout* L = nullptr;
     HzShard sh;
     int set_shard(int rank, int world) override {
@@ -29,8 +31,9 @@ struct CudaBackend : HzBackend {
     int withdraw_batch(uint64_t, const uint8_t*, int, uint8_t*, float*, HzErrBuf*) override { return HZW_E_PARAM; }
     int shard_phase2(const void* records, int sanity, uint8_t* shard_out, float* ms, HzErrBuf* errs) override {
         uint64_t t[32]; int n = hz_shard_pieces(*L, sh, t, 16);
-        launches = 12;
-        return hz_cuda_shard_phase2(d, records, sanity, shard_out, t, n, ms, errs, &d2h);
+        int st = hz_cuda_shard_phase2(d, records, sanity, shard_out, t, n, ms, errs, &d2h);
+        launches = hz_cuda_launches(d);
+        return st;
     }
 };
 

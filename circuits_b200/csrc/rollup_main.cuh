@@ -227,7 +227,7 @@ __device__ __forceinline__ Fr hz_fr_field(const Fr& x, int from, int n) {
     for (int k = 0; k < n; k++) r.l[k >> 5] |= fr_bit(x, from + k) << (k & 31);
     return r;
 }
-__device__ __noinline__ void hz_decode_lite(Comp<MCompute>& c, const HzPlan& pl, int i, DecodeOut<MCompute>& o) {
+static __device__ __noinline__ void hz_decode_lite(Comp<MCompute>& c, const HzPlan& pl, int i, DecodeOut<MCompute>& o) {
     const Fr txc = hz_in(c, pl, IN_txCompressedData, i).v;
     auto sigv = [](const Fr& f) { VC r; r.v = f; r.sig = true; return r; };
     o.fromIdx = sigv(hz_fr_field(txc, 48, 48)); o.toIdx = sigv(hz_fr_field(txc, 96, 48));
@@ -245,7 +245,7 @@ __device__ __forceinline__ VC hz_sigv(const Fr& f, bool sig) { VC r; r.v = f; r.
 
 // head of one SMTProcessor body from its job record (k_smt): everything before the levels; the levels
 // themselves are evaluated by k_smt_levels from the HzLevJob and the state-machine tuples left here
-__device__ __noinline__ void sec_smt_head(Fr* w, HzErrBuf* err, int nLevels1, const HzSmtJob& j, HzSmtMid& out, HzLevJob& lev, Fr* smst) {
+static __device__ __noinline__ void sec_smt_head(Fr* w, HzErrBuf* err, int nLevels1, const HzSmtJob& j, HzSmtMid& out, HzLevJob& lev, Fr* smst) {
     Comp<MCompute> c(w, j.cur, err);
     VC sib[HZ_MAX_LEVELS];
     for (int k = 0; k < nLevels1; k++) sib[k] = c.load(j.sib + k);
@@ -276,7 +276,7 @@ __device__ __forceinline__ VC hz_smt_top(Comp<MCompute>& c, const HzSmtMid& m, c
     return SMTProcessorTop<MCompute>(c, mid);
 }
 // tops of processor 1 and 2, s3, s4, s5 and the root checks of slot i (k_tail)
-__device__ __noinline__ void sec_rollup_tail(Fr* w, HzErrBuf* err, const HzPlan& pl, int i, const HzSmtMid* mids, const Fr& isExit_) {
+static __device__ __noinline__ void sec_rollup_tail(Fr* w, HzErrBuf* err, const HzPlan& pl, int i, const HzSmtMid* mids, const Fr& isExit_) {
     HzPending pend; pend.n = 0;
     Comp<MCompute> c(w, mids[0].cur, err, nullptr, &pend);
     VC oldStateRoot = i == 0 ? hz_in(c, pl, IN_oldStateRoot) : hz_in(c, pl, IN_imStateRoot, i - 1);
@@ -291,7 +291,7 @@ __device__ __noinline__ void sec_rollup_tail(Fr* w, HzErrBuf* err, const HzPlan&
     c.flush_pending();
 }
 // top of the processor of fee tx i
-__device__ __noinline__ void sec_fee_tail(Fr* w, HzErrBuf* err, const HzPlan& pl, int i, const HzSmtMid& mid) {
+static __device__ __noinline__ void sec_fee_tail(Fr* w, HzErrBuf* err, const HzPlan& pl, int i, const HzSmtMid& mid) {
     HzPending pend; pend.n = 0;
     Comp<MCompute> c(w, mid.cur, err, nullptr, &pend);
     VC oldStateRoot = i == 0 ? hz_in(c, pl, IN_imInitStateRootFee) : hz_in(c, pl, IN_imStateRootFee, i - 1);

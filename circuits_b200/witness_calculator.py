@@ -42,7 +42,8 @@ class _Error(ctypes.Structure):
 EXPORTS = ["hzw_create", "hzw_destroy", "hzw_nvars", "hzw_ninputs", "hzw_input_index", "hzw_calculate",
            "hzw_calculate_batch", "hzw_calculate_resident", "hzw_write_wtns", "hzw_get_signal", "hzw_dump_sym",
            "hzw_last_stats", "hzw_last_kernel_ms", "hzw_plan_info", "hzw_set_shard", "hzw_exchange_bytes",
-           "hzw_shard_pieces", "hzw_shard_nvars", "hzw_shard_phase1", "hzw_shard_phase2", "hzw_poseidon_bench", "hzw_int_peak"]
+           "hzw_shard_pieces", "hzw_shard_nvars", "hzw_shard_phase1", "hzw_shard_phase2", "hzw_poseidon_bench", "hzw_int_peak",
+           "hzw_witness_device", "hzw_signal_index", "hzw_witness_read"]
 
 
 def load_library(path=None):
@@ -83,6 +84,10 @@ def load_library(path=None):
                                      ctypes.POINTER(_Error)]
     lib.hzw_shard_phase2.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                      ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_Error)]
+    lib.hzw_witness_device.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int32),
+                                       ctypes.POINTER(ctypes.c_void_p)]
+    lib.hzw_signal_index.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64)]
+    lib.hzw_witness_read.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
     return lib
 
 
@@ -202,6 +207,28 @@ class WitnessCalculator:
         if st != 0:
             self._raise(st, err)
         return ms.value
+
+    # -- device-resident hand-off ------------------------------------------------------------------
+    def witnessDevice(self):
+        """(device pointer, CUDA device ordinal, cudaStream_t) of the witness a resident calculate left in HBM."""
+        ptr, dev, st = ctypes.c_void_p(), ctypes.c_int32(), ctypes.c_void_p()
+        if self._lib.hzw_witness_device(self._ctx, ctypes.byref(ptr), ctypes.byref(dev), ctypes.byref(st)) != 0:
+            raise WitnessError("this backend keeps no device-resident witness")
+        return ptr.value, dev.value, st.value
+
+    def signalIndex(self, name):
+        idx = ctypes.c_uint64()
+        if self._lib.hzw_signal_index(self._ctx, name.encode(), ctypes.byref(idx)) != 0:
+            raise WitnessError("Signal %s not found" % name)
+        return idx.value
+
+    def readWitness(self, first=0, count=None, out=None):
+        """Entries [first, first + count) of the resident witness, copied to the host."""
+        count = self.NVars - first if count is None else count
+        buf = out if out is not None else bytearray(32 * count)
+        if self._lib.hzw_witness_read(self._ctx, first, count, _addr(buf)) != 0:
+            raise WitnessError("hzw_witness_read(%d, %d) failed" % (first, count))
+        return buf
 
     def planInfo(self):
         out = (ctypes.c_uint64 * 12)()
@@ -338,9 +365,18 @@ class ShardedWitnessCalculator(WitnessCalculator):
                 torch.cuda.current_stream().synchronize()
 
     def calculateShard(self, packed, sanityCheck=False, out=None, resident=False):
-        """Both phases and the all-gather; returns (shard buffer, device ms of this rank's kernels)."""
-        self.phase1(packed, sanityCheck)
+        """Both phases and the all-gather; returns (shard buffer, device ms of this rank's kernels).
+        A rank whose phase 1 fails (a violated constraint under sanityCheck is a per-rank event: only the rank
+        that owns the slot sees it) still takes part in the collective, so the other ranks are not left
+        waiting in the all-gather; it raises afterwards."""
+        failure = None
+        try:
+            self.phase1(packed, sanityCheck)
+        except WitnessError as e:
+            failure = e
         self.exchange()
+        if failure is not None:
+            raise failure
         return self.phase2(sanityCheck, out, resident)
 
     @staticmethod

@@ -75,6 +75,20 @@ int hzw_calculate_batch(hzw_ctx* ctx, uint64_t n, const uint8_t* inputs_le32, in
 /* same computation, witness left in device memory (no device->host copy); kernel_ms = device time.
  * inputs_le32 == NULL re-uses the inputs already resident in device memory from the previous call. */
 int hzw_calculate_resident(hzw_ctx* ctx, const uint8_t* inputs_le32, int sanity_check, float* kernel_ms, hzw_error* err);
+/* ---- device-resident hand-off (the step after the path: /root/reference/tools/helpers/actions.js:148-185 feeds the
+ * witness file to the prover) --------------------------------------------------------------------------------
+ * After hzw_calculate_resident (or hzw_shard_phase2 with shard_out == NULL) the witness stays in HBM; a GPU prover
+ * consumes it there instead of paying the PCIe egress:
+ *   hzw_witness_device  base pointer of the witness in device memory (hzw_nvars() x 32 B, entry i at +32 i, little-
+ *                       endian canonical residues, same layout as the host buffer of hzw_calculate), its CUDA device
+ *                       ordinal and the stream (cudaStream_t) the producing kernels were ordered on; valid until the
+ *                       next calculate on this context or hzw_destroy.  On a sharded context only the ranges of
+ *                       hzw_shard_pieces hold this rank's results.
+ *   hzw_signal_index    witness index of a named signal ("main.rollupTx[3].processor1.newRoot"): the layout query
+ *   hzw_witness_read    device -> host copy of entries [first, first + count) of the resident witness */
+int hzw_witness_device(const hzw_ctx* ctx, void** dev_ptr, int32_t* device, void** stream);
+int hzw_signal_index(const hzw_ctx* ctx, const char* name, uint64_t* index);
+int hzw_witness_read(hzw_ctx* ctx, uint64_t first, uint64_t count, uint8_t* out);
 int hzw_write_wtns(const hzw_ctx* ctx, const uint8_t* witness, const char* path);
 int hzw_get_signal(const hzw_ctx* ctx, const uint8_t* witness, const char* name, uint8_t out[32]);
 /* writes "index,name" lines (the `.sym` equivalent) for every signal whose name starts with prefix */
