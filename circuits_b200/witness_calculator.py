@@ -172,7 +172,7 @@ class WitnessCalculator:
 
     # -- circom_runtime surface ----------------------------------------------------------------
     def calculateBinWitness(self, inp, sanityCheck=False, out=None):
-        packed = inp if isinstance(inp, (bytes, bytearray)) or hasattr(inp, "data_ptr") else self.packInput(inp)
+        packed = inp if isinstance(inp, (bytes, bytearray)) or hasattr(inp, "data_ptr") or hasattr(inp, "ctypes") else self.packInput(inp)
         if isinstance(packed, bytes):
             packed = bytearray(packed)
         wit = out if out is not None else bytearray(32 * self.NVars)
