@@ -53,7 +53,13 @@ def make_input(cfg):
     """Packed input (NInputs x 32 B) + expected hashGlobalInputs; cached in /tmp for the other arm."""
     import pickle
     nTx, nLevels, maxL1Tx, maxFeeTx = cfg
-    cache = os.path.join(tempfile.gettempdir(), "hzw_bench_%d_%d_%d_%d.pkl" % cfg)
+    # cached beside the repo's sources (git-ignored): building the 2048-slot batch takes the host mirror ~45 s
+    cdir = os.path.join(ROOT, ".bench_cache")
+    try:
+        os.makedirs(cdir, exist_ok=True)
+    except OSError:
+        cdir = tempfile.gettempdir()
+    cache = os.path.join(cdir, "hzw_bench_%d_%d_%d_%d.pkl" % cfg)
     if os.path.exists(cache):
         try:
             with open(cache, "rb") as f:

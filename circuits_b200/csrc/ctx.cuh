@@ -61,6 +61,8 @@ struct Nm {
 template <class M> struct V;
 template <> struct V<MCompute> {
     Fr v; bool sig;
+    bool ph = false;    // placeholder: the value depends on a hash that another kernel evaluates (Comp::skip_hash);
+                        // entries computed from it are not stored here -- the kernel that knows the hash writes them
 };
 template <> struct V<MLayout> {
     uint32_t idx;   // witness index when the value is a signal, HZ_NOIDX for an expression
@@ -83,16 +85,16 @@ template <> struct Ops<MLayout> {
     static HZ_HD VL pow2(int) { return vl(); }
 };
 
-HZ_HD VC operator+(const VC& a, const VC& b) { return vc(fr_add(a.v, b.v)); }
-HZ_HD VC operator-(const VC& a, const VC& b) { return vc(fr_sub(a.v, b.v)); }
-HZ_HD VC operator*(const VC& a, const VC& b) { return vc(fr_mul(a.v, b.v)); }
-HZ_HD VC operator-(const VC& a) { return vc(fr_neg(a.v)); }
-HZ_HD VC operator+(const VC& a, uint64_t k) { return vc(fr_add(a.v, fr_from_u64(k))); }
-HZ_HD VC operator-(const VC& a, uint64_t k) { return vc(fr_sub(a.v, fr_from_u64(k))); }
-HZ_HD VC operator*(const VC& a, uint64_t k) { return vc(fr_mul_u64(a.v, k)); }
-HZ_HD VC operator-(uint64_t k, const VC& a) { return vc(fr_sub(fr_from_u64(k), a.v)); }
-HZ_HD VC operator+(uint64_t k, const VC& a) { return vc(fr_add(fr_from_u64(k), a.v)); }
-HZ_HD VC operator*(uint64_t k, const VC& a) { return vc(fr_mul_u64(a.v, k)); }
+HZ_HD VC operator+(const VC& a, const VC& b) { VC r = vc(fr_add(a.v, b.v)); r.ph = a.ph || b.ph; return r; }
+HZ_HD VC operator-(const VC& a, const VC& b) { VC r = vc(fr_sub(a.v, b.v)); r.ph = a.ph || b.ph; return r; }
+HZ_HD VC operator*(const VC& a, const VC& b) { VC r = vc(fr_mul(a.v, b.v)); r.ph = a.ph || b.ph; return r; }
+HZ_HD VC operator-(const VC& a) { VC r = vc(fr_neg(a.v)); r.ph = a.ph; return r; }
+HZ_HD VC operator+(const VC& a, uint64_t k) { VC r = vc(fr_add(a.v, fr_from_u64(k))); r.ph = a.ph; return r; }
+HZ_HD VC operator-(const VC& a, uint64_t k) { VC r = vc(fr_sub(a.v, fr_from_u64(k))); r.ph = a.ph; return r; }
+HZ_HD VC operator*(const VC& a, uint64_t k) { VC r = vc(fr_mul_u64(a.v, k)); r.ph = a.ph; return r; }
+HZ_HD VC operator-(uint64_t k, const VC& a) { VC r = vc(fr_sub(fr_from_u64(k), a.v)); r.ph = a.ph; return r; }
+HZ_HD VC operator+(uint64_t k, const VC& a) { VC r = vc(fr_add(fr_from_u64(k), a.v)); r.ph = a.ph; return r; }
+HZ_HD VC operator*(uint64_t k, const VC& a) { VC r = vc(fr_mul_u64(a.v, k)); r.ph = a.ph; return r; }
 HZ_HD VC vinv(const VC& a) { return vc(fr_inv(a.v)); }
 HZ_HD VC vdiv(const VC& a, const VC& b) { return vc(fr_mul(a.v, fr_inv(b.v))); }
 HZ_HD uint32_t vbit(const VC& a, int i) { return fr_bit(a.v, i); }
@@ -154,6 +156,10 @@ struct HzErrBuf { uint32_t count; uint32_t pad; HzErrRec rec[HZ_MAX_ERR]; };
 
 // ---- layout sink (host) -------------------------------------------------------------------
 #ifndef HZ_DEVICE_ONLY
+// where the Poseidon components of width 5 (HashState) and 7 (the message hash of DecodeTx) start, in walk order:
+// the transposed kernels of the device write their entries (recorded while a walk runs with this set)
+struct HzPoseidonStarts { std::vector<uint32_t> t5, t7; };
+static thread_local HzPoseidonStarts* hz_poseidon_starts = nullptr;
 struct LayoutSink {
     // name recording: every signal whose full name starts with `filter` is reported
     bool want_names = false;
@@ -237,11 +243,15 @@ template <> struct Comp<MCompute> {
     bool solo = false;  // device: this thread works alone (no lane group shares its stores)
     bool dry = false;   // values only: nothing is stored, no inverse is queued (k_smtjob derives the SMT jobs of a
                         // slot ahead of k_front by running the same templates this way)
+    bool skip_hash = false;   // device: Poseidon components are stepped over -- their entries and digests come from the
+                              // transposed kernels (k_hstate, k_sighash); with hs_rec set the inputs are recorded for them
+    Fr* hs_rec = nullptr;     // 4 field elements per HashState of this slot / fee tx, in evaluation order
+    int* hs_n = nullptr;
     typedef VC Val;
 
     HZ_HD Comp(Fr* w_, uint32_t cur_, HzErrBuf* err_, HzHints* h_ = nullptr, HzPending* p_ = nullptr)
         : w(w_), cur(cur_), end(HZ_NOIDX), parent(nullptr), err(err_), hints(h_), pend(p_) {}
-    HZ_HD Comp(Comp* p, bool reserved, uint32_t size) : w(p->w), cur(p->cur), parent(reserved ? nullptr : p), err(p->err), hints(p->hints), pend(p->pend), solo(p->solo), dry(p->dry) {
+    HZ_HD Comp(Comp* p, bool reserved, uint32_t size) : w(p->w), cur(p->cur), parent(reserved ? nullptr : p), err(p->err), hints(p->hints), pend(p->pend), solo(p->solo), dry(p->dry), skip_hash(p->skip_hash), hs_rec(p->hs_rec), hs_n(p->hs_n) {
         if (reserved) { end = p->cur + size; p->cur += size; } else end = HZ_NOIDX;
     }
     HZ_HD ~Comp() {
@@ -251,7 +261,7 @@ template <> struct Comp<MCompute> {
 #endif
     }
     Comp(const Comp&) = delete;
-    HZ_HD Comp(Comp&& o) : w(o.w), cur(o.cur), end(o.end), parent(o.parent), err(o.err), hints(o.hints), pend(o.pend), solo(o.solo), dry(o.dry) { o.parent = nullptr; o.end = HZ_NOIDX; }
+    HZ_HD Comp(Comp&& o) : w(o.w), cur(o.cur), end(o.end), parent(o.parent), err(o.err), hints(o.hints), pend(o.pend), solo(o.solo), dry(o.dry), skip_hash(o.skip_hash), hs_rec(o.hs_rec), hs_n(o.hs_n) { o.parent = nullptr; o.end = HZ_NOIDX; }
     // the `inv` entry and the `out` value of IsZero(x) (comparators.circom): inv <-- x != 0 ? 1/x : 0
     HZ_HD VC iszero_inv(const Nm&, const VC& x) {
         const uint32_t slot = cur++;
@@ -344,16 +354,17 @@ template <> struct Comp<MCompute> {
     }
     HZ_HD uint32_t sig(const Nm&) { return cur++; }
     HZ_HD uint32_t sigs(const Nm&, int n) { uint32_t s = cur; cur += n; return s; }
-    HZ_HD VC set(uint32_t slot, const VC& x) { put(slot, x.v); VC r = x; r.sig = true; return r; }
+    HZ_HD VC set(uint32_t slot, const VC& x) { if (!x.ph) put(slot, x.v); VC r = x; r.sig = true; return r; }
     HZ_HD VC seti(const Nm&, uint32_t slot, const VC& x) { return set(slot, x); }
     HZ_HD VC alias(const Nm&, const VC& x) { return x; }
     // `signal s <== x` / wiring of a sub-component input: alias when x is a signal
     HZ_HD VC def(const Nm&, const VC& x) {
         if (x.sig) return x;
-        put(cur++, x.v); VC r = x; r.sig = true; return r;
+        if (!x.ph) put(cur, x.v);
+        cur++; VC r = x; r.sig = true; return r;
     }
     // main-component signals always own their entry
-    HZ_HD VC own(const Nm&, const VC& x) { put(cur++, x.v); VC r = x; r.sig = true; return r; }
+    HZ_HD VC own(const Nm&, const VC& x) { if (!x.ph) put(cur, x.v); cur++; VC r = x; r.sig = true; return r; }
     // only for entries written by an EARLIER kernel or by the caller (main inputs): within a
     // kernel the lanes of a group do not see each other's stores
     HZ_HD VC load(uint32_t idx) const { VC r; r.v = w[idx]; r.sig = true; return r; }

@@ -130,19 +130,15 @@ HZ_HD void hz_hints_record_point(HzHints* h, const Fr& u, const Fr& v) {
 }
 
 #ifdef HZ_DEVICE_ONLY
-// ---- the device's way: all ladders of one signature at once, spread over the lanes of a group ----
+// ---- the device's way: the ladders of a signature walked projectively by k_ed_ladder (k_ladder.cu) ----
 // The doubling chain D_t = 2^t P runs through both segments of EscalarMulAny (Montgomery2Edwards
 // followed by Edwards2Montgomery at the segment boundary is the identity on (u, v)), 253 doublings
-// that nothing can shorten.  Everything else rides along in other lanes, one step behind:
-//   lane 0  D_{t+1} = double(D_t)                                  t = 0..252
-//   lane 1  segment 0 adder  (in1 = D_t, in2 = acc0), t = 1..147;  acc0 <- sum when e[t]
-//   lane 2  segment 1 adder  (in1 = D_t, in2 = acc1), t = 149..253; acc1 starts as D_148
-//   lane 3  EscalarMulFix segment 0 accumulating adder (in1 = accF, in2 = window_t[sel_t]), t = 0..82
-// A doubling and an addition differ only in how the slope lamda = N / Dn is formed; the rest of
-// MontgomeryAdd / MontgomeryDouble is the same map (u3 = lamda^2 - A - u1 - u2, v3 = lamda (u1 - u3) - v1),
-// so after a short role-specific head all lanes run ONE instruction stream.  The 588 denominators
-// are then inverted together: every lane takes a 74-element chunk of Montgomery's trick.
-#define HZ_WIDE_LADDER 1
+// that nothing can shorten.  The other ladders follow it:
+//   D  D_{t+1} = double(D_t)                                       t = 0..252
+//   A  segment 0 adder  (in1 = D_t, in2 = acc0), t = 1..147;  acc0 <- sum when e[t]
+//      segment 1 adder  (in1 = D_t, in2 = acc1), t = 149..253; acc1 starts as D_148
+//   F  EscalarMulFix segment 0 accumulating adder (in1 = accF, in2 = window_t[sel_t]), t = 0..82
+// and the 588 slope denominators (plus the W of the captured points) are inverted together by k_ed_hints.
 #define HZ_LAD_N 588
 // ---- what the ladder leaves for k_ed_fill ---------------------------------------------------------------
 // The witness entries of the ladder steps (BitElementMulAny x 252, the 83 accumulating adders of
@@ -169,46 +165,13 @@ HZ_HD void hz_hints_record_point(HzHints* h, const Fr& u, const Fr& v) {
 #define HZ_SCR_REC (HZ_SCR_AFF + 176)
 // per signature, written by lane 0 of k_eddsa: whether the ladder data is usable, where the three runs of
 // step entries start in the witness, the scalar bits
-struct HzFillRec { uint32_t ok, base_seg0, base_seg1, base_fix; uint32_t e[8]; uint32_t s[8]; uint32_t base_win; uint32_t pad[11]; };
-struct MtOps { Fr N, Dn, W12, X1, X2, Y1; };
-__device__ __forceinline__ MtOps mt_head_dbl(const MtPt& p) {
-    MtOps o;
-    Fr UU = fr_mul_chain(p.U, p.U), UW = fr_mul_chain(p.U, p.W), WW = fr_mul_chain(p.W, p.W), VW = fr_mul_chain(p.V, p.W);
-    Fr AUW = fr_mul_small(UW, (uint32_t)HZ_MT_A);
-    o.N = fr_add(fr_add(fr_add(fr_add(UU, UU), UU), fr_add(AUW, AUW)), WW);
-    o.Dn = fr_add(VW, VW);
-    o.W12 = WW; o.X1 = UW; o.X2 = UW; o.Y1 = VW;
-    return o;
-}
-__device__ __forceinline__ MtOps mt_head_add(const MtPt& p1, const MtPt& p2) {
-    MtOps o;
-    o.X1 = fr_mul_chain(p1.U, p2.W); o.X2 = fr_mul_chain(p2.U, p1.W);
-    o.Y1 = fr_mul_chain(p1.V, p2.W);
-    Fr Y2 = fr_mul_chain(p2.V, p1.W);
-    o.W12 = fr_mul_chain(p1.W, p2.W);
-    o.N = fr_sub(Y2, o.Y1); o.Dn = fr_sub(o.X2, o.X1);
-    return o;
-}
-__device__ __forceinline__ MtPt mt_tail(const MtOps& o) {
-    Fr S = fr_mul_chain(o.Dn, o.Dn);
-    Fr NN = fr_mul_chain(o.N, o.N);
-    Fr G = fr_sub(fr_mul_chain(NN, o.W12), fr_mul_chain(fr_add(fr_add(fr_mul_small(o.W12, (uint32_t)HZ_MT_A), o.X1), o.X2), S));
-    Fr DS = fr_mul_chain(o.Dn, S);
-    MtPt r;
-    r.U = fr_mul_chain(G, o.Dn);
-    r.V = fr_sub(fr_mul_chain(o.N, fr_sub(fr_mul_chain(o.X1, S), G)), fr_mul_chain(o.Y1, DS));
-    r.W = fr_mul_chain(DS, o.W12);
-    return r;
-}
-__device__ __forceinline__ Fr hz_shfl8_fr(const Fr& v, int src) {
-    Fr r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], src, HZ_G);
-    return r;
-}
+struct HzFillRec { uint32_t ok, base_seg0, base_seg1, base_fix; uint32_t e[8]; uint32_t s[8]; uint32_t base_win; uint32_t cur; uint32_t pad[10]; };
+// what the first half of the verifier (k_eddsa) leaves for the second (k_eddsa_tail), after the fill record:
+// the point 8 A, `enabled`, R8 (5 field elements); the witness cursor where the second half starts is rec.cur
+#define HZ_SCR_MID (HZ_SCR_REC + 4)
 // position of ladder element `el` in the hint array, which is in the order the templates consume:
 // [0, 294) segment 0 (doubler, adder per bit), [294] doublers[0], [295, 505) segment 1, [505, 588) fix adders
-__device__ __forceinline__ int hz_lad_pos(int el) {
+__host__ __device__ __forceinline__ int hz_lad_pos(int el) {
     if (el < 147) return 2 * el;
     if (el == 147) return 294;
     if (el < 253) return 295 + 2 * (el - 148);
@@ -216,225 +179,6 @@ __device__ __forceinline__ int hz_lad_pos(int el) {
     if (el < 505) return 295 + 2 * (el - 400) + 1;
     return el;
 }
-// ---- captures for k_ed_fill and the one batched inversion ------------------------------------------------
-__device__ __forceinline__ void hz_lad_capture(Fr* num, Fr* den, Fr* vv, int ex, const MtPt& P, bool& ok) {
-    num[HZ_LAD_N + ex] = P.U; vv[ex] = P.V; den[HZ_LAD_N + ex] = P.W;
-    if (fr_is_zero(P.W)) ok = false;
-}
-// loop-start captures of iteration t: D_t for the doubling role, the accumulators for the others
-__device__ __forceinline__ void hz_lad_captures(int role, int t, Fr* num, Fr* den, Fr* vv, const MtPt& D, const MtPt& acc, bool& ok) {
-    if (role == 0) {
-        if (t <= 144 && (t & 7) == 0) hz_lad_capture(num, den, vv, t >> 3, D, ok);
-        if (t >= 148 && t <= 252 && ((t - 148) & 7) == 0) hz_lad_capture(num, den, vv, 38 + ((t - 148) >> 3), D, ok);
-        if (t == 147) hz_lad_capture(num, den, vv, 77, D, ok);
-    } else if (role == 1) {
-        if (t >= 1 && t <= 145 && ((t - 1) & 7) == 0) hz_lad_capture(num, den, vv, 19 + ((t - 1) >> 3), acc, ok);
-    } else if (role == 2) {
-        if (t >= 149 && ((t - 149) & 7) == 0) hz_lad_capture(num, den, vv, 52 + ((t - 149) >> 3), acc, ok);
-    } else {
-        if (t < 83 && (t & 7) == 0) hz_lad_capture(num, den, vv, 66 + (t >> 3), acc, ok);
-    }
-}
-// Montgomery's trick over the 588 hint denominators and the 81 captured W, a chunk per lane; leaves the hints
-// in template order in hint[], the affine captured points in aff[] and h->lad_ok
-__device__ __forceinline__ void hz_lad_finish(HzHints* h, bool ok) {
-    Fr* hint = h->scratch; Fr* num = hint + HZ_SCR_ARR; Fr* den = num + HZ_SCR_ARR; Fr* pre = den + HZ_SCR_ARR;
-    Fr* vv = h->scratch + HZ_SCR_VV; Fr* aff = h->scratch + HZ_SCR_AFF;
-    const int lane = (int)hz_glane();
-    // any zero denominator in the group: no hints at all
-    {
-        unsigned bad = __ballot_sync(0xffffffffu, !ok);
-        unsigned mine = (bad >> ((threadIdx.x & 31u) & ~7u)) & 0xffu;
-        ok = mine == 0;
-    }
-    __syncwarp();
-    const int per = (HZ_LAD_TOT + HZ_G - 1) / HZ_G;
-    const int c0 = lane * per, c1 = c0 + per < HZ_LAD_TOT ? c0 + per : HZ_LAD_TOT;
-    Fr tot = fr_one();
-    for (int k = c0; k < c1; k++) { pre[k] = tot; Fr dk = den[k]; tot = fr_mul_chain(tot, ok ? dk : fr_one()); }
-    // inverse of the own chunk total = inverse of the product of all chunk totals times the other totals
-    Fr all = fr_one(), others = fr_one();
-    for (int m = 0; m < HZ_G; m++) {
-        Fr tm = hz_shfl8_fr(tot, m);
-        all = fr_mul_chain(all, tm);
-        if (m != lane) others = fr_mul_chain(others, tm);
-    }
-    Fr inv = fr_mul_chain(fr_inv(all), others);
-    if (ok) {
-        for (int k = c1 - 1; k >= c0; k--) {
-            const Fr x = fr_mul_chain(inv, pre[k]);
-            if (k < HZ_LAD_N) hint[hz_lad_pos(k)] = fr_mul_chain(num[k], x);
-            else { aff[2 * (k - HZ_LAD_N)] = fr_mul_chain(num[k], x); aff[2 * (k - HZ_LAD_N) + 1] = fr_mul_chain(vv[k - HZ_LAD_N], x); }
-            inv = fr_mul_chain(inv, den[k]);
-        }
-    }
-    __syncwarp();
-    h->lad_ok = ok ? 1 : 0;
-}
-
-// px, py: the Edwards input of EscalarMulAny (after its zero-point substitution); e: the 254 scalar
-// bits; s: the 253 bits of S.  Leaves h->lad_ok and, if set, the 588 hints in h->scratch[0 .. 588).
-#ifndef HZ_WIDE_LADDER
-static __device__ __noinline__ void hz_hints_eddsa_lanes(HzHints* h, const Fr& px, const Fr& py, const BVT<MCompute, 8>& e,
-                                                 const BVT<MCompute, 8>& s) {
-    h->lad_ok = 0;
-    if (!h->scratch || !h->edtab) return;
-    __syncwarp();
-    Fr* hint = h->scratch; Fr* num = hint + HZ_SCR_ARR; Fr* den = num + HZ_SCR_ARR; Fr* vv = h->scratch + HZ_SCR_VV;
-    const int lane = (int)hz_glane();
-    MtPt D;
-    {
-        Fr y1 = fr_add(fr_one(), py);
-        D.U = fr_mul_chain(y1, px); D.V = y1; D.W = fr_mul_chain(fr_sub(fr_one(), py), px);
-    }
-    bool ok = !fr_is_zero(D.W);
-    MtPt acc = D;
-    const Fr* tab = h->edtab;
-    if (lane == 3) { acc.U = tab[83 * 16]; acc.V = tab[83 * 16 + 1]; acc.W = fr_one(); }
-    for (int t = 0; t <= 253; t++) {
-        if (lane == 2 && t == 148) acc = D;
-        if (lane < 4) hz_lad_captures(lane, t, num, den, vv, D, acc, ok);
-        bool active;
-        int el;
-        MtOps o;
-        Fr hn, hd;
-        if (lane == 0) {
-            active = t <= 252; el = t;
-            o = mt_head_dbl(D);
-            hn = D.W; hd = fr_add(D.V, D.V);
-        } else {
-            MtPt p1 = D, p2 = acc;
-            if (lane == 3) {
-                active = t < 83; el = 505 + t;
-                int tt = active ? t : 0;
-                int sel = (int)(s.bit(3 * tt) | (s.bit(3 * tt + 1) << 1) | (s.bit(3 * tt + 2) << 2));
-                p1 = acc; p2.U = tab[tt * 16 + 2 * sel]; p2.V = tab[tt * 16 + 2 * sel + 1]; p2.W = fr_one();
-            } else if (lane == 1) { active = t >= 1 && t <= 147; el = 253 + (t - 1); }
-            else if (lane == 2) { active = t >= 149; el = 400 + (t - 149); }
-            else { active = false; el = 0; }
-            o = mt_head_add(p1, p2);
-            hn = o.W12; hd = o.Dn;
-        }
-        MtPt r = mt_tail(o);
-        if (active) {
-            num[el] = hn; den[el] = hd;
-            if (fr_is_zero(hd)) ok = false;
-            if (lane == 0 || lane == 3) { if (lane == 0) D = r; else acc = r; }
-            else if (e.bit(t)) acc = r;
-        }
-        // every lane follows lane 0's point
-        D.U = hz_shfl8_fr(D.U, 0); D.V = hz_shfl8_fr(D.V, 0); D.W = hz_shfl8_fr(D.W, 0);
-    }
-    if (lane >= 1 && lane <= 3) hz_lad_capture(num, den, vv, 77 + lane, acc, ok);
-    hz_lad_finish(h, ok);
-}
-#else
-// The same walk with TWO lanes per role (lanes 2r, 2r+1 of the group; r = 0 doubling, 1 / 2 the adders of the
-// two segments, 3 the fixed-base adder): the 14 products of a point operation are split between the pair and
-// exchanged with lane-pair shuffles, 8 multiplication times per step instead of 18 (a doubling is the addition
-// of a point to itself with another slope, so all pairs run one instruction stream):
-//   head     half 0: X1 = U1 W2, Y1 = V1 W2, W12 = W1 W2       half 1: X2 = U2 W1, Y2 = V2 W1, Z = U1 U2
-//   slope    add: N = Y2 - Y1, Dn = X2 - X1                     double: N = 3 Z + 2 A X1 + W12, Dn = 2 Y1
-//   stage 1  half 0: S = Dn^2                                    half 1: NN = N^2
-//   stage 2  half 0: NN W12, X1 S                                half 1: (A W12 + X1 + X2) S, DS = Dn S
-//   stage 3  half 0: U3 = G Dn, W3 = DS W12                      half 1: N (X1 S - G), Y1 DS  (V3 = their difference)
-__device__ __forceinline__ Fr hz_swap1_fr(const Fr& v) {
-    Fr r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.l[i] = __shfl_xor_sync(0xffffffffu, v.l[i], 1, HZ_G);
-    return r;
-}
-__device__ __forceinline__ Fr hz_sel_fr(bool c, const Fr& a, const Fr& b) {
-    Fr r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.l[i] = c ? a.l[i] : b.l[i];
-    return r;
-}
-static __device__ __noinline__ void hz_hints_eddsa_lanes(HzHints* h, const Fr& px, const Fr& py, const BVT<MCompute, 8>& e,
-                                                 const BVT<MCompute, 8>& s) {
-    h->lad_ok = 0;
-    if (!h->scratch || !h->edtab) return;
-    __syncwarp();
-    Fr* hint = h->scratch; Fr* num = hint + HZ_SCR_ARR; Fr* den = num + HZ_SCR_ARR; Fr* vv = h->scratch + HZ_SCR_VV;
-    const int lane = (int)hz_glane(), role = lane >> 1;
-    const bool half = (lane & 1) != 0;
-    MtPt D;
-    {
-        Fr y1 = fr_add(fr_one(), py);
-        D.U = fr_mul_chain(y1, px); D.V = y1; D.W = fr_mul_chain(fr_sub(fr_one(), py), px);
-    }
-    bool ok = !fr_is_zero(D.W);
-    MtPt acc = D;
-    const Fr* tab = h->edtab;
-    if (role == 3) { acc.U = tab[83 * 16]; acc.V = tab[83 * 16 + 1]; acc.W = fr_one(); }
-    // the window entry of the fixed-base adder is read one step ahead: the load is off the step's critical path
-    Fr wnU = fr_zero(), wnV = fr_zero();
-    if (role == 3) { int sel = (int)(s.bit(0) | (s.bit(1) << 1) | (s.bit(2) << 2)); wnU = tab[2 * sel]; wnV = tab[2 * sel + 1]; }
-    for (int t = 0; t <= 253; t++) {
-        if (role == 2 && t == 148) acc = D;
-        if (!half) hz_lad_captures(role, t, num, den, vv, D, acc, ok);
-        bool active;
-        int el;
-        MtPt p1 = D, p2 = acc;
-        if (role == 0) { active = t <= 252; el = t; p2 = D; }
-        else if (role == 1) { active = t >= 1 && t <= 147; el = 253 + (t - 1); }
-        else if (role == 2) { active = t >= 149; el = 400 + (t - 149); }
-        else {
-            active = t < 83; el = 505 + t;
-            p1 = acc; p2.U = wnU; p2.V = wnV; p2.W = fr_one();
-            int tt = t + 1 < 83 ? t + 1 : 0;
-            int sel = (int)(s.bit(3 * tt) | (s.bit(3 * tt + 1) << 1) | (s.bit(3 * tt + 2) << 2));
-            wnU = tab[tt * 16 + 2 * sel]; wnV = tab[tt * 16 + 2 * sel + 1];
-        }
-        // head
-        const Fr b01 = hz_sel_fr(half, p1.W, p2.W);
-        const Fr m0 = fr_mul_chain(hz_sel_fr(half, p2.U, p1.U), b01);
-        const Fr m1 = fr_mul_chain(hz_sel_fr(half, p2.V, p1.V), b01);
-        const Fr m2 = fr_mul_chain(hz_sel_fr(half, p1.U, p1.W), hz_sel_fr(half, p2.U, p2.W));
-        const Fr o0 = hz_swap1_fr(m0), o1 = hz_swap1_fr(m1), o2 = hz_swap1_fr(m2);
-        const Fr X1 = hz_sel_fr(half, o0, m0), X2 = hz_sel_fr(half, m0, o0);
-        const Fr Y1 = hz_sel_fr(half, o1, m1), Y2 = hz_sel_fr(half, m1, o1);
-        const Fr W12 = hz_sel_fr(half, o2, m2), Z = hz_sel_fr(half, m2, o2);
-        Fr N, Dn, hn, hd;
-        if (role == 0) {
-            const Fr AX = fr_mul_small(X1, (uint32_t)HZ_MT_A);
-            N = fr_add(fr_add(fr_add(fr_add(Z, Z), Z), fr_add(AX, AX)), W12);
-            Dn = fr_add(Y1, Y1);
-            hn = D.W; hd = fr_add(D.V, D.V);
-        } else {
-            N = fr_sub(Y2, Y1); Dn = fr_sub(X2, X1);
-            hn = W12; hd = Dn;
-        }
-        // stage 1
-        const Fr q = half ? fr_mul_chain(N, N) : fr_mul_chain(Dn, Dn);
-        const Fr qo = hz_swap1_fr(q);
-        const Fr S = hz_sel_fr(half, qo, q), NN = hz_sel_fr(half, q, qo);
-        const Fr T = fr_add(fr_add(fr_mul_small(W12, (uint32_t)HZ_MT_A), X1), X2);
-        // stage 2
-        const Fr r0 = fr_mul_chain(hz_sel_fr(half, T, NN), hz_sel_fr(half, S, W12));
-        const Fr r1 = fr_mul_chain(hz_sel_fr(half, Dn, X1), S);
-        const Fr r0o = hz_swap1_fr(r0), r1o = hz_swap1_fr(r1);
-        const Fr G = fr_sub(hz_sel_fr(half, r0o, r0), hz_sel_fr(half, r0, r0o));
-        const Fr P2 = hz_sel_fr(half, r1o, r1), DS = hz_sel_fr(half, r1, r1o);
-        // stage 3
-        const Fr s0 = fr_mul_chain(hz_sel_fr(half, N, G), hz_sel_fr(half, fr_sub(P2, G), Dn));
-        const Fr s1 = fr_mul_chain(hz_sel_fr(half, Y1, DS), hz_sel_fr(half, DS, W12));
-        const Fr s0o = hz_swap1_fr(s0), s1o = hz_swap1_fr(s1);
-        MtPt r;
-        r.U = hz_sel_fr(half, s0o, s0); r.W = hz_sel_fr(half, s1o, s1);
-        r.V = fr_sub(hz_sel_fr(half, s0, s0o), hz_sel_fr(half, s1, s1o));
-        if (active) {
-            if (!half) { num[el] = hn; den[el] = hd; }
-            if (fr_is_zero(hd)) ok = false;
-            if (role == 0) D = r; else if (role == 3) acc = r; else if (e.bit(t)) acc = r;
-        }
-        // every lane follows the doubling pair's point
-        D.U = hz_shfl8_fr(D.U, 0); D.V = hz_shfl8_fr(D.V, 0); D.W = hz_shfl8_fr(D.W, 0);
-    }
-    if (!half && role >= 1) hz_lad_capture(num, den, vv, 77 + role, acc, ok);
-    hz_lad_finish(h, ok);
-}
-#endif
 
 // ---- k_ed_fill: the entries of the ladder steps from the ladder's data ------------------------------------
 // One thread per chunk of HZ_FILL_CH consecutive steps.  Entries per step (templates_circomlib.cuh):

@@ -46,6 +46,7 @@ static inline void hz_input_shape(const HzParams& P, int f, int& rank, uint32_t&
 struct HzLayout {
     HzPlan plan;
     std::vector<uint32_t> off_decode, off_rollup, off_fee, off_eddsa, off_jk;   // off_eddsa: start of phase F (getAx) per slot; off_jk: of phases J-K (processor1)
+    std::vector<uint32_t> off_hs, off_hsig;   // where the Poseidon components of the state hashes (4 per slot, then 2 per fee tx) and of the message hashes start
 };
 
 static inline bool hz_params_ok(const HzParams& P) {
@@ -60,6 +61,8 @@ static inline void hz_layout_walk(const HzParams& P, LayoutSink* sink, HzLayout&
     pl.P = P;
     pl.nbits = hz_pre_nbits(P);
     pl.nblocks = (pl.nbits + 64) / 512 + 1;
+    HzPoseidonStarts starts;
+    hz_poseidon_starts = &starts;
     Comp<MLayout> main(1, sink, "main");
     main.sig("hashGlobalInputs");
     for (int f = 0; f < IN_COUNT; f++) {
@@ -114,6 +117,12 @@ static inline void hz_layout_walk(const HzParams& P, LayoutSink* sink, HzLayout&
         (void)h;
     }
     pl.nvars = main.cur;
+    hz_poseidon_starts = nullptr;
+    R.off_hs = starts.t5; R.off_hsig = starts.t7;
+    if (R.off_hs.size() != (size_t)(4 * P.nTx + 2 * P.maxFeeTx) || R.off_hsig.size() != (size_t)P.nTx) {
+        fprintf(stderr, "hzw layout: %zu state hashes and %zu message hashes walked\n", R.off_hs.size(), R.off_hsig.size());
+        abort();
+    }
     pl.off_decode = R.off_decode.data(); pl.off_rollup = R.off_rollup.data(); pl.off_fee = R.off_fee.data();
 }
 

@@ -7,7 +7,8 @@
 struct HzCuda;   // device state of one context
 // returns null and sets *status (HZW_E_DEVICE) when no usable CUDA device / allocation failure
 HzCuda* hz_cuda_create(int device, const HzPlan& plan_host, const uint32_t* off_decode, const uint32_t* off_rollup,
-                       const uint32_t* off_fee, const uint32_t* off_eddsa, const uint32_t* off_jk, int* status);
+                       const uint32_t* off_fee, const uint32_t* off_eddsa, const uint32_t* off_jk,
+                       const uint32_t* off_hs /* 4 nTx + 2 maxFeeTx */, const uint32_t* off_hsig /* nTx */, int* status);
 void hz_cuda_destroy(HzCuda*);
 // inputs: n_inputs x 32 B host; witness_out: nvars x 32 B host or null (resident)
 int hz_cuda_calculate(HzCuda*, const uint8_t* inputs, int sanity, uint8_t* witness_out, float* kernel_ms,

@@ -4,7 +4,9 @@
 //   k_slots.cu    k_front, k_fee_front, k_edjob          (per tx slot / fee tx, from the main inputs)
 //   k_smtjob.cu   k_smtjob                               (SMT job records ahead of k_front)
 //   k_merkle.cu   k_smt, k_smt_levels, k_smt_zero, k_hole_pack, k_tail, the Poseidon-only kernels
-//   k_sig.cu      k_fix_consts, k_ed_const, k_eddsa, k_ed_fill
+//   k_sig.cu      k_fix_consts, k_ed_const, k_eddsa, k_eddsa_tail, k_ed_fill
+//   k_ladder.cu   k_ed_ladder, k_ed_hints
+//   k_poseidon.cu k_hstate, k_sighash                    (state hashes and message hashes, transposed)
 //   k_hasher.cu   k_pack, k_unpack, k_hash_head, k_sha_chain, k_sha_blocks, k_hash_tail, k_withdraw
 //   hzw_run.cu    device memory, streams and the launch order (hz_cuda_*)
 #pragma once
@@ -39,6 +41,10 @@ struct HzCuda {
     HzSmtJob* smt;             // 2 nTx + maxFeeTx: from k_smtjob (slots) and k_fee_front
     HzSmtJob* smt_front;       // 2 nTx: the same as k_front arrives at them (k_tail compares)
     uint32_t* off_jk;          // nTx: where phases J-K of each slot start
+    Fr* hs_in;                 // 4 x (4 nTx + 2 maxFeeTx): inputs of every state hash (k_smtjob, k_fee_front -> k_hstate)
+    uint32_t* hs_cur;          // 4 nTx + 2 maxFeeTx: where their Poseidon components start
+    Fr* sig_in;                // 6 x nTx: inputs of the message hashes (k_edjob -> k_sighash)
+    uint32_t* hsig_cur;        // nTx: where decodeTx[i].hashSig starts
     HzSmtMid* mids;            // 2 nTx + maxFeeTx
     HzLevJob* lev;             // 2 nTx + maxFeeTx: what k_smt leaves for k_smt_levels
     Fr* smst;                  // per processor (nLevels + 1) x 6 state-machine values
@@ -124,9 +130,11 @@ __host__ __device__ static inline HzHeadOff hz_head_off(const HzPlan& pl) {
 __global__ void k_poseidon_pairs(const Fr* in, Fr* sig, Fr* digests, int npairs);
 __global__ void k_poseidon_t3(const Fr* in, Fr* sig, Fr* digests, int nperms);
 __global__ void k_front(HzPlan pl, Fr* w, uint8_t* preb, HzErrBuf* err, HzEddsaJob* jobs, HzSmtJob* smt, Fr* isExit, int s0, int ns);
-__global__ void k_smtjob(HzPlan pl, Fr* w, HzSmtJob* smt, Fr* isExit, const uint32_t* off_jk, int s0, int ns);
-__global__ void k_edjob(HzPlan pl, const Fr* w, HzEddsaJob* jobs, const uint32_t* off_eddsa, int s0, int ns);
-__global__ void k_fee_front(HzPlan pl, Fr* w, HzErrBuf* err, HzSmtJob* smt, int f0, int nf);
+__global__ void k_smtjob(HzPlan pl, Fr* w, HzSmtJob* smt, Fr* isExit, const uint32_t* off_jk, Fr* hs_in, int s0, int ns);
+__global__ void k_hstate(Fr* w, const Fr* hs_in, const uint32_t* hs_cur, HzSmtJob* smt, int nTx, int s0, int ns, int f0, int nf);
+__global__ void k_sighash(Fr* w, const Fr* sig_in, const uint32_t* hsig_cur, HzEddsaJob* jobs, int s0, int ns);
+__global__ void k_edjob(HzPlan pl, const Fr* w, HzEddsaJob* jobs, const uint32_t* off_eddsa, Fr* sig_in, int s0, int ns);
+__global__ void k_fee_front(HzPlan pl, Fr* w, HzErrBuf* err, HzSmtJob* smt, Fr* hs_in, int f0, int nf);
 __global__ void k_smt(HzPlan pl, Fr* w, HzErrBuf* err, const HzSmtJob* smt, HzSmtMid* mids, HzLevJob* lev, Fr* smst, int s0, int ns, int f0, int nf);
 __global__ void k_smt_levels(HzPlan pl, Fr* w, const HzLevJob* jobs, const Fr* smst, HzSmtMid* mids, const Fr* img00, uint8_t* zflag, int s0, int ns, int f0, int nf);
 __global__ void k_hole_pack(HzPlan pl, const Fr* w, const HzLevJob* jobs, const uint8_t* zflag, HzHole* holes, Fr* gl, int s0, int ns, int f0, int nf);
@@ -134,6 +142,9 @@ __global__ void k_smt_zero(HzPlan pl, Fr* w, const HzLevJob* jobs, const Fr* img
 __global__ void k_fix_consts(Fr* wtmp, Fr* cst, Fr* tab, uint32_t* counts);
 __global__ void k_ed_const(HzPlan pl, Fr* w, const uint32_t* off_eddsa, const Fr* img, uint32_t fix_size, int s0, int ns);
 __global__ void k_eddsa(HzPlan pl, Fr* w, HzErrBuf* err, const HzEddsaJob* jobs, const Fr* cst, const Fr* tab, const Fr* img, Fr* scratch, uint32_t win_size, int s0, int ns);
+__global__ void k_eddsa_tail(Fr* w, HzErrBuf* err, const Fr* cst, const Fr* tab, const Fr* img, Fr* scratch, uint32_t win_size, int ns);
+__global__ void k_ed_ladder(Fr* scratch, const Fr* tab, int ns);
+__global__ void k_ed_hints(Fr* scratch, int ns);
 __global__ void k_ed_fill(Fr* w, HzErrBuf* err, const Fr* tab, const Fr* scratch, uint32_t win_stride, int ns);
 __global__ void k_tail(HzPlan pl, Fr* w, HzErrBuf* err, HzErrBuf* ebuf, const HzSmtMid* mids, const Fr* isExit, const Fr* isExit_front,
                        const HzEddsaJob* jobs, const HzEddsaJob* jobs_front, const HzSmtJob* smt, const HzSmtJob* smt_front, int s0, int ns, int f0, int nf);

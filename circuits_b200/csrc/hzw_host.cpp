@@ -38,7 +38,7 @@ struct CudaBackend : HzBackend {
 };
 
 HzBackend* hz_backend_create(const hzw_params& prm, const HzLayout& L, int* status) {
-    HzCuda* d = hz_cuda_create(prm.device, L.plan, L.off_decode.data(), L.off_rollup.data(), L.off_fee.data(), L.off_eddsa.data(), L.off_jk.data(), status);
+    HzCuda* d = hz_cuda_create(prm.device, L.plan, L.off_decode.data(), L.off_rollup.data(), L.off_fee.data(), L.off_eddsa.data(), L.off_jk.data(), L.off_hs.data(), L.off_hsig.data(), status);
     if (!d) return nullptr;
     CudaBackend* b = new CudaBackend(d);
     b->L = &L;

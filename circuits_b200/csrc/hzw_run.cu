@@ -5,7 +5,8 @@
 static void hz_set_ranges(HzCuda* d, int rank, int world);
 
 HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode, const uint32_t* off_rollup,
-                       const uint32_t* off_fee, const uint32_t* off_eddsa, const uint32_t* off_jk, int* status) {
+                       const uint32_t* off_fee, const uint32_t* off_eddsa, const uint32_t* off_jk,
+                       const uint32_t* off_hs, const uint32_t* off_hsig, int* status) {
     *status = HZW_E_DEVICE;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -36,6 +37,13 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaMalloc(&d->off_jk, 4ull * P.nTx) == cudaSuccess;
     ok = ok && cudaMemcpy(d->off_jk, off_jk, 4ull * P.nTx, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMalloc(&d->smt_front, sizeof(HzSmtJob) * 2 * P.nTx) == cudaSuccess;
+    {
+        const size_t nhs = (size_t)4 * P.nTx + 2 * P.maxFeeTx;
+        ok = ok && cudaMalloc(&d->hs_in, sizeof(Fr) * 4 * nhs) == cudaSuccess && cudaMalloc(&d->hs_cur, 4 * nhs) == cudaSuccess;
+        ok = ok && cudaMemcpy(d->hs_cur, off_hs, 4 * nhs, cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->sig_in, sizeof(Fr) * 6 * (size_t)P.nTx) == cudaSuccess && cudaMalloc(&d->hsig_cur, 4ull * P.nTx) == cudaSuccess;
+        ok = ok && cudaMemcpy(d->hsig_cur, off_hsig, 4ull * P.nTx, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
     ok = ok && cudaMalloc(&d->isExit_front, sizeof(Fr) * P.nTx) == cudaSuccess;
     ok = ok && cudaMemcpy(d->off_eddsa, off_eddsa, 4ull * P.nTx, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMalloc(&d->smt, sizeof(HzSmtJob) * (2 * P.nTx + P.maxFeeTx)) == cudaSuccess;
@@ -92,6 +100,10 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
         cudaFuncSetAttribute(k_smt, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_smt_levels, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_tail, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_hstate, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_sighash, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_ed_ladder, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_eddsa_tail, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     }
     // the per-thread frames of the circuit templates are large (sibling arrays, state machines)
     ok = ok && cudaDeviceSetLimit(cudaLimitStackSize, 80 * 1024) == cudaSuccess;
@@ -142,6 +154,7 @@ void hz_cuda_destroy(HzCuda* d) {
     if (!d) return;
     cudaSetDevice(d->device);
     cudaFree(d->w); cudaFree(d->pre); cudaFree(d->chain); cudaFree(d->msgw); cudaFree(d->shawk); cudaFree(d->jobs); cudaFree(d->jobs_front); cudaFree(d->off_eddsa); cudaFree(d->off_jk); cudaFree(d->smt_front); cudaFree(d->isExit_front); cudaFree(d->err);
+    cudaFree(d->hs_in); cudaFree(d->hs_cur); cudaFree(d->sig_in); cudaFree(d->hsig_cur);
     cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit); cudaFree(d->lev); cudaFree(d->smst); cudaFree(d->img00); cudaFree(d->zflag); cudaFree(d->holes); cudaFree(d->gl); cudaFreeHost(d->h_holes); cudaFreeHost(d->h_gl); cudaFreeHost(d->h_img00);
     cudaFree(d->hint_cst); cudaFree(d->hint_tab); cudaFree(d->hint_img); cudaFree(d->hint_scratch); cudaFree(d->recs);
     cudaFree(d->off_decode); cudaFree(d->off_rollup); cudaFree(d->off_fee); cudaFree(d->off_blocks);
@@ -206,16 +219,20 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     CK(cudaStreamWaitEvent(s2, d->ev0, 0));
     CK(cudaEventRecord(d->kev[9], s2));
     if (ns > 0) {
-        d->n_launch++, k_edjob<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, d->jobs, d->off_eddsa, s0, ns);
+        d->n_launch++, k_edjob<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, d->jobs, d->off_eddsa, d->sig_in, s0, ns);
+        d->n_launch++, k_sighash<<<(unsigned)((ns + 31) / 32), 224, 0, s2>>>(d->w, d->sig_in, d->hsig_cur, d->jobs, s0, ns);
         d->n_launch++, k_ed_const<<<592, 256, 0, s2>>>(pl, d->w, d->off_eddsa, d->hint_img, d->fix_size, s0, ns);
             d->n_launch++, k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, s0, ns);
+            d->n_launch++, k_ed_ladder<<<(unsigned)((ns + 31) / 32), 96, 0, s2>>>(d->hint_scratch, d->hint_tab, ns);
+            d->n_launch++, k_ed_hints<<<(unsigned)((ns + 3) / 4), 128, 0, s2>>>(d->hint_scratch, ns);
+            d->n_launch++, k_eddsa_tail<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(d->w, err, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, ns);
         d->n_launch++, k_ed_fill<<<(unsigned)((HZ_FILL_PER_SIG * ns + 127) / 128), 128, 0, s2>>>(d->w, err, d->hint_tab, d->hint_scratch, d->win_stride, ns);
     }
     CK(cudaEventRecord(d->kev[10], s2));
     CK(cudaEventRecord(d->ev_eddsa, s2));
     // the fee transactions need nothing but inputs either: third stream, joined before the merkle kernels
     CK(cudaStreamWaitEvent(d->stream3, d->ev0, 0));
-    if (nf > 0) d->n_launch++, k_fee_front<<<hz_grid(nf), HZ_BLOCK, 0, d->stream3>>>(pl, d->w, err, d->smt + 2 * pl.P.nTx, f0, nf);
+    if (nf > 0) d->n_launch++, k_fee_front<<<hz_grid(nf), HZ_BLOCK, 0, d->stream3>>>(pl, d->w, err, d->smt + 2 * pl.P.nTx, d->hs_in, f0, nf);
     CK(cudaEventRecord(d->ev_fee, d->stream3));
     // k_front on a stream of its own: the merkle kernels take their jobs from k_smtjob
     CK(cudaStreamWaitEvent(d->stream4, d->ev0, 0));
@@ -224,9 +241,11 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     CK(cudaEventRecord(d->kev[12], d->stream4));
     CK(cudaEventRecord(d->ev_front, d->stream4));
     CK(cudaEventRecord(d->kev[0], s));
-    if (ns > 0) d->n_launch++, k_smtjob<<<hz_grid(ns), HZ_BLOCK, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, s0, ns);
-    CK(cudaEventRecord(d->kev[1], s));
+    if (ns > 0) d->n_launch++, k_smtjob<<<hz_grid(ns), HZ_BLOCK, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, d->hs_in, s0, ns);
     CK(cudaStreamWaitEvent(s, d->ev_fee, 0));
+    // the state hashes of the slots and fee txs, transposed: their digests complete the job records
+    if (4 * ns + 2 * nf > 0) d->n_launch++, k_hstate<<<(unsigned)((4 * ns + 2 * nf + 31) / 32), 160, 0, s>>>(d->w, d->hs_in, d->hs_cur, d->smt, pl.P.nTx, s0, ns, f0, nf);
+    CK(cudaEventRecord(d->kev[1], s));
     CK(cudaEventRecord(d->kev[2], s));
     if (2 * ns + nf > 0) {
         d->n_launch++, k_smt<<<hz_grid(2 * ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, f0, nf);
@@ -395,15 +414,17 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
     CK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(d->w) + 64, inputs, 32ull * pl.n_inputs, cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(d->ev0, s));
     CK(cudaStreamWaitEvent(s2, d->ev0, 0));
-    d->n_launch++, k_edjob<<<hz_grid(P.nTx), HZ_BLOCK, 0, s2>>>(pl, d->w, d->jobs, d->off_eddsa, 0, P.nTx);
+    d->n_launch++, k_edjob<<<hz_grid(P.nTx), HZ_BLOCK, 0, s2>>>(pl, d->w, d->jobs, d->off_eddsa, d->sig_in, 0, P.nTx);
+    d->n_launch++, k_sighash<<<(unsigned)((P.nTx + 31) / 32), 224, 0, s2>>>(d->w, d->sig_in, d->hsig_cur, d->jobs, 0, P.nTx);
     CK(cudaStreamWaitEvent(d->stream4, d->ev0, 0));
     d->n_launch++, k_front<<<hz_grid(P.nTx), HZ_BLOCK, 0, d->stream4>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt_front, d->isExit_front, 0, P.nTx);
     CK(cudaEventRecord(d->ev_front, d->stream4));
-    d->n_launch++, k_smtjob<<<hz_grid(P.nTx), HZ_BLOCK, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, 0, P.nTx);
+    d->n_launch++, k_smtjob<<<hz_grid(P.nTx), HZ_BLOCK, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, d->hs_in, 0, P.nTx);
     CK(cudaStreamWaitEvent(s3, d->ev_front, 0));
     CK(cudaStreamWaitEvent(s6, d->ev_front, 0));
     const int F = P.maxFeeTx, h0 = P.nTx / 2;
-    d->n_launch++, k_fee_front<<<hz_grid(F), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt + 2 * P.nTx, 0, F);
+    d->n_launch++, k_fee_front<<<hz_grid(F), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt + 2 * P.nTx, d->hs_in, 0, F);
+    d->n_launch++, k_hstate<<<(unsigned)((4 * P.nTx + 2 * F + 31) / 32), 160, 0, s>>>(d->w, d->hs_in, d->hs_cur, d->smt, P.nTx, 0, P.nTx, 0, F);
     // w[0], w[1] are written by the hasher at the end: entries [2, decodeTx[0]) and the decode ranges go now
     CK(piece(2, d->h_off_rollup0));
     for (int h = 0; h < 2; h++) {
@@ -411,6 +432,9 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
         if (ns > 0) {
             d->n_launch++, k_ed_const<<<592, 256, 0, s2>>>(pl, d->w, d->off_eddsa, d->hint_img, d->fix_size, s0, ns);
             d->n_launch++, k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, s0, ns);
+            d->n_launch++, k_ed_ladder<<<(unsigned)((ns + 31) / 32), 96, 0, s2>>>(d->hint_scratch, d->hint_tab, ns);
+            d->n_launch++, k_ed_hints<<<(unsigned)((ns + 3) / 4), 128, 0, s2>>>(d->hint_scratch, ns);
+            d->n_launch++, k_eddsa_tail<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(d->w, err, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, ns);
             d->n_launch++, k_ed_fill<<<(unsigned)((HZ_FILL_PER_SIG * ns + 127) / 128), 128, 0, s2>>>(d->w, err, d->hint_tab, d->hint_scratch, d->win_stride, ns);
         }
         CK(cudaEventRecord(d->ev_ed[h], s2));

@@ -191,11 +191,11 @@ __global__ void __launch_bounds__(HZ_BLOCK) k_tail(HzPlan pl, Fr* w, HzErrBuf* e
         if (real && hz_glane() == 0) {
             const HzEddsaJob &a = jobs[i], &b = jobs_front[i];
             bool same = fr_eq(a.aySignature, b.aySignature) && fr_eq(a.signSignature, b.signSignature) && fr_eq(a.enabled, b.enabled) &&
-                        fr_eq(a.s1Ay, b.s1Ay) && fr_eq(a.S, b.S) && fr_eq(a.R8x, b.R8x) && fr_eq(a.R8y, b.R8y) && fr_eq(a.M, b.M) && a.cur == b.cur;
+                        fr_eq(a.s1Ay, b.s1Ay) && fr_eq(a.S, b.S) && fr_eq(a.R8x, b.R8x) && fr_eq(a.R8y, b.R8y) && a.cur == b.cur;      // (M and the state hashes come from k_sighash / k_hstate on one side only)
             for (int k = 0; k < 2; k++) {
                 const HzSmtJob &p = smt[2 * i + k], &q2 = smt_front[2 * i + k];
-                same = same && fr_eq(p.oldKey, q2.oldKey) && fr_eq(p.oldValue, q2.oldValue) && fr_eq(p.isOld0, q2.isOld0) && fr_eq(p.newKey, q2.newKey) &&
-                       fr_eq(p.newValue, q2.newValue) && fr_eq(p.fnc0, q2.fnc0) && fr_eq(p.fnc1, q2.fnc1) && p.cur == q2.cur && p.sib == q2.sib && p.sigmask == q2.sigmask;
+                same = same && fr_eq(p.oldKey, q2.oldKey) && fr_eq(p.isOld0, q2.isOld0) && fr_eq(p.newKey, q2.newKey) && fr_eq(p.hsel, q2.hsel) &&
+                       fr_eq(p.fnc0, q2.fnc0) && fr_eq(p.fnc1, q2.fnc1) && p.cur == q2.cur && p.sib == q2.sib && p.sigmask == q2.sigmask && p.ovidx == q2.ovidx;
             }
             same = same && fr_eq(isExit[i], isExit_front[i]);
             if (!same) atomicAdd(&ebuf->pad, 1u);

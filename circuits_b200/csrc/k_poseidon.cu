@@ -1,0 +1,84 @@
+// The Poseidon permutations outside the merkle levels, transposed (see hzw_dev.cuh for the map of the kernels).
+//
+// A slot has four state hashes (HashState, width 5: src/lib/hash-state.circom via src/rollup-tx.circom:297-312,517-532),
+// a fee tx two (src/fee-tx.circom), and a slot's message hash has width 7 (src/decode-tx.circom:254-283).  In the
+// lane-group kernels each of them kept eight lanes busy for 68 rounds with one active lane in the partial rounds, one
+// after the other.  Here thread (warp r, lane c) holds state element r of permutation c, a block of T warps runs 32
+// permutations (as k_smt_levels does for the level hashes): all state hashes of the batch are one launch of 260 blocks,
+// and their digests complete the job records of the merkle processors.  The components' own entries are written here;
+// the template kernels (k_front, k_fee_front, k_smtjob) step over them (Comp::skip_hash).
+#include "hzw_dev.cuh"
+
+template <int T> __device__ __forceinline__ Fr hz_poseidon_tr(uint32_t (*xch)[T][8][32], int r, int c, Fr s, Fr* hw, bool real) {
+    const int rp = poseidon_rp(T), R = 8 + rp;
+    const Fr* C = &hz_poseidon_c(T, 0);
+    Fr m[T];
+#pragma unroll
+    for (int k = 0; k < T; k++) m[k] = hz_poseidon_mr(T, r)[k];
+    if (r == 0 && real) hz_store_fr(&hw[0], s);                 // ark[0].in[0] = 0
+    uint32_t cur = 1;
+    for (int i = 0; i < R; i++) {
+        s = fr_add(s, C[T * i + r]);
+        if (real) hz_store_fr(&hw[cur + r], s);
+        const bool full = i < 4 || i >= rp + 4;
+        const uint32_t sg = cur + 2 * T;
+        if (full || r == 0) {                                   // warp-uniform
+            Fr in2 = fr_mul_chain(s, s);
+            Fr in4 = fr_mul_chain(in2, in2);
+            s = fr_mul_chain(in4, s);
+            if (real) { hz_store_fr(&hw[sg + 3 * r], s); hz_store_fr(&hw[sg + 3 * r + 1], in2); hz_store_fr(&hw[sg + 3 * r + 2], in4); }
+        }
+        uint32_t (*buf)[8][32] = xch[i & 1];
+#pragma unroll
+        for (int k = 0; k < 8; k++) buf[r][k][c] = s.l[k];
+        __syncthreads();
+        Fr a[T];
+#pragma unroll
+        for (int q = 0; q < T; q++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) a[q].l[k] = buf[q][k][c];
+        s = fr_dot_mont_chain<T>(a, m);
+        if (real) hz_store_fr(&hw[cur + T + r], s);
+        cur += 2 * T + (full ? 3 * T : 3);
+    }
+    return s;
+}
+
+// all HashState permutations of the shard: 4 per own slot (old state 1, old state 2, new state 1, new state 2), then 2
+// per own fee tx (old, new).  hs_in: their 4 inputs each, recorded by k_smtjob / k_fee_front; hs_cur: where each
+// component starts (layout walk).  The digests complete the job records: newValue, and oldValue behind its multiplexer.
+__global__ void __launch_bounds__(160) k_hstate(Fr* w, const Fr* hs_in, const uint32_t* hs_cur, HzSmtJob* smt, int nTx, int s0, int ns, int f0, int nf) {
+    __shared__ uint32_t xch[2][5][8][32];
+    const int r = (int)(threadIdx.x >> 5), c = (int)(threadIdx.x & 31);
+    const int P = 4 * ns + 2 * nf;
+    int p = (int)blockIdx.x * 32 + c;
+    const bool real = p < P;
+    if (!real) p = P - 1;
+    int idx, jobi; bool is_new;
+    if (p < 4 * ns) { const int i = s0 + p / 4, k = p % 4; idx = 4 * i + k; jobi = 2 * i + (k & 1); is_new = k >= 2; }
+    else { const int q = p - 4 * ns, i = f0 + q / 2, k = q % 2; idx = 4 * nTx + 2 * i + k; jobi = 2 * nTx + i; is_new = k == 1; }
+    const Fr s = r == 0 ? fr_zero() : hs_in[4 * (size_t)idx + (r - 1)];
+    const Fr d = hz_poseidon_tr<5>(xch, r, c, s, w + hs_cur[idx], real);
+    if (r == 0 && real) {
+        HzSmtJob* j = &smt[jobi];
+        if (is_new) j->newValue = d;
+        else {
+            const Fr ov = fr_add(j->oldValue, fr_mul(fr_sub(fr_one(), j->hsel), d));
+            j->oldValue = ov;
+            if (j->ovidx != HZ_NOIDX) hz_store_fr(&w[j->ovidx], ov);          // s1OldValue / s2OldValue .mux.out[0]
+        }
+    }
+}
+
+// the message hash of every own slot: sig_in = its 6 inputs (k_edjob), hsig_cur = where decodeTx[i].hashSig starts
+__global__ void __launch_bounds__(224) k_sighash(Fr* w, const Fr* sig_in, const uint32_t* hsig_cur, HzEddsaJob* jobs, int s0, int ns) {
+    __shared__ uint32_t xch[2][7][8][32];
+    const int r = (int)(threadIdx.x >> 5), c = (int)(threadIdx.x & 31);
+    int p = (int)blockIdx.x * 32 + c;
+    const bool real = p < ns;
+    if (!real) p = ns - 1;
+    const int i = s0 + p;
+    const Fr s = r == 0 ? fr_zero() : sig_in[6 * (size_t)i + (r - 1)];
+    const Fr d = hz_poseidon_tr<7>(xch, r, c, s, w + hsig_cur[i], real);
+    if (r == 0 && real) jobs[i].M = d;
+}

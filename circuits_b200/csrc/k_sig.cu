@@ -19,20 +19,62 @@ __global__ void __launch_bounds__(256) k_ed_const(HzPlan pl, Fr* w, const uint32
     }
 }
 
+// The signature of a slot in two kernels with the ladder walk between them (k_ladder.cu):
+//   k_eddsa       getAx (the square root) and the first half of the verifier: bits of S and of the message hash,
+//                 the three doublings of A; leaves 8A, the scalar bits and where the second half starts in the
+//                 scratch area of its lane group (HzFillRec, HZ_SCR_MID)
+//   k_eddsa_tail  the second half: both scalar multiplications with the ladders' hints, the final comparison
+__device__ __forceinline__ HzHints hz_sig_hints(const Fr* cst, const Fr* tab, const Fr* img, Fr* scratch, uint32_t win_size) {
+    HzHints h;
+    h.cst = cst; h.ci = 0; h.dat = nullptr; h.di = 0; h.rec = nullptr; h.ri = 0;
+    h.edtab = tab; h.edrec = nullptr; h.ei = 0; h.lad_ok = 0; h.fill = 1; h.prefilled = 1; h.win_c0 = 0; h.win_size = win_size; h.cimg = img; h.fix_shift = 0;
+    h.scratch = scratch + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) / HZ_G) * HZ_HINT_SCRATCH;   // per group, not per slot: padding groups redo a slot
+    return h;
+}
 __global__ void __launch_bounds__(HZ_BLOCK, 3) k_eddsa(HzPlan pl, Fr* w, HzErrBuf* err, const HzEddsaJob* jobs,
                                                     const Fr* cst, const Fr* tab, const Fr* img, Fr* scratch, uint32_t win_size, int s0, int ns) {
     bool real; int i = s0 + hz_item(ns, real);
     const HzEddsaJob& j = jobs[i];
-    HzHints h;
-    h.cst = cst; h.ci = 0; h.dat = nullptr; h.di = 0; h.rec = nullptr; h.ri = 0;
-    h.edtab = tab; h.edrec = nullptr; h.ei = 0; h.lad_ok = 0; h.fill = 1; h.prefilled = 1; h.win_c0 = 0; h.win_size = win_size; h.cimg = img; h.fix_shift = 0; h.scratch = scratch + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) / HZ_G) * HZ_HINT_SCRATCH;   // per group, not per slot: padding groups redo a slot
+    HzHints h = hz_sig_hints(cst, tab, img, scratch, win_size);
     HzPending pend; pend.n = 0;
     Comp<MCompute> c(w, j.cur, real ? err : nullptr, &h, &pend);
     VC vse, sgn, ay, s1Ay, S, R8x, R8y, Msg;
     vse.v = j.enabled; sgn.v = j.signSignature; ay.v = j.aySignature; s1Ay.v = j.s1Ay;
     S.v = j.S; R8x.v = j.R8x; R8y.v = j.R8y; Msg.v = j.M;
     vse.sig = sgn.sig = ay.sig = s1Ay.sig = S.sig = R8x.sig = R8y.sig = Msg.sig = true;
-    hz_phaseF(c, vse, sgn, ay, s1Ay, S, R8x, R8y, Msg);
+    VC ax = AySign2Ax(c.sub("getAx"), ay, sgn);
+    EdMid<MCompute> m;
+    uint32_t cur;
+    {
+        Comp<MCompute> sv = c.sub("sigVerifier");
+        EdDSAPoseidonVerifierHead(sv, vse, ax, s1Ay, S, R8x, R8y, Msg, m);
+        cur = sv.cur;
+    }
+    c.flush_pending();
+    if (hz_glane() == 0) {
+        HzFillRec* rec = reinterpret_cast<HzFillRec*>(h.scratch + HZ_SCR_REC);
+        rec->ok = 0; rec->cur = cur;
+        for (int k = 0; k < 8; k++) { rec->e[k] = m.hbits.val[k]; rec->s[k] = m.sbits.val[k]; }
+        Fr* mid = h.scratch + HZ_SCR_MID;
+        mid[0] = m.d3.x.v; mid[1] = m.d3.y.v; mid[2] = m.en.v; mid[3] = m.R8x.v; mid[4] = m.R8y.v;
+    }
+}
+__global__ void __launch_bounds__(HZ_BLOCK, 3) k_eddsa_tail(Fr* w, HzErrBuf* err, const Fr* cst, const Fr* tab, const Fr* img, Fr* scratch,
+                                                         uint32_t win_size, int ns) {
+    bool real; const int g = hz_item(ns, real);
+    HzHints h = hz_sig_hints(cst, tab, img, scratch, win_size);
+    h.scratch = scratch + (size_t)g * HZ_HINT_SCRATCH;               // the ladder kernels worked per signature
+    const HzFillRec rec = *reinterpret_cast<const HzFillRec*>(h.scratch + HZ_SCR_REC);
+    h.lad_ok = (int)rec.ok;
+    HzPending pend; pend.n = 0;
+    Comp<MCompute> c(w, rec.cur, real ? err : nullptr, &h, &pend);
+    EdMid<MCompute> m;
+    const Fr* mid = h.scratch + HZ_SCR_MID;
+    m.d3.x.v = mid[0]; m.d3.y.v = mid[1]; m.en.v = mid[2]; m.R8x.v = mid[3]; m.R8y.v = mid[4];
+    m.d3.x.sig = m.d3.y.sig = m.en.sig = m.R8x.sig = m.R8y.sig = true;
+    m.hbits.clear(254); m.sbits.clear(253);
+    for (int k = 0; k < 8; k++) { m.hbits.val[k] = rec.e[k]; m.hbits.sg[k] = 0xffffffffu; m.sbits.val[k] = rec.s[k]; m.sbits.sg[k] = 0xffffffffu; }
+    EdDSAPoseidonVerifierTail(c, m);
     c.flush_pending();
 }
 

@@ -8,6 +8,7 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_front(HzPlan pl, Fr* w, uint8_t
     SlotHook<MCompute> hook; hook.eddsa = &jobs[i]; hook.smt = &smt[2 * i]; hook.isExit = &isExit[i]; hook.sz = &pl.sz;
     HzPending pend; pend.n = 0;
     Comp<MCompute> c(w, pl.off_decode[i], real ? err : nullptr, nullptr, &pend);
+    c.skip_hash = true;                      // the message hash and the four state hashes: k_sighash, k_hstate
     DecodeOut<MCompute> d;
     sec_decode(c, pl, i, d, pre);
     c.cur = pl.off_rollup[i];
@@ -24,7 +25,7 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_front(HzPlan pl, Fr* w, uint8_t
 // This kernel derives them from the inputs with the formulas of those templates, so k_eddsa starts at
 // once instead of after k_front.  k_front still records the job the templates arrive at; k_tail compares
 // the two when the sanity check is on.
-__global__ void __launch_bounds__(HZ_BLOCK, 3) k_edjob(HzPlan pl, const Fr* w, HzEddsaJob* jobs, const uint32_t* off_eddsa, int s0, int ns) {
+__global__ void __launch_bounds__(HZ_BLOCK, 3) k_edjob(HzPlan pl, const Fr* w, HzEddsaJob* jobs, const uint32_t* off_eddsa, Fr* sig_in, int s0, int ns) {
     bool real; int i = s0 + hz_item(ns, real);
     const int lane = (int)hz_glane();
     auto in = [&](int f) -> Fr { return w[pl.in_off[f] + (uint32_t)i * pl.in_d1[f]]; };
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_edjob(HzPlan pl, const Fr* w, H
     Fr hs = fr_zero();
     if (lane == 1) hs = txc; else if (lane == 2) hs = e1; else if (lane == 3) hs = in(IN_toBjjAy);
     else if (lane == 4) hs = in(IN_rqTxCompressedDataV2); else if (lane == 5) hs = in(IN_rqToEthAddr); else if (lane == 6) hs = in(IN_rqToBjjAy);
-    const Fr M = hz_poseidon_lanes<7, true>(nullptr, 0, hs, 0);
+    if (lane >= 1 && lane <= 6) sig_in[6 * (size_t)i + (lane - 1)] = hs;          // k_sighash hashes them into jobs[i].M
     // decodeFromBjj: ay = bits 0..253 (mod p), sign = bit 255; the lanes read every 8th bit each
     uint32_t bl[8];
 #pragma unroll
@@ -68,14 +69,16 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_edjob(HzPlan pl, const Fr* w, H
     if (lane == 0) {
         HzEddsaJob& j = jobs[i];
         j.aySignature = fr_mul(s1Ay, vse); j.signSignature = fr_mul(s1Sign, vse); j.enabled = vse; j.s1Ay = s1Ay;
-        j.S = in(IN_s); j.R8x = in(IN_r8x); j.R8y = in(IN_r8y); j.M = M; j.cur = off_eddsa[i];
+        j.S = in(IN_s); j.R8x = in(IN_r8x); j.R8y = in(IN_r8y); j.cur = off_eddsa[i];
     }
 }
 
-__global__ void __launch_bounds__(HZ_BLOCK) k_fee_front(HzPlan pl, Fr* w, HzErrBuf* err, HzSmtJob* smt, int f0, int nf) {
+__global__ void __launch_bounds__(HZ_BLOCK) k_fee_front(HzPlan pl, Fr* w, HzErrBuf* err, HzSmtJob* smt, Fr* hs_in, int f0, int nf) {
     bool real; int i = f0 + hz_item(nf, real);
     HzPending pend; pend.n = 0;
     Comp<MCompute> c(w, pl.off_fee[i], real ? err : nullptr, nullptr, &pend);
+    int hs_n = 0;
+    c.skip_hash = true; c.hs_rec = hs_in + 4 * (size_t)(4 * pl.P.nTx + 2 * i); c.hs_n = &hs_n;      // its two state hashes: k_hstate
     FeeHook<MCompute> hook; hook.smt = &smt[i];
     hook.sib_idx = pl.in_off[IN_siblings3] + (uint32_t)i * pl.in_d1[IN_siblings3];
     sec_fee(c, pl, i, hook, true);

@@ -8,12 +8,15 @@
 // skipped, decodeTx reduced to the fields rollupTx reads -- so the merkle kernels start after a fraction of
 // k_front's time, and k_front itself runs beside them.  k_front still records the jobs it arrives at; k_tail
 // compares the two (always: a difference is an internal error, HzErrBuf.pad).
-__global__ void __launch_bounds__(HZ_BLOCK, 3) k_smtjob(HzPlan pl, Fr* w, HzSmtJob* smt, Fr* isExit, const uint32_t* off_jk, int s0, int ns) {
+__global__ void __launch_bounds__(HZ_BLOCK, 3) k_smtjob(HzPlan pl, Fr* w, HzSmtJob* smt, Fr* isExit, const uint32_t* off_jk, Fr* hs_in, int s0, int ns) {
     bool real; int i = s0 + hz_item(ns, real);
     Comp<MCompute> c(w, pl.off_rollup[i], nullptr);
     c.dry = true;
+    int hs_n = 0;
+    c.skip_hash = true; c.hs_rec = hs_in + 16 * (size_t)i; c.hs_n = &hs_n;       // the four state hashes: inputs recorded for k_hstate
     DecodeOut<MCompute> d;
     hz_decode_lite(c, pl, i, d);
+    c.cur = pl.off_rollup[i];                 // the decode fields were evaluated on this context: back to where rollupTx[i] starts
     PreBits<MCompute> pre; pre.b = nullptr;
     SlotHook<MCompute> hook; hook.eddsa = nullptr; hook.smt = &smt[2 * i]; hook.isExit = &isExit[i]; hook.sz = &pl.sz; hook.jobs_only = true;
     RollupTxOut<MCompute> o;

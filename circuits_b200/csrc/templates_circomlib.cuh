@@ -459,6 +459,17 @@ template <> __device__ __noinline__ VC Poseidon<MCompute>(Comp<MCompute>&& c, co
     const uint32_t c0 = c.cur;
     uint32_t n_own = 0;
     for (int i = 0; i < n; i++) n_own += inputs[i].sig ? 0u : 1u;
+    if (c.skip_hash) {
+        // the permutation is evaluated by a transposed kernel (k_hstate: the state hashes, from the inputs recorded
+        // here; k_sighash: the message hash); nothing on this side reads the digest
+        if (c.hs_rec && n == 4) {
+            const int k = (*c.hs_n)++;
+            if (hz_glane() == 0) for (int i = 0; i < 4; i++) c.hs_rec[4 * k + i] = inputs[i].v;
+        }
+        c.cur = c0 + n_own + poseidon_size(t);
+        VC z; z.v = fr_zero(); z.sig = true; z.ph = true;
+        return z;
+    }
     uint32_t cur = hz_poseidon_head(c, inputs, n);
     const int lane = (int)hz_glane();
     Fr s = (lane >= 1 && lane <= n) ? inputs[lane - 1].v : fr_zero();
@@ -472,6 +483,8 @@ template <> inline VC Poseidon<MCompute>(Comp<MCompute>&& c, const VC* inputs, i
     return PoseidonGeneric<MCompute>(HZ_MV(c), inputs, n);
 }
 template <> inline VL Poseidon<MLayout>(Comp<MLayout>&& c, const VL* inputs, int n) {
+    if (hz_poseidon_starts && n == 4) hz_poseidon_starts->t5.push_back(c.cur);
+    if (hz_poseidon_starts && n == 6) hz_poseidon_starts->t7.push_back(c.cur);
     return PoseidonGeneric<MLayout>(HZ_MV(c), inputs, n);
 }
 #endif
@@ -842,18 +855,8 @@ HZ_HD Fr fr_base8_y() {
 TM struct HintGen;
 template <> struct HintGen<MCompute> {
 #ifdef HZ_DEVICE_ONLY
-    // device: one lane-parallel pass produces the hints of every ladder of the signature (hints.cuh)
-    static HZ_HD void ladder(Comp<MCompute>& c, const VC& px, const VC& py, const BVC& e, const BVC& s) {
-        if (!c.hints) return;
-        // EscalarMulAny's zero-point substitution (escalarmulany.circom): p.x == 0 -> BASE8
-        const bool zp = fr_is_zero(px.v);
-        hz_hints_eddsa_lanes(c.hints, zp ? fr_base8_x() : px.v, zp ? fr_base8_y() : py.v, e, s);
-        if (c.hints->fill && c.hints->scratch && hz_glane() == 0) {
-            HzFillRec* rec = reinterpret_cast<HzFillRec*>(c.hints->scratch + HZ_SCR_REC);
-            rec->ok = (uint32_t)c.hints->lad_ok;
-            for (int k = 0; k < 8; k++) { rec->e[k] = e.val[k]; rec->s[k] = s.val[k]; }
-        }
-    }
+    // device: the hints of every ladder of the signature were produced by k_ed_ladder / k_ed_hints before the
+    // second half of the verifier runs (c.hints->lad_ok: they are usable)
     static HZ_HD void seg_any(Comp<MCompute>& c, const VC&, const VC&, const BVC&, int, int seg) {
         if (!c.hints) return;
         c.hints->dat = c.hints->lad_ok ? c.hints->scratch + (seg == 0 ? 0 : 295) : nullptr;
@@ -905,7 +908,6 @@ template <> struct HintGen<MCompute> {
     static HZ_HD bool fill_any(Comp<MCompute>&, int, int, PtV<MCompute>&, PtV<MCompute>&) { return false; }
     static HZ_HD bool fill_fix(Comp<MCompute>&, int, int, PtV<MCompute>&) { return false; }
     static HZ_HD bool fill_windows(Comp<MCompute>&, int, PtV<MCompute>&, PtV<MCompute>&, PtV<MCompute>&) { return false; }
-    static HZ_HD void ladder(Comp<MCompute>&, const VC&, const VC&, const BVC&, const BVC&) {}
     static HZ_HD void seg_any(Comp<MCompute>& c, const VC& px, const VC& py, const BVC& e, int n, int) { hz_hints_segment_any(c.hints, px.v, py.v, e, n); }
     static HZ_HD void mid(Comp<MCompute>&) {}
     static HZ_HD void seg_fix(Comp<MCompute>& c, const BVC& e, int nW, int seg) { hz_hints_segment_fix(c.hints, e, nW, seg); }
@@ -919,7 +921,6 @@ template <> struct HintGen<MCompute> {
 };
 #ifndef HZ_DEVICE_ONLY
 template <> struct HintGen<MLayout> {
-    static void ladder(Comp<MLayout>&, const VL&, const VL&, const BVT<MLayout, 8>&, const BVT<MLayout, 8>&) {}
     static void seg_any(Comp<MLayout>&, const VL&, const VL&, const BVT<MLayout, 8>&, int, int) {}
     static void mid(Comp<MLayout>&) {}
     static void seg_fix(Comp<MLayout>&, const BVT<MLayout, 8>&, int, int) {}
@@ -1220,15 +1221,20 @@ HZ_FN void hz_record_fix_consts(Fr* wtmp, Fr* cst, Fr* edtab, uint32_t* counts) 
 // ---------------------------------------------------------------------------
 // eddsaposeidon.circom  (src/rollup-tx.circom:472)
 // ---------------------------------------------------------------------------
-TM HZ_FN void EdDSAPoseidonVerifier(Comp<M>&& c, const V<M>& enabled, const V<M>& Ax, const V<M>& Ay,
-                                     const V<M>& S, const V<M>& R8x, const V<M>& R8y, const V<M>& Msg) {
+// The verifier in two halves: everything before the scalar multiplications (bits of S and of the message hash,
+// the three doublings of A) and the multiplications with the final comparison.  Host builds and the layout walk
+// run them back to back; the device runs each half in a kernel of its own with the ladder walk (k_ed_ladder,
+// k_ed_hints) between them, handing over what the second half reads in an EdMid.
+TM struct EdMid { V<M> en, R8x, R8y; PtV<M> d3; BV<M> hbits, sbits; };
+TM HZ_FN void EdDSAPoseidonVerifierHead(Comp<M>& c, const V<M>& enabled, const V<M>& Ax, const V<M>& Ay,
+                                         const V<M>& S, const V<M>& R8x, const V<M>& R8y, const V<M>& Msg, EdMid<M>& m) {
     V<M> en = c.def("enabled", enabled);
     V<M> Ax_ = c.def("Ax", Ax), Ay_ = c.def("Ay", Ay), S_ = c.def("S", S);
     V<M> R8x_ = c.def("R8x", R8x), R8y_ = c.def("R8y", R8y), M_ = c.def("M", Msg);
-    BV<M> sbits = Num2Bits(c.sub("snum2bits"), 253, S_);
+    m.sbits = Num2Bits(c.sub("snum2bits"), 253, S_);
     {
         BV<M> cb; cb.clear(254);
-        bv_copy(cb, 0, sbits, 0, 253);
+        bv_copy(cb, 0, m.sbits, 0, 253);
         cb.put(253, Ops<M>::K(0));
         V<M> cc = CompConstant(c.sub("compConstant"), fr_const_suborder_m1(), cb);
         HZ_CHECK0(c, cc * en);
@@ -1236,18 +1242,26 @@ TM HZ_FN void EdDSAPoseidonVerifier(Comp<M>&& c, const V<M>& enabled, const V<M>
     V<M> hin[5];
     hin[0] = R8x_; hin[1] = R8y_; hin[2] = Ax_; hin[3] = Ay_; hin[4] = M_;
     V<M> h = Poseidon<M>(c.sub("hash"), hin, 5);
-    BV<M> hbits = Num2Bits_strict(c.sub("h2bits"), h);
+    m.hbits = Num2Bits_strict(c.sub("h2bits"), h);
     PtV<M> d1 = BabyDbl(c.sub("dbl1"), Ax_, Ay_);
     PtV<M> d2 = BabyDbl(c.sub("dbl2"), d1.x, d1.y);
-    PtV<M> d3 = BabyDbl(c.sub("dbl3"), d2.x, d2.y);
+    m.d3 = BabyDbl(c.sub("dbl3"), d2.x, d2.y);
     V<M> isz = IsZero(c.sub("isZero"), d2.x);        // dbl3.x is wired to dbl2.xout
     HZ_CHECK0(c, isz * en);
-    HintGen<M>::ladder(c, d3.x, d3.y, hbits, sbits);
-    PtV<M> mulAny = EscalarMulAny254(c.sub("mulAny"), hbits, d3);
-    PtV<M> right = BabyAdd(c.sub("addRight"), R8x_, R8y_, mulAny.x, mulAny.y);
-    PtV<M> left = EscalarMulFix253(c.sub("mulFix"), sbits);
-    ForceEqualIfEnabled(c.sub("eqCheckX"), en, left.x, right.x);
-    ForceEqualIfEnabled(c.sub("eqCheckY"), en, left.y, right.y);
+    m.en = en; m.R8x = R8x_; m.R8y = R8y_;
+}
+TM HZ_FN void EdDSAPoseidonVerifierTail(Comp<M>& c, const EdMid<M>& m) {
+    PtV<M> mulAny = EscalarMulAny254(c.sub("mulAny"), m.hbits, m.d3);
+    PtV<M> right = BabyAdd(c.sub("addRight"), m.R8x, m.R8y, mulAny.x, mulAny.y);
+    PtV<M> left = EscalarMulFix253(c.sub("mulFix"), m.sbits);
+    ForceEqualIfEnabled(c.sub("eqCheckX"), m.en, left.x, right.x);
+    ForceEqualIfEnabled(c.sub("eqCheckY"), m.en, left.y, right.y);
+}
+TM HZ_FN void EdDSAPoseidonVerifier(Comp<M>&& c, const V<M>& enabled, const V<M>& Ax, const V<M>& Ay,
+                                     const V<M>& S, const V<M>& R8x, const V<M>& R8y, const V<M>& Msg) {
+    EdMid<M> m;
+    EdDSAPoseidonVerifierHead(c, enabled, Ax, Ay, S, R8x, R8y, Msg, m);
+    EdDSAPoseidonVerifierTail(c, m);
 }
 
 // ---------------------------------------------------------------------------

@@ -502,7 +502,10 @@ TM struct RollupTxOut { V<M> accFeeOut[HZ_MAX_FEE]; V<M> newStateRoot, newExitRo
 struct HzEddsaJob { Fr aySignature, signSignature, enabled, s1Ay, S, R8x, R8y, M; uint32_t cur; uint32_t pad[7]; };
 // inputs of one SMTProcessor body; sigmask bit k set = input k is a wired signal (no entry of its
 // own), k: 0 oldKey, 1 oldValue, 2 isOld0, 3 newKey, 4 newValue, 5 fnc[0], 6 fnc[1]
-struct HzSmtJob { Fr oldKey, oldValue, isOld0, newKey, newValue, fnc0, fnc1; uint32_t cur, sib, sigmask, pad[5]; };
+// hsel: the selector of the multiplexer in front of oldValue (old state hash against the input oldValue1 / 2): the
+// state hashes are evaluated by k_hstate after the job is recorded, which completes oldValue += (1 - hsel) * hash
+// ovidx: witness index of that multiplexer's output (HZ_NOIDX: oldValue is wired to the hash), which k_hstate writes
+struct HzSmtJob { Fr oldKey, oldValue, isOld0, newKey, newValue, fnc0, fnc1, hsel; uint32_t cur, sib, sigmask, ovidx, pad[4]; };
 // what a body leaves for its top; cur = witness cursor where the top continues
 struct HzSmtMid { Fr enabled, oldKey, newKey, fnc0, fnc1, oc, nc; uint32_t cur, newRootIdx, pad[6]; };
 // what the head of a body leaves for the levels kernel: leaf hashes, the level bits of the new key, where the
@@ -560,6 +563,8 @@ TM struct PhaseJKIn {
     const V<M>* siblings1; V<M> oldKey1, oldValue1, isOld0_1, key1, newValue1, f1[2];
     const V<M>* siblings2; V<M> oldKey2, oldValue2, isOld0_2, key2, newValue2, f2[2];
     uint32_t sib1_idx, sib2_idx;
+    V<M> ins1, ins2;                 // isP1Insert, isP2Insert (what selects oldValue1 / oldValue2)
+    uint32_t ov1_idx, ov2_idx;       // entries of s1OldValue.mux.out[0] / s2OldValue.mux.out[0]
 };
 TM HZ_FN void hz_phaseJK(Comp<M>& c, int nLevels, const PhaseJKIn<M>& in, V<M>& newStateRoot, V<M>& newExitRoot,
                          uint32_t* p2_start = nullptr) {
@@ -589,6 +594,8 @@ HZ_HD void hz_phaseJK_hook(Comp<MCompute>& c, const SlotHook<MCompute>& hk, int 
     (void)nLevels;
     hz_smt_job(&hk.smt[0], c.cur, in.sib1_idx, in.oldKey1, in.oldValue1, in.isOld0_1, in.key1, in.newValue1, in.f1);
     hz_smt_job(&hk.smt[1], c.cur + hk.sz->p2_off, in.sib2_idx, in.oldKey2, in.oldValue2, in.isOld0_2, in.key2, in.newValue2, in.f2);
+    hk.smt[0].hsel = in.ins1.v; hk.smt[1].hsel = in.ins2.v;
+    hk.smt[0].ovidx = in.ov1_idx; hk.smt[1].ovidx = in.ov2_idx;
     *hk.isExit = in.isExit.v;
     c.cur += hk.sz->phaseJK;
     newStateRoot = vc(fr_zero()); newExitRoot = vc(fr_zero());
@@ -674,6 +681,7 @@ TM HZ_FN void RollupTx(Comp<M>&& c, int nLevels, int maxFeeTx, const RollupTxIn<
     V<M> s1EthAddr = Mux1(c.sub("s1EthAddr"), ethAddr1, fromEthAddr, i1);
     V<M> s1TokenID = Mux1(c.sub("s1TokenID"), tokenID1, tokenID, i1);
     V<M> s1OldKey = Mux1(c.sub("s1OldKey"), st.key1, oldKey1, i1);
+    const uint32_t ov1_idx = c.cur;       // all three inputs are signals: the multiplexer's only entry is its output
     V<M> s1OldValue = Mux1(c.sub("s1OldValue"), oldSt1Hash, oldValue1, i1);
     V<M> s2Balance = Mux1(c.sub("s2Balance"), balance2, zero, i2);
     V<M> s2Sign = Mux1(c.sub("s2Sign"), sign2, s1Sign, i2);
@@ -682,6 +690,7 @@ TM HZ_FN void RollupTx(Comp<M>&& c, int nLevels, int maxFeeTx, const RollupTxIn<
     V<M> s2EthAddr = Mux1(c.sub("s2EthAddr"), ethAddr2, s1EthAddr, i2);
     V<M> s2TokenID = Mux1(c.sub("s2TokenID"), tokenID2, s1TokenID, i2);
     V<M> s2OldKey = Mux1(c.sub("s2OldKey"), st.key2, oldKey2, i2);
+    const uint32_t ov2_idx = c.cur;
     V<M> s2OldValue = Mux1(c.sub("s2OldValue"), oldSt2Hash, oldValue2, i2);
     // F - verify eddsa signature (:454-482)
     const V<M>& vse = st.verifySignEnabled;
@@ -709,6 +718,7 @@ TM HZ_FN void RollupTx(Comp<M>&& c, int nLevels, int maxFeeTx, const RollupTxIn<
     jk.key2 = st.key2; jk.newValue2 = newSt2Hash;
     jk.f2[0] = st.P2_fnc0 * bo.isP2Nop; jk.f2[1] = st.P2_fnc1 * bo.isP2Nop;
     jk.sib1_idx = i.sib1_idx; jk.sib2_idx = i.sib2_idx;
+    jk.ins1 = st.isP1Insert; jk.ins2 = st.isP2Insert; jk.ov1_idx = ov1_idx; jk.ov2_idx = ov2_idx;
     hz_phaseJK_hook(c, hook, nLevels, jk, o.newStateRoot, o.newExitRoot);
 }
 
@@ -722,6 +732,7 @@ HZ_HD bool hz_fee_job(const FeeHook<MCompute>& hk, uint32_t cur, const VC& oldKe
                       const VC& newKey, const VC& newValue, const VC* f) {
     if (!hk.smt) return false;
     hz_smt_job(hk.smt, cur, hk.sib_idx, oldKey, oldValue, isOld0, newKey, newValue, f);
+    hk.smt->hsel = fr_zero(); hk.smt->ovidx = HZ_NOIDX;
     return true;
 }
 #ifndef HZ_DEVICE_ONLY
