@@ -226,7 +226,7 @@ struct HzHints {
 // installed the entry is reserved, the value queued, and all queued values of a section are
 // inverted together (one inversion) when the list is flushed.  Without one (CPU port, the
 // reference's way) IsZero inverts on the spot.
-#define HZ_PEND_CAP 96
+#define HZ_PEND_CAP 128
 struct HzPending { uint32_t n; uint32_t idx[HZ_PEND_CAP]; Fr val[HZ_PEND_CAP]; };
 
 // ---- component contexts -------------------------------------------------------------------
@@ -282,13 +282,21 @@ template <> struct Comp<MCompute> {
         Fr pre[HZ_PEND_CAP];
         const int n = (int)pend->n;
         for (int i = 0; i < n; i++) { pre[i] = acc; if (!fr_is_zero(pend->val[i])) acc = fr_mul(acc, pend->val[i]); }
-        Fr t = fr_inv(acc);
+        Fr t = inv1(acc);
         for (int i = n - 1; i >= 0; i--) {
             if (fr_is_zero(pend->val[i])) { put(pend->idx[i], fr_zero()); continue; }
             put(pend->idx[i], fr_mul(t, pre[i]));
             t = fr_mul(t, pend->val[i]);
         }
         pend->n = 0;
+    }
+    // one field inversion; a thread working alone (solo) shares it with the other lanes of its warp when they all
+    // arrive together (each with its own value), a lane group with the other groups of its warp (fr_inv)
+    HZ_HD Fr inv1(const Fr& x) {
+#ifdef HZ_DEVICE_ONLY
+        if (solo) return fr_inv_lanes32(x);
+#endif
+        return fr_inv(x);
     }
     // two divisions whose denominators are both known: one inversion
     HZ_HD void div2(const VC& a1, const VC& b1, const VC& a2, const VC& b2, VC& q1, VC& q2) {
@@ -375,7 +383,7 @@ template <> struct Comp<MCompute> {
         if (!err) return;
         if (fr_eq(lhs.v, rhs.v)) return;
 #ifdef HZ_DEVICE_ONLY
-        if (hz_glane() != 0) return;
+        if (!solo && hz_glane() != 0) return;
 #endif
 #ifdef __CUDA_ARCH__
         uint32_t k = atomicAdd(&err->count, 1u);

@@ -526,6 +526,42 @@ static __device__ __noinline__ Fr fr_inv(const Fr& a) {
     if (z) r = fr_from_u64(0);
     return r;
 }
+// 32 different values, one per lane, inverted with ONE Euclid run (Montgomery's trick across the warp with two
+// shuffle scans); lanes that arrive without the whole warp invert on their own.  inv(0) = 0.
+static __device__ __noinline__ Fr fr_inv_lanes32(const Fr& a) {
+    const bool z = fr_is_zero(a);
+    Fr x = a;
+    if (z) x.l[0] = 1u;
+    if (__activemask() != 0xffffffffu) {
+        Fr r = fr_inv_euclid(x);
+        if (z) r.l[0] = 0u;
+        return r;
+    }
+    const int lane = (int)(threadIdx.x & 31u);
+    Fr below = x, above = x;                  // inclusive products over the lanes up to / from this one
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Fr o;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.l[i] = __shfl_up_sync(0xffffffffu, below.l[i], d);
+        if (lane >= d) below = fr_mul_chain(below, o);
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.l[i] = __shfl_down_sync(0xffffffffu, above.l[i], d);
+        if (lane + d < 32) above = fr_mul_chain(above, o);
+    }
+    Fr all, lo, hi;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        all.l[i] = __shfl_sync(0xffffffffu, below.l[i], 31);
+        lo.l[i] = __shfl_up_sync(0xffffffffu, below.l[i], 1);
+        hi.l[i] = __shfl_down_sync(0xffffffffu, above.l[i], 1);
+    }
+    if (lane == 0) lo = fr_one();
+    if (lane == 31) hi = fr_one();
+    Fr r = fr_mul_chain(fr_inv_euclid(all), fr_mul_chain(lo, hi));
+    if (z) r = fr_zero();
+    return r;
+}
 #endif
 HZ_HD Fr fr_div(const Fr& a, const Fr& b) { return fr_mul(a, fr_inv(b)); }
 

@@ -237,7 +237,7 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     // k_front on a stream of its own: the merkle kernels take their jobs from k_smtjob
     CK(cudaStreamWaitEvent(d->stream4, d->ev0, 0));
     CK(cudaEventRecord(d->kev[11], d->stream4));
-    if (ns > 0) d->n_launch++, k_front<<<hz_grid(ns), HZ_BLOCK, 0, d->stream4>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt_front, d->isExit_front, s0, ns);
+    if (ns > 0) d->n_launch++, k_front<<<(unsigned)((ns + 31) / 32), 32, 0, d->stream4>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt_front, d->isExit_front, s0, ns);
     CK(cudaEventRecord(d->kev[12], d->stream4));
     CK(cudaEventRecord(d->ev_front, d->stream4));
     CK(cudaEventRecord(d->kev[0], s));
@@ -417,7 +417,7 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
     d->n_launch++, k_edjob<<<hz_grid(P.nTx), HZ_BLOCK, 0, s2>>>(pl, d->w, d->jobs, d->off_eddsa, d->sig_in, 0, P.nTx);
     d->n_launch++, k_sighash<<<(unsigned)((P.nTx + 31) / 32), 224, 0, s2>>>(d->w, d->sig_in, d->hsig_cur, d->jobs, 0, P.nTx);
     CK(cudaStreamWaitEvent(d->stream4, d->ev0, 0));
-    d->n_launch++, k_front<<<hz_grid(P.nTx), HZ_BLOCK, 0, d->stream4>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt_front, d->isExit_front, 0, P.nTx);
+    d->n_launch++, k_front<<<(unsigned)((P.nTx + 31) / 32), 32, 0, d->stream4>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt_front, d->isExit_front, 0, P.nTx);
     CK(cudaEventRecord(d->ev_front, d->stream4));
     d->n_launch++, k_smtjob<<<hz_grid(P.nTx), HZ_BLOCK, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, d->hs_in, 0, P.nTx);
     CK(cudaStreamWaitEvent(s3, d->ev_front, 0));

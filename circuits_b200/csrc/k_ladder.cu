@@ -15,35 +15,9 @@
 //               signature (21 elements per lane, the chunk totals combined with shuffle scans, one inversion).
 //               Ratios do not depend on the domain: num~ / den~ = num / den, so the hints come out canonical.
 #include "hzw_dev.cuh"
-#include "fr_montgen.inc"
+#include "fm.cuh"
 
 #define HZ_LAD_SIGS 32
-// R mod p and R^2 mod p (R = 2^256): 1~ and the factor that takes a canonical value into the domain
-__device__ __forceinline__ Fr fm_one() {
-    Fr r; r.l[0] = 0x4ffffffbu; r.l[1] = 0xac96341cu; r.l[2] = 0x9f60cd29u; r.l[3] = 0x36fc7695u;
-    r.l[4] = 0x7879462eu; r.l[5] = 0x666ea36fu; r.l[6] = 0x9a07df2fu; r.l[7] = 0x0e0a77c1u; return r;
-}
-__device__ __forceinline__ Fr fm_R2() {
-    Fr r; r.l[0] = 0xae216da7u; r.l[1] = 0x1bb8e645u; r.l[2] = 0xe35c59e3u; r.l[3] = 0x53fe3ab1u;
-    r.l[4] = 0x53bb8085u; r.l[5] = 0x8c49833du; r.l[6] = 0x7f4e44a5u; r.l[7] = 0x0216d0b1u; return r;
-}
-// A~ = 168698 R mod p (the Montgomery-curve coefficient in the domain)
-__device__ __forceinline__ Fr fm_A() {
-    Fr r; r.l[0] = 0x4ff261ebu; r.l[1] = 0x80625cbdu; r.l[2] = 0xd8efa9b6u; r.l[3] = 0xdeb30882u;
-    r.l[4] = 0x0f1f36e8u; r.l[5] = 0xcc1f1088u; r.l[6] = 0xc3f5c0beu; r.l[7] = 0x23853a11u; return r;
-}
-__device__ __forceinline__ Fr fm_mul(const Fr& a, const Fr& b) { Fr r; fr_mont_mul(r, a, b); return r; }
-__device__ __forceinline__ Fr fm_add(const Fr& a, const Fr& b) { Fr t, r; fr_add_raw(t, a, b); fr_lazy_fold(r, t); return r; }   // < 4p < 2^256
-__device__ __forceinline__ Fr fm_sub(const Fr& a, const Fr& b) {
-    const uint32_t p2[8] = {0xe0000002u, 0x87c3eb27u, 0xf372e122u, 0x5067d090u, 0x0302b0bau, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u};
-    Fr d, e;
-    const uint32_t brw = fr_sub8(d.l, a.l, b.l);
-    hz_add8(e.l, d.l, p2);
-#pragma unroll
-    for (int i = 0; i < 8; i++) d.l[i] = brw ? e.l[i] : d.l[i];
-    return d;
-}
-__device__ __forceinline__ Fr fm_from(const Fr& x) { return fm_mul(x, fm_R2()); }
 struct FmPt { Fr U, V, W; };
 // the shared second half of both maps (hints.cuh: mt_tail) in the domain
 __device__ __forceinline__ FmPt fm_tail(const Fr& N, const Fr& Dn, const Fr& W12, const Fr& X1, const Fr& X2, const Fr& Y1, const Fr& A) {

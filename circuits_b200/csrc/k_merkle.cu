@@ -1,5 +1,6 @@
 // SMT processors: heads, transposed levels, image levels, tops; Poseidon alone (see hzw_dev.cuh).
 #include "hzw_dev.cuh"
+#include "fm.cuh"
 
 // ---- Poseidon alone (the second metric of BASELINE.json: permutations per second) ----------------
 // The SMT level hashes as k_smt evaluates them -- a lane group runs the old-path and the new-path
@@ -38,9 +39,94 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_smt(HzPlan pl, Fr* w, HzErrBuf*
 // processor.  Their 634 entries do not depend on anything, so when a level is (0, 0) in EVERY chain of the
 // block the 65 rounds are skipped, the digest is the constant, and the entries are copied from an image
 // recorded at context creation by k_smt_zero (a wide copy, off the critical chain of the levels).
+// ---- one Poseidon(2) permutation per chain, its dependency chain in the Montgomery domain ----------------------
+// The 65 rounds of a level hash are one chain of products (x -> x^2 -> x^4 -> x^5 -> MDS row, 260 deep), and the
+// levels of a processor are chained on top of that: this is the longest dependency chain of a batch.  Every value on
+// it is a witness entry and must be STORED canonical, but the chain itself does not need canonical values: it runs on
+// lazily reduced Montgomery residues (fm.cuh: 176-instruction products instead of 312) and the canonical value of an
+// entry is recovered beside the chain by one reduction (fr_mont_redc).  In a partial round only element 0 goes through
+// the S-box: warp 0 does nothing but the chain there and publishes its intermediate values in shared memory, the two
+// other warps -- idle during the S-box -- reduce and store them one round later.
+//   xch[b][q]  the three MDS inputs of a round (S-box outputs / passed-through elements), Montgomery
+//   e0[b][0..2] element 0 of a partial round for the helpers: state before the round constant, in2, in4
+__device__ __forceinline__ void hz_sm_put(uint32_t (*a)[32], int c, const Fr& v) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k][c] = v.l[k];
+}
+__device__ __forceinline__ Fr hz_sm_get(const uint32_t (*a)[32], int c) {
+    Fr v;
+#pragma unroll
+    for (int k = 0; k < 8; k++) v.l[k] = a[k][c];
+    return v;
+}
+#include "poseidon_c3_mont.inc"
+// s_in: canonical input of element r (zero for r = 0); hw: where the component's entries start (entry 0 is
+// ark[0].in[0] = 0); returns the canonical mix output of the last round of element r (r = 0: the digest)
+__device__ __forceinline__ Fr hz_poseidon3_chain(uint32_t (*xch)[3][8][32], uint32_t (*e0)[3][8][32], int r, int c, const Fr& s_in,
+                                                 Fr* hw, bool real, const Fr* m) {
+    const Fr* C = &hz_poseidon_c(3, 0);
+    if (r == 0 && real) hz_store_fr(&hw[0], s_in);
+    Fr sm = fm_from(s_in), sc = s_in;                   // the state element, Montgomery and canonical
+    uint32_t cur = 1, prev = 1;
+    bool prev_partial = false;
+    for (int i = 0; i < 65; i++) {
+        const bool full = i < 4 || i >= 61;
+        const Fr xm = fm_add(sm, hz_pc3m_dev[3 * i + r]);
+        const uint32_t sg = cur + 6;
+        if (full || r != 0) {
+            // own canonical entries: mix.out[r] of the round before, ark.out[r] of this one
+            if (i > 0) { sc = fm_canon(sm); if (real) hz_store_fr(&hw[prev + 3 + r], sc); }
+            if (real) hz_store_fr(&hw[cur + r], fr_add(sc, C[3 * i + r]));
+        }
+        if (full) {
+            const Fr in2 = fm_mul(xm, xm), in4 = fm_mul(in2, in2), out = fm_mul(in4, xm);
+            hz_sm_put(xch[i & 1][r], c, out);
+            if (real) { hz_store_fr(&hw[sg + 3 * r], fm_canon(out)); hz_store_fr(&hw[sg + 3 * r + 1], fm_canon(in2)); hz_store_fr(&hw[sg + 3 * r + 2], fm_canon(in4)); }
+        } else if (r == 0) {
+            hz_sm_put(e0[i & 1][0], c, sm);
+            const Fr in2 = fm_mul(xm, xm), in4 = fm_mul(in2, in2), out = fm_mul(in4, xm);
+            hz_sm_put(e0[i & 1][1], c, in2); hz_sm_put(e0[i & 1][2], c, in4);
+            hz_sm_put(xch[i & 1][0], c, out);
+        } else {
+            hz_sm_put(xch[i & 1][r], c, xm);
+        }
+        if (r != 0 && prev_partial) {
+            // element 0 of the partial round before this one, from what warp 0 published then
+            const int b = (i - 1) & 1;
+            const uint32_t psg = prev + 6;
+            if (r == 1) {
+                const Fr s0 = fm_canon(hz_sm_get(e0[b][0], c));           // state 0 entering round i - 1 = mix.out[0] of round i - 2
+                if (real) {
+                    hz_store_fr(&hw[prev - (i - 1 <= 4 ? 15u : 9u) + 3], s0);
+                    hz_store_fr(&hw[prev], fr_add(s0, C[3 * (i - 1)]));
+                    hz_store_fr(&hw[psg + 1], fm_canon(hz_sm_get(e0[b][1], c)));
+                }
+            } else {
+                if (real) {
+                    hz_store_fr(&hw[psg + 2], fm_canon(hz_sm_get(e0[b][2], c)));
+                    hz_store_fr(&hw[psg], fm_canon(hz_sm_get(xch[b][0], c)));
+                }
+            }
+        }
+        __syncthreads();
+        Fr a[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) a[q] = hz_sm_get(xch[i & 1][q], c);
+        fr_mont_dot3(sm, a, m);
+        prev_partial = !full;
+        prev = cur;
+        cur += 6 + (full ? 9 : 3);
+    }
+    // mix.out[r] of the last round (a full one)
+    sc = fm_canon(sm);
+    if (real) hz_store_fr(&hw[prev + 3 + r], sc);
+    return sc;
+}
+
 __global__ void __launch_bounds__(96) k_smt_levels(HzPlan pl, Fr* w, const HzLevJob* jobs, const Fr* smst, HzSmtMid* mids,
                                                    const Fr* img00, uint8_t* zflag, int s0, int ns, int f0, int nf) {
     __shared__ uint32_t xch[2][3][8][32];
+    __shared__ uint32_t e0[2][3][8][32];
     __shared__ uint32_t hin[2][8][32];
     const int r = (int)(threadIdx.x >> 5), c = (int)(threadIdx.x & 31);
     const int njobs = 2 * ns + nf, L = pl.P.nLevels + 1;
@@ -52,7 +138,6 @@ __global__ void __launch_bounds__(96) k_smt_levels(HzPlan pl, Fr* w, const HzLev
     const Fr* stj = smst + (size_t)job * L * 6;
     const Fr o1 = J.o1, n1 = J.n1;
     const uint32_t HS = HZ_SZ_SMTHASH2_WIRED;
-    const Fr* C = &hz_poseidon_c(3, 0);
     Fr m[3];
     for (int k = 0; k < 3; k++) m[k] = hz_poseidon_mr(3, r)[k];
     Fr child = fr_zero();
@@ -92,35 +177,10 @@ __global__ void __launch_bounds__(96) k_smt_levels(HzPlan pl, Fr* w, const HzLev
         }
         const int allz = __syncthreads_and(fr_is_zero(s) ? 1 : 0);
         if (threadIdx.x == 0) zflag[(size_t)blockIdx.x * L + lev] = allz ? 1 : 0;
-        // SMTHash2 (wired L, R) -> Poseidon(2): entry 0 is ark[0].in[0] = 0
+        // SMTHash2 (wired L, R) -> Poseidon(2)
         Fr* hw = w + (side == 0 ? o_oph : o_nph);
         if (allz) s = img00[HZ_IMG00_DIGEST];
-        else if (r == 0) hz_store_fr(&hw[0], s);
-        uint32_t cur = 1;
-        for (int i = 0; i < (allz ? 0 : 65); i++) {
-            s = fr_add(s, C[3 * i + r]);
-            hz_store_fr(&hw[cur + r], s);
-            const bool full = i < 4 || i >= 61;
-            const uint32_t sg = cur + 6;
-            if (full || r == 0) {                       // warp-uniform
-                Fr in2 = fr_mul_chain(s, s);
-                Fr in4 = fr_mul_chain(in2, in2);
-                s = fr_mul_chain(in4, s);
-                hz_store_fr(&hw[sg + 3 * r], s); hz_store_fr(&hw[sg + 3 * r + 1], in2); hz_store_fr(&hw[sg + 3 * r + 2], in4);
-            }
-            uint32_t (*buf)[8][32] = xch[i & 1];
-#pragma unroll
-            for (int k = 0; k < 8; k++) buf[r][k][c] = s.l[k];
-            __syncthreads();
-            Fr a[3];
-#pragma unroll
-            for (int qq = 0; qq < 3; qq++)
-#pragma unroll
-                for (int k = 0; k < 8; k++) a[qq].l[k] = buf[qq][k][c];
-            s = fr_dot_mont_chain<3>(a, m);
-            hz_store_fr(&hw[cur + 3 + r], s);
-            cur += 6 + (full ? 9 : 3);
-        }
+        else s = hz_poseidon3_chain(xch, e0, r, c, s, hw, true, m);
         if (r == 0) {
             if (side == 0) {
                 Fr a0 = fr_mul(o1, fr_add(fr_add(st_bot, st_new1), st_upd));
@@ -212,44 +272,18 @@ __global__ void __launch_bounds__(HZ_BLOCK) k_tail(HzPlan pl, Fr* w, HzErrBuf* e
 // constants are uniform per warp.  Same signals at the same indexes as the lane-group form.
 __global__ void __launch_bounds__(96) k_poseidon_t3(const Fr* in, Fr* sig, Fr* digests, int nperms) {
     __shared__ uint32_t xch[2][3][8][HZ_PT_CHAINS];
+    __shared__ uint32_t e0[2][3][8][HZ_PT_CHAINS];
     const int r = (int)(threadIdx.x >> 5), c = (int)(threadIdx.x & 31);
     int p = (int)blockIdx.x * HZ_PT_CHAINS + c;
     const bool real = p < nperms;
     if (!real) p = nperms - 1;
     const uint32_t size = 1 + 2 * 3 * 65 + 3 * (8 * 3 + 57);
-    Fr* w = sig + (size_t)p * size;
-    // inputs are wires (no entries); entry 0 is ark[0].in[0] = 0
-    Fr s = r == 0 ? fr_zero() : in[2 * p + (r - 1)];
-    if (r == 0 && real) hz_store_fr(&w[0], s);
-    uint32_t cur = 1;
-    const Fr* C = &hz_poseidon_c(3, 0);
     Fr m[3];
     for (int k = 0; k < 3; k++) m[k] = hz_poseidon_mr(3, r)[k];
-    for (int i = 0; i < 65; i++) {
-        s = fr_add(s, C[3 * i + r]);
-        if (real) hz_store_fr(&w[cur + r], s);
-        const bool full = i < 4 || i >= 61;
-        const uint32_t sg = cur + 6;
-        if (full || r == 0) {                       // warp-uniform
-            Fr in2 = fr_mul_chain(s, s);
-            Fr in4 = fr_mul_chain(in2, in2);
-            s = fr_mul_chain(in4, s);
-            if (real) { hz_store_fr(&w[sg + 3 * r], s); hz_store_fr(&w[sg + 3 * r + 1], in2); hz_store_fr(&w[sg + 3 * r + 2], in4); }
-        }
-        uint32_t (*buf)[8][HZ_PT_CHAINS] = xch[i & 1];
-#pragma unroll
-        for (int k = 0; k < 8; k++) buf[r][k][c] = s.l[k];
-        __syncthreads();
-        Fr a[3];
-#pragma unroll
-        for (int q = 0; q < 3; q++)
-#pragma unroll
-            for (int k = 0; k < 8; k++) a[q].l[k] = buf[q][k][c];
-        s = fr_dot_mont_chain<3>(a, m);
-        if (real) hz_store_fr(&w[cur + 3 + r], s);
-        cur += 6 + (full ? 9 : 3);
-    }
-    if (r == 0 && real) digests[p] = s;
+    // inputs are wires (no entries); entry 0 is ark[0].in[0] = 0
+    const Fr s = r == 0 ? fr_zero() : in[2 * p + (r - 1)];
+    const Fr d = hz_poseidon3_chain(xch, e0, r, c, s, sig + (size_t)p * size, real, m);
+    if (r == 0 && real) digests[p] = d;
 }
 
 extern "C" int hzw_poseidon_bench(int device, uint64_t npairs, int reps, const uint8_t* inputs_le32 /* 4 x npairs */,

@@ -2,18 +2,27 @@
 #include "hzw_dev.cuh"
 
 // [s0, s0 + ns): the tx slots of this shard (all of them on one GPU)
-__global__ void __launch_bounds__(HZ_BLOCK, 3) k_front(HzPlan pl, Fr* w, uint8_t* preb, HzErrBuf* err, HzEddsaJob* jobs, HzSmtJob* smt, Fr* isExit, int s0, int ns) {
-    bool real; int i = s0 + hz_item(ns, real);
+// One THREAD per slot (Comp::solo): with the hashes gone to the transposed kernels what is left of decodeTx[i] and
+// rollupTx[i] is bit plumbing and selections -- scalar work that a lane group would repeat in all of its eight lanes.
+// A warp walks 32 consecutive slots; slots of one kind follow the same path through the templates.
+#define HZ_FRONT_BLOCK 32
+__global__ void __launch_bounds__(HZ_FRONT_BLOCK) k_front(HzPlan pl, Fr* w, uint8_t* preb, HzErrBuf* err, HzEddsaJob* jobs, HzSmtJob* smt, Fr* isExit, int s0, int ns) {
+    int g = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const bool real = g < ns;
+    if (!real) g = ns - 1;                   // padding lanes redo the last slot (identical stores): the warp stays whole
+    const int i = s0 + g;
     PreBits<MCompute> pre; pre.b = preb;
     SlotHook<MCompute> hook; hook.eddsa = &jobs[i]; hook.smt = &smt[2 * i]; hook.isExit = &isExit[i]; hook.sz = &pl.sz;
     HzPending pend; pend.n = 0;
     Comp<MCompute> c(w, pl.off_decode[i], real ? err : nullptr, nullptr, &pend);
+    c.solo = true;
     c.skip_hash = true;                      // the message hash and the four state hashes: k_sighash, k_hstate
     DecodeOut<MCompute> d;
     sec_decode(c, pl, i, d, pre);
     c.cur = pl.off_rollup[i];
     RollupTxOut<MCompute> o;
     sec_rollup(c, pl, i, d, o, pre, hook);
+    __syncwarp();
     c.flush_pending();
 }
 

@@ -464,7 +464,7 @@ template <> __device__ __noinline__ VC Poseidon<MCompute>(Comp<MCompute>&& c, co
         // here; k_sighash: the message hash); nothing on this side reads the digest
         if (c.hs_rec && n == 4) {
             const int k = (*c.hs_n)++;
-            if (hz_glane() == 0) for (int i = 0; i < 4; i++) c.hs_rec[4 * k + i] = inputs[i].v;
+            if (c.solo || hz_glane() == 0) for (int i = 0; i < 4; i++) c.hs_rec[4 * k + i] = inputs[i].v;
         }
         c.cur = c0 + n_own + poseidon_size(t);
         VC z; z.v = fr_zero(); z.sig = true; z.ph = true;
