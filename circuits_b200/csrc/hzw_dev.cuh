@@ -6,7 +6,7 @@
 //   k_merkle.cu   k_smt, k_smt_levels, k_smt_zero, k_hole_pack, k_tail, the Poseidon-only kernels
 //   k_sig.cu      k_fix_consts, k_ed_const, k_eddsa, k_eddsa_tail, k_ed_fill
 //   k_ladder.cu   k_ed_ladder, k_ed_hints
-//   k_poseidon.cu k_hstate, k_sighash                    (state hashes and message hashes, transposed)
+//   k_poseidon.cu k_hstate, k_sighash, k_leafhash        (state, message and leaf hashes, transposed)
 //   k_hasher.cu   k_pack, k_unpack, k_hash_head, k_sha_chain, k_sha_blocks, k_hash_tail, k_withdraw
 //   hzw_run.cu    device memory, streams and the launch order (hz_cuda_*)
 #pragma once
@@ -132,6 +132,7 @@ __global__ void k_poseidon_t3(const Fr* in, Fr* sig, Fr* digests, int nperms);
 __global__ void k_front(HzPlan pl, Fr* w, uint8_t* preb, HzErrBuf* err, HzEddsaJob* jobs, HzSmtJob* smt, Fr* isExit, int s0, int ns);
 __global__ void k_smtjob(HzPlan pl, Fr* w, HzSmtJob* smt, Fr* isExit, const uint32_t* off_jk, Fr* hs_in, int s0, int ns);
 __global__ void k_hstate(Fr* w, const Fr* hs_in, const uint32_t* hs_cur, HzSmtJob* smt, int nTx, int s0, int ns, int f0, int nf);
+__global__ void k_leafhash(HzPlan pl, Fr* w, const HzSmtJob* smt, HzLevJob* lev, int s0, int ns, int f0, int nf);
 __global__ void k_sighash(Fr* w, const Fr* sig_in, const uint32_t* hsig_cur, HzEddsaJob* jobs, int s0, int ns);
 __global__ void k_edjob(HzPlan pl, const Fr* w, HzEddsaJob* jobs, const uint32_t* off_eddsa, Fr* sig_in, int s0, int ns);
 __global__ void k_fee_front(HzPlan pl, Fr* w, HzErrBuf* err, HzSmtJob* smt, Fr* hs_in, int f0, int nf);

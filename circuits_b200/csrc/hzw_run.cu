@@ -101,6 +101,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
         cudaFuncSetAttribute(k_smt_levels, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_tail, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_hstate, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_leafhash, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_sighash, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_ed_ladder, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_eddsa_tail, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
@@ -248,7 +249,8 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     CK(cudaEventRecord(d->kev[1], s));
     CK(cudaEventRecord(d->kev[2], s));
     if (2 * ns + nf > 0) {
-        d->n_launch++, k_smt<<<hz_grid(2 * ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, f0, nf);
+        d->n_launch++, k_leafhash<<<(unsigned)((2 * (2 * ns + nf) + 31) / 32), 128, 0, s>>>(pl, d->w, d->smt, d->lev, s0, ns, f0, nf);
+        d->n_launch++, k_smt<<<(unsigned)((2 * ns + nf + 31) / 32), 32, 0, s>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, f0, nf);
         const unsigned lb = (unsigned)((2 * ns + nf + 15) / 16);
         d->n_launch++, k_smt_levels<<<lb, 96, 0, s>>>(pl, d->w, d->lev, d->smst, d->mids, d->img00, d->zflag, s0, ns, f0, nf);
         // the skipped (0, 0) levels are filled in beside the tail and the hash of the inputs
@@ -439,7 +441,8 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
         }
         CK(cudaEventRecord(d->ev_ed[h], s2));
         if (2 * ns + nf > 0) {
-            d->n_launch++, k_smt<<<hz_grid(2 * ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, 0, nf);
+            d->n_launch++, k_leafhash<<<(unsigned)((2 * (2 * ns + nf) + 31) / 32), 128, 0, s>>>(pl, d->w, d->smt, d->lev, s0, ns, 0, nf);
+            d->n_launch++, k_smt<<<(unsigned)((2 * ns + nf + 31) / 32), 32, 0, s>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, 0, nf);
             const unsigned lb = (unsigned)((2 * ns + nf + 15) / 16);
             d->n_launch++, k_smt_levels<<<lb, 96, 0, s>>>(pl, d->w, d->lev, d->smst, d->mids, d->img00, d->zflag, s0, ns, 0, nf);
             d->n_launch++, k_hole_pack<<<(unsigned)(2 * ns + nf), 128, 0, s>>>(pl, d->w, d->lev, d->zflag, d->holes, d->gl, s0, ns, 0, nf);

@@ -16,9 +16,14 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_poseidon_pairs(const Fr* in, Fr
     if (hz_glane() == 0) { digests[2 * q] = oa.v; digests[2 * q + 1] = ob.v; }
 }
 
-__global__ void __launch_bounds__(HZ_BLOCK, 3) k_smt(HzPlan pl, Fr* w, HzErrBuf* err, const HzSmtJob* smt, HzSmtMid* mids, HzLevJob* lev, Fr* smst,
-                                                  int s0, int ns, int f0, int nf) {
-    bool real; int q = hz_item(2 * ns + nf, real);
+// head of every processor body, one THREAD per processor: key bits, level-insert flags (one inversion per warp for the
+// 33 sibling tests of its 32 processors), the state machine; leaves the level job and the state-machine tuples
+__global__ void __launch_bounds__(32) k_smt(HzPlan pl, Fr* w, HzErrBuf* err, const HzSmtJob* smt, HzSmtMid* mids, HzLevJob* lev, Fr* smst,
+                                            int s0, int ns, int f0, int nf) {
+    const int n = 2 * ns + nf;
+    int q = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const bool real = q < n;
+    if (!real) q = n - 1;
     q = hz_smt_job_index(pl, q, s0, ns, f0);
     const int L = pl.P.nLevels + 1;
     sec_smt_head(w, real ? err : nullptr, L, smt[q], mids[q], lev[q], smst + (size_t)q * L * 6);

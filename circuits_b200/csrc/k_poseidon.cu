@@ -15,7 +15,7 @@ template <int T> __device__ __forceinline__ Fr hz_poseidon_tr(uint32_t (*xch)[T]
     Fr m[T];
 #pragma unroll
     for (int k = 0; k < T; k++) m[k] = hz_poseidon_mr(T, r)[k];
-    if (r == 0 && real) hz_store_fr(&hw[0], s);                 // ark[0].in[0] = 0
+    if (r == 0 && real) hz_store_fr(&hw[0], s);                 // ark[0].in[0] = 0 (s is zero for element 0)
     uint32_t cur = 1;
     for (int i = 0; i < R; i++) {
         s = fr_add(s, C[T * i + r]);
@@ -81,4 +81,28 @@ __global__ void __launch_bounds__(224) k_sighash(Fr* w, const Fr* sig_in, const 
     const Fr s = r == 0 ? fr_zero() : sig_in[6 * (size_t)i + (r - 1)];
     const Fr d = hz_poseidon_tr<7>(xch, r, c, s, w + hsig_cur[i], real);
     if (r == 0 && real) jobs[i].M = d;
+}
+
+// the two leaf hashes of every processor of the shard: hash1Old = Poseidon(oldKey, oldValue, 1), hash1New =
+// Poseidon(newKey, newValue, 1) (circomlib smthash_poseidon.circom); their digests go to the level job.  The
+// component starts after the processor's own inputs: newRoot, the inputs that are not wired signals, `enabled`;
+// its first entry is the constant third input.
+__global__ void __launch_bounds__(128) k_leafhash(HzPlan pl, Fr* w, const HzSmtJob* smt, HzLevJob* lev, int s0, int ns, int f0, int nf) {
+    __shared__ uint32_t xch[2][4][8][32];
+    const int r = (int)(threadIdx.x >> 5), c = (int)(threadIdx.x & 31);
+    const int P = 2 * (2 * ns + nf);
+    int p = (int)blockIdx.x * 32 + c;
+    const bool real = p < P;
+    if (!real) p = P - 1;
+    const int job = hz_smt_job_index(pl, p >> 1, s0, ns, f0);
+    const bool is_new = (p & 1) != 0;
+    const HzSmtJob& j = smt[job];
+    const uint32_t h1 = j.cur + 2u + (uint32_t)__popc((~j.sigmask) & 0x7fu) + (is_new ? HZ_SZ_SMTHASH1_WIRED : 0u);
+    Fr s = fr_zero();
+    if (r == 1) s = is_new ? j.newKey : j.oldKey;
+    else if (r == 2) s = is_new ? j.newValue : j.oldValue;
+    else if (r == 3) s = fr_one();
+    if (r == 3 && real) hz_store_fr(&w[h1], s);                    // h.inputs[2] = 1 owns an entry
+    const Fr d = hz_poseidon_tr<4>(xch, r, c, s, w + h1 + 1, real);
+    if (r == 0 && real) { if (is_new) lev[job].n1 = d; else lev[job].o1 = d; }
 }

@@ -247,6 +247,7 @@ __device__ __forceinline__ VC hz_sigv(const Fr& f, bool sig) { VC r; r.v = f; r.
 // themselves are evaluated by k_smt_levels from the HzLevJob and the state-machine tuples left here
 static __device__ __noinline__ void sec_smt_head(Fr* w, HzErrBuf* err, int nLevels1, const HzSmtJob& j, HzSmtMid& out, HzLevJob& lev, Fr* smst) {
     Comp<MCompute> c(w, j.cur, err);
+    c.solo = true; c.skip_hash = true;
     VC sib[HZ_MAX_LEVELS];
     for (int k = 0; k < nLevels1; k++) sib[k] = c.load(j.sib + k);
     VC f[2];
@@ -257,12 +258,12 @@ static __device__ __noinline__ void sec_smt_head(Fr* w, HzErrBuf* err, int nLeve
     SMTProcessorHead<MCompute>(c, nLevels1, hz_sigv(fr_zero(), true), sib, hz_sigv(j.oldKey, j.sigmask & 1u),
                                hz_sigv(j.oldValue, j.sigmask & 2u), hz_sigv(j.isOld0, j.sigmask & 4u),
                                hz_sigv(j.newKey, j.sigmask & 8u), hz_sigv(j.newValue, j.sigmask & 16u), f, mid, hd);
-    const uint32_t lane = hz_glane();
-    for (int k = (int)lane; k < nLevels1 * 6; k += HZ_G) smst[k] = hd.sm[k / 6][k % 6].v;
-    if (lane == 0) {
+    // one thread per processor (the leaf hashes are k_leafhash's: Comp::skip_hash)
+    for (int k = 0; k < nLevels1 * 6; k++) smst[k] = hd.sm[k / 6][k % 6].v;
+    {
         uint64_t bits = 0;
         for (int k = 0; k < nLevels1; k++) bits |= (uint64_t)hd.n2bNew.bit(k) << k;
-        lev.o1 = hd.hash1Old.v; lev.n1 = hd.hash1New.v; lev.lrbits = bits; lev.cur = c.cur; lev.sib = j.sib;
+        lev.lrbits = bits; lev.cur = c.cur; lev.sib = j.sib;           // lev.o1, lev.n1: k_leafhash
         out.enabled = mid.enabled.v; out.oldKey = mid.oldKey.v; out.newKey = mid.newKey.v; out.fnc0 = mid.fnc0.v;
         out.fnc1 = mid.fnc1.v; out.cur = c.cur + hz_smt_levels_size(nLevels1); out.newRootIdx = mid.newRootIdx;
     }

@@ -500,6 +500,14 @@ template <> __device__ __noinline__ void PoseidonDual<MCompute>(Comp<MCompute>&&
     const int t = n + 1;            // t <= 4: both fit the 8-lane group
     uint32_t a0 = cA.cur, b0 = cB.cur, ownA = 0, ownB = 0;
     for (int i = 0; i < n; i++) { ownA += inA[i].sig ? 0u : 1u; ownB += inB[i].sig ? 0u : 1u; }
+    if (cA.skip_hash) {
+        // both permutations are evaluated by a transposed kernel (k_leafhash), entries and digests
+        cA.cur = a0 + ownA + poseidon_size(t);
+        cB.cur = b0 + ownB + poseidon_size(t);
+        oA.v = fr_zero(); oA.sig = true; oA.ph = true;
+        oB = oA;
+        return;
+    }
     uint32_t curA = hz_poseidon_head(cA, inA, n);
     uint32_t curB = hz_poseidon_head(cB, inB, n);
     const int lane = (int)hz_glane();
@@ -555,14 +563,14 @@ TM HZ_FN void SMTHash2Pair(Comp<M>&& cA, const V<M>& LA, const V<M>& RA, Comp<M>
 // 1 / x[i] for all i with one field inversion (Montgomery's trick); 1/0 = 0 as everywhere else
 TM struct BatchInv;
 template <> struct BatchInv<MCompute> {
-    static HZ_HD void run(const VC* x, VC* inv, int n) {
+    static HZ_HD void run(Comp<MCompute>& c, const VC* x, VC* inv, int n) {
         Fr acc = fr_one();
         // prefix products over the non-zero entries, kept in inv[]
         for (int i = 0; i < n; i++) {
             inv[i].v = acc; inv[i].sig = false;
             if (!fr_is_zero(x[i].v)) acc = fr_mul(acc, x[i].v);
         }
-        Fr t = fr_inv(acc);
+        Fr t = c.inv1(acc);
         for (int i = n - 1; i >= 0; i--) {
             if (fr_is_zero(x[i].v)) { inv[i].v = fr_zero(); continue; }
             Fr pre = inv[i].v;
@@ -572,7 +580,7 @@ template <> struct BatchInv<MCompute> {
     }
 };
 template <> struct BatchInv<MLayout> {
-    static HZ_HD void run(const VL*, VL* inv, int n) { for (int i = 0; i < n; i++) inv[i] = vl(); }
+    static HZ_HD void run(Comp<MLayout>&, const VL*, VL* inv, int n) { for (int i = 0; i < n; i++) inv[i] = vl(); }
 };
 
 #define HZ_MAX_LEVELS 49
@@ -584,7 +592,7 @@ TM HZ_FN void SMTLevIns(Comp<M>&& c, int n, const V<M>& enabled, const V<M>* sib
     uint32_t dn = c.sigs("done", n - 2);       // done[n-2] is wired to levIns[n-1]: no entry of its own
     {
         V<M> inv[HZ_MAX_LEVELS];
-        BatchInv<M>::run(sib, inv, n);
+        BatchInv<M>::run(c, sib, inv, n);
         for (int i = 0; i < n; i++) isz[i] = IsZeroWithInv(c.sub(Nm("isZero", i)), sib[i], inv[i]);
     }
     HZ_CHECK0(c, (isz[n - 1] - 1) * en);
