@@ -77,7 +77,7 @@ struct HzCuda {
     uint8_t* recs;             // world x rec_bytes: the gathered exchange records (own one while packing)
     cudaStream_t stream, stream2, stream3, stream4;
     cudaEvent_t ev_half[2], ev_ed[2], ev_done;
-    cudaEvent_t ev0, ev1, ev_front, ev_eddsa, ev_lev, ev_zero, ev_fee;
+    cudaEvent_t ev0, ev1, ev_front, ev_eddsa, ev_lev, ev_zero, ev_fee, ev_jobs, ev_heads;
     cudaEvent_t kev[HZ_NKERN + 3];
 };
 

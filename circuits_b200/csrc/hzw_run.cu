@@ -86,6 +86,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaEventCreateWithFlags(&d->ev_lev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_fee, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_zero, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&d->ev_jobs, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&d->ev_heads, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; k < HZ_NKERN + 3; k++) ok = ok && cudaEventCreate(&d->kev[k]) == cudaSuccess;
     // kernels that are to share an SM must agree on its L1 / shared-memory split: k_smt_levels stages the MDS
     // exchange in shared memory, k_eddsa (running beside it on the second stream) uses none -- without a common
@@ -175,6 +176,8 @@ void hz_cuda_destroy(HzCuda* d) {
     if (d->ev_lev) cudaEventDestroy(d->ev_lev);
     if (d->ev_fee) cudaEventDestroy(d->ev_fee);
     if (d->ev_zero) cudaEventDestroy(d->ev_zero);
+    if (d->ev_jobs) cudaEventDestroy(d->ev_jobs);
+    if (d->ev_heads) cudaEventDestroy(d->ev_heads);
     for (int k = 0; k < HZ_NKERN + 3; k++) if (d->kev[k]) cudaEventDestroy(d->kev[k]);
     delete d->h_off_rollup;
     delete d;
@@ -242,15 +245,20 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     CK(cudaEventRecord(d->kev[12], d->stream4));
     CK(cudaEventRecord(d->ev_front, d->stream4));
     CK(cudaEventRecord(d->kev[0], s));
-    if (ns > 0) d->n_launch++, k_smtjob<<<hz_grid(ns), HZ_BLOCK, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, d->hs_in, s0, ns);
+    if (ns > 0) d->n_launch++, k_smtjob<<<(unsigned)((ns + 31) / 32), 32, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, d->hs_in, s0, ns);
     CK(cudaStreamWaitEvent(s, d->ev_fee, 0));
     // the state hashes of the slots and fee txs, transposed: their digests complete the job records
+    // the processor heads need the jobs but not the hashes: they run on stream 3 beside the two hash kernels
+    CK(cudaEventRecord(d->ev_jobs, s));
+    CK(cudaStreamWaitEvent(d->stream3, d->ev_jobs, 0));
+    if (2 * ns + nf > 0) d->n_launch++, k_smt<<<(unsigned)((2 * ns + nf + 31) / 32), 32, 0, d->stream3>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, f0, nf);
+    CK(cudaEventRecord(d->ev_heads, d->stream3));
     if (4 * ns + 2 * nf > 0) d->n_launch++, k_hstate<<<(unsigned)((4 * ns + 2 * nf + 31) / 32), 160, 0, s>>>(d->w, d->hs_in, d->hs_cur, d->smt, pl.P.nTx, s0, ns, f0, nf);
     CK(cudaEventRecord(d->kev[1], s));
     CK(cudaEventRecord(d->kev[2], s));
     if (2 * ns + nf > 0) {
         d->n_launch++, k_leafhash<<<(unsigned)((2 * (2 * ns + nf) + 31) / 32), 128, 0, s>>>(pl, d->w, d->smt, d->lev, s0, ns, f0, nf);
-        d->n_launch++, k_smt<<<(unsigned)((2 * ns + nf + 31) / 32), 32, 0, s>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, f0, nf);
+        CK(cudaStreamWaitEvent(s, d->ev_heads, 0));
         const unsigned lb = (unsigned)((2 * ns + nf + 15) / 16);
         d->n_launch++, k_smt_levels<<<lb, 96, 0, s>>>(pl, d->w, d->lev, d->smst, d->mids, d->img00, d->zflag, s0, ns, f0, nf);
         // the skipped (0, 0) levels are filled in beside the tail and the hash of the inputs
@@ -421,7 +429,7 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
     CK(cudaStreamWaitEvent(d->stream4, d->ev0, 0));
     d->n_launch++, k_front<<<(unsigned)((P.nTx + 31) / 32), 32, 0, d->stream4>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt_front, d->isExit_front, 0, P.nTx);
     CK(cudaEventRecord(d->ev_front, d->stream4));
-    d->n_launch++, k_smtjob<<<hz_grid(P.nTx), HZ_BLOCK, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, d->hs_in, 0, P.nTx);
+    d->n_launch++, k_smtjob<<<(unsigned)((P.nTx + 31) / 32), 32, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, d->hs_in, 0, P.nTx);
     CK(cudaStreamWaitEvent(s3, d->ev_front, 0));
     CK(cudaStreamWaitEvent(s6, d->ev_front, 0));
     const int F = P.maxFeeTx, h0 = P.nTx / 2;

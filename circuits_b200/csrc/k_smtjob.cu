@@ -8,10 +8,12 @@
 // skipped, decodeTx reduced to the fields rollupTx reads -- so the merkle kernels start after a fraction of
 // k_front's time, and k_front itself runs beside them.  k_front still records the jobs it arrives at; k_tail
 // compares the two (always: a difference is an internal error, HzErrBuf.pad).
-__global__ void __launch_bounds__(HZ_BLOCK, 3) k_smtjob(HzPlan pl, Fr* w, HzSmtJob* smt, Fr* isExit, const uint32_t* off_jk, Fr* hs_in, int s0, int ns) {
-    bool real; int i = s0 + hz_item(ns, real);
+__global__ void __launch_bounds__(32) k_smtjob(HzPlan pl, Fr* w, HzSmtJob* smt, Fr* isExit, const uint32_t* off_jk, Fr* hs_in, int s0, int ns) {
+    int g = (int)(blockIdx.x * blockDim.x + threadIdx.x);           // one thread per slot
+    if (g >= ns) g = ns - 1;
+    const int i = s0 + g;
     Comp<MCompute> c(w, pl.off_rollup[i], nullptr);
-    c.dry = true;
+    c.dry = true; c.solo = true;
     int hs_n = 0;
     c.skip_hash = true; c.hs_rec = hs_in + 16 * (size_t)i; c.hs_n = &hs_n;       // the four state hashes: inputs recorded for k_hstate
     DecodeOut<MCompute> d;
@@ -21,7 +23,6 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_smtjob(HzPlan pl, Fr* w, HzSmtJ
     SlotHook<MCompute> hook; hook.eddsa = nullptr; hook.smt = &smt[2 * i]; hook.isExit = &isExit[i]; hook.sz = &pl.sz; hook.jobs_only = true;
     RollupTxOut<MCompute> o;
     sec_rollup(c, pl, i, d, o, pre, hook);
-    __syncwarp();
-    // the dry walk does not keep the witness cursor: the processors start where the layout walk put them
-    if (hz_glane() == 0) { smt[2 * i].cur = off_jk[i]; smt[2 * i + 1].cur = off_jk[i] + pl.sz.p2_off; }
+    // the dry walk skips the fee accumulator: the processors start where the layout walk put them
+    smt[2 * i].cur = off_jk[i]; smt[2 * i + 1].cur = off_jk[i] + pl.sz.p2_off;
 }
