@@ -49,6 +49,13 @@ def emit(obj):
         os.write(_REAL_STDOUT, data)
 
 
+def bench_config(cfg, cfg_name):
+    """The `config` object of the JSON line: the same in both arms."""
+    return {"workload": cfg_name, "nTx": cfg[0], "nLevels": cfg[1], "maxL1Tx": cfg[2], "maxFeeTx": cfg[3],
+            "l2_flush": "GPU arm: 256 MiB device memset between timed steps, and every step writes the whole witness "
+                        "(far larger than L2); CPU arm: nothing to flush"}
+
+
 def make_input(cfg):
     """Packed input (NInputs x 32 B) + expected hashGlobalInputs; cached in /tmp for the other arm."""
     import pickle
@@ -203,8 +210,7 @@ def run_reference(args, cfg, cfg_name):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "tx/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (BN254 Fr, 254-bit modular)",
-        "data": "synthetic", "config": {"workload": cfg_name, "nTx": cfg[0], "nLevels": cfg[1], "maxL1Tx": cfg[2],
-                                         "maxFeeTx": cfg[3], "l2_flush": "n/a (CPU)"},
+        "data": "synthetic", "config": bench_config(cfg, cfg_name),
         "cpu_baseline": base,
         "e2e": {"value": val, "unit": "tx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0})
@@ -333,57 +339,142 @@ def run_gpu(args, cfg, cfg_name):
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     ms_per_step = float(t_dev.item())
     # -- end to end through the public call, pinned host buffers ---------------------------------
-    e2e_step()
-    barrier()
-    e2e_t = []
-    for _ in range(args.steps):
-        barrier()
-        t = time.perf_counter()
+    # One GPU: WitnessCalculator.calculateBinWitness.  N GPUs: the same call on ONE context that spans the N GPUs of
+    # the box (hzw_params.n_gpus = N; rank 0's process drives them, the exchange runs inside the library and one
+    # whole witness lands in one pinned buffer) -- the other ranks wait on a host-side (gloo) barrier meanwhile, so
+    # that no NCCL kernel spins on their GPUs.
+    if sharded:
+        del pin_out
+        host_group = dist.new_group(backend="gloo")
+        e2e_t, stats, got_hash = [], None, None
+        if rank == 0:
+            wm = wcm.WitnessCalculator(*cfg, device=0, n_gpus=world)
+            pin_full = torch.empty(32 * wm.NVars, dtype=torch.uint8, pin_memory=True)
+            wm.calculateBinWitness(pin_in, False, out=pin_full)
+            for _ in range(args.steps):
+                torch.cuda.synchronize()
+                t = time.perf_counter()
+                wm.calculateBinWitness(pin_in, False, out=pin_full)
+                e2e_t.append(time.perf_counter() - t)
+            stats = wm.lastStats()
+            got_hash = int.from_bytes(bytes(pin_full[32:64].numpy()), "little")
+            wm.close()
+            del pin_full
+        dist.barrier(group=host_group)
+        clocks = sampler.stop() if sampler else None
+        if rank != 0:
+            return
+        e2e_s = sum(e2e_t) / len(e2e_t)
+        io = [float(stats["h2d_bytes"]), float(stats["d2h_bytes"])]
+        launches_per_step = int(stats["gpu_launches"])
+    else:
         e2e_step()
-        e2e_t.append(time.perf_counter() - t)
-    barrier()
-    clocks = sampler.stop() if sampler else None
-    stats = wc.lastStats()
-    t_e2e = torch.tensor([sum(e2e_t) / len(e2e_t)], device="cuda")
-    io = torch.tensor([float(stats["h2d_bytes"]), float(stats["d2h_bytes"])], device="cuda", dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        dist.all_reduce(io, op=dist.ReduceOp.SUM)
-    e2e_s = float(t_e2e.item())
-    if rank == 0:
-        # rank 0 (or the only rank) holds hashGlobalInputs: witness entry 1
+        barrier()
+        e2e_t = []
+        for _ in range(args.steps):
+            barrier()
+            t = time.perf_counter()
+            e2e_step()
+            e2e_t.append(time.perf_counter() - t)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        stats = wc.lastStats()
+        e2e_s = sum(e2e_t) / len(e2e_t)
+        io = [float(stats["h2d_bytes"]), float(stats["d2h_bytes"])]
+        launches_per_step = int(stats["gpu_launches"])
         got_hash = int.from_bytes(bytes(pin_out[32:64].numpy()), "little")
-        if got_hash != expect_hash:
-            raise SystemExit("hashGlobalInputs mismatch: the witness is wrong, refusing to report a number")
+    # hashGlobalInputs is witness entry 1
+    if got_hash != expect_hash:
+        raise SystemExit("hashGlobalInputs mismatch: the witness is wrong, refusing to report a number")
     if rank != 0:
         return
-    # -- roofline of the dominant kernel (rank 0's launches) -------------------------------------
+    # -- roofline (rank 0's launches) ---------------------------------------------------------------
+    # Per-kernel durations: at one GPU from hzw_profile_step (one more batch with every launch serialised on one
+    # stream, an event in front of each: the time a kernel takes ALONE, measured live); on a sharded context from the
+    # intervals of the timed steps (five streams run together there, so an interval also holds its neighbours).
     kmean = {k: sum(v) / len(v) for k, v in kern.items()}
-    top = max(kmean, key=kmean.get)
     F, L1 = cfg[3], cfg[1] + 1
     n_slots = (nTx + world - 1) // world
     n_fee = (F + world - 1) // world
+    n_proc = 2 * n_slots + n_fee
+    SZL = 2 + 4 + 2 * 634 + 3 + 5                  # entries of one SMTProcessorLevel (hzw_dev.cuh HZ_SZL)
+    alone, lev_tot, lev_img = None, n_proc * L1, 0
+    if not sharded:
+        wc.profileStep()
+        runs = [wc.profileStep() for _ in range(3)]
+        alone = {}
+        for r in runs:
+            for name, ms in r:
+                alone[name] = alone.get(name, 0.0) + ms / len(runs)
+        lev_tot, lev_img = wc.imageLevels()
+    kms = alone if alone is not None else kmean
+    top = max(kms, key=kms.get)
     fee_proc = info["feeTx"] - 2 * 980 - 30       # entries of a FeeTx spent in its SMT processor (approx.)
     front_entries = info["decodeTx"] + info["rollupTx"] - info["getAx"] - info["sigVerifier"] - info["processors"]
+    sha_blocks = (info["sha_blocks"] + world - 1) // world
+    # ALGORITHMIC bytes per launch: the witness entries a kernel has to write + the main inputs it reads, 32 B each
     alg_bytes = {
-        # written signals + the main inputs the kernel reads, 32 B each
         "k_front": 32 * n_slots * (front_entries + 362 + 2 * F),
         "k_smtjob": 32 * n_slots * (362 + 2 * F),      # reads only: a dry run for the SMT job records
+        "k_smt_levels": 32 * ((lev_tot - lev_img) * SZL + n_proc * L1),
+        "k_smt_zero": 32 * lev_img * 2 * 634,
+        "k_smt": 32 * n_proc * (info["processors"] // 2 - L1 * SZL) if alone is not None else
+                 32 * (n_slots * (info["processors"] + 2 * L1 + 14) + n_fee * (fee_proc + L1 + 7)),
+        "k_ed_fill": 32 * n_slots * (252 * 9 + 83 * 3 + 83 * 17),
         "k_eddsa": 32 * n_slots * (info["getAx"] + info["sigVerifier"] + 8),
-        "k_smt": 32 * (n_slots * (info["processors"] + 2 * L1 + 14) + n_fee * (fee_proc + L1 + 7)),
-        "k_sha_blocks": 32 * ((info["sha_blocks"] + world - 1) // world) * info["sha_block"],
-    }.get(top, 0)
+        "k_hstate": 32 * (4 * n_slots + 2 * n_fee) * 980,
+        "k_leafhash": 32 * 2 * n_proc * 776,
+        "k_sighash": 32 * n_slots * 1351,
+        "k_sha_blocks": 32 * sha_blocks * info["sha_block"],
+    }
+    # ALGORITHMIC limb products (32 x 32 -> 64) per launch of the Poseidon kernels
+    alg_prod = {
+        "k_smt_levels": (lev_tot - lev_img) * 2 * poseidon_perm_products(3),
+        "k_hstate": (4 * n_slots + 2 * n_fee) * poseidon_perm_products(5),
+        "k_leafhash": 2 * n_proc * poseidon_perm_products(4),
+        "k_sighash": n_slots * poseidon_perm_products(7),
+    }
     peaks, src = measured_peaks()
-    achieved = alg_bytes / (kmean[top] * 1e-3) / 1e9 if kmean[top] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": committed_traffic(top, cfg_name),
-                "peak_source": src + " (copy bandwidth)",
-                "kernel_ms": kmean, "algorithmic_bytes": alg_bytes,
-                "note": "254-bit modular arithmetic: the kernels are bound by dependent integer issue (IMAD.WIDE carry "
-                        "chains), not by HBM; the HBM fraction is reported as the contract asks, see DESIGN.md.  Timed "
-                        "intervals (CUDA events on the launching stream, four streams run together): k_eddsa = k_edjob + "
-                        "k_ed_const + k_eddsa + k_ed_fill, k_smt = k_smt + k_smt_levels; serialised per-launch times in "
-                        "profiles/r1_launches_2048_v15.csv"}
+    try:
+        ipeak = wcm.int_peak(local)
+    except Exception as e:      # a measurement helper must not take the bench line down
+        log("[bench] int peak skipped: %r" % (e,))
+        ipeak = None
+    per_kernel = {}
+    for name, ms in kms.items():
+        e = {"ms": ms}
+        if alg_bytes.get(name) and ms > 0:
+            e["algorithmic_bytes"] = alg_bytes[name]
+            e["hbm_gbs"] = alg_bytes[name] / (ms * 1e-3) / 1e9
+            e["hbm_frac"] = e["hbm_gbs"] / peaks["hbm_gbs"]
+        if alg_prod.get(name) and ms > 0 and ipeak:
+            e["limb_products"] = alg_prod[name]
+            e["int_frac"] = alg_prod[name] / (ms * 1e-3) / ipeak
+        per_kernel[name] = e
+    tk = per_kernel[top]
+    int_bound = "int_frac" in tk
+    roofline = {
+        "bound": "int" if int_bound else "hbm", "kernel": top,
+        "achieved": (tk["limb_products"] / (tk["ms"] * 1e-3)) if int_bound else tk.get("hbm_gbs", 0.0),
+        "peak": ipeak if int_bound else peaks["hbm_gbs"],
+        "unit": "32x32->64 multiply-adds/s over all lanes" if int_bound else "GB/s",
+        "frac": tk["int_frac"] if int_bound else tk.get("hbm_frac", 0.0),
+        "traffic": committed_traffic(top, cfg_name),
+        "peak_source": "measured live (hzw_int_peak: independent IMAD.WIDE.U32 chains, full occupancy)" if int_bound
+                       else src + " (copy bandwidth)",
+        "hbm": {"achieved": tk.get("hbm_gbs"), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": tk.get("hbm_frac"),
+                "algorithmic_bytes": tk.get("algorithmic_bytes"), "peak_source": src + " (copy bandwidth)"},
+        "kernel_ms_source": "hzw_profile_step: each launch alone on one stream, CUDA events, mean of 3 batches" if alone is not None
+                            else "intervals of the timed steps (CUDA events on the launching stream; streams run together)",
+        "kernels": per_kernel, "timed_step_intervals_ms": kmean,
+        "image_levels": {"processor_levels": lev_tot, "copied_from_the_(0,0)_image": lev_img},
+        "step": {"witness_bytes": 32 * info["nvars"], "hbm_gbs": 32 * info["nvars"] / world / (ms_per_step * 1e-3) / 1e9,
+                 "hbm_frac": 32 * info["nvars"] / world / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                 "sum_of_kernels_alone_ms": sum(kms.values()) if alone is not None else None},
+        "note": "254-bit modular arithmetic: the dominant kernels are bound by dependent integer issue (IMAD.WIDE carry "
+                "chains), so the primary bound is the integer-multiply pipe and the HBM fraction is the secondary figure "
+                "(DESIGN.md section 7). Algorithmic work of k_smt_levels / k_smt_zero follows the (0, 0) levels of THIS batch.",
+    }
     base = None
     if world == 1 and not args.no_cpu_baseline:
         if not os.path.exists(CPU_PORT):
@@ -393,35 +484,46 @@ def run_gpu(args, cfg, cfg_name):
         "metric": METRIC, "value": nTx / (ms_per_step * 1e-3), "unit": "tx/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32 limbs (BN254 Fr, 254-bit modular)", "data": "synthetic",
-        "config": {"workload": cfg_name, "nTx": cfg[0], "nLevels": cfg[1], "maxL1Tx": cfg[2], "maxFeeTx": cfg[3],
-                   "witness_signals": info["nvars"], "witness_bytes": 32 * info["nvars"],
-                   "sharding": "tx slots / fee txs / SHA blocks split over %d rank(s); one all-gather of %s B records"
-                               % (world, getattr(wc, "recBytes", 0)) if sharded else "single GPU",
-                   "l2_flush": "256 MiB device memset between timed steps; each step also writes the whole witness"},
-        "e2e": {"value": nTx / e2e_s, "unit": "tx/s", "h2d_bytes_per_step": int(io[0].item()),
-                "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": e2e_s * 1e3},
-        "gpu_launches": int(stats["gpu_launches"]) * args.steps * world,
+        "config": bench_config(cfg, cfg_name),
+        "workload_detail": {"witness_signals": info["nvars"], "witness_bytes": 32 * info["nvars"],
+                            "sharding": "tx slots / fee txs / SHA blocks split over %d rank(s); one all-gather of %s B records"
+                                        % (world, getattr(wc, "recBytes", 0)) if sharded else "single GPU"},
+        "e2e": {"value": nTx / e2e_s, "unit": "tx/s", "h2d_bytes_per_step": int(io[0]),
+                "d2h_bytes_per_step": int(io[1]), "ms_per_step": e2e_s * 1e3,
+                "call": "WitnessCalculator.calculateBinWitness -> hzw_calculate, pinned host buffers, ONE whole witness out"
+                        + (" (one context with n_gpus = %d: exchange inside the library, every GPU copies its ranges "
+                           "to their offsets in the one buffer)" % world if sharded else "")},
+        "gpu_launches": launches_per_step * args.steps if sharded else launches_per_step * args.steps * world,
         "clocks": clocks, "roofline": roofline,
     }
     if world == 1:
         pm = poseidon_metric(local)
         if pm is not None:
             line["poseidon"] = pm
-        try:
-            peak = wcm.int_peak(local)
+        if ipeak:
+            peak = ipeak
             prod = poseidon_products(cfg)
+            skipped = lev_img * 2 * poseidon_perm_products(3)
+            # EdDSA per signature (hints.cuh): 253 + 253 + 83 point operations of 14 products each on the ladder walk, the
+            # same formulas once more when the step entries are written, 3 per element of the batched inversion (669),
+            # the square root of getAx (~1.5 k), Poseidon(5) counted above with the Poseidon kernels
+            ed_mulmods = (253 + 253 + 83) * 14 * 2 + 3 * 669 + 1500
+            ed = n_slots * world * ed_mulmods * 153
             line["int_roofline"] = {
                 "unit": "32x32->64 multiply-adds/s over all lanes", "peak": peak,
                 "peak_source": "measured live (hzw_int_peak: independent IMAD.WIDE.U32 chains, full occupancy)",
-                "achieved": prod / (ms_per_step * 1e-3), "frac": prod / (ms_per_step * 1e-3) / peak,
-                "algorithmic_products_per_step": prod,
-                "note": "Poseidon only (S-boxes: 153 limb products per modular multiplication; MDS rows: 64 t + 100 per row); "
-                        "EdDSA, SHA and glue not counted"}
+                "achieved": (prod - skipped + ed) / (ms_per_step * 1e-3),
+                "frac": (prod - skipped + ed) / (ms_per_step * 1e-3) / peak,
+                "executed_products_per_step": prod - skipped + ed,
+                "poseidon_products_of_the_circuit": prod, "poseidon_products_skipped_as_images": skipped,
+                "eddsa_products_estimate": ed,
+                "frac_counting_the_skipped_levels": (prod + ed) / (ms_per_step * 1e-3) / peak,
+                "note": "whole step: Poseidon (S-boxes: 153 limb products per modular multiplication; MDS rows: 64 t + 100 "
+                        "per row) without the (0, 0) levels this batch copied from the image, plus the EdDSA estimate; "
+                        "SHA-256 and bit plumbing not counted"}
             if pm is not None:
                 pp = pm["perms_per_launch"] * poseidon_perm_products(3)
                 line["poseidon"]["int_frac"] = pp / (pm["ms_per_launch"] * 1e-3) / peak
-        except Exception as e:      # a measurement helper must not take the bench line down
-            log("[bench] int roofline skipped: %r" % (e,))
     if base is not None:
         line["cpu_baseline"] = base
     emit(line)

@@ -12,10 +12,15 @@ struct HzBackend {
     virtual int calculate(const uint8_t* inputs, int sanity, uint8_t* witness_out, bool resident, float* kernel_ms,
                           HzErrBuf* errs) = 0;
     virtual int kernel_ms(float*, const char**, int) { return 0; }
+    virtual int profile_step(float*, const char**, int) { return HZW_E_PARAM; }
+    virtual int image_levels(uint64_t*) { return HZW_E_PARAM; }
     // sharded evaluation: records live in the backend's memory space (device memory for CUDA)
     virtual int set_shard(int rank, int world) = 0;
     virtual uint64_t exchange_bytes() = 0;
     virtual int pieces(uint64_t* table, int cap) = 0;
+    // a context that spans several GPUs (n_gpus > 1): the pieces and the resident witness of its rank r
+    virtual int rank_pieces(int r, uint64_t* table, int cap) { return r == 0 ? pieces(table, cap) : HZW_E_PARAM; }
+    virtual int rank_witness_device(int r, void** ptr, int32_t* device, void** stream) { return r == 0 ? witness_device(ptr, device, stream) : HZW_E_PARAM; }
     virtual int shard_phase1(const uint8_t* inputs, int sanity, void* record_out, HzErrBuf* errs) = 0;
     virtual int shard_phase2(const void* records, int sanity, uint8_t* shard_out, float* kernel_ms, HzErrBuf* errs) = 0;
     // Withdraw(nLevels): n independent instances, inputs n x ninputs x 32 B, witnesses n x nvars x 32 B
@@ -215,6 +220,14 @@ int hzw_witness_device(const hzw_ctx* ctx, void** dev_ptr, int32_t* device, void
     if (!ctx || !dev_ptr) return HZW_E_PARAM;
     return ctx->be->witness_device(dev_ptr, device, stream);
 }
+int hzw_rank_pieces(const hzw_ctx* ctx, int32_t rank, uint64_t* table, int32_t cap) {
+    if (!ctx || !table || cap <= 0) return HZW_E_PARAM;
+    return ctx->be->rank_pieces(rank, table, cap);
+}
+int hzw_rank_witness_device(const hzw_ctx* ctx, int32_t rank, void** dev_ptr, int32_t* device, void** stream) {
+    if (!ctx || !dev_ptr) return HZW_E_PARAM;
+    return ctx->be->rank_witness_device(rank, dev_ptr, device, stream);
+}
 int hzw_witness_read(hzw_ctx* ctx, uint64_t first, uint64_t count, uint8_t* out) {
     if (!ctx || !out || first + count > ctx->nvars()) return HZW_E_PARAM;
     return ctx->be->witness_read(first, count, out);
@@ -262,6 +275,14 @@ int hzw_plan_info(const hzw_ctx* ctx, uint64_t out[12]) {
 int hzw_last_kernel_ms(const hzw_ctx* ctx, float* ms, const char** names, int cap) {
     if (!ctx || !ms || cap <= 0) return HZW_E_PARAM;
     return ctx->be->kernel_ms(ms, names, cap);
+}
+int hzw_profile_step(hzw_ctx* ctx, float* ms, const char** names, int cap) {
+    if (!ctx || ctx->withdraw || !ms || !names || cap <= 0) return HZW_E_PARAM;
+    return ctx->be->profile_step(ms, names, cap);
+}
+int hzw_image_levels(hzw_ctx* ctx, uint64_t out[2]) {
+    if (!ctx || ctx->withdraw || !out) return HZW_E_PARAM;
+    return ctx->be->image_levels(out);
 }
 int hzw_set_shard(hzw_ctx* ctx, int32_t rank, int32_t world) {
     if (!ctx || ctx->withdraw || world < 1 || rank < 0 || rank >= world) return HZW_E_PARAM;

@@ -18,14 +18,23 @@ int hz_cuda_witness_device(HzCuda*, void** ptr, int32_t* device, void** stream);
 int hz_cuda_witness_read(HzCuda*, uint64_t first, uint64_t count, uint8_t* out);
 // per-kernel device times of the last calculate
 int hz_cuda_kernel_ms(HzCuda*, float* ms, const char** names, int cap);
+// one more batch with every launch serialised on one stream: device time of each launch alone, in launch order
+int hz_cuda_profile_step(HzCuda*, float* ms, const char** names, int cap);
+int hz_cuda_image_levels(HzCuda*, uint64_t out[2]);
 
 // ---- sharded evaluation (one context per GPU; include/hzwitness.h, hzw_shard_*) -------------------
 int hz_cuda_set_shard(HzCuda*, int rank, int world);
 uint64_t hz_cuda_exchange_bytes(const HzCuda*);
 uint64_t hz_cuda_launches(const HzCuda*);     // kernels launched since the start of the current calculate / shard phase 1
 int hz_cuda_shard_phase1(HzCuda*, const uint8_t* inputs, int sanity, void* record_out_dev, HzErrBuf* errs);
+// in_place: every piece goes to its own place in a whole-witness buffer instead of back to back into a shard buffer
 int hz_cuda_shard_phase2(HzCuda*, const void* records_dev, int sanity, uint8_t* shard_out, const uint64_t* pieces, int npieces,
-                         float* kernel_ms, HzErrBuf* errs, uint64_t* d2h);
+                         float* kernel_ms, HzErrBuf* errs, uint64_t* d2h, bool in_place = false);
+// one process driving several GPUs: peer access, phase 1 whose pack kernel stores the record into every peer, the wait
+int hz_cuda_enable_peer(HzCuda*, HzCuda* peer);
+uint8_t* hz_cuda_recs(HzCuda*);
+int hz_cuda_multi_phase1(HzCuda*, const uint8_t* inputs, int sanity, uint8_t* const* peer_recs, int world);
+int hz_cuda_multi_wait(HzCuda*, HzCuda* peer);
 
 // ---- Withdraw(nLevels) batches ---------------------------------------------------------------------
 int hz_cuda_probe(int device);       // 0 when the device exists, else HZW_E_DEVICE / HZW_E_PARAM

@@ -24,9 +24,12 @@
 #define HZ_NKERN 10  /* timed intervals; k_smt's covers the head and the levels kernels */
 static const char* const HZ_KERN_NAMES[HZ_NKERN] = {"k_smtjob", "k_fee_front", "k_smt", "k_tail", "k_hash_head",
                                                     "k_sha_chain", "k_sha_blocks", "k_hash_tail", "k_eddsa", "k_front"};
+#define HZ_MAXPROF 40
 #define HZ_BLOCK 128                       /* 16 lane groups per block */
 
 struct HzHole { uint32_t cur, nz; };
+#define HZ_MAX_GPUS 16
+struct HzPeerRecs { uint8_t* p[HZ_MAX_GPUS]; int n; };   // destinations of one rank's exchange record (k_pack)
 struct HzCuda {
     int device;
     HzPlan plan;               // device-pointer version
@@ -78,7 +81,10 @@ struct HzCuda {
     cudaStream_t stream, stream2, stream3, stream4;
     cudaEvent_t ev_half[2], ev_ed[2], ev_done;
     cudaEvent_t ev0, ev1, ev_front, ev_eddsa, ev_lev, ev_zero, ev_fee, ev_jobs, ev_heads;
+    cudaEvent_t ev_xchg;       // this rank's record has been stored into every peer (hz_cuda_multi_phase1)
     cudaEvent_t kev[HZ_NKERN + 3];
+    // profile mode (hz_cuda_profile_step): every launch of a batch on ONE stream, an event in front of each
+    bool prof; int n_prof; cudaEvent_t pev[HZ_MAXPROF + 1]; const char* pname[HZ_MAXPROF];
 };
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "hzw: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return HZW_E_DEVICE; } } while (0)
@@ -149,7 +155,7 @@ __global__ void k_ed_hints(Fr* scratch, int ns);
 __global__ void k_ed_fill(Fr* w, HzErrBuf* err, const Fr* tab, const Fr* scratch, uint32_t win_stride, int ns);
 __global__ void k_tail(HzPlan pl, Fr* w, HzErrBuf* err, HzErrBuf* ebuf, const HzSmtMid* mids, const Fr* isExit, const Fr* isExit_front,
                        const HzEddsaJob* jobs, const HzEddsaJob* jobs_front, const HzSmtJob* smt, const HzSmtJob* smt_front, int s0, int ns, int f0, int nf);
-__global__ void k_pack(HzPlan pl, const Fr* w, const uint8_t* pre, uint8_t* rec, int s0, int ns, int per, int own_last_slot, int own_last_fee);
+__global__ void k_pack(HzPlan pl, const Fr* w, const uint8_t* pre, HzPeerRecs dst, int s0, int ns, int per, int own_last_slot, int own_last_fee);
 __global__ void k_unpack(HzPlan pl, Fr* w, uint8_t* pre, const uint8_t* recs, int world, int per, uint32_t rec_bytes);
 __global__ void k_hash_head(HzPlan pl, Fr* w, uint8_t* pre, HzErrBuf* err, uint32_t* off_blocks);
 __global__ void k_sha_chain(HzPlan pl, const uint8_t* preb, uint32_t* chain, uint32_t* msgw, uint32_t* wk, uint32_t b_begin, uint32_t b_end);

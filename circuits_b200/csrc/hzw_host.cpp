@@ -3,6 +3,7 @@
 // with HZW_E_DEVICE.
 #include "hzw_api.hpp"
 #include "hzw_cuda.h"
+#define HZ_MAX_GPUS_HOST 16
 
 struct CudaBackend : HzBackend {
     HzCuda* d;
@@ -13,6 +14,8 @@ struct CudaBackend : HzBackend {
         return hz_cuda_calculate(d, inputs, sanity, resident ? nullptr : out, ms, errs, &launches, &h2d, &d2h);
     }
     int kernel_ms(float* ms, const char** names, int cap) override { return hz_cuda_kernel_ms(d, ms, names, cap); }
+    int profile_step(float* ms, const char** names, int cap) override { return hz_cuda_profile_step(d, ms, names, cap); }
+    int image_levels(uint64_t out[2]) override { return hz_cuda_image_levels(d, out); }
     int witness_device(void** ptr, int32_t* device, void** stream) override { return hz_cuda_witness_device(d, ptr, device, stream); }
     int witness_read(uint64_t first, uint64_t count, uint8_t* out) override { return hz_cuda_witness_read(d, first, count, out); }
     const HzLayout* L = nullptr;
@@ -37,13 +40,121 @@ struct CudaBackend : HzBackend {
     }
 };
 
+// ---- one process, all the GPUs of a box (hzw_params.n_gpus > 1) --------------------------------------------------
+// One CUDA context per device, rank r of n evaluating its range of slots / fee txs / SHA blocks exactly as a rank of
+// the multi-process form does; the difference is who runs the exchange and where the witness lands:
+//   * the all-gather is done by the pack kernels themselves, storing each rank's record into every peer over NVLink
+//     (hz_cuda_multi_phase1), ordered by one event per rank -- no host synchronisation between the two phases;
+//   * every GPU copies the pieces it owns straight to their offsets in the caller's ONE witness buffer over its own
+//     PCIe link (`./circuit input.json witness.wtns` produces one file: /root/reference/tools/helpers/actions.js:139-143).
+// A host thread per device issues that device's work; they meet once, after queueing phase 1.
+#include <thread>
+struct MultiBackend : HzBackend {
+    std::vector<std::unique_ptr<CudaBackend> > rk;
+    const HzLayout* L = nullptr;
+    int n = 0;
+    std::vector<float> ms_rank;
+    int run(const uint8_t* inputs, int sanity, uint8_t* out, float* ms, HzErrBuf* errs) {
+        std::vector<int> st(n, 0);
+        std::vector<HzErrBuf> eb(n);
+        std::vector<uint8_t*> recs(n);
+        for (int r = 0; r < n; r++) { recs[r] = hz_cuda_recs(rk[r]->d); memset(&eb[r], 0, sizeof(HzErrBuf)); }
+        {
+            std::vector<std::thread> th;
+            for (int r = 0; r < n; r++) th.emplace_back([&, r]() { st[r] = hz_cuda_multi_phase1(rk[r]->d, inputs, sanity, recs.data(), n); });
+            for (auto& t : th) t.join();
+        }
+        for (int r = 0; r < n; r++) if (st[r]) return st[r];       // nothing waits on a peer yet: safe to stop here
+        ms_rank.assign(n, 0.f);
+        {
+            std::vector<std::thread> th;
+            for (int r = 0; r < n; r++) th.emplace_back([&, r]() {
+                for (int q = 0; q < n && !st[r]; q++) if (q != r) st[r] = hz_cuda_multi_wait(rk[r]->d, rk[q]->d);
+                if (st[r]) return;
+                uint64_t t[32]; int np = hz_shard_pieces(*L, rk[r]->sh, t, 16);
+                uint64_t moved = 0;
+                st[r] = hz_cuda_shard_phase2(rk[r]->d, nullptr, sanity, out, t, np, &ms_rank[r], &eb[r], &moved, true);
+                rk[r]->d2h = moved; rk[r]->launches = hz_cuda_launches(rk[r]->d);
+            });
+            for (auto& t : th) t.join();
+        }
+        launches = 0; d2h = 0; h2d = inputs ? (uint64_t)n * 32ull * L->plan.n_inputs : 0;
+        float worst = 0.f;
+        for (int r = 0; r < n; r++) {
+            if (st[r]) return st[r];
+            launches += rk[r]->launches; d2h += rk[r]->d2h;
+            if (ms_rank[r] > worst) worst = ms_rank[r];
+        }
+        if (ms) *ms = worst;                       // device time of the slowest rank (ev0 -> ev1 on its own device)
+        // first failing constraint over all ranks: the records of every rank, lowest witness cursor wins in hz_report
+        memset(errs, 0, sizeof(HzErrBuf));
+        for (int r = 0; r < n; r++) {
+            errs->pad += eb[r].pad;
+            const uint32_t k = eb[r].count < HZ_MAX_ERR ? eb[r].count : HZ_MAX_ERR;
+            for (uint32_t j = 0; j < k; j++) {
+                if (errs->count < HZ_MAX_ERR) errs->rec[errs->count++] = eb[r].rec[j];
+                else {
+                    uint32_t hi = 0;
+                    for (uint32_t q = 1; q < HZ_MAX_ERR; q++) if (errs->rec[q].cur > errs->rec[hi].cur) hi = q;
+                    if (eb[r].rec[j].cur < errs->rec[hi].cur) errs->rec[hi] = eb[r].rec[j];
+                }
+            }
+        }
+        return 0;
+    }
+    int calculate(const uint8_t* inputs, int sanity, uint8_t* out, bool resident, float* ms, HzErrBuf* errs) override {
+        if (!resident && !out) return HZW_E_PARAM;
+        return run(inputs, sanity, resident ? nullptr : out, ms, errs);
+    }
+    int kernel_ms(float* ms, const char** names, int cap) override { return hz_cuda_kernel_ms(rk[0]->d, ms, names, cap); }
+    int set_shard(int, int) override { return HZW_E_PARAM; }       // the context already spans its GPUs
+    uint64_t exchange_bytes() override { return hz_cuda_exchange_bytes(rk[0]->d); }
+    // pieces of rank `cap < 0 ? -cap - 1 : 0`... the table of rank 0; hzw_rank_pieces gives the others
+    int pieces(uint64_t* table, int cap) override { return hz_shard_pieces(*L, rk[0]->sh, table, cap); }
+    int rank_pieces(int r, uint64_t* table, int cap) override { return r < 0 || r >= n ? HZW_E_PARAM : hz_shard_pieces(*L, rk[r]->sh, table, cap); }
+    int shard_phase1(const uint8_t*, int, void*, HzErrBuf*) override { return HZW_E_PARAM; }
+    int shard_phase2(const void*, int, uint8_t*, float*, HzErrBuf*) override { return HZW_E_PARAM; }
+    int withdraw_batch(uint64_t, const uint8_t*, int, uint8_t*, float*, HzErrBuf*) override { return HZW_E_PARAM; }
+    // resident witness: rank r's pieces live on rank r's device
+    int witness_device(void** ptr, int32_t* device, void** stream) override { return hz_cuda_witness_device(rk[0]->d, ptr, device, stream); }
+    int rank_witness_device(int r, void** ptr, int32_t* device, void** stream) override {
+        return r < 0 || r >= n ? HZW_E_PARAM : hz_cuda_witness_device(rk[r]->d, ptr, device, stream);
+    }
+    int witness_read(uint64_t first, uint64_t count, uint8_t* out) override {
+        // entry ranges are read from the rank that owns them
+        for (int r = 0; r < n; r++) {
+            uint64_t t[32]; int np = hz_shard_pieces(*L, rk[r]->sh, t, 16);
+            for (int k = 0; k < np; k++) {
+                const uint64_t a = t[2 * k] > first ? t[2 * k] : first, b = t[2 * k] + t[2 * k + 1] < first + count ? t[2 * k] + t[2 * k + 1] : first + count;
+                if (b > a) { int st = hz_cuda_witness_read(rk[r]->d, a, b - a, out + 32ull * (a - first)); if (st) return st; }
+            }
+        }
+        return 0;
+    }
+};
+
 HzBackend* hz_backend_create(const hzw_params& prm, const HzLayout& L, int* status) {
-    HzCuda* d = hz_cuda_create(prm.device, L.plan, L.off_decode.data(), L.off_rollup.data(), L.off_fee.data(), L.off_eddsa.data(), L.off_jk.data(), L.off_hs.data(), L.off_hsig.data(), status);
-    if (!d) return nullptr;
-    CudaBackend* b = new CudaBackend(d);
-    b->L = &L;
-    b->sh = hz_shard_ranges(L.plan, 0, 1);
-    return b;
+    const int n = prm.n_gpus > 1 ? prm.n_gpus : 1;
+    if (n > HZ_MAX_GPUS_HOST || n > L.plan.P.nTx) { *status = HZW_E_PARAM; return nullptr; }
+    std::vector<std::unique_ptr<CudaBackend> > rk;
+    for (int r = 0; r < n; r++) {
+        HzCuda* d = hz_cuda_create(prm.device + r, L.plan, L.off_decode.data(), L.off_rollup.data(), L.off_fee.data(), L.off_eddsa.data(), L.off_jk.data(), L.off_hs.data(), L.off_hsig.data(), status);
+        if (!d) return nullptr;
+        rk.emplace_back(new CudaBackend(d));
+        rk.back()->L = &L;
+        rk.back()->sh = hz_shard_ranges(L.plan, 0, 1);
+    }
+    if (n == 1) return rk[0].release();
+    MultiBackend* m = new MultiBackend();
+    m->L = &L; m->n = n;
+    for (int r = 0; r < n; r++) {
+        int st = rk[r]->set_shard(r, n);
+        for (int q = 0; q < n && !st; q++) if (q != r) st = hz_cuda_enable_peer(rk[r]->d, rk[q]->d);
+        if (st) { *status = st; delete m; return nullptr; }
+    }
+    m->rk = std::move(rk);
+    *status = 0;
+    return m;
 }
 
 // Withdraw(nLevels): instances are independent; the backend holds no per-circuit device state

@@ -3,6 +3,11 @@
 #include "hzw_dev.cuh"
 
 static void hz_set_ranges(HzCuda* d, int rank, int world);
+// called in front of every launch of a batch: counts it and, in profile mode, brackets it with an event
+static inline void hz_mark(HzCuda* d, const char* name, cudaStream_t st) {
+    d->n_launch++;
+    if (d->prof && d->n_prof < HZ_MAXPROF) { cudaEventRecord(d->pev[d->n_prof], st); d->pname[d->n_prof++] = name; }
+}
 
 HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode, const uint32_t* off_rollup,
                        const uint32_t* off_fee, const uint32_t* off_eddsa, const uint32_t* off_jk,
@@ -86,8 +91,10 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaEventCreateWithFlags(&d->ev_lev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_fee, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_zero, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&d->ev_xchg, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_jobs, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&d->ev_heads, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; k < HZ_NKERN + 3; k++) ok = ok && cudaEventCreate(&d->kev[k]) == cudaSuccess;
+    for (int k = 0; k <= HZ_MAXPROF; k++) ok = ok && cudaEventCreate(&d->pev[k]) == cudaSuccess;
     // kernels that are to share an SM must agree on its L1 / shared-memory split: k_smt_levels stages the MDS
     // exchange in shared memory, k_eddsa (running beside it on the second stream) uses none -- without a common
     // carve-out the second kernel only gets SMs the first has left
@@ -176,9 +183,11 @@ void hz_cuda_destroy(HzCuda* d) {
     if (d->ev_lev) cudaEventDestroy(d->ev_lev);
     if (d->ev_fee) cudaEventDestroy(d->ev_fee);
     if (d->ev_zero) cudaEventDestroy(d->ev_zero);
+    if (d->ev_xchg) cudaEventDestroy(d->ev_xchg);
     if (d->ev_jobs) cudaEventDestroy(d->ev_jobs);
     if (d->ev_heads) cudaEventDestroy(d->ev_heads);
     for (int k = 0; k < HZ_NKERN + 3; k++) if (d->kev[k]) cudaEventDestroy(d->kev[k]);
+    for (int k = 0; k <= HZ_MAXPROF; k++) if (d->pev[k]) cudaEventDestroy(d->pev[k]);
     delete d->h_off_rollup;
     delete d;
 }
@@ -210,7 +219,9 @@ uint64_t hz_cuda_launches(const HzCuda* d) { return d->n_launch; }
 // phase 1: inputs to the device, then everything per slot / fee tx of the shard
 static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     const HzPlan& pl = d->plan;
-    cudaStream_t s = d->stream, s2 = getenv("HZW_SERIAL_STREAMS") ? d->stream : d->stream2;    // (measurement switch)
+    cudaStream_t s = d->stream;
+    // profile mode (hzw_profile_step): every launch on one stream with an event in front of it
+    const cudaStream_t s2 = d->prof ? s : d->stream2, s3 = d->prof ? s : d->stream3, s4 = d->prof ? s : d->stream4, s5 = d->prof ? s : d->stream5;
     HzErrBuf* err = sanity ? d->err : nullptr;
     CK(cudaMemsetAsync(d->err, 0, sizeof(HzErrBuf), s));
     CK(cudaMemsetAsync(d->pre, 0, (size_t)pl.nblocks * 512, s));
@@ -223,70 +234,70 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     CK(cudaStreamWaitEvent(s2, d->ev0, 0));
     CK(cudaEventRecord(d->kev[9], s2));
     if (ns > 0) {
-        d->n_launch++, k_edjob<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, d->jobs, d->off_eddsa, d->sig_in, s0, ns);
-        d->n_launch++, k_sighash<<<(unsigned)((ns + 31) / 32), 224, 0, s2>>>(d->w, d->sig_in, d->hsig_cur, d->jobs, s0, ns);
-        d->n_launch++, k_ed_const<<<592, 256, 0, s2>>>(pl, d->w, d->off_eddsa, d->hint_img, d->fix_size, s0, ns);
-            d->n_launch++, k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, s0, ns);
-            d->n_launch++, k_ed_ladder<<<(unsigned)((ns + 31) / 32), 96, 0, s2>>>(d->hint_scratch, d->hint_tab, ns);
-            d->n_launch++, k_ed_hints<<<(unsigned)((ns + 3) / 4), 128, 0, s2>>>(d->hint_scratch, ns);
-            d->n_launch++, k_eddsa_tail<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(d->w, err, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, ns);
-        d->n_launch++, k_ed_fill<<<(unsigned)((HZ_FILL_PER_SIG * ns + 127) / 128), 128, 0, s2>>>(d->w, err, d->hint_tab, d->hint_scratch, d->win_stride, ns);
+        hz_mark(d, "k_edjob", s2), k_edjob<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, d->jobs, d->off_eddsa, d->sig_in, s0, ns);
+        hz_mark(d, "k_sighash", s2), k_sighash<<<(unsigned)((ns + 31) / 32), 224, 0, s2>>>(d->w, d->sig_in, d->hsig_cur, d->jobs, s0, ns);
+        hz_mark(d, "k_ed_const", s2), k_ed_const<<<592, 256, 0, s2>>>(pl, d->w, d->off_eddsa, d->hint_img, d->fix_size, s0, ns);
+            hz_mark(d, "k_eddsa", s2), k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, s0, ns);
+            hz_mark(d, "k_ed_ladder", s2), k_ed_ladder<<<(unsigned)((ns + 31) / 32), 96, 0, s2>>>(d->hint_scratch, d->hint_tab, ns);
+            hz_mark(d, "k_ed_hints", s2), k_ed_hints<<<(unsigned)((ns + 3) / 4), 128, 0, s2>>>(d->hint_scratch, ns);
+            hz_mark(d, "k_eddsa_tail", s2), k_eddsa_tail<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(d->w, err, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, ns);
+        hz_mark(d, "k_ed_fill", s2), k_ed_fill<<<(unsigned)((HZ_FILL_PER_SIG * ns + 127) / 128), 128, 0, s2>>>(d->w, err, d->hint_tab, d->hint_scratch, d->win_stride, ns);
     }
     CK(cudaEventRecord(d->kev[10], s2));
     CK(cudaEventRecord(d->ev_eddsa, s2));
     // the fee transactions need nothing but inputs either: third stream, joined before the merkle kernels
-    CK(cudaStreamWaitEvent(d->stream3, d->ev0, 0));
-    if (nf > 0) d->n_launch++, k_fee_front<<<hz_grid(nf), HZ_BLOCK, 0, d->stream3>>>(pl, d->w, err, d->smt + 2 * pl.P.nTx, d->hs_in, f0, nf);
-    CK(cudaEventRecord(d->ev_fee, d->stream3));
+    CK(cudaStreamWaitEvent(s3, d->ev0, 0));
+    if (nf > 0) hz_mark(d, "k_fee_front", s3), k_fee_front<<<hz_grid(nf), HZ_BLOCK, 0, s3>>>(pl, d->w, err, d->smt + 2 * pl.P.nTx, d->hs_in, f0, nf);
+    CK(cudaEventRecord(d->ev_fee, s3));
     // k_front on a stream of its own: the merkle kernels take their jobs from k_smtjob
-    CK(cudaStreamWaitEvent(d->stream4, d->ev0, 0));
-    CK(cudaEventRecord(d->kev[11], d->stream4));
-    if (ns > 0) d->n_launch++, k_front<<<(unsigned)((ns + 31) / 32), 32, 0, d->stream4>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt_front, d->isExit_front, s0, ns);
-    CK(cudaEventRecord(d->kev[12], d->stream4));
-    CK(cudaEventRecord(d->ev_front, d->stream4));
+    CK(cudaStreamWaitEvent(s4, d->ev0, 0));
+    CK(cudaEventRecord(d->kev[11], s4));
+    if (ns > 0) hz_mark(d, "k_front", s4), k_front<<<(unsigned)((ns + 31) / 32), 32, 0, s4>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt_front, d->isExit_front, s0, ns);
+    CK(cudaEventRecord(d->kev[12], s4));
+    CK(cudaEventRecord(d->ev_front, s4));
     CK(cudaEventRecord(d->kev[0], s));
-    if (ns > 0) d->n_launch++, k_smtjob<<<(unsigned)((ns + 31) / 32), 32, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, d->hs_in, s0, ns);
+    if (ns > 0) hz_mark(d, "k_smtjob", s), k_smtjob<<<(unsigned)((ns + 31) / 32), 32, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, d->hs_in, s0, ns);
     CK(cudaStreamWaitEvent(s, d->ev_fee, 0));
     // the state hashes of the slots and fee txs, transposed: their digests complete the job records
     // the processor heads need the jobs but not the hashes: they run on stream 3 beside the two hash kernels
     CK(cudaEventRecord(d->ev_jobs, s));
-    CK(cudaStreamWaitEvent(d->stream3, d->ev_jobs, 0));
-    if (2 * ns + nf > 0) d->n_launch++, k_smt<<<(unsigned)((2 * ns + nf + 31) / 32), 32, 0, d->stream3>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, f0, nf);
-    CK(cudaEventRecord(d->ev_heads, d->stream3));
-    if (4 * ns + 2 * nf > 0) d->n_launch++, k_hstate<<<(unsigned)((4 * ns + 2 * nf + 31) / 32), 160, 0, s>>>(d->w, d->hs_in, d->hs_cur, d->smt, pl.P.nTx, s0, ns, f0, nf);
+    CK(cudaStreamWaitEvent(s3, d->ev_jobs, 0));
+    if (2 * ns + nf > 0) hz_mark(d, "k_smt", s3), k_smt<<<(unsigned)((2 * ns + nf + 31) / 32), 32, 0, s3>>>(pl, d->w, err, d->smt, d->mids, d->lev, d->smst, s0, ns, f0, nf);
+    CK(cudaEventRecord(d->ev_heads, s3));
+    if (4 * ns + 2 * nf > 0) hz_mark(d, "k_hstate", s), k_hstate<<<(unsigned)((4 * ns + 2 * nf + 31) / 32), 160, 0, s>>>(d->w, d->hs_in, d->hs_cur, d->smt, pl.P.nTx, s0, ns, f0, nf);
     CK(cudaEventRecord(d->kev[1], s));
     CK(cudaEventRecord(d->kev[2], s));
     if (2 * ns + nf > 0) {
-        d->n_launch++, k_leafhash<<<(unsigned)((2 * (2 * ns + nf) + 31) / 32), 128, 0, s>>>(pl, d->w, d->smt, d->lev, s0, ns, f0, nf);
+        hz_mark(d, "k_leafhash", s), k_leafhash<<<(unsigned)((2 * (2 * ns + nf) + 31) / 32), 128, 0, s>>>(pl, d->w, d->smt, d->lev, s0, ns, f0, nf);
         CK(cudaStreamWaitEvent(s, d->ev_heads, 0));
         const unsigned lb = (unsigned)((2 * ns + nf + 15) / 16);
-        d->n_launch++, k_smt_levels<<<lb, 96, 0, s>>>(pl, d->w, d->lev, d->smst, d->mids, d->img00, d->zflag, s0, ns, f0, nf);
+        hz_mark(d, "k_smt_levels", s), k_smt_levels<<<lb, 96, 0, s>>>(pl, d->w, d->lev, d->smst, d->mids, d->img00, d->zflag, s0, ns, f0, nf);
         // the skipped (0, 0) levels are filled in beside the tail and the hash of the inputs
         CK(cudaEventRecord(d->ev_lev, s));
-        CK(cudaStreamWaitEvent(d->stream3, d->ev_lev, 0));
-        d->n_launch++, k_smt_zero<<<dim3(lb, (unsigned)(pl.P.nLevels + 1)), 256, 0, d->stream3>>>(pl, d->w, d->lev, d->img00, d->zflag, s0, ns, f0, nf);
+        CK(cudaStreamWaitEvent(s3, d->ev_lev, 0));
+        hz_mark(d, "k_smt_zero", s3), k_smt_zero<<<dim3(lb, (unsigned)(pl.P.nLevels + 1)), 256, 0, s3>>>(pl, d->w, d->lev, d->img00, d->zflag, s0, ns, f0, nf);
         if (d->world > 1 && !d->no_holes) {
             // a shard's pieces are copied around the image levels too (hz_cuda_shard_phase2): their records go to the host now
             const uint32_t gs = HZ_GL_STRIDE(pl.P.nLevels + 1);
-            d->n_launch++, k_hole_pack<<<(unsigned)(2 * ns + nf), 128, 0, s>>>(pl, d->w, d->lev, d->zflag, d->holes, d->gl, s0, ns, f0, nf);
+            hz_mark(d, "k_hole_pack", s), k_hole_pack<<<(unsigned)(2 * ns + nf), 128, 0, s>>>(pl, d->w, d->lev, d->zflag, d->holes, d->gl, s0, ns, f0, nf);
             CK(cudaEventRecord(d->ev_pack[0], s));
-            CK(cudaStreamWaitEvent(d->stream5, d->ev_pack[0], 0));
+            CK(cudaStreamWaitEvent(s5, d->ev_pack[0], 0));
             if (ns > 0) {
-                CK(cudaMemcpyAsync(d->h_holes + 2 * s0, d->holes + 2 * s0, sizeof(HzHole) * 2 * ns, cudaMemcpyDeviceToHost, d->stream5));
-                CK(cudaMemcpyAsync(d->h_gl + (size_t)2 * s0 * gs, d->gl + (size_t)2 * s0 * gs, sizeof(Fr) * gs * 2 * ns, cudaMemcpyDeviceToHost, d->stream5));
+                CK(cudaMemcpyAsync(d->h_holes + 2 * s0, d->holes + 2 * s0, sizeof(HzHole) * 2 * ns, cudaMemcpyDeviceToHost, s5));
+                CK(cudaMemcpyAsync(d->h_gl + (size_t)2 * s0 * gs, d->gl + (size_t)2 * s0 * gs, sizeof(Fr) * gs * 2 * ns, cudaMemcpyDeviceToHost, s5));
             }
             if (nf > 0) {
                 const size_t j = (size_t)2 * pl.P.nTx + f0;
-                CK(cudaMemcpyAsync(d->h_holes + j, d->holes + j, sizeof(HzHole) * nf, cudaMemcpyDeviceToHost, d->stream5));
-                CK(cudaMemcpyAsync(d->h_gl + j * gs, d->gl + j * gs, sizeof(Fr) * gs * nf, cudaMemcpyDeviceToHost, d->stream5));
+                CK(cudaMemcpyAsync(d->h_holes + j, d->holes + j, sizeof(HzHole) * nf, cudaMemcpyDeviceToHost, s5));
+                CK(cudaMemcpyAsync(d->h_gl + j * gs, d->gl + j * gs, sizeof(Fr) * gs * nf, cudaMemcpyDeviceToHost, s5));
             }
-            CK(cudaEventRecord(d->ev_info[0], d->stream5));
+            CK(cudaEventRecord(d->ev_info[0], s5));
         }
     }
-    CK(cudaEventRecord(d->ev_zero, d->stream3));
+    CK(cudaEventRecord(d->ev_zero, s3));
     CK(cudaEventRecord(d->kev[3], s));
     CK(cudaStreamWaitEvent(s, d->ev_front, 0));       // the tail compares the jobs, the hash of the inputs reads k_front's pre-image bits
-    if (ns + nf > 0) d->n_launch++, k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->err, d->mids, d->isExit, d->isExit_front, d->jobs, d->jobs_front, d->smt, d->smt_front, s0, ns, f0, nf);
+    if (ns + nf > 0) hz_mark(d, "k_tail", s), k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->err, d->mids, d->isExit, d->isExit_front, d->jobs, d->jobs_front, d->smt, d->smt_front, s0, ns, f0, nf);
     CK(cudaEventRecord(d->kev[4], s));
     return 0;
 }
@@ -295,26 +306,28 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
 static int hz_phase2(HzCuda* d, int sanity) {
     const HzPlan& pl = d->plan;
     cudaStream_t s = d->stream;
+    const cudaStream_t s5 = d->prof ? s : d->stream5;
     HzErrBuf* err = sanity ? d->err : nullptr;
-    d->n_launch++, k_hash_head<<<148, 256, 0, s>>>(pl, d->w, d->pre, d->rank == 0 ? err : nullptr, d->off_blocks);
+    hz_mark(d, "k_hash_head", s), k_hash_head<<<148, 256, 0, s>>>(pl, d->w, d->pre, d->rank == 0 ? err : nullptr, d->off_blocks);
     CK(cudaEventRecord(d->kev[5], s));
     // the chain in two halves: the blocks of the first half are expanded (stream 5) while the second half is walked
     const uint32_t mid = pl.nblocks / 2, bend = d->b0 + d->nb;
-    d->n_launch++, k_sha_chain<<<1, 256, 0, s>>>(pl, d->pre, d->chain, d->msgw, d->shawk, 0, mid);
+    hz_mark(d, "k_sha_chain", s), k_sha_chain<<<1, 256, 0, s>>>(pl, d->pre, d->chain, d->msgw, d->shawk, 0, mid);
     const uint32_t n1 = d->b0 < mid ? (bend < mid ? bend : mid) - d->b0 : 0;       // own blocks below mid
     if (n1 > 0) {
         CK(cudaEventRecord(d->ev_sha[0], s));
-        CK(cudaStreamWaitEvent(d->stream5, d->ev_sha[0], 0));
-        d->n_launch++, k_sha_blocks<<<n1, HZ_SHA_THREADS, 0, d->stream5>>>(pl, d->w, err, d->chain, d->msgw, d->off_blocks, d->b0);
-        CK(cudaEventRecord(d->ev_sha[1], d->stream5));
+        CK(cudaStreamWaitEvent(s5, d->ev_sha[0], 0));
+        hz_mark(d, "k_sha_blocks", s5), k_sha_blocks<<<n1, HZ_SHA_THREADS, 0, s5>>>(pl, d->w, err, d->chain, d->msgw, d->off_blocks, d->b0);
+        CK(cudaEventRecord(d->ev_sha[1], s5));
     }
-    d->n_launch++, k_sha_chain<<<1, 256, 0, s>>>(pl, d->pre, d->chain, d->msgw, d->shawk, mid, pl.nblocks);
+    hz_mark(d, "k_sha_chain", s), k_sha_chain<<<1, 256, 0, s>>>(pl, d->pre, d->chain, d->msgw, d->shawk, mid, pl.nblocks);
     CK(cudaEventRecord(d->kev[6], s));
-    if (d->nb > n1) d->n_launch++, k_sha_blocks<<<d->nb - n1, HZ_SHA_THREADS, 0, s>>>(pl, d->w, err, d->chain, d->msgw, d->off_blocks, d->b0 + n1);
+    if (d->nb > n1) hz_mark(d, "k_sha_blocks", s), k_sha_blocks<<<d->nb - n1, HZ_SHA_THREADS, 0, s>>>(pl, d->w, err, d->chain, d->msgw, d->off_blocks, d->b0 + n1);
     if (n1 > 0) CK(cudaStreamWaitEvent(s, d->ev_sha[1], 0));
     CK(cudaEventRecord(d->kev[7], s));
-    d->n_launch++, k_hash_tail<<<1, 32, 0, s>>>(pl, d->w, d->rank == 0 ? err : nullptr, d->chain);
+    hz_mark(d, "k_hash_tail", s), k_hash_tail<<<1, 32, 0, s>>>(pl, d->w, d->rank == 0 ? err : nullptr, d->chain);
     CK(cudaEventRecord(d->kev[8], s));
+    if (d->prof) CK(cudaEventRecord(d->pev[d->n_prof], s));
     CK(cudaStreamWaitEvent(s, d->ev_eddsa, 0));
     CK(cudaStreamWaitEvent(s, d->ev_zero, 0));
     CK(cudaGetLastError());
@@ -553,7 +566,9 @@ int hz_cuda_shard_phase1(HzCuda* d, const uint8_t* inputs, int sanity, void* rec
     if (st) return st;
     const HzParams& P = d->plan.P;
     int last_slot = d->ns > 0 && d->s0 + d->ns == P.nTx, last_fee = d->nf > 0 && d->f0 + d->nf == P.maxFeeTx;
-    d->n_launch++, k_pack<<<148, 256, 0, d->stream>>>(d->plan, d->w, d->pre, reinterpret_cast<uint8_t*>(record_out), d->s0, d->ns, d->per, last_slot, last_fee);
+    HzPeerRecs dst; memset(&dst, 0, sizeof dst);
+    dst.n = 1; dst.p[0] = reinterpret_cast<uint8_t*>(record_out);
+    d->n_launch++, k_pack<<<148, 256, 0, d->stream>>>(d->plan, d->w, d->pre, dst, d->s0, d->ns, d->per, last_slot, last_fee);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(errs, d->err, sizeof(HzErrBuf), cudaMemcpyDeviceToHost, d->stream));
     CK(cudaStreamSynchronize(d->stream));         // the host binding runs the all-gather on its own stream
@@ -562,8 +577,9 @@ int hz_cuda_shard_phase1(HzCuda* d, const uint8_t* inputs, int sanity, void* rec
 // sharded phase 2: `records` = the gathered records of all ranks (device memory); the shard's witness
 // pieces are copied to `shard_out` (host) back to back in hz_cuda_pieces order
 int hz_cuda_shard_phase2(HzCuda* d, const void* records, int sanity, uint8_t* shard_out, const uint64_t* pieces, int npieces,
-                         float* kernel_ms, HzErrBuf* errs, uint64_t* d2h) {
+                         float* kernel_ms, HzErrBuf* errs, uint64_t* d2h, bool in_place) {
     CK(cudaSetDevice(d->device));
+    if (!records) records = d->recs;              // the library's own all-gather left them there (hz_cuda_multi_phase1)
     if (!records) return HZW_E_PARAM;
     cudaStream_t s = d->stream;
     d->n_launch++, k_unpack<<<148, 256, 0, s>>>(d->plan, d->w, d->pre, reinterpret_cast<const uint8_t*>(records), d->world, d->per, hz_rec_bytes(d->plan.P, d->per));
@@ -591,7 +607,9 @@ int hz_cuda_shard_phase2(HzCuda* d, const void* records, int sanity, uint8_t* sh
         cudaError_t ce = cudaSuccess;
         for (int k = 0; k < npieces && ce == cudaSuccess; k++) {
             const uint64_t a = pieces[2 * k], n = pieces[2 * k + 1];
-            uint8_t* out_v = shard_out + bytes - 32ull * a;          // where witness entry 0 would be for this piece
+            // where witness entry 0 would be for this piece: the pieces back to back in a shard buffer, or each at its
+            // place in ONE whole-witness buffer that every GPU of the box copies into (in_place)
+            uint8_t* out_v = in_place ? shard_out : shard_out + bytes - 32ull * a;
             HzCopier cp{d, out_v, reinterpret_cast<const uint8_t*>(d->w), (unsigned)k};
             if (holes && d->ns > 0 && a == r0 && n == (uint64_t)(*d->h_off_rollup)[d->s0 + d->ns] - r0) {
                 for (unsigned t = 0; t < nthr; t++) workers.emplace_back(hz_fill_holes, d, out_v, 2 * d->s0, 2 * (d->s0 + d->ns), (int)t, (int)nthr);
@@ -627,6 +645,45 @@ int hz_cuda_shard_phase2(HzCuda* d, const void* records, int sanity, uint8_t* sh
     return 0;
 }
 
+// ---- all the GPUs of one box driven by ONE process (hzw_params.n_gpus > 1; hzw_host.cpp: MultiBackend) ----------
+// Every device of the group must be able to store into the others' memory: the exchange is done by the pack kernel.
+int hz_cuda_enable_peer(HzCuda* d, HzCuda* peer) {
+    CK(cudaSetDevice(d->device));
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, d->device, peer->device));
+    if (!can) { fprintf(stderr, "hzw: device %d cannot access device %d (no peer-to-peer path)\n", d->device, peer->device); return HZW_E_DEVICE; }
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    CK(e);
+    return 0;
+}
+uint8_t* hz_cuda_recs(HzCuda* d) { return d->recs; }
+// phase 1 of rank d->rank, nothing waited for: own slots and fee txs, then k_pack stores this rank's record into
+// slot d->rank of EVERY rank's gathered array (peer_recs[r], device memory of rank r) -- compute step and all-gather
+// in one kernel over NVLink -- and ev_xchg marks it
+int hz_cuda_multi_phase1(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* const* peer_recs, int world) {
+    CK(cudaSetDevice(d->device));
+    if (world != d->world || world > HZ_MAX_GPUS) return HZW_E_PARAM;
+    d->n_launch = 0;
+    int st = hz_phase1(d, inputs, sanity);
+    if (st) return st;
+    const HzParams& P = d->plan.P;
+    int last_slot = d->ns > 0 && d->s0 + d->ns == P.nTx, last_fee = d->nf > 0 && d->f0 + d->nf == P.maxFeeTx;
+    HzPeerRecs dst; memset(&dst, 0, sizeof dst);
+    dst.n = world;
+    for (int r = 0; r < world; r++) dst.p[r] = peer_recs[r] + (size_t)d->rank * hz_rec_bytes(P, d->per);
+    d->n_launch++, k_pack<<<148, 256, 0, d->stream>>>(d->plan, d->w, d->pre, dst, d->s0, d->ns, d->per, last_slot, last_fee);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(d->ev_xchg, d->stream));
+    return 0;
+}
+// rank d's main stream goes on only when `peer`'s record has landed (called after every rank has queued its phase 1)
+int hz_cuda_multi_wait(HzCuda* d, HzCuda* peer) {
+    CK(cudaSetDevice(d->device));
+    CK(cudaStreamWaitEvent(d->stream, peer->ev_xchg, 0));
+    return 0;
+}
+
 int hz_cuda_witness_device(HzCuda* d, void** ptr, int32_t* device, void** stream) {
     *ptr = d->w;
     if (device) *device = d->device;
@@ -637,6 +694,41 @@ int hz_cuda_witness_read(HzCuda* d, uint64_t first, uint64_t count, uint8_t* out
     CK(cudaSetDevice(d->device));
     CK(cudaMemcpyAsync(out, d->w + first, 32ull * count, cudaMemcpyDeviceToHost, d->stream));
     CK(cudaStreamSynchronize(d->stream));
+    return 0;
+}
+
+// One batch (inputs already resident) with every launch on the main stream and an event in front of each: the
+// duration of each kernel ALONE, measured live -- what the roofline of a kernel is quoted on (the timed steps run
+// the same launches on five streams, where an interval between two events also holds the kernels beside it).
+int hz_cuda_profile_step(HzCuda* d, float* ms, const char** names, int cap) {
+    CK(cudaSetDevice(d->device));
+    if (d->world != 1) return HZW_E_PARAM;
+    d->prof = true; d->n_prof = 0; d->n_launch = 0;
+    int st = hz_phase1(d, nullptr, 0);
+    if (!st) st = hz_phase2(d, 0);
+    d->prof = false;
+    if (st) return st;
+    CK(cudaStreamSynchronize(d->stream));
+    int n = d->n_prof < cap ? d->n_prof : cap;
+    for (int k = 0; k < n; k++) {
+        if (cudaEventElapsedTime(&ms[k], d->pev[k], d->pev[k + 1]) != cudaSuccess) return HZW_E_DEVICE;
+        names[k] = d->pname[k];
+    }
+    return n;
+}
+
+// processor levels of the shard in total and how many of them the last batch flagged as (0, 0) images (skipped by
+// k_smt_levels, copied by k_smt_zero): what the algorithmic work of those two kernels is counted from
+int hz_cuda_image_levels(HzCuda* d, uint64_t out[2]) {
+    CK(cudaSetDevice(d->device));
+    const int L = d->plan.P.nLevels + 1, nj = 2 * d->ns + d->nf, lb = (nj + 15) / 16;
+    std::vector<uint8_t> z((size_t)lb * L);
+    if (lb > 0) CK(cudaMemcpy(z.data(), d->zflag, z.size(), cudaMemcpyDeviceToHost));
+    out[0] = (uint64_t)nj * L; out[1] = 0;
+    for (int b = 0; b < lb; b++) {
+        const int in_block = b + 1 < lb ? 16 : nj - 16 * b;
+        for (int l = 0; l < L; l++) if (z[(size_t)b * L + l]) out[1] += (uint64_t)in_block;
+    }
     return 0;
 }
 

@@ -7,28 +7,42 @@
 // 2 nLevels + 48 bits) and the three values that close the chains (newLastIdx, newStateRoot,
 // newExitRoot).  A rank's record: per own slot 624 + nL2 bytes (one bit per byte), then 3 x 32 B
 // values and 3 x 4 B flags saying which of them this rank produced.
-__global__ void k_pack(HzPlan pl, const Fr* w, const uint8_t* pre, uint8_t* rec, int s0, int ns, int per, int own_last_slot, int own_last_fee) {
+__global__ void k_pack(HzPlan pl, const Fr* w, const uint8_t* pre, HzPeerRecs dst, int s0, int ns, int per, int own_last_slot, int own_last_fee) {
+    // dst.p[0 .. dst.n): where this rank's record goes -- one buffer when the caller runs the collective (NCCL in
+    // the Python binding), the slot of this rank in EVERY peer's gathered array when the library drives all the GPUs of
+    // a box itself (hz_cuda_multi_phase1): the stores then travel over NVLink as they are produced, and the pack
+    // kernel IS the all-gather
     const HzParams& P = pl.P;
     const uint32_t sb = hz_rec_slot_bytes(P), nL2 = 2u * (uint32_t)P.nLevels + 48u;
     const uint32_t p1 = hz_pre_pos_l1(P), p2 = hz_pre_pos_l2(P);
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    for (uint32_t e = gid; e < (uint32_t)per * sb; e += gsz) {
-        uint32_t q = e / sb, k = e % sb, i = (uint32_t)s0 + q;
-        uint8_t v = 0;
-        if ((int)q < ns) {
-            if (k < 624) v = (int)i < P.maxL1Tx ? pre[p1 + i * 624 + k] : 0;
-            else v = pre[p2 + i * nL2 + (k - 624)];
+    // four record bytes per store: peer stores are 32-bit words ((per * sb) is padded up to a word by hz_rec_vals_off)
+    const uint32_t words = hz_rec_vals_off(P, per) / 4u;
+    for (uint32_t x = gid; x < words; x += gsz) {
+        uint32_t v4 = 0;
+        for (uint32_t b = 0; b < 4; b++) {
+            const uint32_t e = 4u * x + b;
+            if (e >= (uint32_t)per * sb) break;
+            uint32_t q = e / sb, k = e % sb, i = (uint32_t)s0 + q;
+            uint32_t v = 0;
+            if ((int)q < ns) {
+                if (k < 624) v = (int)i < P.maxL1Tx ? pre[p1 + i * 624 + k] : 0;
+                else v = pre[p2 + i * nL2 + (k - 624)];
+            }
+            v4 |= v << (8u * b);
         }
-        rec[e] = v;
+        for (int r = 0; r < dst.n; r++) reinterpret_cast<uint32_t*>(dst.p[r])[x] = v4;
     }
     if (gid == 0) {
-        uint32_t* out = reinterpret_cast<uint32_t*>(rec + hz_rec_vals_off(P, per));
         Fr z = fr_zero();
         const Fr& a = own_last_slot ? w[pl.idx_newLastIdx] : z;
         const Fr& b = own_last_fee ? w[pl.idx_newStateRoot] : z;
         const Fr& c = own_last_slot ? w[pl.idx_newExitRoot] : z;
-        for (int k = 0; k < 8; k++) { out[k] = a.l[k]; out[8 + k] = b.l[k]; out[16 + k] = c.l[k]; }
-        out[24] = (uint32_t)own_last_slot; out[25] = (uint32_t)own_last_fee; out[26] = (uint32_t)own_last_slot;
+        for (int r = 0; r < dst.n; r++) {
+            uint32_t* out = reinterpret_cast<uint32_t*>(dst.p[r] + hz_rec_vals_off(P, per));
+            for (int k = 0; k < 8; k++) { out[k] = a.l[k]; out[8 + k] = b.l[k]; out[16 + k] = c.l[k]; }
+            out[24] = (uint32_t)own_last_slot; out[25] = (uint32_t)own_last_fee; out[26] = (uint32_t)own_last_slot;
+        }
     }
 }
 __global__ void k_unpack(HzPlan pl, Fr* w, uint8_t* pre, const uint8_t* recs, int world, int per, uint32_t rec_bytes) {

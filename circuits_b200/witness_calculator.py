@@ -31,7 +31,7 @@ class WitnessError(Exception):
 class _Params(ctypes.Structure):
     _fields_ = [("circuit_kind", ctypes.c_int32), ("nTx", ctypes.c_int32), ("nLevels", ctypes.c_int32),
                 ("maxL1Tx", ctypes.c_int32), ("maxFeeTx", ctypes.c_int32), ("device", ctypes.c_int32),
-                ("flags", ctypes.c_uint32)]
+                ("n_gpus", ctypes.c_int32), ("flags", ctypes.c_uint32)]
 
 
 class _Error(ctypes.Structure):
@@ -43,7 +43,7 @@ EXPORTS = ["hzw_create", "hzw_destroy", "hzw_nvars", "hzw_ninputs", "hzw_input_i
            "hzw_calculate_batch", "hzw_calculate_resident", "hzw_write_wtns", "hzw_get_signal", "hzw_dump_sym",
            "hzw_last_stats", "hzw_last_kernel_ms", "hzw_plan_info", "hzw_set_shard", "hzw_exchange_bytes",
            "hzw_shard_pieces", "hzw_shard_nvars", "hzw_shard_phase1", "hzw_shard_phase2", "hzw_poseidon_bench", "hzw_int_peak",
-           "hzw_witness_device", "hzw_signal_index", "hzw_witness_read"]
+           "hzw_witness_device", "hzw_signal_index", "hzw_witness_read", "hzw_profile_step", "hzw_image_levels", "hzw_rank_pieces", "hzw_rank_witness_device"]
 
 
 def load_library(path=None):
@@ -71,6 +71,8 @@ def load_library(path=None):
     lib.hzw_dump_sym.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
     lib.hzw_last_kernel_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float),
                                        ctypes.POINTER(ctypes.c_char_p), ctypes.c_int]
+    lib.hzw_profile_step.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float),
+                                     ctypes.POINTER(ctypes.c_char_p), ctypes.c_int]
     lib.hzw_plan_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
     lib.hzw_last_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64),
                                    ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
@@ -114,11 +116,11 @@ class WitnessCalculator:
     prime = P
     n64 = 4
 
-    def __init__(self, nTx, nLevels, maxL1Tx, maxFeeTx, circuit="rollup-main", device=0, lib_path=None):
+    def __init__(self, nTx, nLevels, maxL1Tx, maxFeeTx, circuit="rollup-main", device=0, lib_path=None, n_gpus=1):
         self._lib = load_library(lib_path)
         kind = {"rollup-main": HZW_CIRCUIT_ROLLUP_MAIN, "withdraw": HZW_CIRCUIT_WITHDRAW}[circuit]
         self.params = (nTx, nLevels, maxL1Tx, maxFeeTx)
-        prm = _Params(kind, nTx, nLevels, maxL1Tx, maxFeeTx, device, 0)
+        prm = _Params(kind, nTx, nLevels, maxL1Tx, maxFeeTx, device, n_gpus, 0)
         self._ctx = ctypes.c_void_p()
         st = self._lib.hzw_create(ctypes.byref(prm), None, ctypes.byref(self._ctx))
         if st != 0:
@@ -243,6 +245,24 @@ class WitnessCalculator:
         names = (ctypes.c_char_p * 16)()
         n = self._lib.hzw_last_kernel_ms(self._ctx, ms, names, 16)
         return [(names[i].decode(), ms[i]) for i in range(max(n, 0))]
+
+    def profileStep(self):
+        """[(kernel name, device ms)] of one more batch on the resident inputs with every launch serialised on one
+        stream (`hzw_profile_step`): the time each launch takes ALONE."""
+        ms = (ctypes.c_float * 48)()
+        names = (ctypes.c_char_p * 48)()
+        n = self._lib.hzw_profile_step(self._ctx, ms, names, 48)
+        if n < 0:
+            raise WitnessError("hzw_profile_step failed with code %d" % n)
+        return [(names[i].decode(), ms[i]) for i in range(n)]
+
+    def imageLevels(self):
+        """(SMT processor levels per batch, how many of them were (0, 0) images in the last batch)."""
+        out = (ctypes.c_uint64 * 2)()
+        self._lib.hzw_image_levels.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
+        if self._lib.hzw_image_levels(self._ctx, out) != 0:
+            raise WitnessError("hzw_image_levels failed")
+        return int(out[0]), int(out[1])
 
     def lastStats(self):
         a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()

@@ -49,7 +49,12 @@ typedef struct hzw_ctx hzw_ctx;
 typedef struct {
     int32_t circuit_kind;       /* HZW_CIRCUIT_* */
     int32_t nTx, nLevels, maxL1Tx, maxFeeTx;   /* withdraw uses nLevels only */
-    int32_t device;             /* CUDA device ordinal */
+    int32_t device;             /* CUDA device ordinal (the first one when n_gpus > 1) */
+    int32_t n_gpus;             /* 0 or 1: one GPU.  N > 1: ONE context drives devices device .. device + N - 1 of this
+                                 * box (they must reach each other peer to peer): the tx slots, fee txs and SHA blocks of
+                                 * a batch are split over them, the exchange between the two phases is done by the pack
+                                 * kernels storing into every peer over NVLink, and hzw_calculate lands ONE witness in
+                                 * witness_out, each GPU copying the ranges it owns to their offsets over its own link */
     uint32_t flags;             /* reserved, 0 */
 } hzw_params;
 
@@ -89,6 +94,10 @@ int hzw_calculate_resident(hzw_ctx* ctx, const uint8_t* inputs_le32, int sanity_
 int hzw_witness_device(const hzw_ctx* ctx, void** dev_ptr, int32_t* device, void** stream);
 int hzw_signal_index(const hzw_ctx* ctx, const char* name, uint64_t* index);
 int hzw_witness_read(hzw_ctx* ctx, uint64_t first, uint64_t count, uint8_t* out);
+/* n_gpus > 1: after hzw_calculate_resident rank r's ranges (hzw_rank_pieces: (first index, count) pairs) are valid
+ * in rank r's copy of the witness on its own device (hzw_rank_witness_device); hzw_witness_read gathers from them */
+int hzw_rank_pieces(const hzw_ctx* ctx, int32_t rank, uint64_t* table /* 2 x cap */, int32_t cap);
+int hzw_rank_witness_device(const hzw_ctx* ctx, int32_t rank, void** dev_ptr, int32_t* device, void** stream);
 int hzw_write_wtns(const hzw_ctx* ctx, const uint8_t* witness, const char* path);
 int hzw_get_signal(const hzw_ctx* ctx, const uint8_t* witness, const char* name, uint8_t out[32]);
 /* writes "index,name" lines (the `.sym` equivalent) for every signal whose name starts with prefix */
@@ -100,6 +109,13 @@ int hzw_plan_info(const hzw_ctx* ctx, uint64_t out[12]);
 /* device time of each kernel of the last calculate, in launch order; names are static strings.
  * Returns the number of kernels (<= cap). */
 int hzw_last_kernel_ms(const hzw_ctx* ctx, float* ms, const char** names, int cap);
+/* One more batch on the inputs already resident, every launch serialised on one stream with an event in front of it:
+ * device time of each launch ALONE, in launch order (a measurement aid for the roofline; the witness it leaves is the
+ * same).  Returns the number of launches (<= cap). */
+int hzw_profile_step(hzw_ctx* ctx, float* ms, const char** names, int cap);
+/* out[0] = SMT processor levels this context evaluates per batch, out[1] = how many of them hashed (0, 0) on both paths
+ * in the last batch (their entries are copies of one recorded image: k_smt_levels skips them, k_smt_zero copies them) */
+int hzw_image_levels(hzw_ctx* ctx, uint64_t out[2]);
 /* static description of what the last calculate launched: kernels and bytes, for the bench */
 int hzw_last_stats(const hzw_ctx* ctx, uint64_t* gpu_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 
