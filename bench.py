@@ -28,6 +28,9 @@ CONFIGS = {
     "rollup-main-2048": (2048, 32, 256, 64),
     "rollup-main-344": (344, 32, 256, 64),
     "rollup-main-24": (24, 32, 8, 4),
+    # config 5 of BASELINE.json: 65 536 independent Withdraw(32) witnesses (nTx = instances of the batch)
+    "withdraw-65536": (65536, 32, 0, 1),
+    "withdraw-4096": (4096, 32, 0, 1),
 }
 METRIC = "rollup-main(2048,32) witness tx/sec"
 CPU_PORT = os.path.join(ROOT, "oracle", "_ref", "libhzw_cpu_port.so")
@@ -186,6 +189,29 @@ def run_reference(args, cfg, cfg_name):
     if not os.path.exists(CPU_PORT):
         g.build()
     from circuits_b200.witness_calculator import WitnessCalculator
+    if cfg_name.startswith("withdraw"):
+        import numpy as np
+        n, nLevels = cfg[0], cfg[1]
+        packed, _ = withdraw_batch_inputs(nLevels, n)
+        cpu = WitnessCalculator(1, nLevels, 0, 1, circuit="withdraw", lib_path=CPU_PORT)
+        mm, nin = min(512, n), cpu.NInputs
+        outc = np.empty(32 * cpu.NVars * mm, dtype=np.uint8)
+        sample = bytearray(packed[:32 * nin * mm])
+        for _ in range(args.warmup):
+            cpu.calculateBatch(mm, sample, False, out=outc)
+        t = time.time()
+        for _ in range(args.steps):
+            cpu.calculateBatch(mm, sample, False, out=outc)
+        dt = (time.time() - t) / args.steps
+        val = mm / dt
+        emit({"impl": "reference", "metric": WD_METRIC, "value": val, "unit": "witness/s", "n_gpus": args.gpus, "steps": args.steps,
+              "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+              "dtype": "u32 limbs (BN254 Fr, 254-bit modular)", "data": "synthetic",
+              "config": {"workload": cfg_name, "instances": n, "nLevels": nLevels, "distinct_leaves": min(WD_DISTINCT, n)},
+              "cpu_baseline": {"value": val, "unit": "witness/s", "cores": os.cpu_count() or 1, "kind": "port",
+                               "sample": "%d instances of the batch per step, CPU port of the circuit templates, all host threads" % mm},
+              "e2e": {"value": val, "unit": "witness/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+        return
     inp, _ = make_input(cfg)
     nTx = cfg[0]
     wc = WitnessCalculator(*cfg, lib_path=CPU_PORT)
@@ -529,6 +555,159 @@ def run_gpu(args, cfg, cfg_name):
     emit(line)
 
 
+WD_DISTINCT = 4096
+WD_METRIC = "withdraw(32) witnesses/sec"
+
+
+def withdraw_batch_inputs(nLevels, n):
+    """n packed Withdraw inputs: WD_DISTINCT distinct leaves of ONE exit tree with their inclusion proofs (the host
+    mirror of withdrawUtils builds them with big-integer Poseidon: ~1 minute, cached), repeated to n instances --
+    every instance is evaluated independently, the work per instance does not depend on its values."""
+    import pickle
+    cdir = os.path.join(ROOT, ".bench_cache")
+    try:
+        os.makedirs(cdir, exist_ok=True)
+    except OSError:
+        cdir = tempfile.gettempdir()
+    cache = os.path.join(cdir, "hzw_withdraw_%d_%d.pkl" % (nLevels, WD_DISTINCT))
+    data = None
+    if os.path.exists(cache):
+        try:
+            with open(cache, "rb") as f:
+                data = pickle.load(f)
+        except Exception:
+            data = None
+    if data is None:
+        from circuits_b200.synth import withdraw_inputs
+        t = time.time()
+        cases = withdraw_inputs(nLevels, WD_DISTINCT)
+        names = ["rootExit", "ethAddr", "tokenID", "balance", "idx", "sign", "ay"]
+        packed = bytearray()
+        for inp, _ in cases:
+            vals = [inp[k] for k in names] + list(inp["siblingsState"])
+            packed += b"".join(int(v).to_bytes(32, "little") for v in vals)
+        data = (bytes(packed), [h for _, h in cases])
+        log("[bench] %d withdraw inputs built in %.1f s" % (WD_DISTINCT, time.time() - t))
+        try:
+            tmp = cache + ".%d" % os.getpid()
+            with open(tmp, "wb") as f:
+                pickle.dump(data, f)
+            os.replace(tmp, cache)
+        except Exception:
+            pass
+    packed, hashes = data
+    reps = (n + WD_DISTINCT - 1) // WD_DISTINCT
+    nin = 8 + nLevels
+    return (packed * reps)[:32 * nin * n], (hashes * reps)[:n]
+
+
+def run_withdraw(args, cfg, cfg_name):
+    """Config 5: `n` independent Withdraw(nLevels) witnesses, the instances split over the ranks (no exchange).
+    value = witnesses/s with the witnesses left in HBM (only the public output of each comes back and is checked);
+    e2e = the same through calculateBatch with every witness copied to a pinned host buffer, on a bounded sub-batch
+    (the 65 536 witnesses are 197 GB)."""
+    import numpy as np
+    import torch
+    import __graft_entry__ as g
+    from circuits_b200 import witness_calculator as wcm
+    if not os.path.exists(wcm.DEFAULT_LIB):
+        g.build()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, nLevels = cfg[0], cfg[1]
+    packed, hashes = withdraw_batch_inputs(nLevels, n)
+    per = (n + world - 1) // world
+    k0, k1 = min(rank * per, n), min(rank * per + per, n)
+    wc = wcm.WitnessCalculator(1, nLevels, 0, 1, circuit="withdraw", device=local)
+    nin = wc.NInputs
+    pin_in = torch.empty(32 * nin * (k1 - k0), dtype=torch.uint8, pin_memory=True)
+    pin_in.numpy()[:] = np.frombuffer(packed, dtype=np.uint8)[32 * nin * k0:32 * nin * k1]
+    pub = torch.empty(32 * (k1 - k0), dtype=torch.uint8, pin_memory=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(max(args.warmup, 1)):
+        wc.calculateBatchResident(k1 - k0, pin_in, False, public_out=pub)
+    barrier()
+    step_ms = []
+    for _ in range(args.steps):
+        barrier()
+        _, ms = wc.calculateBatchResident(k1 - k0, pin_in, False, public_out=pub)
+        step_ms.append(ms)
+    barrier()
+    got = pub.numpy().reshape(-1, 32)
+    for j in range(0, k1 - k0, max((k1 - k0) // 257, 1)):
+        if int.from_bytes(bytes(got[j]), "little") != hashes[k0 + j]:
+            raise SystemExit("hashGlobalInputs of instance %d is wrong, refusing to report a number" % (k0 + j))
+    launches = wc.lastStats()["gpu_launches"]
+    t_dev = torch.tensor([sum(step_ms) / len(step_ms)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_dev.item())
+    # end to end on a bounded sub-batch per rank
+    m = min(k1 - k0, 1024)
+    pin_out = torch.empty(32 * wc.NVars * m, dtype=torch.uint8, pin_memory=True)
+    wc.calculateBatch(m, pin_in[:32 * nin * m], False, out=pin_out)
+    e2e_t = []
+    for _ in range(args.steps):
+        barrier()
+        t = time.perf_counter()
+        wc.calculateBatch(m, pin_in[:32 * nin * m], False, out=pin_out)
+        e2e_t.append(time.perf_counter() - t)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    t_e2e = torch.tensor([sum(e2e_t) / len(e2e_t)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    e2e_s = float(t_e2e.item())
+    peaks, src = measured_peaks()
+    try:
+        ipeak = wcm.int_peak(local)
+    except Exception:
+        ipeak = None
+    L1 = nLevels + 1
+    prod = per * (L1 * poseidon_perm_products(3) + 2 * poseidon_perm_products(4) + poseidon_perm_products(5))
+    alg_bytes = per * 32 * (wc.NVars + nin)
+    roofline = {"bound": "hbm", "kernel": "k_withdraw", "achieved": alg_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                "peak_source": src + " (copy bandwidth)", "algorithmic_bytes": alg_bytes,
+                "int": {"limb_products": prod, "frac": prod / (ms_per_step * 1e-3) / ipeak if ipeak else None, "peak": ipeak},
+                "note": "one kernel per chunk of 4096 instances; algorithmic bytes = every witness entry written once + the "
+                        "inputs; 62 % of the entries of an instance are the bit signals of its two SHA-256 blocks"}
+    line = {"metric": WD_METRIC, "value": n / (ms_per_step * 1e-3), "unit": "witness/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 limbs (BN254 Fr, 254-bit modular)", "data": "synthetic",
+            "config": {"workload": cfg_name, "instances": n, "nLevels": nLevels,
+                       "distinct_leaves": min(WD_DISTINCT, n),
+                       "l2_flush": "every step writes %d GB of witnesses per GPU, far larger than L2" % (32 * wc.NVars * per >> 30)},
+            "e2e": {"value": m * world / e2e_s, "unit": "witness/s", "h2d_bytes_per_step": 32 * nin * m * world,
+                    "d2h_bytes_per_step": 32 * wc.NVars * m * world, "ms_per_step": e2e_s * 1e3,
+                    "call": "WitnessCalculator.calculateBatch on a sub-batch of %d instances per GPU, witnesses to pinned host memory" % m},
+            "gpu_launches": int(launches) * args.steps * world, "clocks": clocks, "roofline": roofline}
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = wcm.WitnessCalculator(1, nLevels, 0, 1, circuit="withdraw", lib_path=CPU_PORT)
+        mm = 512
+        outc = np.empty(32 * cpu.NVars * mm, dtype=np.uint8)
+        t = time.time()
+        cpu.calculateBatch(mm, bytearray(packed[:32 * nin * mm]), False, out=outc)
+        dt = time.time() - t
+        line["cpu_baseline"] = {"value": mm / dt, "unit": "witness/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "%d instances of the batch, CPU port of the circuit templates, all host threads, %.1f s" % (mm, dt)}
+    emit(line)
+
+
 def main():
     # the driver reads ONE JSON line from stdout: libraries that print there (NCCL's version banner) go to stderr
     global _REAL_STDOUT
@@ -546,6 +725,8 @@ def main():
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
         run_reference(args, cfg, args.config)
+    elif args.config.startswith("withdraw"):
+        run_withdraw(args, cfg, args.config)
     else:
         run_gpu(args, cfg, args.config)
         try:

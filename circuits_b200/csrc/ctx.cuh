@@ -247,6 +247,8 @@ template <> struct Comp<MCompute> {
                               // transposed kernels (k_hstate, k_sighash); with hs_rec set the inputs are recorded for them
     Fr* hs_rec = nullptr;     // 4 field elements per HashState of this slot / fee tx, in evaluation order
     int* hs_n = nullptr;
+    bool is_main = false;     // a template evaluated as the MAIN component (standalone RollupTx): its own signals are never
+                              // aliased away -- def / alias give every one an entry; not inherited by sub-components
     typedef VC Val;
 
     HZ_HD Comp(Fr* w_, uint32_t cur_, HzErrBuf* err_, HzHints* h_ = nullptr, HzPending* p_ = nullptr)
@@ -261,7 +263,7 @@ template <> struct Comp<MCompute> {
 #endif
     }
     Comp(const Comp&) = delete;
-    HZ_HD Comp(Comp&& o) : w(o.w), cur(o.cur), end(o.end), parent(o.parent), err(o.err), hints(o.hints), pend(o.pend), solo(o.solo), dry(o.dry), skip_hash(o.skip_hash), hs_rec(o.hs_rec), hs_n(o.hs_n) { o.parent = nullptr; o.end = HZ_NOIDX; }
+    HZ_HD Comp(Comp&& o) : w(o.w), cur(o.cur), end(o.end), parent(o.parent), err(o.err), hints(o.hints), pend(o.pend), solo(o.solo), dry(o.dry), skip_hash(o.skip_hash), hs_rec(o.hs_rec), hs_n(o.hs_n), is_main(o.is_main) { o.parent = nullptr; o.end = HZ_NOIDX; }
     // the `inv` entry and the `out` value of IsZero(x) (comparators.circom): inv <-- x != 0 ? 1/x : 0
     HZ_HD VC iszero_inv(const Nm&, const VC& x) {
         const uint32_t slot = cur++;
@@ -364,9 +366,10 @@ template <> struct Comp<MCompute> {
     HZ_HD uint32_t sigs(const Nm&, int n) { uint32_t s = cur; cur += n; return s; }
     HZ_HD VC set(uint32_t slot, const VC& x) { if (!x.ph) put(slot, x.v); VC r = x; r.sig = true; return r; }
     HZ_HD VC seti(const Nm&, uint32_t slot, const VC& x) { return set(slot, x); }
-    HZ_HD VC alias(const Nm&, const VC& x) { return x; }
+    HZ_HD VC alias(const Nm& nm, const VC& x) { return is_main ? own(nm, x) : x; }
     // `signal s <== x` / wiring of a sub-component input: alias when x is a signal
-    HZ_HD VC def(const Nm&, const VC& x) {
+    HZ_HD VC def(const Nm& nm, const VC& x) {
+        if (is_main) return own(nm, x);
         if (x.sig) return x;
         if (!x.ph) put(cur, x.v);
         cur++; VC r = x; r.sig = true; return r;
@@ -402,6 +405,7 @@ template <> struct Comp<MLayout> {
     LayoutSink* sink;
     std::string prefix;
     bool named;
+    bool is_main = false;
     typedef VL Val;
 
     Comp(uint32_t cur_, LayoutSink* s, const std::string& pre) : cur(cur_), end(HZ_NOIDX), parent(nullptr), sink(s), prefix(pre) {
@@ -423,7 +427,7 @@ template <> struct Comp<MLayout> {
         }
     }
     Comp(const Comp&) = delete;
-    Comp(Comp&& o) : cur(o.cur), end(o.end), parent(o.parent), sink(o.sink), prefix(o.prefix), named(o.named) { o.parent = nullptr; o.end = HZ_NOIDX; }
+    Comp(Comp&& o) : cur(o.cur), end(o.end), parent(o.parent), sink(o.sink), prefix(o.prefix), named(o.named), is_main(o.is_main) { o.parent = nullptr; o.end = HZ_NOIDX; }
 
     Comp sub(const Nm& nm) { return Comp(this, nm, false, 0); }
     Comp sub_reserve(const Nm& nm, uint32_t size) { return Comp(this, nm, true, size); }
@@ -447,8 +451,9 @@ template <> struct Comp<MLayout> {
     }
     VL set(uint32_t slot, const VL&) { VL r; r.idx = slot; return r; }
     VL seti(const Nm& nm, uint32_t slot, const VL&) { name(nm, slot); VL r; r.idx = slot; return r; }
-    VL alias(const Nm& nm, const VL& x) { name(nm, x.idx); return x; }
+    VL alias(const Nm& nm, const VL& x) { if (is_main) return own(nm, x); name(nm, x.idx); return x; }
     VL def(const Nm& nm, const VL& x) {
+        if (is_main) return own(nm, x);
         if (x.idx != HZ_NOIDX) { name(nm, x.idx); return x; }
         name(nm, cur); VL r; r.idx = cur++; return r;
     }

@@ -4,6 +4,7 @@
 #pragma once
 #include "rollup_main.cuh"
 #include "withdraw.cuh"
+#include "rollup_tx.cuh"
 #include <string>
 #include <vector>
 #include <cstring>

@@ -25,6 +25,8 @@ struct HzBackend {
     virtual int shard_phase2(const void* records, int sanity, uint8_t* shard_out, float* kernel_ms, HzErrBuf* errs) = 0;
     // Withdraw(nLevels): n independent instances, inputs n x ninputs x 32 B, witnesses n x nvars x 32 B
     virtual int withdraw_batch(uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out, float* kernel_ms, HzErrBuf* errs) = 0;
+    // the same with the witnesses left in device memory: only witness entry 1 (the public output) of every instance comes back
+    virtual int withdraw_resident(uint64_t, const uint8_t*, int, uint8_t*, float*, HzErrBuf*) { return HZW_E_PARAM; }
     // device-resident witness (null / HZW_E_PARAM for a backend without device memory)
     virtual int witness_device(void** ptr, int32_t* device, void** stream) { (void)ptr; (void)device; (void)stream; return HZW_E_PARAM; }
     virtual int witness_read(uint64_t first, uint64_t count, uint8_t* out) { (void)first; (void)count; (void)out; return HZW_E_PARAM; }
@@ -72,18 +74,22 @@ static inline uint32_t hz_xrec_vals_off(const HzParams& P, int per) { return ((u
 static inline uint32_t hz_xrec_bytes(const HzParams& P, int per) { return (hz_xrec_vals_off(P, per) + 3 * 32 + 3 * 4 + 15u) & ~15u; }
 HzBackend* hz_backend_create(const hzw_params& prm, const HzLayout& L, int* status);
 HzBackend* hz_backend_create_withdraw(const hzw_params& prm, const HzWLayout& WL, int* status);
+HzBackend* hz_backend_create_rolluptx(const hzw_params& prm, const HzTLayout& TL, int* status);
 
 struct hzw_ctx {
     hzw_params prm;
     HzParams P;
     HzLayout L;              // rollup-main
     HzWLayout WL;            // withdraw
-    bool withdraw = false;
+    HzTLayout TL;            // standalone rollup-tx
+    bool withdraw = false;   // a circuit whose instances are independent (Withdraw or standalone RollupTx): batches, no shards
+    bool rtx = false;        // ... and it is the standalone RollupTx
     std::unique_ptr<HzBackend> be;
-    uint64_t nvars() const { return withdraw ? WL.nvars : L.plan.nvars; }
-    uint64_t ninputs() const { return withdraw ? WL.n_inputs : L.plan.n_inputs; }
+    uint64_t nvars() const { return rtx ? TL.nvars : (withdraw ? WL.nvars : L.plan.nvars); }
+    uint64_t ninputs() const { return rtx ? TL.n_inputs : (withdraw ? WL.n_inputs : L.plan.n_inputs); }
     void walk(LayoutSink* sk) const {
-        if (withdraw) { HzWLayout t; hz_withdraw_walk(WL.nLevels, sk, t); }
+        if (rtx) { HzTLayout t; hz_rolluptx_walk(TL.nLevels, TL.maxFeeTx, sk, t); }
+        else if (withdraw) { HzWLayout t; hz_withdraw_walk(WL.nLevels, sk, t); }
         else { HzLayout t; hz_layout_walk(P, sk, t); }
     }
 };
@@ -121,6 +127,17 @@ int hzw_create(const hzw_params* prm, const char* layout_map_path, hzw_ctx** out
         *out = c;
         return HZW_OK;
     }
+    if (prm->circuit_kind == HZW_CIRCUIT_ROLLUP_TX) {
+        if (prm->nLevels < 1 || prm->nLevels + 1 > HZ_MAX_LEVELS || prm->maxFeeTx < 1 || prm->maxFeeTx > HZ_MAX_FEE) return HZW_E_PARAM;
+        hzw_ctx* c = new hzw_ctx();
+        c->prm = *prm; c->withdraw = true; c->rtx = true;
+        hz_rolluptx_walk(prm->nLevels, prm->maxFeeTx, nullptr, c->TL);
+        int st = 0;
+        c->be.reset(hz_backend_create_rolluptx(*prm, c->TL, &st));
+        if (!c->be) { delete c; return st ? st : HZW_E_DEVICE; }
+        *out = c;
+        return HZW_OK;
+    }
     if (prm->circuit_kind != HZW_CIRCUIT_ROLLUP_MAIN) return HZW_E_PARAM;
     HzParams P; P.nTx = prm->nTx; P.nLevels = prm->nLevels; P.maxL1Tx = prm->maxL1Tx; P.maxFeeTx = prm->maxFeeTx;
     if (!hz_params_ok(P)) return HZW_E_PARAM;
@@ -139,6 +156,15 @@ uint64_t hzw_ninputs(const hzw_ctx* ctx) { return ctx ? ctx->ninputs() : 0; }
 
 int hzw_input_index(const hzw_ctx* ctx, const char* name, uint64_t* offset, uint64_t* len) {
     if (!ctx || !name) return HZW_E_PARAM;
+    if (ctx->rtx) {
+        uint64_t at = 0;
+        for (int f = 0; f < HZ_ROLLUPTX_NIN; f++) {
+            const uint64_t n = (uint64_t)hz_rolluptx_in_len(f, ctx->TL.nLevels, ctx->TL.maxFeeTx);
+            if (!strcmp(name, HZ_ROLLUPTX_INPUTS[f].name)) { if (offset) *offset = at; if (len) *len = n; return HZW_OK; }
+            at += n;
+        }
+        return HZW_E_NOSIGNAL;
+    }
     if (ctx->withdraw) {
         for (int f = 0; f < WIN_COUNT; f++)
             if (!strcmp(name, HZ_WITHDRAW_INPUT_NAMES[f])) {
@@ -212,6 +238,13 @@ int hzw_calculate_batch(hzw_ctx* ctx, uint64_t n, const uint8_t* inputs, int san
     }
     return HZW_OK;
 }
+int hzw_calculate_batch_resident(hzw_ctx* ctx, uint64_t n, const uint8_t* inputs, int sanity, uint8_t* public_out, float* kernel_ms, hzw_error* err) {
+    if (!ctx || !inputs || !ctx->withdraw) return HZW_E_PARAM;
+    HzErrBuf eb; memset(&eb, 0, sizeof eb);
+    int st = ctx->be->withdraw_resident(n, inputs, sanity, public_out, kernel_ms, &eb);
+    if (st) { if (err) { memset(err, 0, sizeof *err); err->code = st; } return st; }
+    return hz_report(ctx, eb, err);
+}
 int hzw_write_wtns(const hzw_ctx* ctx, const uint8_t* witness, const char* path) {
     if (!ctx || !witness || !path) return HZW_E_PARAM;
     return hz_write_wtns(path, witness, ctx->nvars()) ? HZW_E_IO : HZW_OK;
@@ -261,6 +294,7 @@ int hzw_dump_sym(const hzw_ctx* ctx, const char* prefix, const char* path) {
 }
 int hzw_plan_info(const hzw_ctx* ctx, uint64_t out[12]) {
     if (!ctx || !out) return HZW_E_PARAM;
+    if (ctx->rtx) { for (int k = 0; k < 12; k++) out[k] = 0; out[0] = ctx->TL.nvars; out[1] = ctx->TL.n_inputs; return HZW_OK; }
     if (ctx->withdraw) { for (int k = 0; k < 12; k++) out[k] = 0; out[0] = ctx->WL.nvars; out[1] = ctx->WL.n_inputs; out[4] = HZ_SZ_SHA_BLOCK; out[5] = 2; return HZW_OK; }
     const HzPlan& pl = ctx->L.plan;
     const HzParams& P = ctx->P;

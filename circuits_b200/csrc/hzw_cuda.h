@@ -3,6 +3,7 @@
 #pragma once
 #include "rollup_main.cuh"
 #include "withdraw.cuh"
+#include "rollup_tx.cuh"
 
 struct HzCuda;   // device state of one context
 // returns null and sets *status (HZW_E_DEVICE) when no usable CUDA device / allocation failure
@@ -38,5 +39,11 @@ int hz_cuda_multi_wait(HzCuda*, HzCuda* peer);
 
 // ---- Withdraw(nLevels) batches ---------------------------------------------------------------------
 int hz_cuda_probe(int device);       // 0 when the device exists, else HZW_E_DEVICE / HZW_E_PARAM
-int hz_cuda_withdraw(int device, int nLevels, uint32_t nvars, uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out,
-                     float* kernel_ms, HzErrBuf* errs);
+struct HzWdCuda;                     // device state of a Withdraw context (two witness buffers, two streams)
+// maxFeeTx == 0: Withdraw(nLevels); > 0: the standalone RollupTx(nLevels, maxFeeTx) -- both are batches of independent instances
+HzWdCuda* hz_cuda_withdraw_create(int device, int nLevels, int maxFeeTx, uint32_t n_inputs, uint32_t nvars, int* status);
+void hz_cuda_withdraw_destroy(HzWdCuda*);
+// n instances: inputs n x ninputs x 32 B; out (nullable) n x nvars x 32 B; pub_out (nullable) n x 32 B = witness entry 1
+// of every instance; kernel_ms = device time of the whole call (chunks of the batch pipelined on two streams)
+int hz_cuda_withdraw_batch(HzWdCuda*, uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out, uint8_t* pub_out,
+                           float* kernel_ms, HzErrBuf* errs, uint64_t* launches);

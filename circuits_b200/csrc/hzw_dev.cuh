@@ -162,6 +162,7 @@ __global__ void k_sha_chain(HzPlan pl, const uint8_t* preb, uint32_t* chain, uin
 __global__ void k_sha_blocks(HzPlan pl, Fr* w, HzErrBuf* err, const uint32_t* chain, const uint32_t* msgw, const uint32_t* off_blocks, uint32_t b0);
 __global__ void k_hash_tail(HzPlan pl, Fr* w, HzErrBuf* err, const uint32_t* chain);
 __global__ void k_withdraw(Fr* w, uint32_t nvars, int nLevels, int n, HzErrBuf* err);
+__global__ void k_rolluptx(Fr* w, uint32_t nvars, int nLevels, int maxFeeTx, int n, HzErrBuf* err);
 __device__ __forceinline__ void hz_head_err(HzErrBuf* err, uint32_t cur, uint32_t line, const Fr& lhs) {
     if (!err) return;
     uint32_t k = atomicAdd(&err->count, 1u);

@@ -157,26 +157,71 @@ HzBackend* hz_backend_create(const hzw_params& prm, const HzLayout& L, int* stat
     return m;
 }
 
-// Withdraw(nLevels): instances are independent; the backend holds no per-circuit device state
+// Withdraw(nLevels): instances are independent -- no exchange at all.  One device state per GPU (n_gpus > 1: the
+// instances of a batch are split into contiguous ranges, one host thread per device; config 5 of BASELINE.json).
+struct HzBatchShape { uint32_t n_inputs, nvars; };
 struct CudaWithdrawBackend : HzBackend {
-    int device; HzWLayout WL;
+    std::vector<HzWdCuda*> dev; HzBatchShape WL;
+    ~CudaWithdrawBackend() override { for (auto* d : dev) hz_cuda_withdraw_destroy(d); }
     int calculate(const uint8_t*, int, uint8_t*, bool, float*, HzErrBuf*) override { return HZW_E_PARAM; }
     int set_shard(int, int) override { return HZW_E_PARAM; }
     uint64_t exchange_bytes() override { return 0; }
     int pieces(uint64_t*, int) override { return 0; }
     int shard_phase1(const uint8_t*, int, void*, HzErrBuf*) override { return HZW_E_PARAM; }
     int shard_phase2(const void*, int, uint8_t*, float*, HzErrBuf*) override { return HZW_E_PARAM; }
+    int run(uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out, uint8_t* pub, float* ms, HzErrBuf* errs) {
+        const int g = (int)dev.size();
+        std::vector<int> st(g, 0); std::vector<float> t(g, 0.f); std::vector<HzErrBuf> eb(g); std::vector<uint64_t> nl(g, 0);
+        const uint64_t per = (n + g - 1) / g;
+        auto work = [&](int r) {
+            const uint64_t k0 = per * r < n ? per * r : n, m = k0 + per <= n ? per : n - k0;
+            memset(&eb[r], 0, sizeof(HzErrBuf));
+            st[r] = hz_cuda_withdraw_batch(dev[r], m, inputs + 32ull * WL.n_inputs * k0, sanity, out ? out + 32ull * WL.nvars * k0 : nullptr,
+                                           pub ? pub + 32ull * k0 : nullptr, &t[r], &eb[r], &nl[r]);
+        };
+        if (g == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (int r = 0; r < g; r++) th.emplace_back(work, r);
+            for (auto& x : th) x.join();
+        }
+        memset(errs, 0, sizeof(HzErrBuf));
+        float worst = 0.f; launches = 0;
+        for (int r = 0; r < g; r++) {
+            if (st[r]) return st[r];
+            if (t[r] > worst) worst = t[r];
+            launches += nl[r];
+            if (eb[r].count && !errs->count) *errs = eb[r];          // instances are independent: the first range that failed
+        }
+        if (ms) *ms = worst;
+        h2d = 32ull * WL.n_inputs * n; d2h = (out ? 32ull * WL.nvars * n : 0) + (pub ? 32ull * n : 0);
+        return 0;
+    }
     int withdraw_batch(uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out, float* ms, HzErrBuf* errs) override {
-        launches = 1; h2d = 32ull * WL.n_inputs * n; d2h = 32ull * WL.nvars * n;
-        return hz_cuda_withdraw(device, WL.nLevels, WL.nvars, n, inputs, sanity, out, ms, errs);
+        return run(n, inputs, sanity, out, nullptr, ms, errs);
+    }
+    int withdraw_resident(uint64_t n, const uint8_t* inputs, int sanity, uint8_t* pub, float* ms, HzErrBuf* errs) override {
+        return run(n, inputs, sanity, nullptr, pub, ms, errs);
     }
 };
-HzBackend* hz_backend_create_withdraw(const hzw_params& prm, const HzWLayout& WL, int* status) {
-    int st = hz_cuda_probe(prm.device);
-    if (st) { *status = st; return nullptr; }
+static HzBackend* hz_batch_backend(const hzw_params& prm, int nLevels, int maxFeeTx, uint32_t n_inputs, uint32_t nvars, int* status) {
+    const int n = prm.n_gpus > 1 ? prm.n_gpus : 1;
+    if (n > HZ_MAX_GPUS_HOST) { *status = HZW_E_PARAM; return nullptr; }
     CudaWithdrawBackend* b = new CudaWithdrawBackend();
-    b->device = prm.device; b->WL = WL;
+    b->WL.n_inputs = n_inputs; b->WL.nvars = nvars;
+    for (int r = 0; r < n; r++) {
+        HzWdCuda* d = hz_cuda_withdraw_create(prm.device + r, nLevels, maxFeeTx, n_inputs, nvars, status);
+        if (!d) { delete b; return nullptr; }
+        b->dev.push_back(d);
+    }
+    *status = 0;
     return b;
+}
+HzBackend* hz_backend_create_withdraw(const hzw_params& prm, const HzWLayout& WL, int* status) {
+    return hz_batch_backend(prm, WL.nLevels, 0, WL.n_inputs, WL.nvars, status);
+}
+HzBackend* hz_backend_create_rolluptx(const hzw_params& prm, const HzTLayout& TL, int* status) {
+    return hz_batch_backend(prm, TL.nLevels, TL.maxFeeTx, TL.n_inputs, TL.nvars, status);
 }
 
 // ---- streaming copy for the host side of the end-to-end path (hzw_kernels.cu: hz_fill_holes) -----------------

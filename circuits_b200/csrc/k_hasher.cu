@@ -308,6 +308,16 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_withdraw(Fr* w, uint32_t nvars,
     c.put(0, fr_one());
     c.flush_pending();
 }
+// ---- standalone RollupTx(nLevels, maxFeeTx): one lane group per instance, the template evaluated as the main component
+__global__ void __launch_bounds__(HZ_BLOCK, 2) k_rolluptx(Fr* w, uint32_t nvars, int nLevels, int maxFeeTx, int n, HzErrBuf* err) {
+    bool real; int i = hz_item(n, real);
+    HzPending pend; pend.n = 0;
+    Comp<MCompute> c(w + (size_t)i * nvars, 1, real ? err : nullptr, nullptr, &pend);
+    RollupTxOut<MCompute> o;
+    sec_rolluptx_main(c, nLevels, maxFeeTx, o);
+    c.put(0, fr_one());
+    c.flush_pending();
+}
 int hz_cuda_probe(int device) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -316,35 +326,93 @@ int hz_cuda_probe(int device) {
     }
     return device < 0 || device >= n ? HZW_E_PARAM : 0;
 }
-int hz_cuda_withdraw(int device, int nLevels, uint32_t nvars, uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out,
-                     float* kernel_ms, HzErrBuf* errs) {
-    CK(cudaSetDevice(device));
-    CK(cudaDeviceSetLimit(cudaLimitStackSize, 80 * 1024));
-    const uint32_t nin = 7u + (uint32_t)nLevels + 1u;          // hz_withdraw_ninputs (a device function in this translation unit)
-    const uint64_t chunk = 2048;                 // instances per launch: bounds the device witness buffer (~5.5 GB at nLevels 32)
-    const uint64_t cap = n < chunk ? n : chunk;
-    Fr* w = nullptr; HzErrBuf* err = nullptr;
-    cudaEvent_t e0, e1;
-    CK(cudaMalloc(&w, 32ull * nvars * cap));
-    CK(cudaMalloc(&err, sizeof(HzErrBuf)));
-    CK(cudaMemset(err, 0, sizeof(HzErrBuf)));
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    float total = 0;
-    for (uint64_t k0 = 0; k0 < n; k0 += chunk) {
+// Withdraw batches: a context keeps two witness buffers of `cap` instances each, so that the device->host copy of one
+// chunk (when the caller wants the witnesses) runs beside the kernel of the next; with witness_out == NULL the
+// witnesses stay in HBM (the last two chunks of them) and only the public output of every instance -- witness entry 1,
+// hashGlobalInputs -- goes back.
+struct HzWdCuda {
+    int device, nLevels, maxFeeTx; uint32_t nvars, nin; uint64_t cap;
+    Fr* w[2]; HzErrBuf* err; cudaStream_t st[2]; cudaEvent_t e0, e1, done[2];
+};
+HzWdCuda* hz_cuda_withdraw_create(int device, int nLevels, int maxFeeTx, uint32_t n_inputs, uint32_t nvars, int* status) {
+    *status = hz_cuda_probe(device);
+    if (*status) return nullptr;
+    *status = HZW_E_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    HzWdCuda* d = new HzWdCuda();
+    memset(d, 0, sizeof *d);
+    d->device = device; d->nLevels = nLevels; d->maxFeeTx = maxFeeTx; d->nvars = nvars;
+    d->nin = n_inputs;
+    d->cap = 0;                                   // buffers are sized by the first batch (hz_wd_reserve)
+    bool ok = cudaMalloc(&d->err, sizeof(HzErrBuf)) == cudaSuccess;
+    for (int k = 0; k < 2; k++) ok = ok && cudaStreamCreate(&d->st[k]) == cudaSuccess && cudaEventCreateWithFlags(&d->done[k], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreate(&d->e0) == cudaSuccess && cudaEventCreate(&d->e1) == cudaSuccess;
+    ok = ok && cudaDeviceSetLimit(cudaLimitStackSize, 80 * 1024) == cudaSuccess;
+    if (!ok) { hz_cuda_withdraw_destroy(d); return nullptr; }
+    *status = 0;
+    return d;
+}
+void hz_cuda_withdraw_destroy(HzWdCuda* d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    for (int k = 0; k < 2; k++) { cudaFree(d->w[k]); if (d->st[k]) cudaStreamDestroy(d->st[k]); if (d->done[k]) cudaEventDestroy(d->done[k]); }
+    cudaFree(d->err);
+    if (d->e0) cudaEventDestroy(d->e0);
+    if (d->e1) cudaEventDestroy(d->e1);
+    delete d;
+}
+static int hz_wd_reserve(HzWdCuda* d, uint64_t n) {
+    // instances per launch: 4096 fill the machine with lane groups several times over (12 GB per buffer at nLevels 32)
+    const uint64_t big = d->maxFeeTx > 0 ? 1024 : 4096;
+    const uint64_t want = n < big ? n : big;
+    if (want <= d->cap) return 0;
+    for (int k = 0; k < 2; k++) { cudaFree(d->w[k]); d->w[k] = nullptr; }
+    d->cap = 0;
+    for (int k = 0; k < 2; k++) CK(cudaMalloc(&d->w[k], 32ull * d->nvars * want));
+    d->cap = want;
+    return 0;
+}
+// instances [0, n): inputs n x nin x 32 B (host); out (host, nullable) n x nvars x 32 B; pub_out (host, nullable) n x 32 B
+int hz_cuda_withdraw_batch(HzWdCuda* d, uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out, uint8_t* pub_out,
+                           float* kernel_ms, HzErrBuf* errs, uint64_t* launches) {
+    CK(cudaSetDevice(d->device));
+    if (n == 0) { memset(errs, 0, sizeof(HzErrBuf)); if (kernel_ms) *kernel_ms = 0; return 0; }
+    int st = hz_wd_reserve(d, n);
+    if (st) return st;
+    const uint64_t chunk = d->cap;
+    CK(cudaMemsetAsync(d->err, 0, sizeof(HzErrBuf), d->st[0]));
+    CK(cudaEventRecord(d->e0, d->st[0]));
+    CK(cudaStreamWaitEvent(d->st[1], d->e0, 0));
+    uint64_t nl = 0; int c = 0;
+    for (uint64_t k0 = 0; k0 < n; k0 += chunk, c++) {
         const uint64_t m = n - k0 < chunk ? n - k0 : chunk;
-        // inputs go to entries [2, 2 + nin) of each instance
-        CK(cudaMemcpy2D(reinterpret_cast<uint8_t*>(w) + 64, 32ull * nvars, inputs + 32ull * nin * k0, 32ull * nin, 32ull * nin, m, cudaMemcpyHostToDevice));
-        CK(cudaEventRecord(e0));
-        k_withdraw<<<hz_grid((int)m), HZ_BLOCK>>>(w, nvars, nLevels, (int)m, sanity ? err : nullptr);
-        CK(cudaEventRecord(e1));
+        const int b = c & 1;
+        Fr* w = d->w[b];
+        const uint8_t* in0 = inputs + 32ull * d->nin * k0;
+        if (d->maxFeeTx > 0) {
+            // the inputs of a RollupTx sit in three runs around the outputs declared among them (hz_rolluptx_in_index)
+            const uint32_t F = (uint32_t)d->maxFeeTx, nin = d->nin;
+            const uint32_t run[3][3] = {{0, 2 * F, 1}, {2 * F, nin - 1 - 2 * F, 1 + 3 * F}, {nin - 1, 1, 1 + F + nin}};   // first input, count, witness index
+            for (int q = 0; q < 3; q++)
+                CK(cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(w) + 32ull * run[q][2], 32ull * d->nvars, in0 + 32ull * run[q][0], 32ull * nin,
+                                     32ull * run[q][1], m, cudaMemcpyHostToDevice, d->st[b]));
+            k_rolluptx<<<hz_grid((int)m), HZ_BLOCK, 0, d->st[b]>>>(w, d->nvars, d->nLevels, d->maxFeeTx, (int)m, sanity ? d->err : nullptr);
+        } else {
+            // inputs go to entries [2, 2 + nin) of each instance
+            CK(cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(w) + 64, 32ull * d->nvars, in0, 32ull * d->nin, 32ull * d->nin, m, cudaMemcpyHostToDevice, d->st[b]));
+            k_withdraw<<<hz_grid((int)m), HZ_BLOCK, 0, d->st[b]>>>(w, d->nvars, d->nLevels, (int)m, sanity ? d->err : nullptr);
+        }
+        nl++;
         CK(cudaGetLastError());
-        CK(cudaMemcpy(out + 32ull * nvars * k0, w, 32ull * nvars * m, cudaMemcpyDeviceToHost));
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, e0, e1));
-        total += ms;
+        if (out) CK(cudaMemcpyAsync(out + 32ull * d->nvars * k0, w, 32ull * d->nvars * m, cudaMemcpyDeviceToHost, d->st[b]));
+        if (pub_out) CK(cudaMemcpy2DAsync(pub_out + 32ull * k0, 32, reinterpret_cast<uint8_t*>(w) + 32, 32ull * d->nvars, 32, m, cudaMemcpyDeviceToHost, d->st[b]));
     }
-    CK(cudaMemcpy(errs, err, sizeof(HzErrBuf), cudaMemcpyDeviceToHost));
-    if (kernel_ms) *kernel_ms = total;
-    cudaFree(w); cudaFree(err); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CK(cudaEventRecord(d->done[1], d->st[1]));
+    CK(cudaStreamWaitEvent(d->st[0], d->done[1], 0));
+    CK(cudaEventRecord(d->e1, d->st[0]));
+    CK(cudaMemcpyAsync(errs, d->err, sizeof(HzErrBuf), cudaMemcpyDeviceToHost, d->st[0]));
+    CK(cudaStreamSynchronize(d->st[0]));
+    if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, d->e0, d->e1));
+    if (launches) *launches = nl;
     return 0;
 }

@@ -576,8 +576,10 @@ TM HZ_FN void hz_phaseJK(Comp<M>& c, int nLevels, const PhaseJKIn<M>& in, V<M>& 
     V<M> p2 = SMTProcessor(c.sub("processor2"), nLevels + 1, s3, in.siblings2, in.oldKey2, in.oldValue2,
                            in.isOld0_2, in.key2, in.newValue2, in.f2);
     // K - select output roots (:577-590)
-    newStateRoot = c.alias("newStateRoot", Mux1(c.sub("s4"), p2, p1, in.isExit));
-    newExitRoot = c.alias("newExitRoot", Mux1(c.sub("s5"), in.oldExitRoot, p2, in.isExit));
+    // (a RollupTx evaluated as the main component has reserved entries for its two roots: RollupTx sets them)
+    newStateRoot = Mux1(c.sub("s4"), p2, p1, in.isExit);
+    newExitRoot = Mux1(c.sub("s5"), in.oldExitRoot, p2, in.isExit);
+    if (!c.is_main) { newStateRoot = c.alias("newStateRoot", newStateRoot); newExitRoot = c.alias("newExitRoot", newExitRoot); }
 }
 HZ_HD void hz_smt_job(HzSmtJob* j, uint32_t cur, uint32_t sib, const VC& oldKey, const VC& oldValue, const VC& isOld0,
                       const VC& newKey, const VC& newValue, const VC* f) {
@@ -615,7 +617,10 @@ TM HZ_FN void RollupTx(Comp<M>&& c, int nLevels, int maxFeeTx, const RollupTxIn<
     V<M> feePlanTokens[HZ_MAX_FEE], accFeeIn[HZ_MAX_FEE];
     for (int k = 0; k < maxFeeTx; k++) feePlanTokens[k] = c.def(Nm("feePlanTokens", k), i.feePlanTokens[k]);
     for (int k = 0; k < maxFeeTx; k++) accFeeIn[k] = c.def(Nm("accFeeIn", k), i.accFeeIn[k]);
-    // accFeeOut[] are wired to feeAccumulator outputs
+    // accFeeOut[] are wired to feeAccumulator outputs -- unless this template is the main component (standalone
+    // RollupTx, HZW_CIRCUIT_ROLLUP_TX): main's signals own their entries, at their declaration points
+    const bool mn = c.is_main;
+    const uint32_t slot_accOut = mn ? c.sigs("accFeeOut", maxFeeTx) : 0;
     RqWin<M> win;
     for (int k = 0; k < 3; k++) win.futV2[k] = c.def(Nm("futureTxCompressedDataV2", k), i.win.futV2[k]);
     for (int k = 0; k < 4; k++) win.pastV2[k] = c.def(Nm("pastTxCompressedDataV2", k), i.win.pastV2[k]);
@@ -647,12 +652,16 @@ TM HZ_FN void RollupTx(Comp<M>&& c, int nLevels, int maxFeeTx, const RollupTxIn<
     for (int k = 0; k < nLevels + 1; k++) siblings2[k] = c.def(Nm("siblings2", k), i.siblings2[k]);
     V<M> isOld0_2 = c.def("isOld0_2", i.isOld0_2), oldKey2 = c.def("oldKey2", i.oldKey2), oldValue2 = c.def("oldValue2", i.oldValue2);
     V<M> oldStateRoot = c.def("oldStateRoot", i.oldStateRoot);
+    const uint32_t slot_nsr = mn ? c.sig("newStateRoot") : 0;
     V<M> oldExitRoot = c.def("oldExitRoot", i.oldExitRoot);
-    // newStateRoot, newExitRoot, isAmountNullified, loadAmount are wired to sub-component outputs
+    const uint32_t slot_ner = mn ? c.sig("newExitRoot") : 0, slot_ian = mn ? c.sig("isAmountNullified") : 0;
+    const uint32_t slot_la = mn ? c.sig("loadAmount") : 0;
+    // (as a sub-component) newStateRoot, newExitRoot, isAmountNullified, loadAmount are wired to sub-component outputs
 
     // A - compute tx-states (:183-209)
     BV<M> la_bits = Num2Bits(c.sub("n2bloadAmountF"), 40, loadAmountF);
-    V<M> loadAmount = c.alias("loadAmount", DecodeFloatBin(c.sub("dfLoadAmount"), la_bits));
+    V<M> la_v = DecodeFloatBin(c.sub("dfLoadAmount"), la_bits);
+    V<M> loadAmount = mn ? c.set(slot_la, la_v) : c.alias("loadAmount", la_v);
     StatesOut<M> st = RollupTxStates(c.sub("states"), fromIdx, toIdx, toEthAddr, auxFromIdx, auxToIdx, amount,
                                      newExit, loadAmount, newAccount, oc, fromEthAddr, ethAddr1, tokenID, tokenID1, tokenID2);
     // B - check request transaction fields (:213-231)
@@ -700,11 +709,11 @@ TM HZ_FN void RollupTx(Comp<M>&& c, int nLevels, int maxFeeTx, const RollupTxIn<
     // G - update balances (:486-499)
     BalanceOut<M> bo = BalanceUpdater(c.sub("balanceUpdater"), s1Balance, s2Balance, amount, loadAmount, userFee,
                                       oc, st.nop, st.nullifyLoadAmount, st.nullifyAmount);
-    o.isAmountNullified = c.alias("isAmountNullified", bo.isAmountNullified);
+    o.isAmountNullified = mn ? c.set(slot_ian, bo.isAmountNullified) : c.alias("isAmountNullified", bo.isAmountNullified);
     // H - accumulate fees (:501-512)
     if (!hz_jobs_only(hook)) {
         FeeAccumulator(c.sub("feeAccumulator"), maxFeeTx, tokenID, bo.fee2Charge, feePlanTokens, accFeeIn, o.accFeeOut);
-        for (int k = 0; k < maxFeeTx; k++) c.alias(Nm("accFeeOut", k), o.accFeeOut[k]);
+        for (int k = 0; k < maxFeeTx; k++) { if (mn) o.accFeeOut[k] = c.set(slot_accOut + (uint32_t)k, o.accFeeOut[k]); else c.alias(Nm("accFeeOut", k), o.accFeeOut[k]); }
     }
     // I - compute hash new states (:517-532)
     V<M> newSt1Hash = HashState(c.sub("newSt1Hash"), s1TokenID, s1Nonce + (1 - oc), s1Sign, bo.newS, s1Ay, s1EthAddr);
@@ -720,6 +729,7 @@ TM HZ_FN void RollupTx(Comp<M>&& c, int nLevels, int maxFeeTx, const RollupTxIn<
     jk.sib1_idx = i.sib1_idx; jk.sib2_idx = i.sib2_idx;
     jk.ins1 = st.isP1Insert; jk.ins2 = st.isP2Insert; jk.ov1_idx = ov1_idx; jk.ov2_idx = ov2_idx;
     hz_phaseJK_hook(c, hook, nLevels, jk, o.newStateRoot, o.newExitRoot);
+    if (mn) { o.newStateRoot = c.set(slot_nsr, o.newStateRoot); o.newExitRoot = c.set(slot_ner, o.newExitRoot); }
 }
 
 // ---------------------------------------------------------------------------

@@ -20,6 +20,7 @@ from .field import P
 
 HZW_CIRCUIT_ROLLUP_MAIN = 0
 HZW_CIRCUIT_WITHDRAW = 1
+HZW_CIRCUIT_ROLLUP_TX = 2
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(_HERE, "libhzwitness.so")
 
@@ -43,7 +44,7 @@ EXPORTS = ["hzw_create", "hzw_destroy", "hzw_nvars", "hzw_ninputs", "hzw_input_i
            "hzw_calculate_batch", "hzw_calculate_resident", "hzw_write_wtns", "hzw_get_signal", "hzw_dump_sym",
            "hzw_last_stats", "hzw_last_kernel_ms", "hzw_plan_info", "hzw_set_shard", "hzw_exchange_bytes",
            "hzw_shard_pieces", "hzw_shard_nvars", "hzw_shard_phase1", "hzw_shard_phase2", "hzw_poseidon_bench", "hzw_int_peak",
-           "hzw_witness_device", "hzw_signal_index", "hzw_witness_read", "hzw_profile_step", "hzw_image_levels", "hzw_rank_pieces", "hzw_rank_witness_device"]
+           "hzw_witness_device", "hzw_signal_index", "hzw_witness_read", "hzw_profile_step", "hzw_image_levels", "hzw_rank_pieces", "hzw_rank_witness_device", "hzw_calculate_batch_resident"]
 
 
 def load_library(path=None):
@@ -118,7 +119,7 @@ class WitnessCalculator:
 
     def __init__(self, nTx, nLevels, maxL1Tx, maxFeeTx, circuit="rollup-main", device=0, lib_path=None, n_gpus=1):
         self._lib = load_library(lib_path)
-        kind = {"rollup-main": HZW_CIRCUIT_ROLLUP_MAIN, "withdraw": HZW_CIRCUIT_WITHDRAW}[circuit]
+        kind = {"rollup-main": HZW_CIRCUIT_ROLLUP_MAIN, "withdraw": HZW_CIRCUIT_WITHDRAW, "rollup-tx": HZW_CIRCUIT_ROLLUP_TX}[circuit]
         self.params = (nTx, nLevels, maxL1Tx, maxFeeTx)
         prm = _Params(kind, nTx, nLevels, maxL1Tx, maxFeeTx, device, n_gpus, 0)
         self._ctx = ctypes.c_void_p()
@@ -194,6 +195,22 @@ class WitnessCalculator:
         if st != 0:
             self._raise(st, err)
         return wit
+
+    def calculateBatchResident(self, n, packed, sanityCheck=False, public_out=None):
+        """`n` independent witnesses left in device memory (`hzw_calculate_batch_resident`; Withdraw): returns
+        (the public output of every instance, n x 32 B; device ms of the call)."""
+        if isinstance(packed, bytes):
+            packed = bytearray(packed)
+        pub = public_out if public_out is not None else bytearray(32 * n)
+        err = _Error()
+        ms = ctypes.c_float()
+        self._lib.hzw_calculate_batch_resident.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int,
+                                                           ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_Error)]
+        st = self._lib.hzw_calculate_batch_resident(self._ctx, n, _addr(packed), 1 if sanityCheck else 0, _addr(pub),
+                                                    ctypes.byref(ms), ctypes.byref(err))
+        if st != 0:
+            self._raise(st, err)
+        return pub, ms.value
 
     def calculateWitness(self, inp, sanityCheck=False):
         b = bytes(self.calculateBinWitness(inp, sanityCheck))

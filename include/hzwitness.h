@@ -36,6 +36,10 @@ extern "C" {
 
 #define HZW_CIRCUIT_ROLLUP_MAIN 0
 #define HZW_CIRCUIT_WITHDRAW 1
+/* RollupTx(nLevels, maxFeeTx) as a circuit of its own (`component main = RollupTx(...)`, the way
+ * /root/reference/test/rollup-tx.test.js:56-920 compiles it): inputs are the template's input signals in declaration
+ * order (/root/reference/src/rollup-tx.circom:93-170); instances are independent (hzw_calculate / hzw_calculate_batch) */
+#define HZW_CIRCUIT_ROLLUP_TX 2
 
 #define HZW_OK 0
 #define HZW_E_PARAM (-1)        /* bad parameters / null pointers */
@@ -77,6 +81,11 @@ int hzw_calculate(hzw_ctx* ctx, const uint8_t* inputs_le32, int sanity_check, ui
 /* n independent instances: inputs n x ninputs x 32 B, witnesses n x nvars x 32 B (withdraw) */
 int hzw_calculate_batch(hzw_ctx* ctx, uint64_t n, const uint8_t* inputs_le32, int sanity_check, uint8_t* witness_out,
                         hzw_error* err);
+/* the batch with the witnesses left in device memory: public_out (nullable) receives witness entry 1 -- the public output
+ * hashGlobalInputs -- of every instance, n x 32 B; kernel_ms = device time of the whole call (slowest GPU when n_gpus > 1:
+ * the instances are split into contiguous ranges, one per GPU, no exchange).  Withdraw contexts only. */
+int hzw_calculate_batch_resident(hzw_ctx* ctx, uint64_t n, const uint8_t* inputs_le32, int sanity_check, uint8_t* public_out,
+                                 float* kernel_ms, hzw_error* err);
 /* same computation, witness left in device memory (no device->host copy); kernel_ms = device time.
  * inputs_le32 == NULL re-uses the inputs already resident in device memory from the previous call. */
 int hzw_calculate_resident(hzw_ctx* ctx, const uint8_t* inputs_le32, int sanity_check, float* kernel_ms, hzw_error* err);

@@ -209,6 +209,34 @@ struct CpuWithdrawBackend : HzBackend {
         return 0;
     }
 };
+// standalone RollupTx(nLevels, maxFeeTx): the template as the main component, one instance per call / per thread
+struct CpuRollupTxBackend : HzBackend {
+    HzTLayout TL;
+    int calculate(const uint8_t*, int, uint8_t*, bool, float*, HzErrBuf*) override { return HZW_E_PARAM; }
+    int set_shard(int, int) override { return HZW_E_PARAM; }
+    uint64_t exchange_bytes() override { return 0; }
+    int pieces(uint64_t*, int) override { return 0; }
+    int shard_phase1(const uint8_t*, int, void*, HzErrBuf*) override { return HZW_E_PARAM; }
+    int shard_phase2(const void*, int, uint8_t*, float*, HzErrBuf*) override { return HZW_E_PARAM; }
+    int withdraw_batch(uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out, float*, HzErrBuf* errs) override {
+        hz_parallel_for((int)n, [&](int i) {
+            Fr* w = reinterpret_cast<Fr*>(out) + (size_t)i * TL.nvars;
+            memset(&w[0], 0, 32);
+            w[0].l[0] = 1;
+            for (uint32_t k = 0; k < TL.n_inputs; k++)
+                memcpy(&w[hz_rolluptx_in_index(k, TL.nLevels, TL.maxFeeTx)], inputs + 32ull * ((size_t)TL.n_inputs * i + k), 32);
+            Comp<MCompute> c(w, 1, sanity ? errs : nullptr);
+            RollupTxOut<MCompute> o;
+            sec_rolluptx_main(c, TL.nLevels, TL.maxFeeTx, o);
+        });
+        return 0;
+    }
+};
+HzBackend* hz_backend_create_rolluptx(const hzw_params&, const HzTLayout& TL, int*) {
+    CpuRollupTxBackend* b = new CpuRollupTxBackend();
+    b->TL = TL;
+    return b;
+}
 HzBackend* hz_backend_create_withdraw(const hzw_params&, const HzWLayout& WL, int*) {
     CpuWithdrawBackend* b = new CpuWithdrawBackend();
     b->WL = WL;

@@ -879,6 +879,23 @@ def rollup_main_witness(nTx, nLevels, maxL1Tx, maxFeeTx, inputs, sanity=True):
     return witness(main), main, ctx
 
 
+ROLLUP_TX_INPUTS = (["feePlanTokens", "accFeeIn", "futureTxCompressedDataV2", "pastTxCompressedDataV2", "futureToEthAddr",
+                     "pastToEthAddr", "futureToBjjAy", "pastToBjjAy", "fromIdx", "auxFromIdx", "toIdx", "auxToIdx", "toBjjAy",
+                     "toBjjSign", "toEthAddr", "amount", "tokenID", "nonce", "userFee", "rqOffset", "onChain", "newAccount",
+                     "rqTxCompressedDataV2", "rqToEthAddr", "rqToBjjAy", "sigL2Hash", "s", "r8x", "r8y", "fromEthAddr",
+                     "fromBjjCompressed", "loadAmountF", "tokenID1", "nonce1", "sign1", "balance1", "ay1", "ethAddr1",
+                     "siblings1", "isOld0_1", "oldKey1", "oldValue1", "tokenID2", "nonce2", "sign2", "balance2", "newExit",
+                     "ay2", "ethAddr2", "siblings2", "isOld0_2", "oldKey2", "oldValue2", "oldStateRoot", "oldExitRoot"])
+
+
+def rollup_tx_witness(nLevels, maxFeeTx, inputs, sanity=True):
+    """RollupTx(nLevels, maxFeeTx) as the main component (`component main = RollupTx(...)`,
+    /root/reference/test/rollup-tx.test.js:56-63): inputs keyed by the template's input names
+    (/root/reference/src/rollup-tx.circom:93-170)."""
+    main, ctx, _ = run_template(RollupTx, nLevels, maxFeeTx, inputs, sanity=sanity)
+    return witness(main), main, ctx
+
+
 def withdraw_witness(nLevels, inputs, sanity=True):
     main, ctx, _ = run_template(Withdraw, nLevels, inputs, sanity=sanity)
     return witness(main), main, ctx
