@@ -16,6 +16,7 @@
 #include "fr.cuh"
 
 #ifndef HZ_DEVICE_ONLY
+#include "formats.hpp"
 #include <string>
 #include <vector>
 #include <cstdio>
@@ -165,6 +166,8 @@ struct LayoutSink {
     bool want_names = false;
     std::string filter;
     std::vector<std::pair<std::string, uint32_t> >* out = nullptr;
+    // ... or, with `hashed` set, as (64-bit hash of the name, index): what resolving a whole .sym against the layout needs
+    std::vector<std::pair<uint64_t, uint32_t> >* hashed = nullptr;
     // reverse lookup: name of the first signal declared at witness index `find_idx`
     bool find_mode = false;
     uint32_t find_idx = 0;
@@ -440,7 +443,10 @@ template <> struct Comp<MLayout> {
         }
         if (named) {
             std::string full = prefix + "." + hz_nm(nm);
-            if (full.compare(0, sink->filter.size(), sink->filter) == 0) sink->out->push_back(std::make_pair(full, idx));
+            if (full.compare(0, sink->filter.size(), sink->filter) == 0) {
+                if (sink->hashed) sink->hashed->push_back(std::make_pair(hz_hash64(full.data(), full.size()), idx));
+                else sink->out->push_back(std::make_pair(full, idx));
+            }
         }
     }
     uint32_t sig(const Nm& nm) { name(nm, cur); return cur++; }

@@ -27,6 +27,13 @@ struct HzBackend {
     virtual int withdraw_batch(uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out, float* kernel_ms, HzErrBuf* errs) = 0;
     // the same with the witnesses left in device memory: only witness entry 1 (the public output) of every instance comes back
     virtual int withdraw_resident(uint64_t, const uint8_t*, int, uint8_t*, float*, HzErrBuf*) { return HZW_E_PARAM; }
+    // a circom .sym applied as a layout map (formats.hpp): src[v] = own index of the compiler's witness entry v
+    virtual int set_layout_map(const uint32_t*, uint64_t) { return HZW_E_PARAM; }
+    // the batch with the witness delivered in the compiler's layout (n_out entries)
+    virtual int calculate_mapped(const uint8_t*, int, uint8_t*, bool, float*, HzErrBuf*) { return HZW_E_PARAM; }
+    virtual int read_mapped(uint64_t, uint64_t, uint8_t*) { return HZW_E_PARAM; }
+    // A.w * B.w = C.w over an .r1cs; witness null = the resident one
+    virtual int r1cs_check(const HzR1cs&, const uint8_t*, uint64_t*, uint64_t*, float*) { return HZW_E_PARAM; }
     // device-resident witness (null / HZW_E_PARAM for a backend without device memory)
     virtual int witness_device(void** ptr, int32_t* device, void** stream) { (void)ptr; (void)device; (void)stream; return HZW_E_PARAM; }
     virtual int witness_read(uint64_t first, uint64_t count, uint8_t* out) { (void)first; (void)count; (void)out; return HZW_E_PARAM; }
@@ -85,7 +92,11 @@ struct hzw_ctx {
     bool withdraw = false;   // a circuit whose instances are independent (Withdraw or standalone RollupTx): batches, no shards
     bool rtx = false;        // ... and it is the standalone RollupTx
     std::unique_ptr<HzBackend> be;
-    uint64_t nvars() const { return rtx ? TL.nvars : (withdraw ? WL.nvars : L.plan.nvars); }
+    HzLayoutMap map;         // set when hzw_create was given a circom .sym: every index that crosses the boundary is the compiler's
+    uint64_t own_nvars() const { return rtx ? TL.nvars : (withdraw ? WL.nvars : L.plan.nvars); }
+    uint64_t nvars() const { return map.active() ? map.src.size() : own_nvars(); }
+    // own index -> the index the caller sees (HZ_NOIDX: the compiler's layout does not hold that signal)
+    uint32_t out_index(uint32_t own) const { return map.active() ? (own < map.inv.size() ? map.inv[own] : HZ_NOIDX) : own; }
     uint64_t ninputs() const { return rtx ? TL.n_inputs : (withdraw ? WL.n_inputs : L.plan.n_inputs); }
     void walk(LayoutSink* sk) const {
         if (rtx) { HzTLayout t; hz_rolluptx_walk(TL.nLevels, TL.maxFeeTx, sk, t); }
@@ -113,9 +124,28 @@ static inline std::string hz_dec(const Fr& f) {
 
 extern "C" {
 
+static int hz_apply_sym(hzw_ctx* c, const char* path) {
+    // every signal name of the circuit, hashed, against the names of the .sym
+    std::vector<std::pair<uint64_t, uint32_t> > names;
+    LayoutSink sk; sk.want_names = true; sk.filter = "main"; sk.hashed = &names;
+    c->walk(&sk);
+    std::string why;
+    int rc = hz_load_sym(path, names, (uint32_t)c->own_nvars(), c->map, &why);
+    if (rc) { fprintf(stderr, "hzw: layout map %s refused: %s\n", path, why.c_str()); return rc == -1 ? HZW_E_IO : HZW_E_PARAM; }
+    return c->be->set_layout_map(c->map.src.data(), c->map.src.size());
+}
+static int hzw_create_inner(const hzw_params* prm, hzw_ctx** out);
 int hzw_create(const hzw_params* prm, const char* layout_map_path, hzw_ctx** out) {
     if (!prm || !out) return HZW_E_PARAM;
-    if (layout_map_path) return HZW_E_PARAM;      // a circom .sym map is not applied yet: refuse rather than ignore it
+    // a layout map is applied by a context of one GPU evaluating one circuit instance per call
+    if (layout_map_path && (prm->n_gpus > 1 || prm->circuit_kind != HZW_CIRCUIT_ROLLUP_MAIN)) return HZW_E_PARAM;
+    int st = hzw_create_inner(prm, out);
+    if (st || !layout_map_path) return st;
+    st = hz_apply_sym(*out, layout_map_path);
+    if (st) { delete *out; *out = nullptr; }
+    return st;
+}
+static int hzw_create_inner(const hzw_params* prm, hzw_ctx** out) {
     if (prm->circuit_kind == HZW_CIRCUIT_WITHDRAW) {
         if (prm->nLevels < 1 || prm->nLevels > 48) return HZW_E_PARAM;
         hzw_ctx* c = new hzw_ctx();
@@ -212,7 +242,7 @@ static int hz_report(hzw_ctx* ctx, HzErrBuf& eb, hzw_error* err) {
 int hzw_calculate(hzw_ctx* ctx, const uint8_t* inputs, int sanity, uint8_t* witness_out, hzw_error* err) {
     if (!ctx || !inputs || !witness_out) return HZW_E_PARAM;
     HzErrBuf eb; memset(&eb, 0, sizeof eb);
-    int st = ctx->withdraw ? ctx->be->withdraw_batch(1, inputs, sanity, witness_out, nullptr, &eb)
+    int st = ctx->map.active() ? ctx->be->calculate_mapped(inputs, sanity, witness_out, false, nullptr, &eb) : ctx->withdraw ? ctx->be->withdraw_batch(1, inputs, sanity, witness_out, nullptr, &eb)
                            : ctx->be->calculate(inputs, sanity, witness_out, false, nullptr, &eb);
     if (st) { if (err) { memset(err, 0, sizeof *err); err->code = st; } return st; }
     return hz_report(ctx, eb, err);
@@ -220,7 +250,8 @@ int hzw_calculate(hzw_ctx* ctx, const uint8_t* inputs, int sanity, uint8_t* witn
 int hzw_calculate_resident(hzw_ctx* ctx, const uint8_t* inputs, int sanity, float* kernel_ms, hzw_error* err) {
     if (!ctx || ctx->withdraw) return HZW_E_PARAM;
     HzErrBuf eb; memset(&eb, 0, sizeof eb);
-    int st = ctx->be->calculate(inputs, sanity, nullptr, true, kernel_ms, &eb);
+    int st = ctx->map.active() ? ctx->be->calculate_mapped(inputs, sanity, nullptr, true, kernel_ms, &eb)
+                               : ctx->be->calculate(inputs, sanity, nullptr, true, kernel_ms, &eb);
     if (st) { if (err) { memset(err, 0, sizeof *err); err->code = st; } return st; }
     return hz_report(ctx, eb, err);
 }
@@ -249,6 +280,17 @@ int hzw_write_wtns(const hzw_ctx* ctx, const uint8_t* witness, const char* path)
     if (!ctx || !witness || !path) return HZW_E_PARAM;
     return hz_write_wtns(path, witness, ctx->nvars()) ? HZW_E_IO : HZW_OK;
 }
+int hzw_r1cs_check(hzw_ctx* ctx, const char* r1cs_path, const uint8_t* witness, uint64_t* n_constraints, uint64_t* n_bad,
+                   uint64_t* first_bad, float* kernel_ms) {
+    if (!ctx || !r1cs_path || ctx->withdraw) return HZW_E_PARAM;
+    HzR1cs R; std::string why;
+    uint8_t prime[32]; hz_fr_to_le32(fr_P(), prime);
+    int rc = hz_load_r1cs(r1cs_path, prime, R, &why);
+    if (rc) { fprintf(stderr, "hzw: %s: %s\n", r1cs_path, why.c_str()); return rc == -1 ? HZW_E_IO : HZW_E_PARAM; }
+    if (R.n_wires > ctx->nvars()) { fprintf(stderr, "hzw: %s has %u wires, the witness %llu entries\n", r1cs_path, R.n_wires, (unsigned long long)ctx->nvars()); return HZW_E_PARAM; }
+    if (n_constraints) *n_constraints = R.n_constraints;
+    return ctx->be->r1cs_check(R, witness, n_bad, first_bad, kernel_ms);
+}
 int hzw_witness_device(const hzw_ctx* ctx, void** dev_ptr, int32_t* device, void** stream) {
     if (!ctx || !dev_ptr) return HZW_E_PARAM;
     return ctx->be->witness_device(dev_ptr, device, stream);
@@ -263,6 +305,7 @@ int hzw_rank_witness_device(const hzw_ctx* ctx, int32_t rank, void** dev_ptr, in
 }
 int hzw_witness_read(hzw_ctx* ctx, uint64_t first, uint64_t count, uint8_t* out) {
     if (!ctx || !out || first + count > ctx->nvars()) return HZW_E_PARAM;
+    if (ctx->map.active()) return ctx->be->read_mapped(first, count, out);
     return ctx->be->witness_read(first, count, out);
 }
 int hzw_signal_index(const hzw_ctx* ctx, const char* name, uint64_t* index) {
@@ -270,7 +313,7 @@ int hzw_signal_index(const hzw_ctx* ctx, const char* name, uint64_t* index) {
     std::vector<std::pair<std::string, uint32_t> > v;
     LayoutSink sk; sk.want_names = true; sk.filter = name; sk.out = &v;
     ctx->walk(&sk);
-    for (auto& e : v) if (e.first == name && e.second != HZ_NOIDX) { *index = e.second; return HZW_OK; }
+    for (auto& e : v) if (e.first == name && e.second != HZ_NOIDX && ctx->out_index(e.second) != HZ_NOIDX) { *index = ctx->out_index(e.second); return HZW_OK; }
     return HZW_E_NOSIGNAL;
 }
 int hzw_get_signal(const hzw_ctx* ctx, const uint8_t* witness, const char* name, uint8_t out[32]) {
@@ -278,7 +321,7 @@ int hzw_get_signal(const hzw_ctx* ctx, const uint8_t* witness, const char* name,
     std::vector<std::pair<std::string, uint32_t> > v;
     LayoutSink sk; sk.want_names = true; sk.filter = name; sk.out = &v;
     ctx->walk(&sk);
-    for (auto& e : v) if (e.first == name && e.second != HZ_NOIDX) { memcpy(out, witness + 32ull * e.second, 32); return HZW_OK; }
+    for (auto& e : v) if (e.first == name && e.second != HZ_NOIDX && ctx->out_index(e.second) != HZ_NOIDX) { memcpy(out, witness + 32ull * ctx->out_index(e.second), 32); return HZW_OK; }
     return HZW_E_NOSIGNAL;
 }
 int hzw_dump_sym(const hzw_ctx* ctx, const char* prefix, const char* path) {
@@ -288,7 +331,7 @@ int hzw_dump_sym(const hzw_ctx* ctx, const char* prefix, const char* path) {
     ctx->walk(&sk);
     FILE* f = fopen(path, "w");
     if (!f) return HZW_E_IO;
-    for (auto& e : v) fprintf(f, "%u,%s\n", e.second, e.first.c_str());
+    for (auto& e : v) if (ctx->out_index(e.second) != HZ_NOIDX) fprintf(f, "%u,%s\n", ctx->out_index(e.second), e.first.c_str());
     fclose(f);
     return HZW_OK;
 }

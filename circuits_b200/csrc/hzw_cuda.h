@@ -37,6 +37,13 @@ uint8_t* hz_cuda_recs(HzCuda*);
 int hz_cuda_multi_phase1(HzCuda*, const uint8_t* inputs, int sanity, uint8_t* const* peer_recs, int world);
 int hz_cuda_multi_wait(HzCuda*, HzCuda* peer);
 
+// ---- formats around the path (k_formats.cu): layout map of a circom .sym, .r1cs constraint check ----------------
+struct HzR1cs;
+int hz_cuda_set_map(HzCuda*, const uint32_t* src, uint64_t n_out);
+int hz_cuda_remap(HzCuda*);                  // resident witness -> the compiler's layout, on the main stream
+int hz_cuda_read_mapped(HzCuda*, uint64_t first, uint64_t count, uint8_t* out);
+int hz_cuda_r1cs_check(HzCuda*, const HzR1cs& R, const uint8_t* witness, uint64_t* n_bad, uint64_t* first_bad, float* ms);
+
 // ---- Withdraw(nLevels) batches ---------------------------------------------------------------------
 int hz_cuda_probe(int device);       // 0 when the device exists, else HZW_E_DEVICE / HZW_E_PARAM
 struct HzWdCuda;                     // device state of a Withdraw context (two witness buffers, two streams)

@@ -83,6 +83,9 @@ struct HzCuda {
     cudaEvent_t ev0, ev1, ev_front, ev_eddsa, ev_lev, ev_zero, ev_fee, ev_jobs, ev_heads;
     cudaEvent_t ev_xchg;       // this rank's record has been stored into every peer (hz_cuda_multi_phase1)
     cudaEvent_t kev[HZ_NKERN + 3];
+    // layout map (a circom .sym applied when the witness leaves the device): compiler's index -> own index, and the
+    // witness gathered into the compiler's layout
+    uint32_t* map_src; Fr* w_out; uint64_t n_out;
     // profile mode (hz_cuda_profile_step): every launch of a batch on ONE stream, an event in front of each
     bool prof; int n_prof; cudaEvent_t pev[HZ_MAXPROF + 1]; const char* pname[HZ_MAXPROF];
 };

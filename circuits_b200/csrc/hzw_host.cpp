@@ -18,6 +18,22 @@ struct CudaBackend : HzBackend {
     int image_levels(uint64_t out[2]) override { return hz_cuda_image_levels(d, out); }
     int witness_device(void** ptr, int32_t* device, void** stream) override { return hz_cuda_witness_device(d, ptr, device, stream); }
     int witness_read(uint64_t first, uint64_t count, uint8_t* out) override { return hz_cuda_witness_read(d, first, count, out); }
+    // a circom .sym as a layout map: the batch is evaluated in this library's layout, a gather kernel puts it into the
+    // compiler's, and that is what leaves the device (one plain copy: the map decides which entries exist at all)
+    uint64_t n_out = 0;
+    int set_layout_map(const uint32_t* src, uint64_t n) override { n_out = n; return hz_cuda_set_map(d, src, n); }
+    int calculate_mapped(const uint8_t* inputs, int sanity, uint8_t* out, bool resident, float* ms, HzErrBuf* errs) override {
+        if (!n_out || (!resident && !out)) return HZW_E_PARAM;
+        int st = hz_cuda_calculate(d, inputs, sanity, nullptr, ms, errs, &launches, &h2d, &d2h);
+        if (!st) st = hz_cuda_remap(d);
+        launches++;
+        if (!st && !resident) { st = hz_cuda_read_mapped(d, 0, n_out, out); d2h += 32ull * n_out; }
+        return st;
+    }
+    int read_mapped(uint64_t first, uint64_t count, uint8_t* out) override { return hz_cuda_read_mapped(d, first, count, out); }
+    int r1cs_check(const HzR1cs& R, const uint8_t* witness, uint64_t* n_bad, uint64_t* first_bad, float* ms) override {
+        return hz_cuda_r1cs_check(d, R, witness, n_bad, first_bad, ms);
+    }
     const HzLayout* L = nullptr;
     HzShard sh;
     int set_shard(int rank, int world) override {

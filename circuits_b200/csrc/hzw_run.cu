@@ -167,6 +167,7 @@ void hz_cuda_destroy(HzCuda* d) {
     cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit); cudaFree(d->lev); cudaFree(d->smst); cudaFree(d->img00); cudaFree(d->zflag); cudaFree(d->holes); cudaFree(d->gl); cudaFreeHost(d->h_holes); cudaFreeHost(d->h_gl); cudaFreeHost(d->h_img00);
     cudaFree(d->hint_cst); cudaFree(d->hint_tab); cudaFree(d->hint_img); cudaFree(d->hint_scratch); cudaFree(d->recs);
     cudaFree(d->off_decode); cudaFree(d->off_rollup); cudaFree(d->off_fee); cudaFree(d->off_blocks);
+    cudaFree(d->map_src); cudaFree(d->w_out);
     if (d->stream) cudaStreamDestroy(d->stream);
     if (d->stream2) cudaStreamDestroy(d->stream2);
     if (d->stream3) cudaStreamDestroy(d->stream3);

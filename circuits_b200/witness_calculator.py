@@ -44,7 +44,7 @@ EXPORTS = ["hzw_create", "hzw_destroy", "hzw_nvars", "hzw_ninputs", "hzw_input_i
            "hzw_calculate_batch", "hzw_calculate_resident", "hzw_write_wtns", "hzw_get_signal", "hzw_dump_sym",
            "hzw_last_stats", "hzw_last_kernel_ms", "hzw_plan_info", "hzw_set_shard", "hzw_exchange_bytes",
            "hzw_shard_pieces", "hzw_shard_nvars", "hzw_shard_phase1", "hzw_shard_phase2", "hzw_poseidon_bench", "hzw_int_peak",
-           "hzw_witness_device", "hzw_signal_index", "hzw_witness_read", "hzw_profile_step", "hzw_image_levels", "hzw_rank_pieces", "hzw_rank_witness_device", "hzw_calculate_batch_resident"]
+           "hzw_witness_device", "hzw_signal_index", "hzw_witness_read", "hzw_profile_step", "hzw_image_levels", "hzw_rank_pieces", "hzw_rank_witness_device", "hzw_calculate_batch_resident", "hzw_r1cs_check"]
 
 
 def load_library(path=None):
@@ -117,13 +117,14 @@ class WitnessCalculator:
     prime = P
     n64 = 4
 
-    def __init__(self, nTx, nLevels, maxL1Tx, maxFeeTx, circuit="rollup-main", device=0, lib_path=None, n_gpus=1):
+    def __init__(self, nTx, nLevels, maxL1Tx, maxFeeTx, circuit="rollup-main", device=0, lib_path=None, n_gpus=1, sym=None):
         self._lib = load_library(lib_path)
         kind = {"rollup-main": HZW_CIRCUIT_ROLLUP_MAIN, "withdraw": HZW_CIRCUIT_WITHDRAW, "rollup-tx": HZW_CIRCUIT_ROLLUP_TX}[circuit]
         self.params = (nTx, nLevels, maxL1Tx, maxFeeTx)
         prm = _Params(kind, nTx, nLevels, maxL1Tx, maxFeeTx, device, n_gpus, 0)
         self._ctx = ctypes.c_void_p()
-        st = self._lib.hzw_create(ctypes.byref(prm), None, ctypes.byref(self._ctx))
+        # sym: path of a circom `.sym` of this circuit -- witness indexes then follow the compiler's layout
+        st = self._lib.hzw_create(ctypes.byref(prm), None if sym is None else str(sym).encode(), ctypes.byref(self._ctx))
         if st != 0:
             self._ctx = None
             raise WitnessError("hzw_create failed with code %d (no CUDA device? bad parameters?)" % st)
@@ -248,6 +249,20 @@ class WitnessCalculator:
         if self._lib.hzw_witness_read(self._ctx, first, count, _addr(buf)) != 0:
             raise WitnessError("hzw_witness_read(%d, %d) failed" % (first, count))
         return buf
+
+    def checkConstraints(self, r1cs_path, witness=None):
+        """`circuit.checkConstraints(witness)` of the circom tester on the GPU: every constraint of an iden3 .r1cs
+        over `witness` (bytes in the file's wire numbering) or, with None, over the witness resident on the device.
+        Returns (constraints, violated, index of the first violated one or None, device ms)."""
+        n, bad, first, ms = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_float()
+        self._lib.hzw_r1cs_check.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64),
+                                             ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_float)]
+        wb = None if witness is None else (witness if hasattr(witness, "ctypes") or hasattr(witness, "data_ptr") else bytearray(witness))
+        st = self._lib.hzw_r1cs_check(self._ctx, str(r1cs_path).encode(), None if wb is None else _addr(wb), ctypes.byref(n),
+                                      ctypes.byref(bad), ctypes.byref(first), ctypes.byref(ms))
+        if st != 0:
+            raise WitnessError("hzw_r1cs_check(%s) failed with code %d" % (r1cs_path, st))
+        return n.value, bad.value, (None if bad.value == 0 else first.value), ms.value
 
     def planInfo(self):
         out = (ctypes.c_uint64 * 12)()

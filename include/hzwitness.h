@@ -70,6 +70,14 @@ typedef struct {
     char where[256];            /* component path when it could be resolved */
 } hzw_error;
 
+/* layout_map_path (nullable): a circom `.sym` of the same circuit (`circom -s`: lines `labelIdx,varIdx,componentIdx,name`).
+ * With it every witness index that crosses this boundary is the COMPILER's: hzw_nvars() is the number of witness entries
+ * of the compiler's layout (a reduced `-r` build keeps fewer than this library evaluates), hzw_calculate / hzw_write_wtns
+ * deliver the entries in the compiler's order (a gather kernel on the device before the copy), hzw_signal_index /
+ * hzw_get_signal / hzw_dump_sym answer in it.  Every name in the file must be a signal of this circuit and every witness
+ * index must be named, else HZW_E_PARAM (the reason goes to stderr).  One GPU, HZW_CIRCUIT_ROLLUP_MAIN.  Replaces what
+ * the reference gets from compiling with `sym: true` (/root/reference/test/rollup-main.test.js:52,
+ * /root/reference/tools/helpers/actions.js:41). */
 int hzw_create(const hzw_params* params, const char* layout_map_path /* nullable */, hzw_ctx** out);
 void hzw_destroy(hzw_ctx* ctx);
 uint64_t hzw_nvars(const hzw_ctx* ctx);
@@ -108,6 +116,13 @@ int hzw_witness_read(hzw_ctx* ctx, uint64_t first, uint64_t count, uint8_t* out)
 int hzw_rank_pieces(const hzw_ctx* ctx, int32_t rank, uint64_t* table /* 2 x cap */, int32_t cap);
 int hzw_rank_witness_device(const hzw_ctx* ctx, int32_t rank, void** dev_ptr, int32_t* device, void** stream);
 int hzw_write_wtns(const hzw_ctx* ctx, const uint8_t* witness, const char* path);
+/* The constraints of an iden3 `.r1cs` (v1, BN254) evaluated over a witness: A.w * B.w = C.w, one GPU thread per constraint.
+ * witness: host buffer of at least nWires entries in the numbering the file uses, or NULL = the witness resident on the
+ * device after hzw_calculate_resident (gathered into the compiler's layout when the context has a layout map).
+ * n_bad = violated constraints, first_bad = lowest index of one (~0 if none).  The independent check the reference's tests
+ * get from `circuit.checkConstraints(witness)` / `loadConstraints()` (/root/reference/test/rollup-main.test.js:52-54). */
+int hzw_r1cs_check(hzw_ctx* ctx, const char* r1cs_path, const uint8_t* witness /* nullable */, uint64_t* n_constraints,
+                   uint64_t* n_bad, uint64_t* first_bad, float* kernel_ms /* nullable */);
 int hzw_get_signal(const hzw_ctx* ctx, const uint8_t* witness, const char* name, uint8_t out[32]);
 /* writes "index,name" lines (the `.sym` equivalent) for every signal whose name starts with prefix */
 int hzw_dump_sym(const hzw_ctx* ctx, const char* prefix, const char* path);

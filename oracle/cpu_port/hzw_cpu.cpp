@@ -130,6 +130,32 @@ struct CpuBackend : HzBackend {
         return 0;
     }
     int withdraw_batch(uint64_t, const uint8_t*, int, uint8_t*, float*, HzErrBuf*) override { return HZW_E_PARAM; }
+    // ---- a circom .sym as a layout map, the .r1cs constraint check: host loops (the checker's side of formats.hpp)
+    std::vector<uint32_t> map_src;
+    int set_layout_map(const uint32_t* src, uint64_t n) override { map_src.assign(src, src + n); return 0; }
+    int calculate_mapped(const uint8_t* inputs, int sanity, uint8_t* out, bool resident, float* ms, HzErrBuf* errs) override {
+        if (resident || !out || map_src.empty()) return HZW_E_PARAM;
+        std::vector<Fr> own(L.plan.nvars);
+        int st = calculate(inputs, sanity, reinterpret_cast<uint8_t*>(own.data()), false, ms, errs);
+        if (st) return st;
+        Fr* o = reinterpret_cast<Fr*>(out);
+        for (size_t v = 0; v < map_src.size(); v++) o[v] = own[map_src[v]];
+        return 0;
+    }
+    int r1cs_check(const HzR1cs& R, const uint8_t* witness, uint64_t* n_bad, uint64_t* first_bad, float*) override {
+        if (!witness) return HZW_E_PARAM;            // nothing stays resident in the CPU port
+        const Fr* w = reinterpret_cast<const Fr*>(witness);
+        const Fr* coef = reinterpret_cast<const Fr*>(R.coef.data());
+        uint64_t bad = 0, first = ~0ull;
+        auto lc = [&](uint64_t a, uint64_t b) { Fr s = fr_zero(); for (uint64_t t = a; t < b; t++) s = fr_add(s, fr_mul(coef[t], w[R.wire[t]])); return s; };
+        for (uint32_t c = 0; c < R.n_constraints; c++) {
+            const Fr A = lc(R.off[3ull * c], R.off[3ull * c + 1]), B = lc(R.off[3ull * c + 1], R.off[3ull * c + 2]), C = lc(R.off[3ull * c + 2], R.off[3ull * c + 3]);
+            if (!fr_eq(fr_mul(A, B), C)) { bad++; if (first == ~0ull) first = c; }
+        }
+        if (n_bad) *n_bad = bad;
+        if (first_bad) *first_bad = first;
+        return 0;
+    }
     // ---- shards: the same protocol as the CUDA library, records in host memory -------------------
     int set_shard(int rank, int world) override { sh = hz_shard_ranges(L.plan, rank, world); return 0; }
     uint64_t exchange_bytes() override { return hz_xrec_bytes(L.plan.P, sh.per); }
