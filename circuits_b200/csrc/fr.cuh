@@ -11,6 +11,7 @@
 // The same source compiles for the host (g++) so that the circuit templates can be checked
 // on a CPU against the oracle; the product only ever runs the device instantiation.
 #pragma once
+#include <string.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__) && defined(HZ_DEVICE_ONLY)
@@ -287,6 +288,61 @@ HZ_HDN Fr fr_mul_u64_dev(const Fr& a, uint64_t k) {
     if (k < (1ull << 20)) return fr_mul_small(a, (uint32_t)k);
     return fr_mul_chain(a, fr_from_u64(k));
 }
+#elif defined(__SIZEOF_INT128__) && defined(__x86_64__)
+// Host (the CPU port, i.e. the CPU baseline of the benchmark): 4 x 64-bit limbs with 128-bit products, the arithmetic
+// the reference's ffiasm field uses (4 x 4 64-bit Montgomery CIOS).  Witness entries are canonical
+// residues, so a product of two of them is two Montgomery steps: redc(a b) = a b / R, redc(that * R^2) = a b; values
+// 0 and 1 are handled as the reference's "short" elements are, without a multiplication.
+typedef unsigned __int128 hz_u128;
+static const uint64_t HZ_P64[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+static const uint64_t HZ_R2_64[4] = {0x1bb8e645ae216da7ull, 0x53fe3ab1e35c59e3ull, 0x8c49833d53bb8085ull, 0x216d0b17f4e44a5ull};
+#define HZ_NINV64 0xc2e1f593efffffffull
+static inline void hz_mul64_acc(uint64_t* T /* 9 limbs */, const uint64_t* a, const uint64_t* b) {     // T += a * b
+    for (int i = 0; i < 4; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < 4; j++) { hz_u128 x = (hz_u128)a[i] * b[j] + T[i + j] + c; T[i + j] = (uint64_t)x; c = (uint64_t)(x >> 64); }
+        for (int k = i + 4; c && k < 9; k++) { hz_u128 x = (hz_u128)T[k] + c; T[k] = (uint64_t)x; c = (uint64_t)(x >> 64); }
+    }
+}
+// T (9 limbs, below 8 p^2) -> T / 2^256 mod p, canonical
+static inline void hz_redc64(uint64_t* T, uint64_t* out) {
+    for (int i = 0; i < 4; i++) {
+        const uint64_t m = T[i] * HZ_NINV64;
+        uint64_t c = 0;
+        for (int j = 0; j < 4; j++) { hz_u128 x = (hz_u128)m * HZ_P64[j] + T[i + j] + c; T[i + j] = (uint64_t)x; c = (uint64_t)(x >> 64); }
+        for (int k = i + 4; c && k < 9; k++) { hz_u128 x = (hz_u128)T[k] + c; T[k] = (uint64_t)x; c = (uint64_t)(x >> 64); }
+    }
+    uint64_t r[5] = {T[4], T[5], T[6], T[7], T[8]};
+    for (;;) {                                   // below 3 p: at most two subtractions
+        uint64_t d[4]; uint64_t bw = 0;
+        for (int j = 0; j < 4; j++) { hz_u128 x = (hz_u128)r[j] - HZ_P64[j] - bw; d[j] = (uint64_t)x; bw = (uint64_t)(x >> 64) & 1u; }
+        if (r[4] == 0 && bw) break;
+        r[4] -= bw;
+        for (int j = 0; j < 4; j++) r[j] = d[j];
+    }
+    for (int j = 0; j < 4; j++) out[j] = r[j];
+}
+static inline Fr hz_mont_pair64(const uint64_t* T0 /* 9 limbs, consumed */) {
+    uint64_t T[9], u[4];
+    for (int i = 0; i < 9; i++) T[i] = T0[i];
+    hz_redc64(T, u);
+    for (int i = 0; i < 9; i++) T[i] = 0;
+    hz_mul64_acc(T, u, HZ_R2_64);
+    hz_redc64(T, u);
+    Fr r; memcpy(r.l, u, 32);
+    return r;
+}
+HZ_HDN Fr fr_mul(const Fr& a, const Fr& b) {
+    const uint32_t bh = b.l[1] | b.l[2] | b.l[3] | b.l[4] | b.l[5] | b.l[6] | b.l[7];
+    if (bh == 0 && b.l[0] <= 1u) return b.l[0] ? a : b;
+    const uint32_t ah = a.l[1] | a.l[2] | a.l[3] | a.l[4] | a.l[5] | a.l[6] | a.l[7];
+    if (ah == 0 && a.l[0] <= 1u) return a.l[0] ? b : a;
+    uint64_t x[4], y[4], T[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    memcpy(x, a.l, 32); memcpy(y, b.l, 32);
+    hz_mul64_acc(T, x, y);
+    return hz_mont_pair64(T);
+}
+#define HZ_HOST_MONT64 1
 #else
 HZ_HDN Fr fr_mul(const Fr& a, const Fr& b) {
     uint32_t t[16];
@@ -304,6 +360,16 @@ HZ_HD Fr fr_mul_u64(const Fr& a, uint64_t k) { return fr_mul(a, fr_from_u64(k));
 // ---- Montgomery row: sum_{j<n} s[j] * cR[j]  (cR = c * 2^256 mod p)  -> canonical -----------
 // n <= 7: the unreduced sum stays below 7 p^2 < 2^511.
 HZ_HDN Fr fr_dot_mont(const Fr* s, const Fr* cR, int n) {
+#ifdef HZ_HOST_MONT64
+    {
+        // host: 64-bit limbs, n products accumulated on 9 limbs, one Montgomery reduction (the constants carry the R)
+        uint64_t T[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, x[4], y[4], u[4];
+        for (int k = 0; k < n; k++) { memcpy(x, s[k].l, 32); memcpy(y, cR[k].l, 32); hz_mul64_acc(T, x, y); }
+        hz_redc64(T, u);
+        Fr r; memcpy(r.l, u, 32);
+        return r;
+    }
+#endif
     uint32_t t[17];
     for (int i = 0; i < 17; i++) t[i] = 0;
     for (int k = 0; k < n; k++) {
@@ -356,7 +422,42 @@ HZ_HD void fr_half_mod(Fr& x) {         // x/2 mod p
         fr_shr1(x, 0);
     }
 }
-#ifndef HZ_DEVICE_ONLY
+#ifdef HZ_HOST_MONT64
+// host: the same binary extended Euclid on 64-bit limbs, runs of trailing zeros taken in one go
+static inline uint64_t hz_sub64(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+    uint64_t bw = 0;
+    for (int j = 0; j < 4; j++) { hz_u128 x = (hz_u128)a[j] - b[j] - bw; r[j] = (uint64_t)x; bw = (uint64_t)(x >> 64) & 1u; }
+    return bw;
+}
+static inline void hz_half_mod64(uint64_t* x) {
+    uint64_t top = 0;
+    if (x[0] & 1u) { uint64_t c = 0; for (int j = 0; j < 4; j++) { hz_u128 t = (hz_u128)x[j] + HZ_P64[j] + c; x[j] = (uint64_t)t; c = (uint64_t)(t >> 64); } top = c; }
+    for (int j = 0; j < 3; j++) x[j] = (x[j] >> 1) | (x[j + 1] << 63);
+    x[3] = (x[3] >> 1) | (top << 63);
+}
+static inline void hz_shr1_64(uint64_t* x) { for (int j = 0; j < 3; j++) x[j] = (x[j] >> 1) | (x[j + 1] << 63); x[3] >>= 1; }
+static inline bool hz_is_one64(const uint64_t* x) { return x[0] == 1 && (x[1] | x[2] | x[3]) == 0; }
+static inline bool hz_geq64(const uint64_t* a, const uint64_t* b) {
+    for (int j = 3; j >= 0; j--) { if (a[j] > b[j]) return true; if (a[j] < b[j]) return false; }
+    return true;
+}
+static inline void hz_submod64(uint64_t* x, const uint64_t* y) {          // x = x - y mod p
+    if (hz_sub64(x, x, y)) { uint64_t c = 0; for (int j = 0; j < 4; j++) { hz_u128 t = (hz_u128)x[j] + HZ_P64[j] + c; x[j] = (uint64_t)t; c = (uint64_t)(t >> 64); } }
+}
+HZ_HDN Fr fr_inv(const Fr& a) {
+    if (fr_is_zero(a)) return a;
+    uint64_t u[4], v[4] = {HZ_P64[0], HZ_P64[1], HZ_P64[2], HZ_P64[3]}, x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
+    memcpy(u, a.l, 32);
+    while (!hz_is_one64(u) && !hz_is_one64(v)) {
+        while (!(u[0] & 1u)) { hz_shr1_64(u); hz_half_mod64(x1); }
+        while (!(v[0] & 1u)) { hz_shr1_64(v); hz_half_mod64(x2); }
+        if (hz_geq64(u, v)) { hz_sub64(u, u, v); hz_submod64(x1, x2); }
+        else { hz_sub64(v, v, u); hz_submod64(x2, x1); }
+    }
+    Fr r; memcpy(r.l, hz_is_one64(u) ? x1 : x2, 32);
+    return r;
+}
+#elif !defined(HZ_DEVICE_ONLY)
 HZ_HDN Fr fr_inv(const Fr& a) {
     if (fr_is_zero(a)) return a;
     Fr u = a, v = fr_P(), x1 = fr_one(), x2 = fr_zero();
