@@ -18,14 +18,15 @@ import sys
 
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="python -m circuits_b200.cli", description=__doc__.split("\n\n")[0])
-    ap.add_argument("--circuit", default="rollup-main", choices=["rollup-main", "withdraw"])
+    ap.add_argument("--circuit", default="rollup-main", choices=["rollup-main", "withdraw", "rollup-tx"])
+    ap.add_argument("--sym", default=None, help="circom .sym of the circuit: the witness is written in the compiler's layout")
     ap.add_argument("--nTx", type=int, default=1)
     ap.add_argument("--nLevels", type=int, required=True)
     ap.add_argument("--maxL1Tx", type=int, default=0)
     ap.add_argument("--maxFeeTx", type=int, default=1)
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--sanity", action="store_true", help="check every `===` of the circuit (sanityCheck)")
-    ap.add_argument("--lib", default=None, help="shared library behind the C ABI (default: the CUDA library)")
+    ap.add_argument("--lib", default=None, help=argparse.SUPPRESS)      # tests only: the checker's library behind the same C ABI
     ap.add_argument("input", help="input.json")
     ap.add_argument("output", help="witness.wtns, or witness.json for the decimal-string array")
     args = ap.parse_args(argv)
@@ -37,7 +38,11 @@ def main(argv=None):
         return 1
     try:
         wc = WitnessCalculator(args.nTx, args.nLevels, args.maxL1Tx, args.maxFeeTx, circuit=args.circuit,
-                               device=args.device, lib_path=args.lib)
+                               device=args.device, lib_path=args.lib, sym=args.sym)
+        if args.circuit == "rollup-main" and not args.output.endswith(".json"):
+            # straight from device memory into the file, chunk by chunk: no copy of the witness in this process
+            wc.calculateToWtns(inp, args.output, args.sanity)
+            return 0
         w = wc.calculateBinWitness(inp, args.sanity)
     except WitnessError as e:
         sys.stderr.write("%s\n" % e)

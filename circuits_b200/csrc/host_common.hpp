@@ -144,10 +144,8 @@ static inline void hz_withdraw_walk(int nLevels, LayoutSink* sink, HzWLayout& R)
 }
 
 // `.wtns` container, snarkjs 0.3.59 wtns_utils.writeBin layout
-static inline int hz_write_wtns(const char* path, const uint8_t* witness, uint64_t nvars) {
-    FILE* f = fopen(path, "wb");
-    if (!f) return -2;
-    uint8_t hdr[4 + 4 + 4 + 4 + 8 + 4 + 32 + 4 + 4 + 8];
+#define HZ_WTNS_HEADER 76
+static inline void hz_wtns_header(uint8_t hdr[HZ_WTNS_HEADER], uint64_t nvars) {
     uint8_t* p = hdr;
     auto u32 = [&](uint32_t v) { for (int i = 0; i < 4; i++) *p++ = (uint8_t)(v >> (8 * i)); };
     auto u64 = [&](uint64_t v) { for (int i = 0; i < 8; i++) *p++ = (uint8_t)(v >> (8 * i)); };
@@ -158,8 +156,14 @@ static inline int hz_write_wtns(const char* path, const uint8_t* witness, uint64
     for (int i = 0; i < 8; i++) u32(P.l[i]);
     u32((uint32_t)nvars);
     u32(2); u64(32ull * nvars);
+}
+static inline int hz_write_wtns(const char* path, const uint8_t* witness, uint64_t nvars) {
+    FILE* f = fopen(path, "wb");
+    if (!f) return -2;
+    uint8_t hdr[HZ_WTNS_HEADER];
+    hz_wtns_header(hdr, nvars);
     size_t ok = fwrite(hdr, 1, sizeof hdr, f);
     ok += fwrite(witness, 32, nvars, f);
-    fclose(f);
-    return ok == sizeof hdr + nvars ? 0 : -5;
+    if (fclose(f) != 0) return -2;
+    return ok == sizeof hdr + nvars ? 0 : -2;
 }

@@ -32,6 +32,8 @@ struct HzBackend {
     // the batch with the witness delivered in the compiler's layout (n_out entries)
     virtual int calculate_mapped(const uint8_t*, int, uint8_t*, bool, float*, HzErrBuf*) { return HZW_E_PARAM; }
     virtual int read_mapped(uint64_t, uint64_t, uint8_t*) { return HZW_E_PARAM; }
+    // the batch straight into a `.wtns` file (no file when a constraint is violated under sanity)
+    virtual int calculate_to_wtns(const uint8_t*, int, const char*, float*, HzErrBuf*) { return HZW_E_PARAM; }
     // A.w * B.w = C.w over an .r1cs; witness null = the resident one
     virtual int r1cs_check(const HzR1cs&, const uint8_t*, uint64_t*, uint64_t*, float*) { return HZW_E_PARAM; }
     // device-resident witness (null / HZW_E_PARAM for a backend without device memory)
@@ -279,6 +281,13 @@ int hzw_calculate_batch_resident(hzw_ctx* ctx, uint64_t n, const uint8_t* inputs
 int hzw_write_wtns(const hzw_ctx* ctx, const uint8_t* witness, const char* path) {
     if (!ctx || !witness || !path) return HZW_E_PARAM;
     return hz_write_wtns(path, witness, ctx->nvars()) ? HZW_E_IO : HZW_OK;
+}
+int hzw_calculate_to_wtns(hzw_ctx* ctx, const uint8_t* inputs, int sanity, const char* path, float* kernel_ms, hzw_error* err) {
+    if (!ctx || !inputs || !path || ctx->withdraw) return HZW_E_PARAM;
+    HzErrBuf eb; memset(&eb, 0, sizeof eb);
+    int st = ctx->be->calculate_to_wtns(inputs, sanity, path, kernel_ms, &eb);
+    if (st) { if (err) { memset(err, 0, sizeof *err); err->code = st; } return st; }
+    return hz_report(ctx, eb, err);
 }
 int hzw_r1cs_check(hzw_ctx* ctx, const char* r1cs_path, const uint8_t* witness, uint64_t* n_constraints, uint64_t* n_bad,
                    uint64_t* first_bad, float* kernel_ms) {

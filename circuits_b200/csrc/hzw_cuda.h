@@ -42,6 +42,8 @@ struct HzR1cs;
 int hz_cuda_set_map(HzCuda*, const uint32_t* src, uint64_t n_out);
 int hz_cuda_remap(HzCuda*);                  // resident witness -> the compiler's layout, on the main stream
 int hz_cuda_read_mapped(HzCuda*, uint64_t first, uint64_t count, uint8_t* out);
+// the resident witness (gathered one under a layout map) written behind `header` in chunks, copies and writes overlapped
+int hz_cuda_stream_wtns(HzCuda*, const char* path, const uint8_t* header, size_t header_len, uint64_t* d2h);
 int hz_cuda_r1cs_check(HzCuda*, const HzR1cs& R, const uint8_t* witness, uint64_t* n_bad, uint64_t* first_bad, float* ms);
 
 // ---- Withdraw(nLevels) batches ---------------------------------------------------------------------

@@ -31,6 +31,16 @@ struct CudaBackend : HzBackend {
         return st;
     }
     int read_mapped(uint64_t first, uint64_t count, uint8_t* out) override { return hz_cuda_read_mapped(d, first, count, out); }
+    int calculate_to_wtns(const uint8_t* inputs, int sanity, const char* path, float* ms, HzErrBuf* errs) override {
+        int st = n_out ? calculate_mapped(inputs, sanity, nullptr, true, ms, errs) : calculate(inputs, sanity, nullptr, true, ms, errs);
+        if (st || errs->count || errs->pad) return st;          // a violated constraint: no file, as the reference's binary
+        uint8_t hdr[HZ_WTNS_HEADER];
+        hz_wtns_header(hdr, n_out ? n_out : L->plan.nvars);
+        uint64_t moved = 0;
+        st = hz_cuda_stream_wtns(d, path, hdr, sizeof hdr, &moved);
+        d2h += moved;
+        return st;
+    }
     int r1cs_check(const HzR1cs& R, const uint8_t* witness, uint64_t* n_bad, uint64_t* first_bad, float* ms) override {
         return hz_cuda_r1cs_check(d, R, witness, n_bad, first_bad, ms);
     }

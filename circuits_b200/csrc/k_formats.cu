@@ -104,3 +104,46 @@ int hz_cuda_r1cs_check(HzCuda* d, const HzR1cs& R, const uint8_t* witness, uint6
     if (e1) cudaEventDestroy(e1);
     return rc;
 }
+
+// ---- streaming `.wtns` writer --------------------------------------------------------------------------------------
+// The witness resident on the device (the gathered one under a layout map) goes to the file in 64 MiB chunks through two
+// pinned buffers: chunk k + 1 crosses PCIe while chunk k is written -- the host never holds the 8 GB witness, and the
+// file is complete when the call returns (`./circuit input.json witness.wtns`, /root/reference/tools/helpers/actions.js:139-143).
+#include <fcntl.h>
+#include <unistd.h>
+int hz_cuda_stream_wtns(HzCuda* d, const char* path, const uint8_t* header, size_t header_len, uint64_t* d2h) {
+    CK(cudaSetDevice(d->device));
+    const Fr* w = d->n_out ? d->w_out : d->w;
+    const uint64_t n = d->n_out ? d->n_out : d->plan.nvars;
+    const size_t chunk = (size_t)64 << 20;
+    const uint64_t total = 32ull * n;
+    int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return HZW_E_IO;
+    uint8_t* buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int rc = 0;
+    auto put = [&](const uint8_t* p, size_t len) { while (len) { ssize_t k = write(fd, p, len); if (k <= 0) return false; p += k; len -= (size_t)k; } return true; };
+    do {
+        if (!put(header, header_len)) { rc = HZW_E_IO; break; }
+        for (int k = 0; k < 2; k++) if (cudaMallocHost(&buf[k], chunk) != cudaSuccess || cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) rc = HZW_E_DEVICE;
+        if (rc) break;
+        const uint64_t nchunks = (total + chunk - 1) / chunk;
+        auto issue = [&](uint64_t k) {
+            const uint64_t at = k * chunk, len = total - at < chunk ? total - at : chunk;
+            return cudaMemcpyAsync(buf[k & 1], reinterpret_cast<const uint8_t*>(w) + at, len, cudaMemcpyDeviceToHost, d->stream) == cudaSuccess &&
+                   cudaEventRecord(ev[k & 1], d->stream) == cudaSuccess;
+        };
+        if (nchunks && !issue(0)) { rc = HZW_E_DEVICE; break; }
+        for (uint64_t k = 0; k < nchunks && !rc; k++) {
+            if (cudaEventSynchronize(ev[k & 1]) != cudaSuccess) { rc = HZW_E_DEVICE; break; }
+            if (k + 1 < nchunks && !issue(k + 1)) { rc = HZW_E_DEVICE; break; }      // crosses the link while chunk k is written
+            const uint64_t at = k * chunk, len = total - at < chunk ? total - at : chunk;
+            if (!put(buf[k & 1], len)) rc = HZW_E_IO;
+        }
+        cudaStreamSynchronize(d->stream);
+    } while (0);
+    if (close(fd) != 0 && !rc) rc = HZW_E_IO;
+    for (int k = 0; k < 2; k++) { if (buf[k]) cudaFreeHost(buf[k]); if (ev[k]) cudaEventDestroy(ev[k]); }
+    if (d2h) *d2h = total;
+    return rc;
+}

@@ -44,7 +44,7 @@ EXPORTS = ["hzw_create", "hzw_destroy", "hzw_nvars", "hzw_ninputs", "hzw_input_i
            "hzw_calculate_batch", "hzw_calculate_resident", "hzw_write_wtns", "hzw_get_signal", "hzw_dump_sym",
            "hzw_last_stats", "hzw_last_kernel_ms", "hzw_plan_info", "hzw_set_shard", "hzw_exchange_bytes",
            "hzw_shard_pieces", "hzw_shard_nvars", "hzw_shard_phase1", "hzw_shard_phase2", "hzw_poseidon_bench", "hzw_int_peak",
-           "hzw_witness_device", "hzw_signal_index", "hzw_witness_read", "hzw_profile_step", "hzw_image_levels", "hzw_rank_pieces", "hzw_rank_witness_device", "hzw_calculate_batch_resident", "hzw_r1cs_check"]
+           "hzw_witness_device", "hzw_signal_index", "hzw_witness_read", "hzw_profile_step", "hzw_image_levels", "hzw_rank_pieces", "hzw_rank_witness_device", "hzw_calculate_batch_resident", "hzw_r1cs_check", "hzw_calculate_to_wtns"]
 
 
 def load_library(path=None):
@@ -185,6 +185,21 @@ class WitnessCalculator:
         if st != 0:
             self._raise(st, err)
         return wit
+
+    def calculateToWtns(self, inp, path, sanityCheck=False):
+        """`./circuit input.json witness.wtns` in one call (`hzw_calculate_to_wtns`): the witness is streamed from
+        device memory into the file; returns the device ms of the kernels."""
+        packed = inp if isinstance(inp, (bytes, bytearray)) or hasattr(inp, "data_ptr") or hasattr(inp, "ctypes") else self.packInput(inp)
+        if isinstance(packed, bytes):
+            packed = bytearray(packed)
+        err, ms = _Error(), ctypes.c_float()
+        self._lib.hzw_calculate_to_wtns.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p,
+                                                    ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_Error)]
+        st = self._lib.hzw_calculate_to_wtns(self._ctx, _addr(packed), 1 if sanityCheck else 0, str(path).encode(),
+                                             ctypes.byref(ms), ctypes.byref(err))
+        if st != 0:
+            self._raise(st, err)
+        return ms.value
 
     def calculateBatch(self, n, packed, sanityCheck=False, out=None):
         """`n` independent witnesses of one circuit in a single call (`hzw_calculate_batch`; Withdraw)."""

@@ -116,6 +116,12 @@ int hzw_witness_read(hzw_ctx* ctx, uint64_t first, uint64_t count, uint8_t* out)
 int hzw_rank_pieces(const hzw_ctx* ctx, int32_t rank, uint64_t* table /* 2 x cap */, int32_t cap);
 int hzw_rank_witness_device(const hzw_ctx* ctx, int32_t rank, void** dev_ptr, int32_t* device, void** stream);
 int hzw_write_wtns(const hzw_ctx* ctx, const uint8_t* witness, const char* path);
+/* `./circuit input.json witness.wtns` in one call (/root/reference/tools/helpers/actions.js:139-143): the batch is
+ * evaluated with the witness left in HBM and streamed into the file in chunks through two pinned buffers, each chunk
+ * crossing PCIe while the previous one is written -- the 8 GB witness never sits in host memory.  With a layout map the
+ * file holds the compiler's layout.  A violated constraint (sanity_check) writes no file.  HZW_CIRCUIT_ROLLUP_MAIN, one GPU. */
+int hzw_calculate_to_wtns(hzw_ctx* ctx, const uint8_t* inputs_le32, int sanity_check, const char* path, float* kernel_ms /* nullable */,
+                          hzw_error* err);
 /* The constraints of an iden3 `.r1cs` (v1, BN254) evaluated over a witness: A.w * B.w = C.w, one GPU thread per constraint.
  * witness: host buffer of at least nWires entries in the numbering the file uses, or NULL = the witness resident on the
  * device after hzw_calculate_resident (gathered into the compiler's layout when the context has a layout map).

@@ -142,6 +142,13 @@ struct CpuBackend : HzBackend {
         for (size_t v = 0; v < map_src.size(); v++) o[v] = own[map_src[v]];
         return 0;
     }
+    int calculate_to_wtns(const uint8_t* inputs, int sanity, const char* path, float* ms, HzErrBuf* errs) override {
+        const uint64_t n = map_src.empty() ? L.plan.nvars : map_src.size();
+        std::vector<uint8_t> w(32 * n);
+        int st = map_src.empty() ? calculate(inputs, sanity, w.data(), false, ms, errs) : calculate_mapped(inputs, sanity, w.data(), false, ms, errs);
+        if (st || errs->count) return st;
+        return hz_write_wtns(path, w.data(), n) ? HZW_E_IO : 0;
+    }
     int r1cs_check(const HzR1cs& R, const uint8_t* witness, uint64_t* n_bad, uint64_t* first_bad, float*) override {
         if (!witness) return HZW_E_PARAM;            // nothing stays resident in the CPU port
         const Fr* w = reinterpret_cast<const Fr*>(witness);

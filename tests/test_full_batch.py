@@ -137,3 +137,25 @@ def test_world1_sharded_context_after_another_batch(built, small_bb):
     wc.calculateShard(wc.packInput(other), False)
     buf, _ = wc.calculateShard(wc.packInput(inp), False)
     assert bytes(ShardedWitnessCalculator.assemble(wc.NVars, [(wc.pieces(), bytes(buf))])) == want
+
+
+def test_streamed_wtns_file_equals_the_host_buffer(built, tmp_path):
+    """hzw_calculate_to_wtns at rollup-main(344, 32, 256, 64): the 1.4 GB file written chunk by chunk from device memory
+    holds the header of snarkjs' writer and, behind it, byte for byte what hzw_calculate puts in a host buffer."""
+    import bench
+    from circuits_b200.witness_calculator import WitnessCalculator
+    prm = bench.CONFIGS["rollup-main-344"]
+    inp, expect_hash = bench.make_input(prm)
+    wc = WitnessCalculator(*prm)
+    packed = np.frombuffer(bytes(wc.packInput(inp)), dtype=np.uint8).copy()
+    ref = np.empty(32 * wc.NVars, dtype=np.uint8)
+    wc.calculateBinWitness(packed, False, out=ref)
+    path = str(tmp_path / "witness.wtns")
+    wc.calculateToWtns(packed, path, False)
+    assert os.path.getsize(path) == 76 + ref.size
+    body = np.memmap(path, dtype=np.uint8, mode="r", offset=76)
+    assert _first_diff(np.ascontiguousarray(body), ref) is None
+    head = open(path, "rb").read(76)
+    assert head[:4] == b"wtns" and int.from_bytes(head[60:64], "little") == wc.NVars
+    assert int.from_bytes(bytes(body[32:64]), "little") == expect_hash
+    wc.close()
