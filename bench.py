@@ -435,6 +435,11 @@ def run_gpu(args, cfg, cfg_name):
         lev_tot, lev_img = wc.imageLevels()
     kms = alone if alone is not None else kmean
     top = max(kms, key=kms.get)
+    # two kernels share the top within a few percent from run to run (k_smt_levels, k_front): the one with a counted
+    # integer workload is reported when it is within 10 % of the longest, so that the line does not flip between rounds
+    for name in ("k_smt_levels",):
+        if name in kms and kms[name] >= 0.9 * kms[top]:
+            top = name
     fee_proc = info["feeTx"] - 2 * 980 - 30       # entries of a FeeTx spent in its SMT processor (approx.)
     front_entries = info["decodeTx"] + info["rollupTx"] - info["getAx"] - info["sigVerifier"] - info["processors"]
     sha_blocks = (info["sha_blocks"] + world - 1) // world

@@ -174,14 +174,25 @@ __device__ __forceinline__ uint32_t hz_sha_sched(uint32_t w2, uint32_t w7, uint3
 // walks it -- but only the 64 rounds: the message schedule does not depend on the chaining value, so all
 // threads of the block first expand it for every SHA block (W[t] + K[t], 64 words per block), and the walking
 // thread reads the next block's words while it works on the current one.
+// The walk is one dependency chain of 49 024 rounds, so what counts is the number of DEPENDENT instructions per round:
+// h and d are old values (e and a of three rounds ago), so h + wk and d + h + wk are formed off the chain and the new
+// e and a are one three-input add behind their sigma: rotate -> xor3 -> add3, three instructions per round on either
+// chain (five with the textbook grouping t1 = h + S1 + ch + wk; e = d + t1; a = t1 + S0 + maj).
+__device__ __forceinline__ uint32_t hz_add3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("{\n .reg .u32 t;\n add.u32 t, %1, %2;\n add.u32 %0, t, %3;\n}" : "=r"(r) : "r"(a), "r"(b), "r"(c));   // ptxas fuses the pair into one IADD3
+    return r;
+}
 __device__ __forceinline__ void hz_sha_round_wk(uint32_t* v, uint32_t wk) {
-    uint32_t S1 = hz_rr(v[4], 6) ^ hz_rr(v[4], 11) ^ hz_rr(v[4], 25);
-    uint32_t ch = (v[4] & v[5]) ^ (~v[4] & v[6]);
-    uint32_t t1 = (v[7] + wk) + (S1 + ch);
-    uint32_t S0 = hz_rr(v[0], 2) ^ hz_rr(v[0], 13) ^ hz_rr(v[0], 22);
-    uint32_t mj = (v[0] & v[1]) ^ (v[0] & v[2]) ^ (v[1] & v[2]);
-    uint32_t t2 = S0 + mj;
-    v[7] = v[6]; v[6] = v[5]; v[5] = v[4]; v[4] = v[3] + t1; v[3] = v[2]; v[2] = v[1]; v[1] = v[0]; v[0] = t1 + t2;
+    const uint32_t hw = v[7] + wk, dhw = v[3] + hw;                         // off the chains
+    const uint32_t S1 = hz_rr(v[4], 6) ^ hz_rr(v[4], 11) ^ hz_rr(v[4], 25);
+    const uint32_t ch = (v[4] & v[5]) ^ (~v[4] & v[6]);
+    const uint32_t e_new = hz_add3(S1, ch, dhw);
+    const uint32_t t1 = hz_add3(S1, ch, hw);
+    const uint32_t S0 = hz_rr(v[0], 2) ^ hz_rr(v[0], 13) ^ hz_rr(v[0], 22);
+    const uint32_t mj = (v[0] & v[1]) ^ (v[0] & v[2]) ^ (v[1] & v[2]);
+    const uint32_t a_new = hz_add3(S0, mj, t1);
+    v[7] = v[6]; v[6] = v[5]; v[5] = v[4]; v[4] = e_new; v[3] = v[2]; v[2] = v[1]; v[1] = v[0]; v[0] = a_new;
 }
 // Launched twice per batch, [0, nblocks / 2) (with the expansion of every block's schedule) and the rest, so that
 // the bit signals of the first half's blocks (k_sha_blocks) are written while the second half is walked.

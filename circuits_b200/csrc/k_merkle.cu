@@ -128,13 +128,61 @@ __device__ __forceinline__ Fr hz_poseidon3_chain(uint32_t (*xch)[3][8][32], uint
     return sc;
 }
 
+// ---- siblings through the bulk-copy engine -----------------------------------------------------------------------
+// The sibling of a level is a main input (siblings1 / siblings2 / siblingsState rows of the batch: 33 x 32 B per
+// processor in HBM).  Warp 0 needs one per processor and level, at the head of that level's dependency chain; instead
+// of a global load there, warp 1 -- idle while warp 0 does the glue of a level -- has the copy engine fetch the NEXT
+// level's 16 siblings into shared memory (cp.async.bulk, 32 B each, completion counted on an mbarrier) while the
+// current level's 65 rounds run.  Two buffers, one mbarrier each, parity per use.
+__device__ __forceinline__ uint32_t hz_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void hz_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(hz_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void hz_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(hz_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hz_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(hz_smem_u32(dst)), "l"(src), "r"(bytes), "r"(hz_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void hz_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(hz_smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 __global__ void __launch_bounds__(96) k_smt_levels(HzPlan pl, Fr* w, const HzLevJob* jobs, const Fr* smst, HzSmtMid* mids,
                                                    const Fr* img00, uint8_t* zflag, int s0, int ns, int f0, int nf) {
     __shared__ uint32_t xch[2][3][8][32];
     __shared__ uint32_t e0[2][3][8][32];
     __shared__ uint32_t hin[2][8][32];
+    __shared__ __align__(32) Fr sibs[2][16];
+    __shared__ __align__(8) uint64_t sbar[2];
     const int r = (int)(threadIdx.x >> 5), c = (int)(threadIdx.x & 31);
     const int njobs = 2 * ns + nf, L = pl.P.nLevels + 1;
+    if (threadIdx.x == 0) {
+        hz_mbar_init(&sbar[0], 1); hz_mbar_init(&sbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // lane c < 16 of warp 1 fetches the siblings of processor 16 blockIdx.x + c
+    uint32_t stage_sib = 0;
+    if (r == 1 && c < 16) {
+        int qq = (int)blockIdx.x * 16 + c;
+        if (qq >= njobs) qq = njobs - 1;
+        stage_sib = jobs[hz_smt_job_index(pl, qq, s0, ns, f0)].sib;
+    }
+    auto stage = [&](int lev) {
+        if (r != 1) return;
+        uint64_t* b = &sbar[lev & 1];
+        if (c == 0) hz_mbar_expect_tx(b, 16u * 32u);
+        __syncwarp();
+        if (c < 16) hz_bulk_g2s(&sibs[lev & 1][c], &w[stage_sib + (uint32_t)lev], 32u, b);
+    };
+    uint32_t sph[2] = {0u, 0u};
+    stage(L - 1);
     int q = (int)blockIdx.x * 16 + (c >> 1);
     if (q >= njobs) q = njobs - 1;                    // padding chains redo the last processor (identical stores)
     const int job = hz_smt_job_index(pl, q, s0, ns, f0);
@@ -151,9 +199,13 @@ __global__ void __launch_bounds__(96) k_smt_levels(HzPlan pl, Fr* w, const HzLev
         const uint32_t lb = J.cur + (bottom ? 0u : 2u + (uint32_t)(L - 1 - lev) * HZ_SZ_SMT_LEVEL);
         const uint32_t o_aux = lb + 2 + (bottom ? 2u : 0u), o_oph = o_aux + 4, o_nph = o_oph + HS, o_osw = o_nph + HS, o_nsw = o_osw + 3;
         Fr st_top, st_old0, st_bot, st_new1, st_upd;
+        // the next level's siblings start crossing now: their buffer was last read two levels up, several barriers ago
+        if (lev > 0) stage(lev - 1);
         if (r == 0) {
             st_top = stj[lev * 6 + 0]; st_old0 = stj[lev * 6 + 1]; st_bot = stj[lev * 6 + 2]; st_new1 = stj[lev * 6 + 3]; st_upd = stj[lev * 6 + 5];
-            const Fr sib = w[J.sib + lev];
+            hz_mbar_wait(&sbar[lev & 1], sph[lev & 1]);
+            sph[lev & 1] ^= 1u;
+            const Fr sib = sibs[lev & 1][c >> 1];
             const Fr lr = fr_from_u64((J.lrbits >> lev) & 1ull);
             Fr hL, hR;
             if (side == 0) {
