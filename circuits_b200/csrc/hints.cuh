@@ -157,6 +157,13 @@ HZ_HD void hz_hints_record_point(HzHints* h, const Fr& u, const Fr& v) {
 #define HZ_FILL_CF 11                      /* chunks of the 83 fixed-base adders */
 #define HZ_FILL_CHUNKS (HZ_FILL_C0 + HZ_FILL_C1 + HZ_FILL_CF)
 #define HZ_LAD_EX 81
+// the points k_ed_ladder leaves per signature for k_ed_conv, 3 Fr (X, Y, Z) each: D_t (t = 0..253), the segment
+// accumulator before step t (t = 1..253), the fixed-base accumulator before step t (t = 0..82), the two final accumulators
+#define HZ_PT_D 0
+#define HZ_PT_A 762
+#define HZ_PT_F 1521
+#define HZ_PT_FIN 1770
+#define HZ_PTS 1776
 #define HZ_LAD_TOT (HZ_LAD_N + HZ_LAD_EX)
 // scratch of a lane group: hint[704] num[704] den[704] pre[704] vv[96] aff[176], then the fill record
 #define HZ_SCR_ARR 704

@@ -27,6 +27,7 @@ struct HzBackend {
     virtual int withdraw_batch(uint64_t n, const uint8_t* inputs, int sanity, uint8_t* out, float* kernel_ms, HzErrBuf* errs) = 0;
     // the same with the witnesses left in device memory: only witness entry 1 (the public output) of every instance comes back
     virtual int withdraw_resident(uint64_t, const uint8_t*, int, uint8_t*, float*, HzErrBuf*) { return HZW_E_PARAM; }
+    virtual int debug_read(int, uint64_t, uint64_t, uint64_t, uint8_t*) { return HZW_E_PARAM; }
     // a circom .sym applied as a layout map (formats.hpp): src[v] = own index of the compiler's witness entry v
     virtual int set_layout_map(const uint32_t*, uint64_t) { return HZW_E_PARAM; }
     // the batch with the witness delivered in the compiler's layout (n_out entries)
@@ -311,6 +312,10 @@ int hzw_rank_pieces(const hzw_ctx* ctx, int32_t rank, uint64_t* table, int32_t c
 int hzw_rank_witness_device(const hzw_ctx* ctx, int32_t rank, void** dev_ptr, int32_t* device, void** stream) {
     if (!ctx || !dev_ptr) return HZW_E_PARAM;
     return ctx->be->rank_witness_device(rank, dev_ptr, device, stream);
+}
+int hzw_debug_read(hzw_ctx* ctx, int which, uint64_t g, uint64_t first, uint64_t count, uint8_t* out) {
+    if (!ctx || !out || ctx->withdraw) return HZW_E_PARAM;
+    return ctx->be->debug_read(which, g, first, count, out);
 }
 int hzw_witness_read(hzw_ctx* ctx, uint64_t first, uint64_t count, uint8_t* out) {
     if (!ctx || !out || first + count > ctx->nvars()) return HZW_E_PARAM;

@@ -17,6 +17,7 @@ int hz_cuda_calculate(HzCuda*, const uint8_t* inputs, int sanity, uint8_t* witne
 // device-resident hand-off: base of the witness in HBM, its device and the stream its kernels were ordered on
 int hz_cuda_witness_device(HzCuda*, void** ptr, int32_t* device, void** stream);
 int hz_cuda_witness_read(HzCuda*, uint64_t first, uint64_t count, uint8_t* out);
+int hz_cuda_debug_read(HzCuda*, int which, uint64_t g, uint64_t first, uint64_t count, uint8_t* out);
 // per-kernel device times of the last calculate
 int hz_cuda_kernel_ms(HzCuda*, float* ms, const char** names, int cap);
 // one more batch with every launch serialised on one stream: device time of each launch alone, in launch order

@@ -69,6 +69,8 @@ struct HzCuda {
     Fr* hint_tab;              // HZ_EDTAB_LEN: its window entries
     Fr* hint_img;              // witness image of EscalarMulFix from the recording pass (constant entries are copied from it)
     Fr* hint_scratch;          // per lane group of k_eddsa: work area of the hint generators
+    Fr* ed_tab;                // the window entries in the cached twisted-Edwards form the ladder adds (k_ed_tab, once)
+    Fr* ed_pts;                // per signature: the points of every ladder step (k_ed_ladder -> k_ed_conv)
     uint32_t fix_size, win_size, win_stride;   // entries of EscalarMulFix; of the windows + carry adders of its segment 0; per window
     HzErrBuf* err;
     uint32_t *off_decode, *off_rollup, *off_fee;
@@ -153,7 +155,9 @@ __global__ void k_fix_consts(Fr* wtmp, Fr* cst, Fr* tab, uint32_t* counts);
 __global__ void k_ed_const(HzPlan pl, Fr* w, const uint32_t* off_eddsa, const Fr* img, uint32_t fix_size, int s0, int ns);
 __global__ void k_eddsa(HzPlan pl, Fr* w, HzErrBuf* err, const HzEddsaJob* jobs, const Fr* cst, const Fr* tab, const Fr* img, Fr* scratch, uint32_t win_size, int s0, int ns);
 __global__ void k_eddsa_tail(Fr* w, HzErrBuf* err, const Fr* cst, const Fr* tab, const Fr* img, Fr* scratch, uint32_t win_size, int ns);
-__global__ void k_ed_ladder(Fr* scratch, const Fr* tab, int ns);
+__global__ void k_ed_ladder(Fr* scratch, const Fr* edtab, Fr* pts, int ns);
+__global__ void k_ed_conv(Fr* scratch, const Fr* tab, const Fr* pts, int ns);
+__global__ void k_ed_tab(const Fr* tab, Fr* edtab, int npoints, int init_point);
 __global__ void k_ed_hints(Fr* scratch, int ns);
 __global__ void k_ed_fill(Fr* w, HzErrBuf* err, const Fr* tab, const Fr* scratch, uint32_t win_stride, int ns);
 __global__ void k_tail(HzPlan pl, Fr* w, HzErrBuf* err, HzErrBuf* ebuf, const HzSmtMid* mids, const Fr* isExit, const Fr* isExit_front,

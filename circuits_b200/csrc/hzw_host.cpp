@@ -18,6 +18,7 @@ struct CudaBackend : HzBackend {
     int image_levels(uint64_t out[2]) override { return hz_cuda_image_levels(d, out); }
     int witness_device(void** ptr, int32_t* device, void** stream) override { return hz_cuda_witness_device(d, ptr, device, stream); }
     int witness_read(uint64_t first, uint64_t count, uint8_t* out) override { return hz_cuda_witness_read(d, first, count, out); }
+    int debug_read(int which, uint64_t g, uint64_t first, uint64_t count, uint8_t* out) override { return hz_cuda_debug_read(d, which, g, first, count, out); }
     // a circom .sym as a layout map: the batch is evaluated in this library's layout, a gather kernel puts it into the
     // compiler's, and that is what leaves the device (one plain copy: the map decides which entries exist at all)
     uint64_t n_out = 0;

@@ -69,6 +69,8 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaMalloc(&d->hint_cst, sizeof(Fr) * HZ_CST_MAX) == cudaSuccess;
     ok = ok && cudaMalloc(&d->hint_tab, sizeof(Fr) * HZ_EDTAB_LEN) == cudaSuccess;
     ok = ok && cudaMalloc(&d->hint_scratch, sizeof(Fr) * HZ_HINT_SCRATCH * (size_t)hz_grid(P.nTx) * (HZ_BLOCK / HZ_G)) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->ed_tab, sizeof(Fr) * (4 * (HZ_EDTAB_LEN / 2) + 4)) == cudaSuccess;
+    ok = ok && cudaMalloc(&d->ed_pts, sizeof(Fr) * HZ_PTS * (size_t)P.nTx) == cudaSuccess;
     ok = ok && cudaMalloc(&d->err, sizeof(HzErrBuf)) == cudaSuccess;
     ok = ok && cudaMalloc(&d->off_decode, 4ull * P.nTx) == cudaSuccess;
     ok = ok && cudaMalloc(&d->off_rollup, 4ull * P.nTx) == cudaSuccess;
@@ -112,6 +114,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
         cudaFuncSetAttribute(k_leafhash, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_sighash, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_ed_ladder, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_ed_conv, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_eddsa_tail, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     }
     // the per-thread frames of the circuit templates are large (sibling arrays, state machines)
@@ -142,6 +145,9 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
                 ok = false;
             }
             d->fix_size = hc[4]; d->win_size = hc[3]; d->win_stride = hc[3] / 83;
+            // the window entries once more, in the form the ladder walk adds (k_ladder.cu)
+            d->n_launch++, k_ed_tab<<<(HZ_EDTAB_LEN / 2 + 63) / 64, 64, 0, d->stream>>>(d->hint_tab, d->ed_tab, HZ_EDTAB_LEN / 2, 83 * 8);
+            ok = ok && cudaStreamSynchronize(d->stream) == cudaSuccess;
             if (ok && (hc[3] == 0 || hc[3] % 83 != 0 || hc[4] > ph.sz.sigVerifier || ph.sz.mulfix_off + hc[4] > ph.sz.getAx + ph.sz.sigVerifier)) {
                 fprintf(stderr, "hzw: EscalarMulFix image (%u entries, windows %u) does not fit the layout\n", hc[4], hc[3]);
                 ok = false;
@@ -165,7 +171,7 @@ void hz_cuda_destroy(HzCuda* d) {
     cudaFree(d->w); cudaFree(d->pre); cudaFree(d->chain); cudaFree(d->msgw); cudaFree(d->shawk); cudaFree(d->jobs); cudaFree(d->jobs_front); cudaFree(d->off_eddsa); cudaFree(d->off_jk); cudaFree(d->smt_front); cudaFree(d->isExit_front); cudaFree(d->err);
     cudaFree(d->hs_in); cudaFree(d->hs_cur); cudaFree(d->sig_in); cudaFree(d->hsig_cur);
     cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit); cudaFree(d->lev); cudaFree(d->smst); cudaFree(d->img00); cudaFree(d->zflag); cudaFree(d->holes); cudaFree(d->gl); cudaFreeHost(d->h_holes); cudaFreeHost(d->h_gl); cudaFreeHost(d->h_img00);
-    cudaFree(d->hint_cst); cudaFree(d->hint_tab); cudaFree(d->hint_img); cudaFree(d->hint_scratch); cudaFree(d->recs);
+    cudaFree(d->hint_cst); cudaFree(d->hint_tab); cudaFree(d->hint_img); cudaFree(d->hint_scratch); cudaFree(d->ed_tab); cudaFree(d->ed_pts); cudaFree(d->recs);
     cudaFree(d->off_decode); cudaFree(d->off_rollup); cudaFree(d->off_fee); cudaFree(d->off_blocks);
     cudaFree(d->map_src); cudaFree(d->w_out);
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -239,7 +245,8 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
         hz_mark(d, "k_sighash", s2), k_sighash<<<(unsigned)((ns + 31) / 32), 224, 0, s2>>>(d->w, d->sig_in, d->hsig_cur, d->jobs, s0, ns);
         hz_mark(d, "k_ed_const", s2), k_ed_const<<<592, 256, 0, s2>>>(pl, d->w, d->off_eddsa, d->hint_img, d->fix_size, s0, ns);
             hz_mark(d, "k_eddsa", s2), k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, s0, ns);
-            hz_mark(d, "k_ed_ladder", s2), k_ed_ladder<<<(unsigned)((ns + 31) / 32), 96, 0, s2>>>(d->hint_scratch, d->hint_tab, ns);
+            hz_mark(d, "k_ed_ladder", s2), k_ed_ladder<<<(unsigned)((ns + 7) / 8), 96, 0, s2>>>(d->hint_scratch, d->ed_tab, d->ed_pts, ns);
+            hz_mark(d, "k_ed_conv", s2), k_ed_conv<<<(unsigned)(((size_t)ns * HZ_LAD_TOT + 127) / 128), 128, 0, s2>>>(d->hint_scratch, d->hint_tab, d->ed_pts, ns);
             hz_mark(d, "k_ed_hints", s2), k_ed_hints<<<(unsigned)((ns + 3) / 4), 128, 0, s2>>>(d->hint_scratch, ns);
             hz_mark(d, "k_eddsa_tail", s2), k_eddsa_tail<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(d->w, err, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, ns);
         hz_mark(d, "k_ed_fill", s2), k_ed_fill<<<(unsigned)((HZ_FILL_PER_SIG * ns + 127) / 128), 128, 0, s2>>>(d->w, err, d->hint_tab, d->hint_scratch, d->win_stride, ns);
@@ -456,7 +463,8 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
         if (ns > 0) {
             d->n_launch++, k_ed_const<<<592, 256, 0, s2>>>(pl, d->w, d->off_eddsa, d->hint_img, d->fix_size, s0, ns);
             d->n_launch++, k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, s0, ns);
-            d->n_launch++, k_ed_ladder<<<(unsigned)((ns + 31) / 32), 96, 0, s2>>>(d->hint_scratch, d->hint_tab, ns);
+            d->n_launch++, k_ed_ladder<<<(unsigned)((ns + 7) / 8), 96, 0, s2>>>(d->hint_scratch, d->ed_tab, d->ed_pts, ns);
+            d->n_launch++, k_ed_conv<<<(unsigned)(((size_t)ns * HZ_LAD_TOT + 127) / 128), 128, 0, s2>>>(d->hint_scratch, d->hint_tab, d->ed_pts, ns);
             d->n_launch++, k_ed_hints<<<(unsigned)((ns + 3) / 4), 128, 0, s2>>>(d->hint_scratch, ns);
             d->n_launch++, k_eddsa_tail<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(d->w, err, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, ns);
             d->n_launch++, k_ed_fill<<<(unsigned)((HZ_FILL_PER_SIG * ns + 127) / 128), 128, 0, s2>>>(d->w, err, d->hint_tab, d->hint_scratch, d->win_stride, ns);
@@ -685,6 +693,15 @@ int hz_cuda_multi_wait(HzCuda* d, HzCuda* peer) {
     return 0;
 }
 
+// introspection for the tests of the signature pipeline: Fr entries of the per-signature work areas
+// (which = 0: hint scratch of signature g, 1: its ladder points, 2: the cached window table)
+int hz_cuda_debug_read(HzCuda* d, int which, uint64_t g, uint64_t first, uint64_t count, uint8_t* out) {
+    CK(cudaSetDevice(d->device));
+    const Fr* base = which == 0 ? d->hint_scratch + g * HZ_HINT_SCRATCH : (which == 1 ? d->ed_pts + g * HZ_PTS : d->ed_tab);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, base + first, sizeof(Fr) * count, cudaMemcpyDeviceToHost));
+    return 0;
+}
 int hz_cuda_witness_device(HzCuda* d, void** ptr, int32_t* device, void** stream) {
     *ptr = d->w;
     if (device) *device = d->device;

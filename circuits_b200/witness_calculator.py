@@ -44,7 +44,7 @@ EXPORTS = ["hzw_create", "hzw_destroy", "hzw_nvars", "hzw_ninputs", "hzw_input_i
            "hzw_calculate_batch", "hzw_calculate_resident", "hzw_write_wtns", "hzw_get_signal", "hzw_dump_sym",
            "hzw_last_stats", "hzw_last_kernel_ms", "hzw_plan_info", "hzw_set_shard", "hzw_exchange_bytes",
            "hzw_shard_pieces", "hzw_shard_nvars", "hzw_shard_phase1", "hzw_shard_phase2", "hzw_poseidon_bench", "hzw_int_peak",
-           "hzw_witness_device", "hzw_signal_index", "hzw_witness_read", "hzw_profile_step", "hzw_image_levels", "hzw_rank_pieces", "hzw_rank_witness_device", "hzw_calculate_batch_resident", "hzw_r1cs_check", "hzw_calculate_to_wtns"]
+           "hzw_witness_device", "hzw_signal_index", "hzw_witness_read", "hzw_profile_step", "hzw_image_levels", "hzw_rank_pieces", "hzw_rank_witness_device", "hzw_calculate_batch_resident", "hzw_r1cs_check", "hzw_calculate_to_wtns", "hzw_debug_read"]
 
 
 def load_library(path=None):

@@ -111,6 +111,9 @@ int hzw_calculate_resident(hzw_ctx* ctx, const uint8_t* inputs_le32, int sanity_
 int hzw_witness_device(const hzw_ctx* ctx, void** dev_ptr, int32_t* device, void** stream);
 int hzw_signal_index(const hzw_ctx* ctx, const char* name, uint64_t* index);
 int hzw_witness_read(hzw_ctx* ctx, uint64_t first, uint64_t count, uint8_t* out);
+/* test introspection of the signature pipeline: `count` field elements from `first` of the work area of signature g
+ * (which = 0: the hint scratch, 1: the points of its ladder walk, 2: the cached window table; see csrc/hints.cuh) */
+int hzw_debug_read(hzw_ctx* ctx, int which, uint64_t g, uint64_t first, uint64_t count, uint8_t* out);
 /* n_gpus > 1: after hzw_calculate_resident rank r's ranges (hzw_rank_pieces: (first index, count) pairs) are valid
  * in rank r's copy of the witness on its own device (hzw_rank_witness_device); hzw_witness_read gathers from them */
 int hzw_rank_pieces(const hzw_ctx* ctx, int32_t rank, uint64_t* table /* 2 x cap */, int32_t cap);
