@@ -49,8 +49,11 @@ __device__ __forceinline__ void hz_lad_put(Fr* p, const Fr& v) {
 // never writes what a lane behind still reads).  Shuffles would do, but in code the compiler cannot prove convergent
 // (the role of a warp is a function of threadIdx) every one of them is wrapped in its own synchronisation.
 typedef uint32_t HzQuadBuf[8][32];
+// the product as ONE copy of code that every stage of every role calls: inlined at its 16 call sites the walk is 175 KB
+// of straight-line code and its top stall is the instruction fetch
+__device__ __noinline__ Fr fm_mul_shared(const Fr a, const Fr b) { return fm_mul(a, b); }
 __device__ __forceinline__ void hz_quad_stage(HzQuadBuf& xb, const Fr& a, const Fr& b, Fr& v0, Fr& v1, Fr& v2, Fr& v3) {
-    const Fr mine = fm_mul(a, b);
+    const Fr mine = fm_mul_shared(a, b);
     const int lane = (int)(threadIdx.x & 31u), base = lane & 28;
 #pragma unroll
     for (int k = 0; k < 8; k++) xb[k][lane] = mine.l[k];

@@ -5,7 +5,7 @@
 # samples per instruction; profiles/lineprof.py joins the two by instruction order.
 rep=$1; out=$2; shift 2
 tmp=$(mktemp -d)
-( cd $tmp && cuobjdump -xelf all /root/repo/circuits_b200/libhzwitness.so >/dev/null && nvdisasm -gi -c hzw_kernels.sm_100a.cubin > all.sass 2>/dev/null )
+( cd $tmp && cuobjdump -xelf all /root/repo/circuits_b200/libhzwitness.so >/dev/null && for c in *.sm_100a.cubin; do nvdisasm -gi -c $c; done > all.sass 2>/dev/null )
 for spec in "$@"; do
   m=${spec%%:*}; k=${spec##*:}
   ncu -i $rep --page source --csv --print-source sass -k $k > $tmp/src.csv 2>/dev/null
