@@ -57,6 +57,8 @@ struct HzCuda {
     struct HzHole* holes; struct HzHole* h_holes;   // per job: where its levels start, how many bottom levels are (0, 0) images
     Fr* gl; Fr* h_gl;          // per job: the entries between those images (level headers, switchers), compact
     Fr* h_img00;               // host copy of the image
+    uint32_t* bitpack; uint32_t* h_bitpack;   // the SHA block signals packed 32 per word (+ one flag word at the end) and their host copy
+    cudaEvent_t ev_bits;
     cudaStream_t stream5, stream6;
     cudaEvent_t ev_pack[2], ev_info[2], ev_sha[2];
     uint64_t last_d2h;
@@ -165,6 +167,7 @@ __global__ void k_tail(HzPlan pl, Fr* w, HzErrBuf* err, HzErrBuf* ebuf, const Hz
 __global__ void k_pack(HzPlan pl, const Fr* w, const uint8_t* pre, HzPeerRecs dst, int s0, int ns, int per, int own_last_slot, int own_last_fee);
 __global__ void k_unpack(HzPlan pl, Fr* w, uint8_t* pre, const uint8_t* recs, int world, int per, uint32_t rec_bytes);
 __global__ void k_hash_head(HzPlan pl, Fr* w, uint8_t* pre, HzErrBuf* err, uint32_t* off_blocks);
+__global__ void k_bitpack(const Fr* w, uint64_t count, uint32_t* packed, uint32_t* notbit);
 __global__ void k_sha_chain(HzPlan pl, const uint8_t* preb, uint32_t* chain, uint32_t* msgw, uint32_t* wk, uint32_t b_begin, uint32_t b_end);
 __global__ void k_sha_blocks(HzPlan pl, Fr* w, HzErrBuf* err, const uint32_t* chain, const uint32_t* msgw, const uint32_t* off_blocks, uint32_t b0);
 __global__ void k_hash_tail(HzPlan pl, Fr* w, HzErrBuf* err, const uint32_t* chain);

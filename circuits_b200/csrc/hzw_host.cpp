@@ -265,3 +265,18 @@ void hz_host_copy_stream(uint8_t* dst, const uint8_t* src, size_t n) {
     else memcpy(dst, src, n);
 }
 void hz_host_copy_fence() { _mm_sfence(); }
+// bit k of words[] -> the 32-byte field element 0 or 1 at out + 32 k (the packed transfer of the SHA block signals)
+__attribute__((target("avx2"))) static void hz_expand_bits_avx2(uint8_t* out, const uint32_t* words, size_t nwords) {
+    const __m256i one = _mm256_set_epi64x(0, 0, 0, 1), zero = _mm256_setzero_si256();
+    for (size_t i = 0; i < nwords; i++) {
+        const uint32_t wv = words[i];
+        __m256i* o = reinterpret_cast<__m256i*>(out + 1024 * i);
+        for (int b = 0; b < 32; b++) _mm256_stream_si256(o + b, (wv >> b) & 1u ? one : zero);
+    }
+}
+void hz_host_expand_bits(uint8_t* out, const uint32_t* words, size_t nwords) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0) { hz_expand_bits_avx2(out, words, nwords); return; }
+    for (size_t i = 0; i < nwords; i++)
+        for (int b = 0; b < 32; b++) { uint8_t* o = out + 1024 * i + 32 * b; memset(o, 0, 32); o[0] = (uint8_t)((words[i] >> b) & 1u); }
+}

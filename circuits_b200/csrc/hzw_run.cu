@@ -63,6 +63,9 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
         ok = ok && cudaMalloc(&d->holes, sizeof(HzHole) * nj) == cudaSuccess && cudaMallocHost(&d->h_holes, sizeof(HzHole) * nj) == cudaSuccess;
         ok = ok && cudaMalloc(&d->gl, sizeof(Fr) * gs * nj) == cudaSuccess && cudaMallocHost(&d->h_gl, sizeof(Fr) * gs * nj) == cudaSuccess;
         ok = ok && cudaMallocHost(&d->h_img00, sizeof(Fr) * HZ_HS) == cudaSuccess;
+        const size_t nbw = (size_t)ph.nblocks * HZ_SZ_SHA_BLOCK / 32 + 1;
+        ok = ok && cudaMalloc(&d->bitpack, 4 * nbw) == cudaSuccess && cudaMallocHost(&d->h_bitpack, 4 * nbw) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&d->ev_bits, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaStreamCreate(&d->stream5) == cudaSuccess && cudaStreamCreate(&d->stream6) == cudaSuccess;
         for (int k = 0; k < 2; k++) ok = ok && cudaEventCreateWithFlags(&d->ev_pack[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&d->ev_info[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&d->ev_sha[k], cudaEventDisableTiming) == cudaSuccess;
     }
@@ -170,7 +173,7 @@ void hz_cuda_destroy(HzCuda* d) {
     cudaSetDevice(d->device);
     cudaFree(d->w); cudaFree(d->pre); cudaFree(d->chain); cudaFree(d->msgw); cudaFree(d->shawk); cudaFree(d->jobs); cudaFree(d->jobs_front); cudaFree(d->off_eddsa); cudaFree(d->off_jk); cudaFree(d->smt_front); cudaFree(d->isExit_front); cudaFree(d->err);
     cudaFree(d->hs_in); cudaFree(d->hs_cur); cudaFree(d->sig_in); cudaFree(d->hsig_cur);
-    cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit); cudaFree(d->lev); cudaFree(d->smst); cudaFree(d->img00); cudaFree(d->zflag); cudaFree(d->holes); cudaFree(d->gl); cudaFreeHost(d->h_holes); cudaFreeHost(d->h_gl); cudaFreeHost(d->h_img00);
+    cudaFree(d->smt); cudaFree(d->mids); cudaFree(d->isExit); cudaFree(d->lev); cudaFree(d->smst); cudaFree(d->img00); cudaFree(d->zflag); cudaFree(d->holes); cudaFree(d->gl); cudaFreeHost(d->h_holes); cudaFreeHost(d->h_gl); cudaFreeHost(d->h_img00); cudaFree(d->bitpack); cudaFreeHost(d->h_bitpack); if (d->ev_bits) cudaEventDestroy(d->ev_bits);
     cudaFree(d->hint_cst); cudaFree(d->hint_tab); cudaFree(d->hint_img); cudaFree(d->hint_scratch); cudaFree(d->ed_tab); cudaFree(d->ed_pts); cudaFree(d->recs);
     cudaFree(d->off_decode); cudaFree(d->off_rollup); cudaFree(d->off_fee); cudaFree(d->off_blocks);
     cudaFree(d->map_src); cudaFree(d->w_out);
@@ -349,6 +352,7 @@ static int hz_phase2(HzCuda* d, int sanity) {
 // half is evaluated; the rest (second half, fee txs, hasherInputs) at the end.
 void hz_host_copy_stream(uint8_t* dst, const uint8_t* src, size_t n);   // hzw_host.cpp: non-temporal stores
 void hz_host_copy_fence();
+void hz_host_expand_bits(uint8_t* out, const uint32_t* words, size_t nwords);
 // host side of the holes: the images and the glue entries of jobs [j0, j1) written into the caller's buffer
 static void hz_fill_holes(const HzCuda* d, uint8_t* out, int j0, int j1, int part, int parts) {
     const uint32_t gs = HZ_GL_STRIDE(d->plan.P.nLevels + 1);
@@ -497,6 +501,17 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
     CK(cudaEventRecord(d->ev_eddsa, s2));
     int st = hz_phase2(d, sanity);
     if (st) return st;
+    // the bit signals of the SHA blocks cross the link packed (k_bitpack) and are expanded by the host threads
+    // (whole words of 32 entries; the few entries left over go with the piece behind them)
+    const uint64_t sha0 = pl.off_sha_blocks, sha_n = (uint64_t)pl.nblocks * HZ_SZ_SHA_BLOCK / 32 * 32;
+    const bool packed = sha_n >= (1u << 15) && !d->no_holes && !getenv("HZW_NO_BITPACK");
+    if (packed) {
+        CK(cudaMemsetAsync(d->bitpack + sha_n / 32, 0, 4, s));
+        d->n_launch++, k_bitpack<<<1184, 256, 0, s>>>(d->w + sha0, sha_n, d->bitpack, d->bitpack + sha_n / 32);
+        CK(cudaMemcpyAsync(d->h_bitpack, d->bitpack, 4 * (sha_n / 32 + 1), cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(d->ev_bits, s));
+        d->last_d2h += 4 * (sha_n / 32 + 1);
+    }
     CK(cudaEventRecord(d->ev_done, s));
     // everything is queued; from here the host follows the device.  Half 0: its hole records, then host threads
     // rebuild its images while the copy engine moves the rest of its range around them
@@ -524,8 +539,24 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
         if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s6, d->ev_done, 0);
     }
     if (ce == cudaSuccess) ce = slots_around(h0, P.nTx);
-    if (ce == cudaSuccess) ce = pieces_around(d->h_off_fee0, pl.nvars, 2 * P.nTx, 2 * P.nTx + F);
+    bool expand = false;
+    if (packed) {
+        if (ce == cudaSuccess) ce = pieces_around(d->h_off_fee0, sha0, 2 * P.nTx, 2 * P.nTx + F);
+        if (ce == cudaSuccess) ce = piece(sha0 + sha_n, pl.nvars);
+        if (ce == cudaSuccess) ce = cudaEventSynchronize(d->ev_bits);
+        if (ce == cudaSuccess) {
+            expand = d->h_bitpack[sha_n / 32] == 0;
+            if (!expand) ce = piece(sha0, sha0 + sha_n);          // an entry was not a bit: the range as it is
+        }
+    } else if (ce == cudaSuccess) ce = pieces_around(d->h_off_fee0, pl.nvars, 2 * P.nTx, 2 * P.nTx + F);
     if (ce == cudaSuccess) ce = piece(0, 2);
+    if (expand) {
+        const size_t nw = sha_n / 32, per = (nw + nthr - 1) / nthr;
+        for (unsigned t = 0; t < nthr; t++) {
+            const size_t w0 = (size_t)t * per, w1 = w0 + per < nw ? w0 + per : nw;
+            if (w0 < w1) workers.emplace_back([=]() { hz_host_expand_bits(out + 32 * (sha0 + 32 * w0), d->h_bitpack + w0, w1 - w0); hz_host_copy_fence(); });
+        }
+    }
     const double t_issued = ms_since();
     for (auto& t : workers) t.join();
     const double t_filled = ms_since();

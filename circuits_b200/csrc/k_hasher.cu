@@ -310,6 +310,23 @@ __global__ void k_hash_tail(HzPlan pl, Fr* w, HzErrBuf* err, const uint32_t* cha
 }
 
 // ---- Withdraw(nLevels): one lane group per instance, each with its own witness range ----------------
+// The entries of the sha256compression blocks are bit signals, 23 M of them at 2048 slots (0.7 GB as field elements).
+// On their way to a host buffer they travel packed: 32 consecutive entries per word (lane = bit), and *notbit is
+// raised if an entry is anything but 0 or 1 -- the host then copies the range as it is.  count is a multiple of 32.
+__global__ void __launch_bounds__(256) k_bitpack(const Fr* w, uint64_t count, uint32_t* packed, uint32_t* notbit) {
+    const uint64_t nwords = count / 32;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = (int)(threadIdx.x & 31);
+    bool bad = false;
+    for (uint64_t wd = warp; wd < nwords; wd += nwarps) {
+        const uint4* p = reinterpret_cast<const uint4*>(w + 32 * wd + lane);
+        const uint4 a = __ldcs(p), b = __ldcs(p + 1);
+        bad = bad || (a.x > 1u) || ((a.y | a.z | a.w | b.x | b.y | b.z | b.w) != 0u);
+        const uint32_t bits = __ballot_sync(0xffffffffu, a.x & 1u);
+        if (lane == 0) packed[wd] = bits;
+    }
+    if (bad) atomicOr(notbit, 1u);
+}
 __global__ void __launch_bounds__(HZ_BLOCK, 3) k_withdraw(Fr* w, uint32_t nvars, int nLevels, int n, HzErrBuf* err) {
     bool real; int i = hz_item(n, real);
     HzPending pend; pend.n = 0;

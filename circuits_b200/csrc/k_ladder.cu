@@ -334,10 +334,11 @@ __global__ void __launch_bounds__(128) k_ed_hints(Fr* scratch, int ns) {
     Fr* scr = scratch + (size_t)g * HZ_HINT_SCRATCH;
     Fr* hint = scr; Fr* num = scr + HZ_SCR_ARR; Fr* den = scr + 2 * HZ_SCR_ARR; Fr* pre = scr + 3 * HZ_SCR_ARR;
     Fr* vv = scr + HZ_SCR_VV; Fr* aff = scr + HZ_SCR_AFF;
-    const int c0 = lane * HZ_HINT_PER, c1 = c0 + HZ_HINT_PER < HZ_LAD_TOT ? c0 + HZ_HINT_PER : HZ_LAD_TOT;
+    // lane l takes the elements l, l + 32, l + 64, ...: Montgomery's trick does not care which elements share a chunk,
+    // and this way the 32 lanes of a load touch 32 consecutive field elements
     bool ok = true;
     Fr tot = fr_one();
-    for (int k = c0; k < c1; k++) {
+    for (int k = lane; k < HZ_LAD_TOT; k += 32) {
         const Fr dk = hz_canon2p(den[k]);
         den[k] = dk;
         if (fr_is_zero(dk)) ok = false;
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(128) k_ed_hints(Fr* scratch, int ns) {
     if (lane == 31) hi = fr_one();
     Fr inv = fr_mul_chain(fr_inv_euclid(all), fr_mul_chain(lo, hi));      // 1 / (own chunk total)
     if (ok) {
-        for (int k = c1 - 1; k >= c0; k--) {
+        for (int k = lane + 32 * ((HZ_LAD_TOT - 1 - lane) / 32); k >= 0; k -= 32) {
             const Fr x = fr_mul_chain(inv, pre[k]);
             const Fr nk = hz_canon2p(num[k]);
             if (k < HZ_LAD_N) hint[hz_lad_pos(k)] = fr_mul_chain(nk, x);
