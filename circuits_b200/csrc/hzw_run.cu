@@ -628,6 +628,16 @@ int hz_cuda_shard_phase2(HzCuda* d, const void* records, int sanity, uint8_t* sh
     uint64_t bytes = 0;
     std::vector<std::thread> workers;
     d->last_d2h = 0;
+    // this rank's SHA blocks leave packed, as on the end-to-end path of one GPU (k_bitpack)
+    const uint64_t sha_a = (uint64_t)d->plan.off_sha_blocks + (uint64_t)d->b0 * HZ_SZ_SHA_BLOCK, sha_n = (uint64_t)d->nb * HZ_SZ_SHA_BLOCK / 32 * 32;
+    const bool packed = shard_out && sha_n >= (1u << 15) && !d->no_holes && !getenv("HZW_NO_BITPACK");
+    if (packed) {
+        CK(cudaMemsetAsync(d->bitpack + sha_n / 32, 0, 4, s));
+        d->n_launch++, k_bitpack<<<1184, 256, 0, s>>>(d->w + sha_a, sha_n, d->bitpack, d->bitpack + sha_n / 32);
+        CK(cudaMemcpyAsync(d->h_bitpack, d->bitpack, 4 * (sha_n / 32 + 1), cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(d->ev_bits, s));
+    }
+    uint8_t* sha_out = nullptr;                    // where witness entry 0 would be for the piece with the SHA blocks
     if (shard_out) {
         // as on the end-to-end path of one GPU: the image levels of the shard's processors are rebuilt in the shard
         // buffer by host threads, the pieces are copied around them
@@ -651,7 +661,8 @@ int hz_cuda_shard_phase2(HzCuda* d, const void* records, int sanity, uint8_t* sh
             // place in ONE whole-witness buffer that every GPU of the box copies into (in_place)
             uint8_t* out_v = in_place ? shard_out : shard_out + bytes - 32ull * a;
             HzCopier cp{d, out_v, reinterpret_cast<const uint8_t*>(d->w), (unsigned)k};
-            if (holes && d->ns > 0 && a == r0 && n == (uint64_t)(*d->h_off_rollup)[d->s0 + d->ns] - r0) {
+            if (packed && a == sha_a && n >= sha_n) { sha_out = out_v; ce = cp.piece(a + sha_n, a + n); }
+            else if (holes && d->ns > 0 && a == r0 && n == (uint64_t)(*d->h_off_rollup)[d->s0 + d->ns] - r0) {
                 for (unsigned t = 0; t < nthr; t++) workers.emplace_back(hz_fill_holes, d, out_v, 2 * d->s0, 2 * (d->s0 + d->ns), (int)t, (int)nthr);
                 ce = cp.slots_around(d->s0, d->s0 + d->ns);
             } else if (holes && d->nf > 0) {
@@ -670,6 +681,20 @@ int hz_cuda_shard_phase2(HzCuda* d, const void* records, int sanity, uint8_t* sh
                 } else ce = cp.piece(a, a + n);
             } else ce = cp.piece(a, a + n);
             bytes += 32ull * n;
+        }
+        if (sha_out && ce == cudaSuccess) {
+            ce = cudaEventSynchronize(d->ev_bits);
+            d->last_d2h += 4 * (sha_n / 32 + 1);
+            if (ce == cudaSuccess && d->h_bitpack[sha_n / 32] != 0) {           // an entry was not a bit: the range as it is
+                HzCopier cp{d, sha_out, reinterpret_cast<const uint8_t*>(d->w), 0u};
+                ce = cp.piece(sha_a, sha_a + sha_n);
+            } else if (ce == cudaSuccess) {
+                const size_t nw = sha_n / 32, per = (nw + nthr - 1) / nthr;
+                for (unsigned t = 0; t < nthr; t++) {
+                    const size_t w0 = (size_t)t * per, w1 = w0 + per < nw ? w0 + per : nw;
+                    if (w0 < w1) workers.emplace_back([=]() { hz_host_expand_bits(sha_out + 32 * (sha_a + 32 * w0), d->h_bitpack + w0, w1 - w0); hz_host_copy_fence(); });
+                }
+            }
         }
         for (auto& t : workers) t.join();
         CK(ce);
