@@ -77,7 +77,7 @@ static inline int hz_shard_pieces(const HzLayout& L, const HzShard& d, uint64_t*
     if (d.rank == 0) add(pl.off_hasher_tail, pl.nvars);
     return n;
 }
-// exchange record of one rank (see k_pack in hzw_kernels.cu): per own slot 624 + nL2 bytes of pre-image
+// exchange record of one rank (see k_pack in k_hasher.cu): per own slot 624 + nL2 bytes of pre-image
 // bits, then newLastIdx / newStateRoot / newExitRoot (3 x 32 B) and 3 x 4 B "this rank produced it" flags
 static inline uint32_t hz_xrec_slot_bytes(const HzParams& P) { return 624u + 2u * (uint32_t)P.nLevels + 48u; }
 static inline uint32_t hz_xrec_vals_off(const HzParams& P, int per) { return ((uint32_t)per * hz_xrec_slot_bytes(P) + 3u) & ~3u; }

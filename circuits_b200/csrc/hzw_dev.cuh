@@ -156,7 +156,7 @@ __global__ void k_smt_zero(HzPlan pl, Fr* w, const HzLevJob* jobs, const Fr* img
 __global__ void k_fix_consts(Fr* wtmp, Fr* cst, Fr* tab, uint32_t* counts);
 __global__ void k_ed_const(HzPlan pl, Fr* w, const uint32_t* off_eddsa, const Fr* img, uint32_t fix_size, int s0, int ns);
 __global__ void k_eddsa(HzPlan pl, Fr* w, HzErrBuf* err, const HzEddsaJob* jobs, const Fr* cst, const Fr* tab, const Fr* img, Fr* scratch, uint32_t win_size, int s0, int ns);
-__global__ void k_eddsa_tail(Fr* w, HzErrBuf* err, const Fr* cst, const Fr* tab, const Fr* img, Fr* scratch, uint32_t win_size, int ns);
+__global__ void k_eddsa_tail(Fr* w, HzErrBuf* err, const Fr* cst, const Fr* tab, const Fr* img, Fr* scratch, uint32_t win_size, uint32_t fix_size, int ns);
 __global__ void k_ed_ladder(Fr* scratch, const Fr* edtab, Fr* pts, int ns);
 __global__ void k_ed_conv(Fr* scratch, const Fr* tab, const Fr* pts, int ns);
 __global__ void k_ed_tab(const Fr* tab, Fr* edtab, int npoints, int init_point);

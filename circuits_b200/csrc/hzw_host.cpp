@@ -251,7 +251,7 @@ HzBackend* hz_backend_create_rolluptx(const hzw_params& prm, const HzTLayout& TL
     return hz_batch_backend(prm, TL.nLevels, TL.maxFeeTx, TL.n_inputs, TL.nvars, status);
 }
 
-// ---- streaming copy for the host side of the end-to-end path (hzw_kernels.cu: hz_fill_holes) -----------------
+// ---- streaming copy for the host side of the end-to-end path (hzw_run.cu: hz_fill_holes) -----------------
 // The rebuilt images are written once and not read again by this process: non-temporal stores keep them out of
 // the caches and spare the read-for-ownership of every line.  n is a multiple of 32, dst is 32-byte aligned.
 #include <immintrin.h>

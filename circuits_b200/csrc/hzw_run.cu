@@ -251,7 +251,7 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
             hz_mark(d, "k_ed_ladder", s2), k_ed_ladder<<<(unsigned)((ns + 7) / 8), 96, 0, s2>>>(d->hint_scratch, d->ed_tab, d->ed_pts, ns);
             hz_mark(d, "k_ed_conv", s2), k_ed_conv<<<(unsigned)(((size_t)ns * HZ_LAD_TOT + 127) / 128), 128, 0, s2>>>(d->hint_scratch, d->hint_tab, d->ed_pts, ns);
             hz_mark(d, "k_ed_hints", s2), k_ed_hints<<<(unsigned)((ns + 3) / 4), 128, 0, s2>>>(d->hint_scratch, ns);
-            hz_mark(d, "k_eddsa_tail", s2), k_eddsa_tail<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(d->w, err, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, ns);
+            hz_mark(d, "k_eddsa_tail", s2), k_eddsa_tail<<<(unsigned)((ns + 7) / 8), HZ_BLOCK, 0, s2>>>(d->w, err, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, d->fix_size, ns);
         hz_mark(d, "k_ed_fill", s2), k_ed_fill<<<(unsigned)((HZ_FILL_PER_SIG * ns + 127) / 128), 128, 0, s2>>>(d->w, err, d->hint_tab, d->hint_scratch, d->win_stride, ns);
     }
     CK(cudaEventRecord(d->kev[10], s2));
@@ -470,7 +470,7 @@ static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity,
             d->n_launch++, k_ed_ladder<<<(unsigned)((ns + 7) / 8), 96, 0, s2>>>(d->hint_scratch, d->ed_tab, d->ed_pts, ns);
             d->n_launch++, k_ed_conv<<<(unsigned)(((size_t)ns * HZ_LAD_TOT + 127) / 128), 128, 0, s2>>>(d->hint_scratch, d->hint_tab, d->ed_pts, ns);
             d->n_launch++, k_ed_hints<<<(unsigned)((ns + 3) / 4), 128, 0, s2>>>(d->hint_scratch, ns);
-            d->n_launch++, k_eddsa_tail<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(d->w, err, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, ns);
+            d->n_launch++, k_eddsa_tail<<<(unsigned)((ns + 7) / 8), HZ_BLOCK, 0, s2>>>(d->w, err, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, d->fix_size, ns);
             d->n_launch++, k_ed_fill<<<(unsigned)((HZ_FILL_PER_SIG * ns + 127) / 128), 128, 0, s2>>>(d->w, err, d->hint_tab, d->hint_scratch, d->win_stride, ns);
         }
         CK(cudaEventRecord(d->ev_ed[h], s2));

@@ -53,28 +53,48 @@ __global__ void __launch_bounds__(HZ_BLOCK, 3) k_eddsa(HzPlan pl, Fr* w, HzErrBu
     c.flush_pending();
     if (hz_glane() == 0) {
         HzFillRec* rec = reinterpret_cast<HzFillRec*>(h.scratch + HZ_SCR_REC);
-        rec->ok = 0; rec->cur = cur;
+        rec->ok = 0; rec->cur = cur; rec->pad[1] = j.cur + pl.sz.mulfix_off;      // where sigVerifier.mulFix starts
         for (int k = 0; k < 8; k++) { rec->e[k] = m.hbits.val[k]; rec->s[k] = m.sbits.val[k]; }
         Fr* mid = h.scratch + HZ_SCR_MID;
         mid[0] = m.d3.x.v; mid[1] = m.d3.y.v; mid[2] = m.en.v; mid[3] = m.R8x.v; mid[4] = m.R8y.v;
     }
 }
+// Two sides per signature, in different warps of the same block: warps 0-1 walk the variable-base side (mulAny,
+// addRight) of the block's 8 signatures, warps 2-3 the fixed-base multiplication (a component of its own, at the cursor
+// k_eddsa noted).  What is left of both after the ladders are conversions and BabyAdds, each waiting for one Euclid
+// inversion: 11 in a row on one side, 6 on the other, where one lane group walked all 17.  The fixed-base result meets
+// the other side in shared memory for the two comparisons.
 __global__ void __launch_bounds__(HZ_BLOCK, 3) k_eddsa_tail(Fr* w, HzErrBuf* err, const Fr* cst, const Fr* tab, const Fr* img, Fr* scratch,
-                                                         uint32_t win_size, int ns) {
-    bool real; const int g = hz_item(ns, real);
+                                                         uint32_t win_size, uint32_t fix_size, int ns) {
+    __shared__ Fr left_sh[HZ_BLOCK / HZ_G / 2][2];
+    const int side = (int)(threadIdx.x >> 6), gl = (int)((threadIdx.x & 63u) / HZ_G);
+    int g = (int)blockIdx.x * (HZ_BLOCK / HZ_G / 2) + gl;
+    const bool real = g < ns;
+    if (!real) g = ns - 1;                                        // padding groups redo the last signature (identical stores)
     HzHints h = hz_sig_hints(cst, tab, img, scratch, win_size);
     h.scratch = scratch + (size_t)g * HZ_HINT_SCRATCH;               // the ladder kernels worked per signature
     const HzFillRec rec = *reinterpret_cast<const HzFillRec*>(h.scratch + HZ_SCR_REC);
     h.lad_ok = (int)rec.ok;
     HzPending pend; pend.n = 0;
-    Comp<MCompute> c(w, rec.cur, real ? err : nullptr, &h, &pend);
+    Comp<MCompute> c(w, side == 0 ? rec.cur : rec.pad[1], real ? err : nullptr, &h, &pend);
     EdMid<MCompute> m;
     const Fr* mid = h.scratch + HZ_SCR_MID;
     m.d3.x.v = mid[0]; m.d3.y.v = mid[1]; m.en.v = mid[2]; m.R8x.v = mid[3]; m.R8y.v = mid[4];
     m.d3.x.sig = m.d3.y.sig = m.en.sig = m.R8x.sig = m.R8y.sig = true;
     m.hbits.clear(254); m.sbits.clear(253);
     for (int k = 0; k < 8; k++) { m.hbits.val[k] = rec.e[k]; m.hbits.sg[k] = 0xffffffffu; m.sbits.val[k] = rec.s[k]; m.sbits.sg[k] = 0xffffffffu; }
-    EdDSAPoseidonVerifierTail(c, m);
+    PtV<MCompute> right, left;
+    if (side == 0) right = EdDSAPoseidonVerifierTailAny(c, m);
+    else {
+        left = EscalarMulFix253(c.sub("mulFix"), m.sbits);
+        if (hz_glane() == 0) { left_sh[gl][0] = left.x.v; left_sh[gl][1] = left.y.v; }
+    }
+    __syncthreads();
+    if (side == 0) {
+        left.x.v = left_sh[gl][0]; left.y.v = left_sh[gl][1]; left.x.sig = left.y.sig = true;
+        c.cur = rec.pad[1] + fix_size;                                 // behind the fixed-base component
+        EdDSAPoseidonVerifierTailEq(c, m, left, right);
+    }
     c.flush_pending();
 }
 

@@ -1265,6 +1265,16 @@ TM HZ_FN void EdDSAPoseidonVerifierTail(Comp<M>& c, const EdMid<M>& m) {
     ForceEqualIfEnabled(c.sub("eqCheckX"), m.en, left.x, right.x);
     ForceEqualIfEnabled(c.sub("eqCheckY"), m.en, left.y, right.y);
 }
+// the second half in the pieces k_eddsa_tail evaluates side by side: the variable-base side up to `right`, the
+// fixed-base multiplication (a component of its own: EscalarMulFix253 at its cursor), the two comparisons
+TM HZ_FN PtV<M> EdDSAPoseidonVerifierTailAny(Comp<M>& c, const EdMid<M>& m) {
+    PtV<M> mulAny = EscalarMulAny254(c.sub("mulAny"), m.hbits, m.d3);
+    return BabyAdd(c.sub("addRight"), m.R8x, m.R8y, mulAny.x, mulAny.y);
+}
+TM HZ_FN void EdDSAPoseidonVerifierTailEq(Comp<M>& c, const EdMid<M>& m, const PtV<M>& left, const PtV<M>& right) {
+    ForceEqualIfEnabled(c.sub("eqCheckX"), m.en, left.x, right.x);
+    ForceEqualIfEnabled(c.sub("eqCheckY"), m.en, left.y, right.y);
+}
 TM HZ_FN void EdDSAPoseidonVerifier(Comp<M>&& c, const V<M>& enabled, const V<M>& Ax, const V<M>& Ay,
                                      const V<M>& S, const V<M>& R8x, const V<M>& R8y, const V<M>& Msg) {
     EdMid<M> m;
