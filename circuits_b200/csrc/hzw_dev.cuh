@@ -53,6 +53,10 @@ struct HzCuda {
     Fr* smst;                  // per processor (nLevels + 1) x 6 state-machine values
     Fr* img00;                 // the 634 entries of SMTHash2(0, 0) and, at [HZ_IMG00_DIGEST], its digest
     uint8_t* zflag;            // per block of k_smt_levels and level: the level hashed (0, 0) in every chain of the block
+    // the early walk (hz_early_hash): the last slot and the last fee tx once more, ahead of the batch, on work areas of their own
+    HzSmtJob* e_smt; HzSmtMid* e_mids; HzLevJob* e_lev; Fr* e_smst; Fr* e_isExit; Fr* e_hs_in; uint8_t* e_zflag;
+    cudaStream_t stream7; cudaEvent_t ev_edjob, ev_hash;
+    bool early;                // this batch's hasherInputs were launched by hz_early_hash
     // end-to-end path: the (0, 0) levels at the bottom of every processor are not copied to the host but rebuilt there
     struct HzHole* holes; struct HzHole* h_holes;   // per job: where its levels start, how many bottom levels are (0, 0) images
     Fr* gl; Fr* h_gl;          // per job: the entries between those images (level headers, switchers), compact
@@ -86,7 +90,7 @@ struct HzCuda {
     cudaEvent_t ev_half[2], ev_ed[2], ev_done;
     cudaEvent_t ev0, ev1, ev_front, ev_eddsa, ev_lev, ev_zero, ev_fee, ev_jobs, ev_heads;
     cudaEvent_t ev_xchg;       // this rank's record has been stored into every peer (hz_cuda_multi_phase1)
-    cudaEvent_t kev[HZ_NKERN + 3];
+    cudaEvent_t kev[HZ_NKERN + 4];
     // layout map (a circom .sym applied when the witness leaves the device): compiler's index -> own index, and the
     // witness gathered into the compiler's layout
     uint32_t* map_src; Fr* w_out; uint64_t n_out;

@@ -56,6 +56,17 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaMalloc(&d->lev, sizeof(HzLevJob) * (2 * P.nTx + P.maxFeeTx)) == cudaSuccess;
     ok = ok && cudaMalloc(&d->smst, sizeof(Fr) * 6 * (size_t)(P.nLevels + 1) * (2 * P.nTx + P.maxFeeTx)) == cudaSuccess;
     ok = ok && cudaMalloc(&d->isExit, sizeof(Fr) * P.nTx) == cudaSuccess;
+    {
+        const size_t nj = (size_t)2 * P.nTx + P.maxFeeTx, nhs = (size_t)4 * P.nTx + 2 * P.maxFeeTx;
+        ok = ok && cudaMalloc(&d->e_smt, sizeof(HzSmtJob) * nj) == cudaSuccess && cudaMalloc(&d->e_mids, sizeof(HzSmtMid) * nj) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->e_lev, sizeof(HzLevJob) * nj) == cudaSuccess && cudaMalloc(&d->e_smst, sizeof(Fr) * 6 * (size_t)(P.nLevels + 1) * nj) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->e_isExit, sizeof(Fr) * P.nTx) == cudaSuccess && cudaMalloc(&d->e_hs_in, sizeof(Fr) * 4 * nhs) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->e_zflag, (size_t)2 * (P.nLevels + 1)) == cudaSuccess;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);         // its few small launches should not queue behind the batch's
+        ok = ok && cudaStreamCreateWithPriority(&d->stream7, cudaStreamDefault, hi) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&d->ev_edjob, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&d->ev_hash, cudaEventDisableTiming) == cudaSuccess;
+    }
     ok = ok && cudaMalloc(&d->img00, sizeof(Fr) * (HZ_IMG00_DIGEST + 1)) == cudaSuccess;
     ok = ok && cudaMalloc(&d->zflag, (size_t)((2 * P.nTx + P.maxFeeTx + 15) / 16 + 1) * (P.nLevels + 1)) == cudaSuccess;
     {
@@ -98,7 +109,7 @@ HzCuda* hz_cuda_create(int device, const HzPlan& ph, const uint32_t* off_decode,
     ok = ok && cudaEventCreateWithFlags(&d->ev_zero, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_xchg, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&d->ev_jobs, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&d->ev_heads, cudaEventDisableTiming) == cudaSuccess;
-    for (int k = 0; k < HZ_NKERN + 3; k++) ok = ok && cudaEventCreate(&d->kev[k]) == cudaSuccess;
+    for (int k = 0; k < HZ_NKERN + 4; k++) ok = ok && cudaEventCreate(&d->kev[k]) == cudaSuccess;
     for (int k = 0; k <= HZ_MAXPROF; k++) ok = ok && cudaEventCreate(&d->pev[k]) == cudaSuccess;
     // kernels that are to share an SM must agree on its L1 / shared-memory split: k_smt_levels stages the MDS
     // exchange in shared memory, k_eddsa (running beside it on the second stream) uses none -- without a common
@@ -196,7 +207,11 @@ void hz_cuda_destroy(HzCuda* d) {
     if (d->ev_xchg) cudaEventDestroy(d->ev_xchg);
     if (d->ev_jobs) cudaEventDestroy(d->ev_jobs);
     if (d->ev_heads) cudaEventDestroy(d->ev_heads);
-    for (int k = 0; k < HZ_NKERN + 3; k++) if (d->kev[k]) cudaEventDestroy(d->kev[k]);
+    for (int k = 0; k < HZ_NKERN + 4; k++) if (d->kev[k]) cudaEventDestroy(d->kev[k]);
+    cudaFree(d->e_smt); cudaFree(d->e_mids); cudaFree(d->e_lev); cudaFree(d->e_smst); cudaFree(d->e_isExit); cudaFree(d->e_hs_in); cudaFree(d->e_zflag);
+    if (d->stream7) cudaStreamDestroy(d->stream7);
+    if (d->ev_edjob) cudaEventDestroy(d->ev_edjob);
+    if (d->ev_hash) cudaEventDestroy(d->ev_hash);
     for (int k = 0; k <= HZ_MAXPROF; k++) if (d->pev[k]) cudaEventDestroy(d->pev[k]);
     delete d->h_off_rollup;
     delete d;
@@ -226,6 +241,7 @@ int hz_cuda_set_shard(HzCuda* d, int rank, int world) {
 uint64_t hz_cuda_exchange_bytes(const HzCuda* d) { return hz_rec_bytes(d->plan.P, d->per); }
 uint64_t hz_cuda_launches(const HzCuda* d) { return d->n_launch; }
 
+static int hz_early_hash(HzCuda* d, int sanity);
 // phase 1: inputs to the device, then everything per slot / fee tx of the shard
 static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     const HzPlan& pl = d->plan;
@@ -238,6 +254,9 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     if (inputs) CK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(d->w) + 64, inputs, 32ull * pl.n_inputs, cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(d->ev0, s));
     const int s0 = d->s0, ns = d->ns, f0 = d->f0, nf = d->nf;
+    // the merkle chain is the longest of the batch: its first kernel is launched first
+    CK(cudaEventRecord(d->kev[0], s));
+    if (ns > 0) hz_mark(d, "k_smtjob", s), k_smtjob<<<(unsigned)((ns + 31) / 32), 32, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, d->hs_in, s0, ns);
     // the signatures are the longest chain of a slot and need little from the rest of it: their jobs come
     // straight from the inputs (k_edjob) and they run on the second stream from the start, beside k_front
     // and the merkle levels -- no kernel fills the machine alone
@@ -246,6 +265,7 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     if (ns > 0) {
         hz_mark(d, "k_edjob", s2), k_edjob<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, d->jobs, d->off_eddsa, d->sig_in, s0, ns);
         hz_mark(d, "k_sighash", s2), k_sighash<<<(unsigned)((ns + 31) / 32), 224, 0, s2>>>(d->w, d->sig_in, d->hsig_cur, d->jobs, s0, ns);
+        CK(cudaEventRecord(d->ev_edjob, s2));
         hz_mark(d, "k_ed_const", s2), k_ed_const<<<592, 256, 0, s2>>>(pl, d->w, d->off_eddsa, d->hint_img, d->fix_size, s0, ns);
             hz_mark(d, "k_eddsa", s2), k_eddsa<<<hz_grid(ns), HZ_BLOCK, 0, s2>>>(pl, d->w, err, d->jobs, d->hint_cst, d->hint_tab, d->hint_img, d->hint_scratch, d->win_size, s0, ns);
             hz_mark(d, "k_ed_ladder", s2), k_ed_ladder<<<(unsigned)((ns + 7) / 8), 96, 0, s2>>>(d->hint_scratch, d->ed_tab, d->ed_pts, ns);
@@ -266,8 +286,8 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     if (ns > 0) hz_mark(d, "k_front", s4), k_front<<<(unsigned)((ns + 31) / 32), 32, 0, s4>>>(pl, d->w, d->pre, err, d->jobs_front, d->smt_front, d->isExit_front, s0, ns);
     CK(cudaEventRecord(d->kev[12], s4));
     CK(cudaEventRecord(d->ev_front, s4));
-    CK(cudaEventRecord(d->kev[0], s));
-    if (ns > 0) hz_mark(d, "k_smtjob", s), k_smtjob<<<(unsigned)((ns + 31) / 32), 32, 0, s>>>(pl, d->w, d->smt, d->isExit, d->off_jk, d->hs_in, s0, ns);
+    d->early = d->world == 1 && !d->prof && ns >= 2 && pl.P.maxFeeTx >= 1 && !getenv("HZW_NO_EARLY_HASH");
+    if (d->early) { int st = hz_early_hash(d, sanity); if (st) return st; }
     CK(cudaStreamWaitEvent(s, d->ev_fee, 0));
     // the state hashes of the slots and fee txs, transposed: their digests complete the job records
     // the processor heads need the jobs but not the hashes: they run on stream 3 beside the two hash kernels
@@ -309,19 +329,17 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     CK(cudaEventRecord(d->kev[3], s));
     CK(cudaStreamWaitEvent(s, d->ev_front, 0));       // the tail compares the jobs, the hash of the inputs reads k_front's pre-image bits
     if (ns + nf > 0) hz_mark(d, "k_tail", s), k_tail<<<hz_grid(ns + nf), HZ_BLOCK, 0, s>>>(pl, d->w, err, d->err, d->mids, d->isExit, d->isExit_front, d->jobs, d->jobs_front, d->smt, d->smt_front, s0, ns, f0, nf);
-    CK(cudaEventRecord(d->kev[4], s));
+    CK(cudaEventRecord(d->kev[13], s));
     return 0;
 }
-// phase 2: hasherInputs; every shard walks the whole SHA chain (it is serial and short) and expands
-// its own range of blocks
-static int hz_phase2(HzCuda* d, int sanity) {
+// hasherInputs on stream `s`: every shard walks the whole SHA chain (it is serial and short) and expands its own range
+// of blocks, the first half of them on `s5` while the second half of the chain is walked
+static int hz_launch_hash(HzCuda* d, int sanity, cudaStream_t s, cudaStream_t s5) {
     const HzPlan& pl = d->plan;
-    cudaStream_t s = d->stream;
-    const cudaStream_t s5 = d->prof ? s : d->stream5;
     HzErrBuf* err = sanity ? d->err : nullptr;
+    CK(cudaEventRecord(d->kev[4], s));
     hz_mark(d, "k_hash_head", s), k_hash_head<<<148, 256, 0, s>>>(pl, d->w, d->pre, d->rank == 0 ? err : nullptr, d->off_blocks);
     CK(cudaEventRecord(d->kev[5], s));
-    // the chain in two halves: the blocks of the first half are expanded (stream 5) while the second half is walked
     const uint32_t mid = pl.nblocks / 2, bend = d->b0 + d->nb;
     hz_mark(d, "k_sha_chain", s), k_sha_chain<<<1, 256, 0, s>>>(pl, d->pre, d->chain, d->msgw, d->shawk, 0, mid);
     const uint32_t n1 = d->b0 < mid ? (bend < mid ? bend : mid) - d->b0 : 0;       // own blocks below mid
@@ -338,6 +356,42 @@ static int hz_phase2(HzCuda* d, int sanity) {
     CK(cudaEventRecord(d->kev[7], s));
     hz_mark(d, "k_hash_tail", s), k_hash_tail<<<1, 32, 0, s>>>(pl, d->w, d->rank == 0 ? err : nullptr, d->chain);
     CK(cudaEventRecord(d->kev[8], s));
+    return 0;
+}
+// The hash of the inputs is a serial walk (766 blocks at 2048 slots) that needs, besides the pre-image bits k_front
+// leaves, three values from the END of the batch: newLastIdx and newExitRoot of the last slot, newStateRoot of the last
+// fee tx (src/rollup-main.circom:437-441).  Every root before those is a main input (imStateRoot, imExitRoot,
+// imInitStateRootFee, imStateRootFee), so the last slot and the last fee tx can be walked on their own: this puts them
+// through the same kernels ahead of the batch on a high-priority stream and work areas of their own (the batch
+// evaluates them again with everything else and stores the same entries), and the SHA walk runs beside the merkle
+// levels of the batch instead of behind them.
+static int hz_early_hash(HzCuda* d, int sanity) {
+    const HzPlan& pl = d->plan;
+    const cudaStream_t s7 = d->stream7;
+    const int ls = pl.P.nTx - 1, lf = pl.P.maxFeeTx - 1;
+    CK(cudaStreamWaitEvent(s7, d->ev0, 0));
+    d->n_launch++, k_smtjob<<<1, 32, 0, s7>>>(pl, d->w, d->e_smt, d->e_isExit, d->off_jk, d->e_hs_in, ls, 1);
+    d->n_launch++, k_fee_front<<<hz_grid(1), HZ_BLOCK, 0, s7>>>(pl, d->w, nullptr, d->e_smt + 2 * pl.P.nTx, d->e_hs_in, lf, 1);
+    d->n_launch++, k_smt<<<1, 32, 0, s7>>>(pl, d->w, nullptr, d->e_smt, d->e_mids, d->e_lev, d->e_smst, ls, 1, lf, 1);
+    d->n_launch++, k_hstate<<<1, 160, 0, s7>>>(d->w, d->e_hs_in, d->hs_cur, d->e_smt, pl.P.nTx, ls, 1, lf, 1);
+    d->n_launch++, k_leafhash<<<1, 128, 0, s7>>>(pl, d->w, d->e_smt, d->e_lev, ls, 1, lf, 1);
+    d->n_launch++, k_smt_levels<<<1, 96, 0, s7>>>(pl, d->w, d->e_lev, d->e_smst, d->e_mids, d->img00, d->e_zflag, ls, 1, lf, 1);
+    CK(cudaStreamWaitEvent(s7, d->ev_front, 0));
+    CK(cudaStreamWaitEvent(s7, d->ev_edjob, 0));
+    d->n_launch++, k_tail<<<hz_grid(2), HZ_BLOCK, 0, s7>>>(pl, d->w, nullptr, d->err, d->e_mids, d->e_isExit, d->isExit_front, d->jobs, d->jobs_front, d->e_smt, d->smt_front, ls, 1, lf, 1);
+    int st = hz_launch_hash(d, sanity, s7, d->stream5);
+    if (st) return st;
+    CK(cudaEventRecord(d->ev_hash, s7));
+    return 0;
+}
+// phase 2: hasherInputs (unless the early walk has launched it already), then everything joins the main stream
+static int hz_phase2(HzCuda* d, int sanity) {
+    cudaStream_t s = d->stream;
+    if (d->early) CK(cudaStreamWaitEvent(s, d->ev_hash, 0));
+    else {
+        int st = hz_launch_hash(d, sanity, s, d->prof ? s : d->stream5);
+        if (st) return st;
+    }
     if (d->prof) CK(cudaEventRecord(d->pev[d->n_prof], s));
     CK(cudaStreamWaitEvent(s, d->ev_eddsa, 0));
     CK(cudaStreamWaitEvent(s, d->ev_zero, 0));
@@ -432,6 +486,7 @@ struct HzCopier {
     }
 };
 static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* out) {
+    d->early = false;
     const HzPlan& pl = d->plan;
     const HzParams& P = pl.P;
     cudaStream_t s = d->stream, s2 = d->stream2, s3 = d->stream3, s5 = d->stream5;
@@ -810,7 +865,7 @@ int hz_cuda_kernel_ms(HzCuda* d, float* ms, const char** names, int cap) {
     int n = cap < HZ_NKERN ? cap : HZ_NKERN;
     for (int k = 0; k < n; k++) {
         // kernels 0..7 are bracketed by kev[k], kev[k+1] on the main stream; k_eddsa by kev[9], kev[10]
-        cudaEvent_t a = k < 8 ? d->kev[k] : (k == 8 ? d->kev[9] : d->kev[11]), b = k < 8 ? d->kev[k + 1] : (k == 8 ? d->kev[10] : d->kev[12]);
+        cudaEvent_t a = k < 8 ? d->kev[k] : (k == 8 ? d->kev[9] : d->kev[11]), b = k == 3 ? d->kev[13] : (k < 8 ? d->kev[k + 1] : (k == 8 ? d->kev[10] : d->kev[12]));
         if (cudaEventElapsedTime(&ms[k], a, b) != cudaSuccess) return HZW_E_DEVICE;
         if (names) names[k] = HZ_KERN_NAMES[k];
     }
