@@ -113,6 +113,20 @@ def test_dense_tree_and_mixed_image_counts(built):
     _check_all_paths(prm, packed, bb.getHashInputs())
 
 
+@pytest.mark.parametrize("prm, accounts", [((45, 24, 11, 5), 40), ((9, 16, 3, 1), 16), ((70, 32, 70, 3), 24)])
+def test_ragged_sizes(built, prm, accounts):
+    """Sizes that fit none of the kernels' units: slot counts that are no multiple of 8 (ladder and tail blocks,
+    groups of the pitched copies), 16 (level blocks) or 32 (warps of the per-slot kernels), an odd number of fee txs, a
+    batch of L1 slots only (every key off the curve), depths other than 32 (multiples of 8: the host-side batch builder
+    assembles the hash pre-image by bytes); the SHA block range ends inside a word of the packed transfer."""
+    from circuits_b200.synth import bench_batch
+    bb = bench_batch(*prm, n_accounts=accounts)
+    cpu = cpu_port_calculator(*prm)
+    packed = np.frombuffer(bytes(cpu.packInput(bb.getInput())), dtype=np.uint8).copy()
+    cpu.close()
+    _check_all_paths(prm, packed, bb.getHashInputs())
+
+
 def test_non_uniform_slot_groups(built, mixed32):
     """Every transaction type within one group of eight slots: processors of NOP / exit / insert slots have
     different image counts and offsets, so the pitched copies cannot be used and the copies go piece by piece."""
