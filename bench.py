@@ -289,7 +289,7 @@ def poseidon_products(cfg):
 def committed_traffic(kernel, cfg_name):
     """dram bytes per launch of the dominant kernel, from the ncu --set full capture summarised under profiles/."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json")) as f:
             t = json.load(f)
         return t.get(cfg_name, {}).get(kernel)
     except Exception:
