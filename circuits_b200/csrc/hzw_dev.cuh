@@ -57,6 +57,7 @@ struct HzCuda {
     HzSmtJob* e_smt; HzSmtMid* e_mids; HzLevJob* e_lev; Fr* e_smst; Fr* e_isExit; Fr* e_hs_in; uint8_t* e_zflag;
     cudaStream_t stream7; cudaEvent_t ev_edjob, ev_hash;
     bool early;                // this batch's hasherInputs were launched by hz_early_hash
+    bool xearly;               // sharded context: the exchange record is packed on stream 7 ahead of the merkle levels, phase 2 hashes there
     // end-to-end path: the (0, 0) levels at the bottom of every processor are not copied to the host but rebuilt there
     struct HzHole* holes; struct HzHole* h_holes;   // per job: where its levels start, how many bottom levels are (0, 0) images
     Fr* gl; Fr* h_gl;          // per job: the entries between those images (level headers, switchers), compact

@@ -242,6 +242,7 @@ uint64_t hz_cuda_exchange_bytes(const HzCuda* d) { return hz_rec_bytes(d->plan.P
 uint64_t hz_cuda_launches(const HzCuda* d) { return d->n_launch; }
 
 static int hz_early_hash(HzCuda* d, int sanity);
+static int hz_early_exchange(HzCuda* d);
 // phase 1: inputs to the device, then everything per slot / fee tx of the shard
 static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     const HzPlan& pl = d->plan;
@@ -288,6 +289,8 @@ static int hz_phase1(HzCuda* d, const uint8_t* inputs, int sanity) {
     CK(cudaEventRecord(d->ev_front, s4));
     d->early = d->world == 1 && !d->prof && ns >= 2 && pl.P.maxFeeTx >= 1 && !getenv("HZW_NO_EARLY_HASH");
     if (d->early) { int st = hz_early_hash(d, sanity); if (st) return st; }
+    d->xearly = d->world > 1 && !d->prof && pl.P.nTx >= 2 && pl.P.maxFeeTx >= 1 && !getenv("HZW_NO_EARLY_HASH");
+    if (d->xearly) { int st = hz_early_exchange(d); if (st) return st; }
     CK(cudaStreamWaitEvent(s, d->ev_fee, 0));
     // the state hashes of the slots and fee txs, transposed: their digests complete the job records
     // the processor heads need the jobs but not the hashes: they run on stream 3 beside the two hash kernels
@@ -365,29 +368,52 @@ static int hz_launch_hash(HzCuda* d, int sanity, cudaStream_t s, cudaStream_t s5
 // through the same kernels ahead of the batch on a high-priority stream and work areas of their own (the batch
 // evaluates them again with everything else and stores the same entries), and the SHA walk runs beside the merkle
 // levels of the batch instead of behind them.
-static int hz_early_hash(HzCuda* d, int sanity) {
+// the walk itself: the last slot (n_s = 1) and / or the last fee tx (n_f = 1) on stream 7, up to their tails
+static int hz_early_walk(HzCuda* d, int n_s, int n_f) {
     const HzPlan& pl = d->plan;
     const cudaStream_t s7 = d->stream7;
     const int ls = pl.P.nTx - 1, lf = pl.P.maxFeeTx - 1;
-    CK(cudaStreamWaitEvent(s7, d->ev0, 0));
-    d->n_launch++, k_smtjob<<<1, 32, 0, s7>>>(pl, d->w, d->e_smt, d->e_isExit, d->off_jk, d->e_hs_in, ls, 1);
-    d->n_launch++, k_fee_front<<<hz_grid(1), HZ_BLOCK, 0, s7>>>(pl, d->w, nullptr, d->e_smt + 2 * pl.P.nTx, d->e_hs_in, lf, 1);
-    d->n_launch++, k_smt<<<1, 32, 0, s7>>>(pl, d->w, nullptr, d->e_smt, d->e_mids, d->e_lev, d->e_smst, ls, 1, lf, 1);
-    d->n_launch++, k_hstate<<<1, 160, 0, s7>>>(d->w, d->e_hs_in, d->hs_cur, d->e_smt, pl.P.nTx, ls, 1, lf, 1);
-    d->n_launch++, k_leafhash<<<1, 128, 0, s7>>>(pl, d->w, d->e_smt, d->e_lev, ls, 1, lf, 1);
-    d->n_launch++, k_smt_levels<<<1, 96, 0, s7>>>(pl, d->w, d->e_lev, d->e_smst, d->e_mids, d->img00, d->e_zflag, ls, 1, lf, 1);
+    if (n_s) d->n_launch++, k_smtjob<<<1, 32, 0, s7>>>(pl, d->w, d->e_smt, d->e_isExit, d->off_jk, d->e_hs_in, ls, 1);
+    if (n_f) d->n_launch++, k_fee_front<<<hz_grid(1), HZ_BLOCK, 0, s7>>>(pl, d->w, nullptr, d->e_smt + 2 * pl.P.nTx, d->e_hs_in, lf, 1);
+    d->n_launch++, k_smt<<<1, 32, 0, s7>>>(pl, d->w, nullptr, d->e_smt, d->e_mids, d->e_lev, d->e_smst, ls, n_s, lf, n_f);
+    d->n_launch++, k_hstate<<<1, 160, 0, s7>>>(d->w, d->e_hs_in, d->hs_cur, d->e_smt, pl.P.nTx, ls, n_s, lf, n_f);
+    d->n_launch++, k_leafhash<<<1, 128, 0, s7>>>(pl, d->w, d->e_smt, d->e_lev, ls, n_s, lf, n_f);
+    d->n_launch++, k_smt_levels<<<1, 96, 0, s7>>>(pl, d->w, d->e_lev, d->e_smst, d->e_mids, d->img00, d->e_zflag, ls, n_s, lf, n_f);
     CK(cudaStreamWaitEvent(s7, d->ev_front, 0));
     CK(cudaStreamWaitEvent(s7, d->ev_edjob, 0));
-    d->n_launch++, k_tail<<<hz_grid(2), HZ_BLOCK, 0, s7>>>(pl, d->w, nullptr, d->err, d->e_mids, d->e_isExit, d->isExit_front, d->jobs, d->jobs_front, d->e_smt, d->smt_front, ls, 1, lf, 1);
-    int st = hz_launch_hash(d, sanity, s7, d->stream5);
+    d->n_launch++, k_tail<<<hz_grid(n_s + n_f), HZ_BLOCK, 0, s7>>>(pl, d->w, nullptr, d->err, d->e_mids, d->e_isExit, d->isExit_front, d->jobs, d->jobs_front, d->e_smt, d->smt_front, ls, n_s, lf, n_f);
+    return 0;
+}
+static int hz_early_hash(HzCuda* d, int sanity) {
+    CK(cudaStreamWaitEvent(d->stream7, d->ev0, 0));
+    int st = hz_early_walk(d, 1, 1);
     if (st) return st;
-    CK(cudaEventRecord(d->ev_hash, s7));
+    st = hz_launch_hash(d, sanity, d->stream7, d->stream5);
+    if (st) return st;
+    CK(cudaEventRecord(d->ev_hash, d->stream7));
+    return 0;
+}
+// A shard does the same for the exchange: its record (pre-image bits of its slots, and the closing values if it owns
+// the last slot / fee tx) is complete after k_front and the early walk, long before its merkle levels are.  The record
+// is packed on stream 7 then, the collective and the SHA walk of phase 2 run beside the levels, and the main stream only
+// joins at the end.
+static int hz_early_exchange(HzCuda* d) {
+    const HzParams& P = d->plan.P;
+    const int n_s = d->ns > 0 && d->s0 + d->ns == P.nTx, n_f = d->nf > 0 && d->f0 + d->nf == P.maxFeeTx;
+    CK(cudaStreamWaitEvent(d->stream7, d->ev0, 0));
+    if (n_s + n_f > 0) return hz_early_walk(d, n_s, n_f);
+    CK(cudaStreamWaitEvent(d->stream7, d->ev_front, 0));
     return 0;
 }
 // phase 2: hasherInputs (unless the early walk has launched it already), then everything joins the main stream
 static int hz_phase2(HzCuda* d, int sanity) {
     cudaStream_t s = d->stream;
-    if (d->early) CK(cudaStreamWaitEvent(s, d->ev_hash, 0));
+    if (d->xearly) {
+        int st = hz_launch_hash(d, sanity, d->stream7, d->stream5);
+        if (st) return st;
+        CK(cudaEventRecord(d->ev_hash, d->stream7));
+    }
+    if (d->early || d->xearly) CK(cudaStreamWaitEvent(s, d->ev_hash, 0));
     else {
         int st = hz_launch_hash(d, sanity, s, d->prof ? s : d->stream5);
         if (st) return st;
@@ -486,7 +512,7 @@ struct HzCopier {
     }
 };
 static int hz_calculate_overlapped(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* out) {
-    d->early = false;
+    d->early = false; d->xearly = false;
     const HzPlan& pl = d->plan;
     const HzParams& P = pl.P;
     cudaStream_t s = d->stream, s2 = d->stream2, s3 = d->stream3, s5 = d->stream5;
@@ -663,10 +689,12 @@ int hz_cuda_shard_phase1(HzCuda* d, const uint8_t* inputs, int sanity, void* rec
     int last_slot = d->ns > 0 && d->s0 + d->ns == P.nTx, last_fee = d->nf > 0 && d->f0 + d->nf == P.maxFeeTx;
     HzPeerRecs dst; memset(&dst, 0, sizeof dst);
     dst.n = 1; dst.p[0] = reinterpret_cast<uint8_t*>(record_out);
-    d->n_launch++, k_pack<<<148, 256, 0, d->stream>>>(d->plan, d->w, d->pre, dst, d->s0, d->ns, d->per, last_slot, last_fee);
+    const cudaStream_t ps = d->xearly ? d->stream7 : d->stream;      // early exchange: the record is complete long before the levels are
+    d->n_launch++, k_pack<<<148, 256, 0, ps>>>(d->plan, d->w, d->pre, dst, d->s0, d->ns, d->per, last_slot, last_fee);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(errs, d->err, sizeof(HzErrBuf), cudaMemcpyDeviceToHost, d->stream));
-    CK(cudaStreamSynchronize(d->stream));         // the host binding runs the all-gather on its own stream
+    if (d->xearly) memset(errs, 0, sizeof(HzErrBuf));      // the kernels are still running: phase 2 reports what they find
+    else CK(cudaMemcpyAsync(errs, d->err, sizeof(HzErrBuf), cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(ps));                // the host binding runs the all-gather on its own stream
     return 0;
 }
 // sharded phase 2: `records` = the gathered records of all ranks (device memory); the shard's witness
@@ -677,7 +705,7 @@ int hz_cuda_shard_phase2(HzCuda* d, const void* records, int sanity, uint8_t* sh
     if (!records) records = d->recs;              // the library's own all-gather left them there (hz_cuda_multi_phase1)
     if (!records) return HZW_E_PARAM;
     cudaStream_t s = d->stream;
-    d->n_launch++, k_unpack<<<148, 256, 0, s>>>(d->plan, d->w, d->pre, reinterpret_cast<const uint8_t*>(records), d->world, d->per, hz_rec_bytes(d->plan.P, d->per));
+    d->n_launch++, k_unpack<<<148, 256, 0, d->xearly ? d->stream7 : s>>>(d->plan, d->w, d->pre, reinterpret_cast<const uint8_t*>(records), d->world, d->per, hz_rec_bytes(d->plan.P, d->per));
     int st = hz_phase2(d, sanity);
     if (st) return st;
     uint64_t bytes = 0;
@@ -792,15 +820,16 @@ int hz_cuda_multi_phase1(HzCuda* d, const uint8_t* inputs, int sanity, uint8_t* 
     HzPeerRecs dst; memset(&dst, 0, sizeof dst);
     dst.n = world;
     for (int r = 0; r < world; r++) dst.p[r] = peer_recs[r] + (size_t)d->rank * hz_rec_bytes(P, d->per);
-    d->n_launch++, k_pack<<<148, 256, 0, d->stream>>>(d->plan, d->w, d->pre, dst, d->s0, d->ns, d->per, last_slot, last_fee);
+    const cudaStream_t ps = d->xearly ? d->stream7 : d->stream;
+    d->n_launch++, k_pack<<<148, 256, 0, ps>>>(d->plan, d->w, d->pre, dst, d->s0, d->ns, d->per, last_slot, last_fee);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(d->ev_xchg, d->stream));
+    CK(cudaEventRecord(d->ev_xchg, ps));
     return 0;
 }
 // rank d's main stream goes on only when `peer`'s record has landed (called after every rank has queued its phase 1)
 int hz_cuda_multi_wait(HzCuda* d, HzCuda* peer) {
     CK(cudaSetDevice(d->device));
-    CK(cudaStreamWaitEvent(d->stream, peer->ev_xchg, 0));
+    CK(cudaStreamWaitEvent(d->xearly ? d->stream7 : d->stream, peer->ev_xchg, 0));
     return 0;
 }
 

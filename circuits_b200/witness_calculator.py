@@ -421,8 +421,14 @@ class ShardedWitnessCalculator(WitnessCalculator):
         import torch.distributed as dist
         if self.world > 1:
             if self._rec.is_cuda:
-                dist.all_gather_into_tensor(self._recs, self._rec, group=self.group)
-                torch.cuda.current_stream().synchronize()
+                # on a stream of its own: torch's default stream is the legacy NULL stream, and a collective queued behind
+                # it would wait for every kernel of the library's (blocking) streams -- phase 1 returns while the merkle
+                # levels are still running (early exchange), and the all-gather is to run beside them
+                if getattr(self, "_xs", None) is None:
+                    self._xs = torch.cuda.Stream(device=self._rec.device)
+                with torch.cuda.stream(self._xs):
+                    dist.all_gather_into_tensor(self._recs, self._rec, group=self.group)
+                self._xs.synchronize()
             else:
                 parts = list(self._recs.split(self.recBytes))
                 dist.all_gather(parts, self._rec, group=self.group)
