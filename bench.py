@@ -178,9 +178,14 @@ def cpu_baseline(cfg, packed, budget_s=15.0):
     n_s = len(range(0, nTx, stride))
     os.environ.pop("HZW_CPU_SAMPLE_STRIDE", None)
     wc.close()
+    import shutil
+    # the reference's own calculator needs node (wasm) or circom + a C++ toolchain with ffiasm / gmp (multithreaded C++):
+    # probed on the box that runs the bench, reported either way ("kind" stays "port" while neither is there)
+    probe = {t: shutil.which(t) for t in ("node", "circom", "snarkjs", "nasm")}
     return {"value": n_s / dt, "unit": "tx/s", "cores": cores, "kind": "port",
             "sample": "every %d-th tx slot / fee tx / SHA block of the %d-slot batch (%d slots, %.1f s wall), "
-                      "CPU port of the circuit templates, %d threads" % (stride, nTx, n_s, dt, cores)}, stride
+                      "CPU port of the circuit templates, %d threads" % (stride, nTx, n_s, dt, cores),
+            "reference_toolchain_probe": probe}, stride
 
 
 def run_reference(args, cfg, cfg_name):
