@@ -106,3 +106,52 @@ __global__ void __launch_bounds__(128) k_leafhash(HzPlan pl, Fr* w, const HzSmtJ
     const Fr d = hz_poseidon_tr<4>(xch, r, c, s, w + h1 + 1, real);
     if (r == 0 && real) { if (is_new) lev[job].n1 = d; else lev[job].o1 = d; }
 }
+
+// ---- permutations/s per width (the second metric of BASELINE.md) --------------------------------------------------
+// nperms independent Poseidon(T - 1) hashes with every signal of the component stored (entries per permutation:
+// 1 + 2 T R + 3 T 8 + 3 rp, the wired size of circomlib's Poseidon), transposed as above: in = T - 1 inputs per
+// permutation.  T = 3 is k_poseidon_t3 (k_merkle.cu), the loop of the level hashes with its chain in the Montgomery domain.
+template <int T> __global__ void __launch_bounds__(32 * T) k_poseidon_tr_bench(const Fr* in, Fr* sig, Fr* digests, int nperms, uint32_t size) {
+    __shared__ uint32_t xch[2][T][8][32];
+    const int r = (int)(threadIdx.x >> 5), c = (int)(threadIdx.x & 31);
+    int p = (int)blockIdx.x * 32 + c;
+    const bool real = p < nperms;
+    if (!real) p = nperms - 1;
+    const Fr s = r == 0 ? fr_zero() : in[(size_t)(T - 1) * p + (r - 1)];
+    const Fr d = hz_poseidon_tr<T>(xch, r, c, s, sig + (size_t)p * size, real);
+    if (r == 0 && real) digests[p] = d;
+}
+extern "C" int hzw_poseidon_bench_t(int device, int t, uint64_t nperms, int reps, const uint8_t* inputs_le32 /* (t - 1) x nperms x 32 B */,
+                                    uint8_t* digests_le32 /* nperms x 32 B, nullable */, float* ms_per_rep, uint64_t* signal_bytes) {
+    if (t < 4 || t > 7 || nperms == 0 || nperms > (1u << 20) || reps <= 0 || !inputs_le32) return HZW_E_PARAM;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return HZW_E_DEVICE;
+    CK(cudaSetDevice(device));
+    const int rp = t == 4 ? 56 : (t == 7 ? 63 : 60), R = 8 + rp;      // poseidon_rp(t) (templates_circomlib.cuh), host side
+    const uint32_t size = 1u + 2u * (uint32_t)(t * R) + 3u * (uint32_t)(t * 8) + 3u * (uint32_t)rp;
+    Fr *in = nullptr, *sig = nullptr, *dg = nullptr;
+    cudaEvent_t e0, e1;
+    CK(cudaMalloc(&in, 32ull * (t - 1) * nperms));
+    CK(cudaMalloc(&sig, 32ull * size * nperms));
+    CK(cudaMalloc(&dg, 32ull * nperms));
+    CK(cudaMemcpy(in, inputs_le32, 32ull * (t - 1) * nperms, cudaMemcpyHostToDevice));
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const unsigned grid = (unsigned)((nperms + 31) / 32);
+    for (int r = -1; r < reps; r++) {                       // r = -1: warm-up
+        if (r == 0) CK(cudaEventRecord(e0));
+        if (t == 4) k_poseidon_tr_bench<4><<<grid, 128>>>(in, sig, dg, (int)nperms, size);
+        else if (t == 5) k_poseidon_tr_bench<5><<<grid, 160>>>(in, sig, dg, (int)nperms, size);
+        else if (t == 6) k_poseidon_tr_bench<6><<<grid, 192>>>(in, sig, dg, (int)nperms, size);
+        else k_poseidon_tr_bench<7><<<grid, 224>>>(in, sig, dg, (int)nperms, size);
+    }
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms_per_rep) *ms_per_rep = ms / reps;
+    if (signal_bytes) *signal_bytes = 32ull * size * nperms;
+    if (digests_le32) CK(cudaMemcpy(digests_le32, dg, 32ull * nperms, cudaMemcpyDeviceToHost));
+    cudaFree(in); cudaFree(sig); cudaFree(dg); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}

@@ -44,7 +44,7 @@ EXPORTS = ["hzw_create", "hzw_destroy", "hzw_nvars", "hzw_ninputs", "hzw_input_i
            "hzw_calculate_batch", "hzw_calculate_resident", "hzw_write_wtns", "hzw_get_signal", "hzw_dump_sym",
            "hzw_last_stats", "hzw_last_kernel_ms", "hzw_plan_info", "hzw_set_shard", "hzw_exchange_bytes",
            "hzw_shard_pieces", "hzw_shard_nvars", "hzw_shard_phase1", "hzw_shard_phase2", "hzw_poseidon_bench", "hzw_int_peak",
-           "hzw_witness_device", "hzw_signal_index", "hzw_witness_read", "hzw_profile_step", "hzw_image_levels", "hzw_rank_pieces", "hzw_rank_witness_device", "hzw_calculate_batch_resident", "hzw_r1cs_check", "hzw_calculate_to_wtns", "hzw_debug_read"]
+           "hzw_witness_device", "hzw_signal_index", "hzw_witness_read", "hzw_profile_step", "hzw_image_levels", "hzw_rank_pieces", "hzw_rank_witness_device", "hzw_calculate_batch_resident", "hzw_r1cs_check", "hzw_calculate_to_wtns", "hzw_debug_read", "hzw_poseidon_bench_t"]
 
 
 def load_library(path=None):
@@ -492,3 +492,20 @@ def int_peak(device=0, lib_path=None):
     if lib.hzw_int_peak(device, ctypes.byref(v)) != 0:
         raise WitnessError("hzw_int_peak failed")
     return v.value
+
+
+def poseidon_width(t, inputs, reps=1, device=0):
+    """Poseidon(t - 1) of every tuple in `inputs` on the GPU with the transposed kernel of width t = 4..7
+    (`hzw_poseidon_bench_t`, every signal of the component stored): (digests, ms per launch, signal bytes per launch)."""
+    lib = load_library()
+    lib.hzw_poseidon_bench_t.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64)]
+    n = len(inputs)
+    buf = bytearray(b"".join(int(x).to_bytes(32, "little") for tup in inputs for x in tup))
+    assert len(buf) == 32 * (t - 1) * n
+    out = bytearray(32 * n)
+    ms, sb = ctypes.c_float(), ctypes.c_uint64()
+    st = lib.hzw_poseidon_bench_t(device, t, n, reps, _addr(buf), _addr(out), ctypes.byref(ms), ctypes.byref(sb))
+    if st != 0:
+        raise WitnessError("hzw_poseidon_bench_t failed with code %d" % st)
+    return [int.from_bytes(out[32 * i:32 * i + 32], "little") for i in range(n)], ms.value, sb.value

@@ -183,6 +183,10 @@ int hzw_shard_phase2(hzw_ctx* ctx, const void* records, int sanity_check, uint8_
  * lane-group form used inside the SMT kernel; both store the same signals at the same indexes. */
 int hzw_poseidon_bench(int device, uint64_t npairs, int reps, const uint8_t* inputs_le32 /* 4 x npairs x 32 B */,
                        uint8_t* digests_le32 /* 2 x npairs x 32 B, nullable */, float* ms_per_rep);
+/* the same for the other widths of the path (t = 4 leaf hashes, 5 state hashes, 6 the verifier's hash, 7 the message
+ * hash): nperms Poseidon(t - 1) hashes, transposed kernel, every signal of the component stored; digests nullable */
+int hzw_poseidon_bench_t(int device, int t, uint64_t nperms, int reps, const uint8_t* inputs_le32 /* (t - 1) x nperms x 32 B */,
+                         uint8_t* digests_le32 /* nperms x 32 B */, float* ms_per_rep, uint64_t* signal_bytes);
 
 /* Measured ceiling of the integer-multiply pipe: 32 x 32 -> 64-bit multiply-adds per second over all
  * lanes of the device (independent chains, full occupancy); the denominator of bench.py's integer roofline. */

@@ -149,3 +149,20 @@ def test_poseidon_lane_kernel_known_answers(built):
         assert got[0][0] == 0x115cc0f5e7d690413df64c6b9662e9cf2a3617f2743245519e19607a4417189a
         for (a, b, c, d), (x, y) in zip(quads, got):
             assert x == poseidon_hash([a, b]) and y == poseidon_hash([c, d])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("t", [4, 5, 6, 7])
+def test_transposed_poseidon_of_every_width(built, t):
+    """The transposed permutation at the other widths of the path (leaf, state, verifier and message hashes) against the
+    oracle's big-integer Poseidon: seeded tuples, the all-zero and all-(p - 1) inputs, a count that is no multiple of 32."""
+    import random
+    from circuits_b200.witness_calculator import poseidon_width
+    from oracle.poseidon_constants import poseidon_hash
+    from oracle.field import P
+    rng = random.Random(40 + t)
+    tuples = [tuple(range(1, t))] + [tuple(rng.randrange(P) for _ in range(t - 1)) for _ in range(41)]
+    tuples += [(0,) * (t - 1), (P - 1,) * (t - 1)]
+    got, _, _ = poseidon_width(t, tuples)
+    for tup, d in zip(tuples, got):
+        assert d == poseidon_hash(list(tup)), tup
