@@ -65,7 +65,7 @@ def make_input(cfg):
     """Packed input (NInputs x 32 B) + expected hashGlobalInputs; cached in /tmp for the other arm."""
     import pickle
     nTx, nLevels, maxL1Tx, maxFeeTx = cfg
-    # cached beside the repo's sources (git-ignored): building the 2048-slot batch takes the host mirror ~45 s
+    # cached beside the repo's sources (git-ignored): building the 2048-slot batch takes the host mirror ~45 s, 3.6 s with its hashes on the GPU
     cdir = os.path.join(ROOT, ".bench_cache")
     try:
         os.makedirs(cdir, exist_ok=True)
@@ -80,8 +80,16 @@ def make_input(cfg):
             pass
     from circuits_b200.synth import bench_batch
     t = time.time()
-    bb = bench_batch(nTx, nLevels, maxL1Tx, maxFeeTx)
-    log("[bench] synthetic batch built in %.1f s" % (time.time() - t))
+    # with a GPU the trees of the batch are hashed on it, wave by wave (circuits_b200/batchtree.py: same inputs, 3.6 s
+    # instead of 45 for the 2048-slot batch and the 16 batches that populate its 4096 accounts); the CPU arm builds on the host
+    on_gpu = False
+    try:
+        import torch
+        on_gpu = torch.cuda.is_available()
+    except Exception:
+        pass
+    bb = bench_batch(nTx, nLevels, maxL1Tx, maxFeeTx, deferred=on_gpu)
+    log("[bench] synthetic batch built in %.1f s (%s)" % (time.time() - t, "hashes on the GPU: %d in %d launches" % (bb.hashes.hashes, bb.hashes.launches) if on_gpu else "host"))
     data = (bb.getInput(), bb.getHashInputs())
     try:
         tmp = cache + ".%d" % os.getpid()

@@ -155,3 +155,40 @@ extern "C" int hzw_poseidon_bench_t(int device, int t, uint64_t nperms, int reps
     cudaFree(in); cudaFree(sig); cudaFree(dg); cudaEventDestroy(e0); cudaEventDestroy(e1);
     return 0;
 }
+
+// ---- digests only: the hashes of the batch builder (circuits_b200/batchtree.py) ------------------------------------
+// n independent Poseidon(T - 1) hashes, transposed as above, nothing stored but the digest: what the sparse Merkle trees
+// of a batch need, one launch per wave of equal dependency depth.
+template <int T> __global__ void __launch_bounds__(32 * T) k_poseidon_digest(const Fr* in, Fr* digests, int nperms) {
+    __shared__ uint32_t xch[2][T][8][32];
+    const int r = (int)(threadIdx.x >> 5), c = (int)(threadIdx.x & 31);
+    int p = (int)blockIdx.x * 32 + c;
+    const bool real = p < nperms;
+    if (!real) p = nperms - 1;
+    const Fr s = r == 0 ? fr_zero() : in[(size_t)(T - 1) * p + (r - 1)];
+    const Fr d = hz_poseidon_tr<T>(xch, r, c, s, nullptr, false);
+    if (r == 0 && real) digests[p] = d;
+}
+extern "C" int hzw_poseidon_hash(int device, int t, uint64_t n, const uint8_t* inputs_le32 /* (t - 1) x n x 32 B */, uint8_t* digests_le32 /* n x 32 B */) {
+    if (t < 3 || t > 7 || n == 0 || n > (1u << 24) || !inputs_le32 || !digests_le32) return HZW_E_PARAM;
+    int nd = 0;
+    if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0 || device < 0 || device >= nd) return HZW_E_DEVICE;
+    CK(cudaSetDevice(device));
+    Fr *in = nullptr, *dg = nullptr;
+    CK(cudaMalloc(&in, 32ull * (t - 1) * n));
+    if (cudaMalloc(&dg, 32ull * n) != cudaSuccess) { cudaFree(in); return HZW_E_DEVICE; }
+    cudaError_t e = cudaMemcpy(in, inputs_le32, 32ull * (t - 1) * n, cudaMemcpyHostToDevice);
+    const unsigned grid = (unsigned)((n + 31) / 32);
+    if (e == cudaSuccess) {
+        if (t == 3) k_poseidon_digest<3><<<grid, 96>>>(in, dg, (int)n);
+        else if (t == 4) k_poseidon_digest<4><<<grid, 128>>>(in, dg, (int)n);
+        else if (t == 5) k_poseidon_digest<5><<<grid, 160>>>(in, dg, (int)n);
+        else if (t == 6) k_poseidon_digest<6><<<grid, 192>>>(in, dg, (int)n);
+        else k_poseidon_digest<7><<<grid, 224>>>(in, dg, (int)n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(digests_le32, dg, 32ull * n, cudaMemcpyDeviceToHost);
+    cudaFree(in); cudaFree(dg);
+    if (e != cudaSuccess) { fprintf(stderr, "hzw: CUDA error %s in hzw_poseidon_hash\n", cudaGetErrorString(e)); return HZW_E_DEVICE; }
+    return 0;
+}

@@ -15,6 +15,7 @@ import hashlib
 from .field import P
 from .poseidon import poseidon
 from .smt import SMT, pad_siblings
+from .batchtree import DeferredSMT, HashBatch, Lazy, materialize
 from . import babyjub, float40
 from .feetable import compute_fee
 
@@ -78,9 +79,13 @@ class Account:
 
 
 class RollupDB:
-    def __init__(self, chain_id=0):
+    def __init__(self, chain_id=0, deferred=False, hasher=None):
+        """deferred: the trees of a batch are `batchtree.DeferredSMT`s -- every Poseidon hash of the batch (state, leaf
+        and node hashes) is evaluated when the batch is built, in waves, by `hasher(t, tuples)` (default: the transposed
+        Poseidon kernels on the GPU) instead of one by one on the host.  Same inputs either way."""
         self.chainID = chain_id
-        self.stateTree = SMT()
+        self.hashes = HashBatch(hasher) if deferred else None
+        self.stateTree = DeferredSMT(self.hashes, 48) if deferred else SMT()
         self.states = {}            # idx -> state dict
         self.lastIdx = FIRST_IDX
         self.lastBatch = 0
@@ -103,6 +108,8 @@ class RollupDB:
 
 
 def _copy_tree(t):
+    if isinstance(t, DeferredSMT):
+        return t.copy()
     n = SMT()
     n.root = t.root
     n.db = t.db          # node store is append-only and content-addressed: safe to share
@@ -114,13 +121,14 @@ class BatchBuilder:
         self.nTx, self.nLevels, self.maxL1Tx, self.maxFeeTx = nTx, nLevels, maxL1Tx, maxFeeTx
         self.chainID = db.chainID
         self.currentNumBatch = db.lastBatch + 1
+        self.hashes = db.hashes
         self.stateTree = _copy_tree(db.stateTree)
         self.states = {k: dict(v) for k, v in db.states.items()}
-        self.exitTree = SMT()
+        self.exitTree = DeferredSMT(self.hashes, 48) if self.hashes else SMT()
         self.exitStates = {}
         self.oldLastIdx = db.lastIdx
         self.finalIdx = db.lastIdx
-        self.oldStateRoot = db.stateTree.root
+        self.oldStateRoot = int(db.stateTree.root)
         self.txs = []
         self.feePlanTokens = []
         self.feeIdxs = []
@@ -145,6 +153,12 @@ class BatchBuilder:
     # -- helpers --------------------------------------------------------------
     def _zeros(self, n):
         return [0] * n
+
+    def _hash_state(self, st):
+        if self.hashes is None:
+            return hash_state(st)
+        e0 = st["tokenID"] + (st["nonce"] << 32) + (st["sign"] << 72)
+        return self.hashes.hash((e0, st["balance"], st["ay"], st["ethAddr"]))
 
     def _process(self, tx, I, accFee):
         """Apply one tx to the trees; append its per-slot inputs to I."""
@@ -239,11 +253,11 @@ class BatchBuilder:
             new1["nonce"] = s1["nonce"] + (0 if onChain else 1)
             new1["balance"] = newBalSender
             if newAccount:
-                r = self.stateTree.insert(finalFromIdx, hash_state(new1))
+                r = self.stateTree.insert(finalFromIdx, self._hash_state(new1))
                 isOld0_1 = 1 if r["isOld0"] else 0
                 oldKey1, oldValue1 = r["oldKey"], r["oldValue"]
             else:
-                r = self.stateTree.update(finalFromIdx, hash_state(new1))
+                r = self.stateTree.update(finalFromIdx, self._hash_state(new1))
             sib1 = pad_siblings(r["siblings"], L)
             self.states[finalFromIdx] = new1
 
@@ -255,21 +269,21 @@ class BatchBuilder:
                 if newExit:
                     new2 = dict(tokenID=s1["tokenID"], nonce=0, sign=s1["sign"], balance=effAmt3,
                                 ay=s1["ay"], ethAddr=s1["ethAddr"])
-                    r = self.exitTree.insert(finalFromIdx, hash_state(new2))
+                    r = self.exitTree.insert(finalFromIdx, self._hash_state(new2))
                     isOld0_2 = 1 if r["isOld0"] else 0
                     oldKey2, oldValue2 = r["oldKey"], r["oldValue"]
                     st2 = dict(zero_state)
                 else:
                     new2 = dict(st2)
                     new2["balance"] = st2["balance"] + effAmt3
-                    r = self.exitTree.update(finalFromIdx, hash_state(new2))
+                    r = self.exitTree.update(finalFromIdx, self._hash_state(new2))
                 self.exitStates[finalFromIdx] = new2
             else:
                 if st2 is None:
                     st2 = dict(self.states[finalToIdx])
                 new2 = dict(st2)
                 new2["balance"] = st2["balance"] + effAmt3
-                r = self.stateTree.update(finalToIdx, hash_state(new2))
+                r = self.stateTree.update(finalToIdx, self._hash_state(new2))
                 self.states[finalToIdx] = new2
             sib2 = pad_siblings(r["siblings"], L)
 
@@ -381,7 +395,7 @@ class BatchBuilder:
                     raise ValueError("fee idx token mismatch")
                 new = dict(st)
                 new["balance"] = st["balance"] + accFee[j]
-                r = self.stateTree.update(idx, hash_state(new))
+                r = self.stateTree.update(idx, self._hash_state(new))
                 sib = pad_siblings(r["siblings"], L)
                 self.states[idx] = new
             for k in ("tokenID", "nonce", "sign", "balance", "ay", "ethAddr"):
@@ -389,8 +403,11 @@ class BatchBuilder:
             I["siblings3"].append(sib)
             if j < maxFeeTx - 1:
                 I["imStateRootFee"].append(self.stateTree.root)
-        self.newStateRoot = self.stateTree.root
-        self.newExitRoot = self.exitTree.root
+        if self.hashes is not None:
+            self.hashes.resolve()           # every hash of the batch, wave by wave (batchtree.py)
+            I = materialize(I)
+        self.newStateRoot = int(self.stateTree.root)
+        self.newExitRoot = int(self.exitTree.root)
         self.input = I
         self.built = True
         return self

@@ -18,22 +18,29 @@ _B8_DOUBLES = None
 
 
 def _mul_base8(k):
-    """Fixed-base scalar multiplication on the precomputed doubles of Base8 (host speed only)."""
+    """Fixed-base scalar multiplication on the precomputed doubles of Base8, accumulated in extended coordinates
+    (unified addition, one inversion at the end): host speed only."""
     global _B8_DOUBLES
     if _B8_DOUBLES is None:
         t, pt = [], babyjub.BASE8
         for _ in range(254):
-            t.append(pt)
+            t.append((pt[0], pt[1], pt[0] * pt[1] % babyjub.P))
             pt = babyjub.add(pt, pt)
         _B8_DOUBLES = t
-    acc = (0, 1)
+    P, A, D = babyjub.P, babyjub.A, babyjub.D
+    X, Y, Z, T = 0, 1, 1, 0
     i = 0
     while k:
         if k & 1:
-            acc = babyjub.add(acc, _B8_DOUBLES[i])
+            x2, y2, t2 = _B8_DOUBLES[i]
+            a, b, c = X * x2 % P, Y * y2 % P, D * T % P * t2 % P
+            e = ((X + Y) * (x2 + y2) - a - b) % P
+            f, g, h = (Z - c) % P, (Z + c) % P, (b - A * a) % P
+            X, Y, Z, T = e * f % P, g * h % P, f * g % P, e * h % P
         k >>= 1
         i += 1
-    return acc
+    zi = pow(Z, -1, P)
+    return (X * zi % P, Y * zi % P)
 
 
 class FastAccount(Account):
@@ -84,7 +91,7 @@ def small_batch(nTx=3, nLevels=16, maxL1Tx=2, maxFeeTx=2):
     return bb
 
 
-def bench_batch(nTx, nLevels, maxL1Tx, maxFeeTx, n_accounts=None, n_keys=64, seed=SEED, n_l2=None):
+def bench_batch(nTx, nLevels, maxL1Tx, maxFeeTx, n_accounts=None, n_keys=64, seed=SEED, n_l2=None, deferred=False, hasher=None):
     """The benchmark batch: `maxL1Tx` deposits + (nTx - maxL1Tx) signed transfers.
 
     `n_keys` distinct key pairs are shared round-robin by the accounts (key generation is the slow
@@ -93,7 +100,7 @@ def bench_batch(nTx, nLevels, maxL1Tx, maxFeeTx, n_accounts=None, n_keys=64, see
     if n_accounts is None:
         n_accounts = max(2 * nTx, 16)
     keys = [FastAccount(k) for k in range(n_keys)]
-    db = RollupDB(chain_id=0)
+    db = RollupDB(chain_id=0, deferred=deferred, hasher=hasher)     # deferred: the hashes of every batch on the GPU (batchtree.py)
     owners = {}
     # populate: batches of createAccountDeposit (generate-input.js:61-82)
     todo = n_accounts
@@ -118,6 +125,7 @@ def bench_batch(nTx, nLevels, maxL1Tx, maxFeeTx, n_accounts=None, n_keys=64, see
     nonces = {}
     bal = {i: db.states[i]["balance"] for i in idxs}
     n_l2 = nTx - n_l1 if n_l2 is None else n_l2
+    to_sign = []
     for _ in range(n_l2):
         a, b = rng.sample(idxs, 2)
         amountF = float40.floor_fix2float(bal[a] // 5)
@@ -127,15 +135,45 @@ def bench_batch(nTx, nLevels, maxL1Tx, maxFeeTx, n_accounts=None, n_keys=64, see
         if bal[a] < amount + fee:
             amountF, amount, fee = 0, 0, 0
         tx = dict(fromIdx=a, toIdx=b, tokenID=1, amountF=amountF, nonce=nonces.get(a, 0), userFee=176, onChain=0)
-        owners[a].sign_tx(tx, 0)
+        if deferred:
+            to_sign.append((owners[a], tx))
+        else:
+            owners[a].sign_tx(tx, 0)
         bb.addTx(tx)
         nonces[a] = nonces.get(a, 0) + 1
         bal[a] -= amount + fee
         bal[b] += amount
+    if to_sign:
+        _sign_batch(to_sign, bb, db.hashes.hasher)
     bb.addToken(1)
     bb.addFeeIdx(idxs[rng.randrange(len(idxs))])
     bb.build()
     return bb
+
+
+def _sign_batch(to_sign, bb, hasher):
+    """EdDSA-Poseidon signatures of a batch with the two hashes of every signature (message hash, width 7; the
+    verifier's hash of R8, A, M, width 6) evaluated together: same values as Account.sign_tx one by one."""
+    from .rollupdb import build_tx_compressed_data
+    msgs = hasher(7, [(build_tx_compressed_data(tx, 0),
+                       tx.get("toEthAddr", 0) | (tx.get("amountF", 0) << 160) | (tx.get("maxNumBatch", 0) << 200),
+                       tx.get("toBjjAy", 0), tx.get("rqTxCompressedDataV2", 0), tx.get("rqToEthAddr", 0), tx.get("rqToBjjAy", 0))
+                      for _, tx in to_sign])
+    rs, r8s = [], []
+    for (acc, tx), msg in zip(to_sign, msgs):
+        acc._n += 1
+        seed = int.from_bytes(hashlib.sha256(b"r-%d-%d" % (msg, acc._n)).digest(), "big")
+        r = (seed % (babyjub.SUBORDER - 1)) + 1
+        rs.append(r)
+        r8s.append(_mul_base8(r))
+    hms = hasher(6, [(r8[0], r8[1], acc.key.pub[0], acc.key.pub[1], msg) for (acc, _), r8, msg in zip(to_sign, r8s, msgs)])
+    for (acc, tx), r, r8, hm in zip(to_sign, rs, r8s, hms):
+        tx["r8x"], tx["r8y"], tx["s"] = r8[0], r8[1], (r + hm * acc.key.s) % babyjub.SUBORDER
+    # bb.txs holds copies made by addTx, in the order they were added after the L1 txs
+    l2 = [t for t in bb.txs if not t.get("onChain")]
+    assert len(l2) == len(to_sign)
+    for dst, (_, src) in zip(l2, to_sign):
+        dst["r8x"], dst["r8y"], dst["s"] = src["r8x"], src["r8y"], src["s"]
 
 
 def withdraw_inputs(nLevels, n, seed=SEED):
@@ -170,13 +208,13 @@ def withdraw_inputs(nLevels, n, seed=SEED):
     return out
 
 
-def mixed_batch(nLevels=16, nTx=12, maxL1Tx=7, maxFeeTx=3):
+def mixed_batch(nLevels=16, nTx=12, maxL1Tx=7, maxFeeTx=3, deferred=False, hasher=None):
     """One batch with every transaction type of the protocol, after the cases of
     /root/reference/test/rollup-main.test.js:65-878 and rollup-main-L1.test.js:88-487: L1 createAccountDeposit,
     deposit, createAccountDepositTransfer, depositTransfer, forceTransfer, forceExit, an L1 nullified by a wrong
     token; L2 transfer, exit, a second exit of the same account (update of the exit leaf), transfer with
     request-offset linkage left empty; NOP padding; two fee tokens and collectors."""
-    db = RollupDB(chain_id=0)
+    db = RollupDB(chain_id=0, deferred=deferred, hasher=hasher)
     acc = [Account(k + 1) for k in range(4)]
     bb = db.buildBatch(4, nLevels, 4, 1)
     for a, amt, tok in ((acc[0], 10000, 1), (acc[1], 5000, 1), (acc[2], 7000, 2), (acc[3], 0, 1)):

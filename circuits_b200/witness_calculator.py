@@ -44,7 +44,7 @@ EXPORTS = ["hzw_create", "hzw_destroy", "hzw_nvars", "hzw_ninputs", "hzw_input_i
            "hzw_calculate_batch", "hzw_calculate_resident", "hzw_write_wtns", "hzw_get_signal", "hzw_dump_sym",
            "hzw_last_stats", "hzw_last_kernel_ms", "hzw_plan_info", "hzw_set_shard", "hzw_exchange_bytes",
            "hzw_shard_pieces", "hzw_shard_nvars", "hzw_shard_phase1", "hzw_shard_phase2", "hzw_poseidon_bench", "hzw_int_peak",
-           "hzw_witness_device", "hzw_signal_index", "hzw_witness_read", "hzw_profile_step", "hzw_image_levels", "hzw_rank_pieces", "hzw_rank_witness_device", "hzw_calculate_batch_resident", "hzw_r1cs_check", "hzw_calculate_to_wtns", "hzw_debug_read", "hzw_poseidon_bench_t"]
+           "hzw_witness_device", "hzw_signal_index", "hzw_witness_read", "hzw_profile_step", "hzw_image_levels", "hzw_rank_pieces", "hzw_rank_witness_device", "hzw_calculate_batch_resident", "hzw_r1cs_check", "hzw_calculate_to_wtns", "hzw_debug_read", "hzw_poseidon_bench_t", "hzw_poseidon_hash"]
 
 
 def load_library(path=None):
@@ -509,3 +509,18 @@ def poseidon_width(t, inputs, reps=1, device=0):
     if st != 0:
         raise WitnessError("hzw_poseidon_bench_t failed with code %d" % st)
     return [int.from_bytes(out[32 * i:32 * i + 32], "little") for i in range(n)], ms.value, sb.value
+
+
+def poseidon_hash_batch(t, tuples, device=0):
+    """Poseidon(t - 1) of every tuple on the GPU, digests only (`hzw_poseidon_hash`)."""
+    lib = load_library()
+    lib.hzw_poseidon_hash.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
+    n = len(tuples)
+    if n == 0:
+        return []
+    buf = bytearray(b"".join([x.to_bytes(32, "little") for tup in tuples for x in tup]))
+    out = bytearray(32 * n)
+    st = lib.hzw_poseidon_hash(device, t, n, _addr(buf), _addr(out))
+    if st != 0:
+        raise WitnessError("hzw_poseidon_hash failed with code %d" % st)
+    return [int.from_bytes(out[32 * i:32 * i + 32], "little") for i in range(n)]

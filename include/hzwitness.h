@@ -187,6 +187,10 @@ int hzw_poseidon_bench(int device, uint64_t npairs, int reps, const uint8_t* inp
  * hash): nperms Poseidon(t - 1) hashes, transposed kernel, every signal of the component stored; digests nullable */
 int hzw_poseidon_bench_t(int device, int t, uint64_t nperms, int reps, const uint8_t* inputs_le32 /* (t - 1) x nperms x 32 B */,
                          uint8_t* digests_le32 /* nperms x 32 B */, float* ms_per_rep, uint64_t* signal_bytes);
+/* digests only: n independent Poseidon(t - 1) hashes (t = 3..7) on the device, nothing stored but the result.  What the
+ * batch builder's trees hash with, one call per wave (circuits_b200/batchtree.py; the reference builds its batches with
+ * circomlib's smt.js, /root/reference/tools/generate-input.js:61-109). */
+int hzw_poseidon_hash(int device, int t, uint64_t n, const uint8_t* inputs_le32 /* (t - 1) x n x 32 B */, uint8_t* digests_le32 /* n x 32 B */);
 
 /* Measured ceiling of the integer-multiply pipe: 32 x 32 -> 64-bit multiply-adds per second over all
  * lanes of the device (independent chains, full occupancy); the denominator of bench.py's integer roofline. */

@@ -166,3 +166,16 @@ def test_transposed_poseidon_of_every_width(built, t):
     got, _, _ = poseidon_width(t, tuples)
     for tup, d in zip(tuples, got):
         assert d == poseidon_hash(list(tup)), tup
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("t", [3, 4, 5, 6, 7])
+def test_digest_only_poseidon(built, t):
+    """hzw_poseidon_hash (what the batch builder's trees hash with): digests only, every width."""
+    import random
+    from circuits_b200.witness_calculator import poseidon_hash_batch
+    from oracle.poseidon_constants import poseidon_hash
+    from oracle.field import P
+    rng = random.Random(90 + t)
+    tuples = [tuple(rng.randrange(P) for _ in range(t - 1)) for _ in range(70)] + [(0,) * (t - 1)]
+    assert poseidon_hash_batch(t, tuples) == [poseidon_hash(list(x)) for x in tuples]
