@@ -61,7 +61,7 @@ def bench_config(cfg, cfg_name):
                         "(far larger than L2); CPU arm: nothing to flush"}
 
 
-def make_input(cfg):
+def make_input(cfg, allow_gpu=True):
     """Packed input (NInputs x 32 B) + expected hashGlobalInputs; cached in /tmp for the other arm."""
     import pickle
     nTx, nLevels, maxL1Tx, maxFeeTx = cfg
@@ -85,7 +85,7 @@ def make_input(cfg):
     on_gpu = False
     try:
         import torch
-        on_gpu = torch.cuda.is_available()
+        on_gpu = allow_gpu and torch.cuda.is_available()       # the reference arm touches nothing of the CUDA library
     except Exception:
         pass
     bb = bench_batch(nTx, nLevels, maxL1Tx, maxFeeTx, deferred=on_gpu)
@@ -227,7 +227,7 @@ def run_reference(args, cfg, cfg_name):
                                "sample": "%d instances of the batch per step, CPU port of the circuit templates, all host threads" % mm},
               "e2e": {"value": val, "unit": "witness/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
         return
-    inp, _ = make_input(cfg)
+    inp, _ = make_input(cfg, allow_gpu=False)
     nTx = cfg[0]
     wc = WitnessCalculator(*cfg, lib_path=CPU_PORT)
     packed = wc.packInput(inp)

@@ -70,8 +70,10 @@ class HashBatch:
 
 
 def gpu_hasher(t, tuples):
+    import os
     from . import witness_calculator as wcm
-    return wcm.poseidon_hash_batch(t, tuples)
+    # one process per GPU (torchrun): every rank hashes on its own device
+    return wcm.poseidon_hash_batch(t, tuples, device=int(os.environ.get("LOCAL_RANK", "0")))
 
 
 def materialize(x):
