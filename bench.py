@@ -30,6 +30,7 @@ CONFIGS = {
     "rollup-main-24": (24, 32, 8, 4),
     # what one rank of eight holds of the 2048-slot batch (256 slots, 8 fee txs): per-kernel latency floors, not a bench line
     "rollup-main-256": (256, 32, 32, 8),
+    "rollup-main-1024": (1024, 32, 128, 32),
     # config 5 of BASELINE.json: 65 536 independent Withdraw(32) witnesses (nTx = instances of the batch)
     "withdraw-65536": (65536, 32, 0, 1),
     "withdraw-4096": (4096, 32, 0, 1),
