@@ -126,6 +126,34 @@ def test_two_shards_on_one_gpu_equal_the_whole(built):
     assert bytes(ShardedWitnessCalculator.assemble(whole.NVars, shards)) == want
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("world, prm", [(3, (13, 16, 5, 2)), (5, (11, 16, 4, 3))])
+def test_uneven_shards_with_different_owners_of_the_closing_values(built, world, prm):
+    """Shards of unequal size where the last slot and the last fee tx belong to DIFFERENT ranks (and one rank has no fee
+    tx at all): the early exchange walks them on their owners (hz_early_exchange: n_s = 1, n_f = 0 on one rank, the other
+    way round on another), every rank packs its record ahead of its merkle levels."""
+    import torch
+    from circuits_b200.synth import bench_batch
+    from circuits_b200.witness_calculator import ShardedWitnessCalculator
+    bb = bench_batch(*prm, n_accounts=16)
+    whole = _cuda(*prm)
+    packed = whole.packInput(bb.getInput())
+    want = bytes(whole.calculateBinWitness(packed, True))
+    assert int.from_bytes(want[32:64], "little") == bb.getHashInputs()
+    ranks = [ShardedWitnessCalculator(*prm, rank=r, world=world) for r in range(world)]
+    for wc in ranks:
+        wc.phase1(packed, True)
+    recs = torch.cat([wc._rec for wc in ranks])
+    shards = []
+    for wc in ranks:
+        wc._recs.copy_(recs)
+        torch.cuda.synchronize()
+        buf, _ = wc.phase2(True)
+        shards.append((wc.pieces(), bytes(buf)))
+    assert sum(c for pcs, _ in shards for _, c in pcs) == whole.NVars
+    assert bytes(ShardedWitnessCalculator.assemble(whole.NVars, shards)) == want
+
+
 def test_copy_paths_without_rebuilt_images(built, monkeypatch):
     """With many ranks per host the image levels are copied like everything else (a rank has no threads to
     rebuild them with): the same witnesses from the end-to-end path and from two shards with HZW_NO_HOLES set."""
