@@ -163,7 +163,10 @@ int hzw_last_stats(const hzw_ctx* ctx, uint64_t* gpu_launches, uint64_t* h2d_byt
  * the caller with ONE all-gather (NCCL in the Python binding) between the two phases.
  *   hzw_set_shard      rank / world of this context (default 0 / 1: everything)
  *   hzw_exchange_bytes size of one rank's record
- *   hzw_shard_phase1   inputs -> own slots and fee txs; writes the own record to record_out
+ *   hzw_shard_phase1   inputs -> own slots and fee txs; writes the own record to record_out.  With world > 1 it returns
+ *                      as soon as the RECORD is complete (it is packed ahead of the merkle levels, which are still running:
+ *                      the collective is meant to run beside them); a constraint failure of this rank's slots is then
+ *                      reported by hzw_shard_phase2, which must follow
  *   hzw_shard_phase2   records = world x exchange_bytes, gathered; hasherInputs, own SHA blocks; copies the
  *                      witness pieces this rank owns to shard_out, back to back
  *   hzw_shard_pieces   the (witness index, count) pairs of those pieces; hzw_shard_nvars their total
