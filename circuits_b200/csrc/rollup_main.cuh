@@ -66,6 +66,14 @@ TM HZ_HD V<M> hz_in(const Comp<M>& c, const HzPlan& pl, int f, int a = 0, int b 
     return c.load(pl.in_off[f] + (uint32_t)a * pl.in_d1[f] + (uint32_t)b);
 }
 
+// main inputs the dry walk of k_smtjob never reads the VALUE of (fee plan and accumulated fees: the fee accumulator is
+// skipped there; siblings: the processors are not evaluated, their jobs carry the siblings' witness index): each is a
+// dependent global load at the head of the merkle chain, so the dry walk gets a wired zero instead
+TM HZ_HD V<M> hz_in_unless_dry(const Comp<M>& c, const HzPlan& pl, int f, int a = 0, int b = 0) {
+    if (hz_is_dry(c)) return c.known(0, Ops<M>::K(0));
+    return hz_in(c, pl, f, a, b);
+}
+
 // ---- section B/C: decodeTx[i]  (:223-265) ---------------------------------------------------
 TM HZ_FN void sec_decode(Comp<M>& c, const HzPlan& pl, int i, DecodeOut<M>& o, PreBits<M>& pre) {
     const HzParams& P = pl.P;
@@ -142,8 +150,8 @@ TM HZ_FN void sec_rollup(Comp<M>& c, const HzPlan& pl, int i, const DecodeOut<M>
     const int nTx = P.nTx, L = P.nLevels + 1;
     RollupTxIn<M> t;
     for (int k = 0; k < P.maxFeeTx; k++) {
-        t.feePlanTokens[k] = hz_in(c, pl, IN_feePlanTokens, k);
-        t.accFeeIn[k] = i == 0 ? Ops<M>::K(0) : hz_in(c, pl, IN_imAccFeeOut, i - 1, k);
+        t.feePlanTokens[k] = hz_in_unless_dry(c, pl, IN_feePlanTokens, k);
+        t.accFeeIn[k] = i == 0 ? Ops<M>::K(0) : hz_in_unless_dry(c, pl, IN_imAccFeeOut, i - 1, k);
     }
     for (int j = 0; j < 3; j++) {
         int q = i + j + 1;
@@ -176,12 +184,12 @@ TM HZ_FN void sec_rollup(Comp<M>& c, const HzPlan& pl, int i, const DecodeOut<M>
     t.loadAmountF = hz_in(c, pl, IN_loadAmountF, i);
     t.tokenID1 = hz_in(c, pl, IN_tokenID1, i); t.nonce1 = hz_in(c, pl, IN_nonce1, i); t.sign1 = hz_in(c, pl, IN_sign1, i);
     t.balance1 = hz_in(c, pl, IN_balance1, i); t.ay1 = hz_in(c, pl, IN_ay1, i); t.ethAddr1 = hz_in(c, pl, IN_ethAddr1, i);
-    for (int k = 0; k < L; k++) t.siblings1[k] = hz_in(c, pl, IN_siblings1, i, k);
+    for (int k = 0; k < L; k++) t.siblings1[k] = hz_in_unless_dry(c, pl, IN_siblings1, i, k);
     t.isOld0_1 = hz_in(c, pl, IN_isOld0_1, i); t.oldKey1 = hz_in(c, pl, IN_oldKey1, i); t.oldValue1 = hz_in(c, pl, IN_oldValue1, i);
     t.tokenID2 = hz_in(c, pl, IN_tokenID2, i); t.nonce2 = hz_in(c, pl, IN_nonce2, i); t.sign2 = hz_in(c, pl, IN_sign2, i);
     t.balance2 = hz_in(c, pl, IN_balance2, i); t.newExit = hz_in(c, pl, IN_newExit, i); t.ay2 = hz_in(c, pl, IN_ay2, i);
     t.ethAddr2 = hz_in(c, pl, IN_ethAddr2, i);
-    for (int k = 0; k < L; k++) t.siblings2[k] = hz_in(c, pl, IN_siblings2, i, k);
+    for (int k = 0; k < L; k++) t.siblings2[k] = hz_in_unless_dry(c, pl, IN_siblings2, i, k);
     t.isOld0_2 = hz_in(c, pl, IN_isOld0_2, i); t.oldKey2 = hz_in(c, pl, IN_oldKey2, i); t.oldValue2 = hz_in(c, pl, IN_oldValue2, i);
     t.oldStateRoot = i == 0 ? hz_in(c, pl, IN_oldStateRoot) : hz_in(c, pl, IN_imStateRoot, i - 1);
     t.oldExitRoot = i == 0 ? Ops<M>::K(0) : hz_in(c, pl, IN_imExitRoot, i - 1);
