@@ -128,18 +128,22 @@ def test_two_shards_on_one_gpu_equal_the_whole(built):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world, prm", [(3, (13, 16, 5, 2)), (5, (11, 16, 4, 3))])
-def test_uneven_shards_with_different_owners_of_the_closing_values(built, world, prm):
+def test_uneven_shards_with_different_owners_of_the_closing_values(built, world, prm, monkeypatch):
     """Shards of unequal size where the last slot and the last fee tx belong to DIFFERENT ranks (and one rank has no fee
     tx at all): the early exchange walks them on their owners (hz_early_exchange: n_s = 1, n_f = 0 on one rank, the other
     way round on another), every rank packs its record ahead of its merkle levels."""
     import torch
     from circuits_b200.synth import bench_batch
     from circuits_b200.witness_calculator import ShardedWitnessCalculator
+    monkeypatch.setenv("HZW_EARLY_HASH", "1")         # the early paths are for long SHA walks: forced on at this size
     bb = bench_batch(*prm, n_accounts=16)
     whole = _cuda(*prm)
     packed = whole.packInput(bb.getInput())
     want = bytes(whole.calculateBinWitness(packed, True))
     assert int.from_bytes(want[32:64], "little") == bb.getHashInputs()
+    whole.calculateResident(packed, True)             # the single-GPU early walk at this size too
+    got = bytearray(len(want)); whole.readWitness(out=got)
+    assert bytes(got) == want
     ranks = [ShardedWitnessCalculator(*prm, rank=r, world=world) for r in range(world)]
     for wc in ranks:
         wc.phase1(packed, True)
