@@ -18,27 +18,32 @@ _B8_DOUBLES = None
 
 
 def _mul_base8(k):
-    """Fixed-base scalar multiplication on the precomputed doubles of Base8, accumulated in extended coordinates
-    (unified addition, one inversion at the end): host speed only."""
+    """Fixed-base scalar multiplication on a table of 4-bit windows of Base8 (d * 16^w * Base8, d = 1..15), accumulated
+    in extended coordinates (unified addition, one inversion at the end): host speed only."""
     global _B8_DOUBLES
     if _B8_DOUBLES is None:
-        t, pt = [], babyjub.BASE8
-        for _ in range(254):
-            t.append((pt[0], pt[1], pt[0] * pt[1] % babyjub.P))
-            pt = babyjub.add(pt, pt)
+        t, base = [], babyjub.BASE8
+        for _ in range(64):
+            row, pt = [None], base
+            for d in range(1, 16):
+                row.append((pt[0], pt[1], pt[0] * pt[1] % babyjub.P))
+                pt = babyjub.add(pt, base)
+            t.append(row)
+            base = pt                      # 16 * base
         _B8_DOUBLES = t
     P, A, D = babyjub.P, babyjub.A, babyjub.D
     X, Y, Z, T = 0, 1, 1, 0
-    i = 0
+    w = 0
     while k:
-        if k & 1:
-            x2, y2, t2 = _B8_DOUBLES[i]
+        d = k & 15
+        if d:
+            x2, y2, t2 = _B8_DOUBLES[w][d]
             a, b, c = X * x2 % P, Y * y2 % P, D * T % P * t2 % P
             e = ((X + Y) * (x2 + y2) - a - b) % P
             f, g, h = (Z - c) % P, (Z + c) % P, (b - A * a) % P
             X, Y, Z, T = e * f % P, g * h % P, f * g % P, e * h % P
-        k >>= 1
-        i += 1
+        k >>= 4
+        w += 1
     zi = pow(Z, -1, P)
     return (X * zi % P, Y * zi % P)
 
